@@ -1,0 +1,229 @@
+"""gseg -- B200-native graph-based image segmentation (host-side Python mirror of include/gseg.h).
+
+The product is `libgseg.so` (hand-written sm_100a CUDA kernels behind a C-ABI).  This module only
+builds it, loads it with ctypes and wraps the handle; it contains no compute and no fallback: if
+the library is missing or no CUDA device is present every compute call raises.
+
+Import it with importlib (the directory name is not a Python identifier):
+    gseg = importlib.import_module("graph-algorithm-image-segmentation-gpgpu_b200")
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_ROOT = os.path.dirname(_HERE)
+CSRC = os.path.join(_HERE, "csrc")
+LIB_PATH = os.path.join(_HERE, "libgseg.so")
+CLI_PATH = os.path.join(_HERE, "gseg")
+HEADER = os.path.join(_ROOT, "include", "gseg.h")
+
+FELZ, HIER, SUPERPIX = 0, 1, 2
+MEM_HOST, MEM_DEVICE = 0, 1
+FLAG_GRAPH, FLAG_KEEP_PLANES = 1, 2
+
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+              "-Xcompiler", "-fPIC,-ffp-contract=off"]
+
+
+def _newer(target, sources):
+    if not os.path.exists(target):
+        return True
+    t = os.path.getmtime(target)
+    return any(os.path.getmtime(s) > t for s in sources)
+
+
+def build(force=False, verbose=False):
+    """Compile libgseg.so (and the gseg CLI) in-tree for sm_100a with nvcc.  Works without a GPU."""
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [HEADER]
+    if force or _newer(LIB_PATH, srcs):
+        cmd = ["nvcc"] + NVCC_FLAGS + ["-shared", "-o", LIB_PATH, os.path.join(CSRC, "gseg_api.cu")]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    cli_src = os.path.join(CSRC, "gseg_cli.cpp")
+    if os.path.exists(cli_src) and (force or _newer(CLI_PATH, [cli_src, LIB_PATH, HEADER])):
+        cmd = ["g++", "-O2", "-std=c++17", "-o", CLI_PATH, cli_src, "-I", os.path.join(_ROOT, "include"),
+               "-L", _HERE, "-lgseg", "-Wl,-rpath,$ORIGIN"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.check_call(cmd)
+    return LIB_PATH
+
+
+class Params(C.Structure):
+    _fields_ = [("sigma", C.c_float), ("k", C.c_float), ("min_size", C.c_int32), ("connectivity", C.c_int32),
+                ("variant", C.c_int32), ("max_levels", C.c_int32), ("max_rounds", C.c_int32), ("flags", C.c_uint32)]
+
+
+class RoundStat(C.Structure):
+    _fields_ = [("n_components", C.c_int64), ("n_edges", C.c_int64), ("n_merged", C.c_int64),
+                ("phase", C.c_int32), ("reserved", C.c_int32)]
+
+
+_lib = None
+
+
+def load():
+    """Load libgseg.so; raises (never falls back) when it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError("libgseg.so is not built (run __graft_entry__.build()); there is no fallback path")
+    L = C.CDLL(LIB_PATH)
+    vp, i32, u64 = C.c_void_p, C.c_int, C.c_uint64
+    L.gseg_version.restype = i32
+    L.gseg_strerror.restype = C.c_char_p
+    L.gseg_strerror.argtypes = [i32]
+    L.gseg_last_error.restype = C.c_char_p
+    L.gseg_last_error.argtypes = [vp]
+    L.gseg_create.argtypes = [C.POINTER(vp), i32, i32, i32]
+    L.gseg_destroy.argtypes = [vp]
+    L.gseg_destroy.restype = None
+    L.gseg_set_stream.argtypes = [vp, vp]
+    L.gseg_segment.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(Params)]
+    L.gseg_segment_async.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(Params)]
+    L.gseg_wait.argtypes = [vp]
+    L.gseg_num_levels.argtypes = [vp]
+    L.gseg_num_components.argtypes = [vp, i32]
+    L.gseg_labels.argtypes = [vp, i32, vp, i32]
+    L.gseg_labels_all.argtypes = [vp, vp, i32, i32]
+    L.gseg_colorize.argtypes = [vp, i32, u64, vp, i32]
+    L.gseg_weights.argtypes = [vp, vp, i32]
+    L.gseg_blurred.argtypes = [vp, vp, i32]
+    L.gseg_stats.argtypes = [vp, C.POINTER(RoundStat), i32]
+    L.gseg_synth.argtypes = [vp, vp, i32, i32, u64, i32]
+    L.gseg_sort_pairs_u64.argtypes = [vp, vp, vp, C.c_int64, i32, i32]
+    _lib = L
+    return L
+
+
+class GsegError(RuntimeError):
+    pass
+
+
+def _is_torch(x):
+    return type(x).__module__.startswith("torch")
+
+
+def _ptr(x):
+    if _is_torch(x):
+        return x.data_ptr(), (MEM_DEVICE if x.is_cuda else MEM_HOST)
+    return x.ctypes.data, MEM_HOST
+
+
+class Segmenter:
+    """One gseg context (one GPU, one stream).  Mirrors the reference executables' parameter list:
+    image, sigma, k, min_size, connectivity, variant / hierarchy level (BASELINE.json north_star)."""
+
+    def __init__(self, max_w, max_h, device=0):
+        self.L = load()
+        self.h = C.c_void_p()
+        rc = self.L.gseg_create(C.byref(self.h), device, max_w, max_h)
+        if rc != 0:
+            raise GsegError("gseg_create: %s" % self.L.gseg_strerror(rc).decode())
+        self.device = device
+        self.w = self.hh = 0
+        self.D = 2
+
+    def close(self):
+        if self.h:
+            self.L.gseg_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc < 0:
+            raise GsegError("%s: %s (%s)" % (what, self.L.gseg_strerror(rc).decode(),
+                                             self.L.gseg_last_error(self.h).decode()))
+        return rc
+
+    def set_stream(self, cuda_stream_ptr):
+        self._ck(self.L.gseg_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "gseg_set_stream")
+
+    def params(self, sigma=0.8, k=300.0, min_size=20, connectivity=4, variant=FELZ, max_levels=0, max_rounds=0,
+               flags=0):
+        return Params(sigma, k, min_size, connectivity, variant, max_levels, max_rounds, flags)
+
+    def segment(self, img, params=None, wait=True, **kw):
+        """img: (h, w, 3) uint8 numpy array / torch CPU tensor (host) or torch CUDA tensor (device)."""
+        p = params if params is not None else self.params(**kw)
+        hh, w = int(img.shape[0]), int(img.shape[1])
+        if _is_torch(img):
+            assert img.dtype.__str__() == "torch.uint8" and img.is_contiguous()
+            stride = img.stride(0)
+        else:
+            assert img.dtype == np.uint8 and img.flags["C_CONTIGUOUS"]
+            stride = img.strides[0]
+        ptr, kind = _ptr(img)
+        self.w, self.hh, self.D = w, hh, (4 if p.connectivity == 8 else 2)
+        self._keep = img
+        fn = self.L.gseg_segment if wait else self.L.gseg_segment_async
+        self._ck(fn(self.h, C.c_void_p(ptr), w, hh, stride, kind, C.byref(p)), "gseg_segment")
+        return self
+
+    def wait(self):
+        self._ck(self.L.gseg_wait(self.h), "gseg_wait")
+        return self
+
+    def num_levels(self):
+        return self._ck(self.L.gseg_num_levels(self.h), "gseg_num_levels")
+
+    def num_components(self, level=-1):
+        return self._ck(self.L.gseg_num_components(self.h, level), "gseg_num_components")
+
+    def labels(self, level=-1, out=None):
+        if out is None:
+            out = np.empty((self.hh, self.w), np.int32)
+        ptr, kind = _ptr(out)
+        self._ck(self.L.gseg_labels(self.h, level, C.c_void_p(ptr), kind), "gseg_labels")
+        return out
+
+    def labels_all(self, max_levels=64, out=None):
+        n = min(max_levels, self.num_levels())
+        if out is None:
+            out = np.empty((max(n, 1), self.hh, self.w), np.int32)
+        ptr, kind = _ptr(out)
+        got = self._ck(self.L.gseg_labels_all(self.h, C.c_void_p(ptr), int(out.shape[0]), kind), "gseg_labels_all")
+        return out[:got]
+
+    def colorize(self, level=-1, seed=1, out=None):
+        if out is None:
+            out = np.empty((self.hh, self.w, 3), np.uint8)
+        ptr, kind = _ptr(out)
+        self._ck(self.L.gseg_colorize(self.h, level, seed, C.c_void_p(ptr), kind), "gseg_colorize")
+        return out
+
+    def weights(self):
+        out = np.empty(self.hh * self.w * self.D, np.float32)
+        self._ck(self.L.gseg_weights(self.h, C.c_void_p(out.ctypes.data), MEM_HOST), "gseg_weights")
+        return out
+
+    def blurred(self):
+        out = np.empty((3, self.hh, self.w), np.float32)
+        self._ck(self.L.gseg_blurred(self.h, C.c_void_p(out.ctypes.data), MEM_HOST), "gseg_blurred")
+        return out
+
+    def stats(self):
+        arr = (RoundStat * 64)()
+        n = self._ck(self.L.gseg_stats(self.h, arr, 64), "gseg_stats")
+        return [(arr[i].n_components, arr[i].n_edges, arr[i].n_merged, arr[i].phase) for i in range(n)]
+
+    def synth(self, w, h, seed, out=None):
+        if out is None:
+            out = np.empty((h, w, 3), np.uint8)
+        ptr, kind = _ptr(out)
+        self._ck(self.L.gseg_synth(self.h, C.c_void_p(ptr), w, h, seed, kind), "gseg_synth")
+        return out
+
+    def sort_pairs(self, keys_dev_ptr, vals_dev_ptr, n, begin_bit=0, end_bit=64):
+        self._ck(self.L.gseg_sort_pairs_u64(self.h, C.c_void_p(keys_dev_ptr), C.c_void_p(vals_dev_ptr), n,
+                                            begin_bit, end_bit), "gseg_sort_pairs_u64")

@@ -1,0 +1,147 @@
+// gseg_device.cuh -- device-side building blocks shared by every kernel of the engine:
+// control block, relaxed global loads/stores, warp/block scans and the single-pass
+// decoupled look-back prefix (the scan under every compaction).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+typedef unsigned int u32;
+typedef unsigned long long u64;
+
+#define GSEG_KEY_NONE 0xFFFFFFFFFFFFFFFFull
+#define GSEG_INF_BITS 0x7F800000u
+#define GSEG_MAXR 64 /* hard cap on rounds per run */
+#define GSEG_MAXMASK 64
+
+enum { PH_PRED = 0, PH_MINSIZE = 1, PH_DONE = 2 };
+enum { DERR_NONE = 0, DERR_SCAN = 1, DERR_ARENA = 2 };
+
+// Parameters of one run; filled by the host in pinned memory and copied into GsegCtl::p.
+struct GsegRunParams {
+    const uint8_t *rgb; // device pointer of the input image
+    int w, h, stride, D, variant;
+    float k;
+    int min_size, max_rounds, max_levels;
+    u32 arena_cap;  // capacity of the supervertex-map arena in u32 entries
+    u32 epoch_base; // first look-back tag of this run (monotonic across runs)
+    int mask_len;
+    float mask[GSEG_MAXMASK];
+};
+
+// Device-resident control block: all round-to-round state lives here so that a whole run can be
+// replayed as one CUDA graph without the host reading anything back between rounds (the reference
+// copies a 4-byte flag to the host every round, Report.pdf p5).
+struct GsegCtl {
+    GsegRunParams p;
+    u32 Vcur, Ecur;   // components / live edges entering the current round
+    u32 Vnext, Enext; // produced by the component scan / the edge compaction
+    u32 phase, round, levels, error;
+    u32 ticketC, ticketE; // dynamic tile tickets of the two look-back scans
+    u32 map_off[GSEG_MAXR + 1]; // arena offset of round r's old->new supervertex map
+    u32 stV[GSEG_MAXR], stE[GSEG_MAXR], stM[GSEG_MAXR], stP[GSEG_MAXR], stVafter[GSEG_MAXR];
+};
+
+__device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
+    u64 v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(u64 *p, u64 v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ u32 ld_relaxed_u32(const u32 *p) {
+    u32 v;
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ u32 warp_incl_scan(u32 v, int lane) {
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        u32 t = __shfl_up_sync(0xFFFFFFFFu, v, o);
+        if (lane >= o) v += t;
+    }
+    return v;
+}
+
+// Exclusive scan of one value per thread over a block of NT threads. s: >= 34 u32 of shared memory.
+// Leaves the block total in s[32]. Contains two __syncthreads().
+template <int NT>
+__device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *s) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    u32 inc = warp_incl_scan(v, lane);
+    if (lane == 31) s[wid] = inc;
+    __syncthreads();
+    if (wid == 0) {
+        u32 x = lane < NT / 32 ? s[lane] : 0u;
+        u32 xi = warp_incl_scan(x, lane);
+        s[lane] = xi - x;
+        if (lane == 31) s[32] = xi;
+    }
+    __syncthreads();
+    return s[wid] + inc - v;
+}
+
+// ---- decoupled look-back ---------------------------------------------------------------------
+// status word: [63:34] tag (30 bit, unique per scan launch), [33:32] state, [31:0] value.
+#define ST_AGG 1u
+#define ST_INC 2u
+__device__ __forceinline__ u64 pack_status(u32 tag, u32 state, u32 val) {
+    return ((u64)((tag << 2) | state) << 32) | (u64)val;
+}
+
+// Called by all 32 lanes of warp 0 with the tile's aggregate; returns the exclusive prefix of the
+// tile (sum of the aggregates of all lower tiles).  Tiles MUST be handed out through an atomic
+// ticket so that every lower tile belongs to a block that is already running.  A bounded spin
+// turns a protocol bug into an error code instead of a hung GPU.
+__device__ __forceinline__ u32 lookback_prefix(u64 *status, u32 tile, u32 tag, u32 aggregate, u32 *err) {
+    const int lane = threadIdx.x & 31;
+    if (tile == 0) {
+        if (lane == 0) st_relaxed_u64(status, pack_status(tag, ST_INC, aggregate));
+        return 0u;
+    }
+    if (lane == 0) st_relaxed_u64(status + tile, pack_status(tag, ST_AGG, aggregate));
+    u32 excl = 0u, spins = 0u;
+    int look = (int)tile - 1;
+    for (;;) {
+        const int idx = look - lane;
+        const u64 s = idx >= 0 ? ld_relaxed_u64(status + idx) : pack_status(tag, ST_INC, 0u);
+        const u32 hi = (u32)(s >> 32);
+        const bool valid = (hi >> 2) == tag && (hi & 3u) != 0u;
+        const bool inc = valid && (hi & 3u) == ST_INC;
+        const u32 incm = __ballot_sync(0xFFFFFFFFu, inc);
+        const u32 invm = __ballot_sync(0xFFFFFFFFu, !valid);
+        const int first = incm ? __ffs(incm) - 1 : 32;
+        const u32 need = first >= 31 ? 0xFFFFFFFFu : ((2u << first) - 1u);
+        if (invm & need) {
+            if (++spins > (1u << 22)) {
+                if (lane == 0) *err = DERR_SCAN;
+                return excl;
+            }
+            continue;
+        }
+        u32 v = lane <= first ? (u32)s : 0u;
+#pragma unroll
+        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        excl += v;
+        if (first < 32) break;
+        look -= 32;
+    }
+    if (lane == 0) st_relaxed_u64(status + tile, pack_status(tag, ST_INC, excl + aggregate));
+    return excl;
+}
+
+// Per-block exclusive offset of `cnt` items inside a globally ordered compaction.
+// Returns this thread's global output offset; s[32] = tile total, s[33] = tile prefix.
+template <int NT>
+__device__ __forceinline__ u32 tile_offset(u32 cnt, u32 tile, u32 tag, u64 *status, u32 *err, u32 *s) {
+    const u32 ex = block_excl_scan<NT>(cnt, s);
+    if (threadIdx.x < 32) {
+        const u32 pre = lookback_prefix(status, tile, tag, s[32], err);
+        if (threadIdx.x == 0) s[33] = pre;
+    }
+    __syncthreads();
+    return s[33] + ex;
+}
+
+__device__ __forceinline__ u64 make_key(u32 wbits, u32 idx) { return ((u64)wbits << 32) | (u64)idx; }

@@ -1,0 +1,136 @@
+/*
+ * gseg.h -- C-ABI of the B200-native graph-segmentation engine (libgseg.so).
+ *
+ * Drop-in boundary for the segmentation hot path of
+ * akankshabaranwal/graph-algorithm-image-segmentation-GPGPU.  The mounted reference holds no source
+ * (SURVEY.md section 0), so no reference header can be cited line by line; each entry point cites the
+ * reference *stage* it replaces (Report.pdf page / section) and the parameter list BASELINE.json's
+ * north_star fixes: input image, sigma, k, min_size, hierarchy level -> label image + hierarchy.
+ * The closest published signature is F&H `segment`'s
+ *     image<rgb>* segment_image(image<rgb>* im, float sigma, float c, int min_size, int* num_ccs)
+ * (Report.pdf ref [23], the report's CPU baseline, p4 "Baseline"), which gseg_segment + gseg_labels
+ * replace.
+ *
+ * Conventions: plain pointers and sizes only; 0 = success, negative = gseg_status; nothing throws
+ * across the boundary; the caller owns every input/output buffer, the context owns all device
+ * scratch (allocated once in gseg_create, never inside gseg_segment); one context per GPU per host
+ * thread, contexts are independent and not thread-safe.  There is no CPU fallback: every entry
+ * point that computes requires a CUDA device and fails with GSEG_E_CUDA otherwise.
+ */
+#ifndef GSEG_H
+#define GSEG_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GSEG_VERSION 100
+
+/* variant -- which reference branch's semantics to run */
+#define GSEG_FELZ 0     /* cuda-mst-naive: Boruvka + Felzenszwalb predicate + min-size (Report p2-3 s3.1) */
+#define GSEG_HIER 1     /* fastmst_segment: one hierarchy level per Boruvka round, no predicate (p3-4 s3.2.2-3) */
+#define GSEG_SUPERPIX 2 /* superpixel_gpu: per-round re-weighting by Sobel strength x mean colour (p4 s3.2.4) */
+
+#define GSEG_MEM_HOST 0
+#define GSEG_MEM_DEVICE 1
+
+/* flags */
+#define GSEG_FLAG_GRAPH 1u      /* replay the whole round schedule as one CUDA graph (no per-round host sync) */
+#define GSEG_FLAG_KEEP_PLANES 2u /* keep blurred planes / weights readable after the call (gseg_blurred/weights) */
+
+typedef enum gseg_status {
+    GSEG_OK = 0,
+    GSEG_E_ARG = -1,     /* bad argument (null pointer, size, connectivity, variant, sigma range) */
+    GSEG_E_CUDA = -2,    /* CUDA runtime error or no device; gseg_last_error() has the text */
+    GSEG_E_SIZE = -3,    /* image larger than the context was created for */
+    GSEG_E_ARENA = -4,   /* supervertex-map arena exhausted (pathological round count) */
+    GSEG_E_INTERNAL = -5, /* device-side watchdog tripped */
+    GSEG_E_STATE = -6,   /* result requested before a successful gseg_segment */
+    GSEG_E_LEVEL = -7    /* hierarchy level out of range */
+} gseg_status;
+
+/* Parameters of one segmentation (BASELINE.json north_star: sigma, k, min_size, hierarchy level). */
+typedef struct gseg_params {
+    float sigma;          /* Gaussian pre-filter (Report p2 s2.1; p3 s3.2 par.2); 0 < 4*sigma+1 <= 64 taps */
+    float k;              /* Felzenszwalb scale parameter (Report p2 par.1); FELZ only */
+    int32_t min_size;     /* min-size post-merge (Report p3 step 6 "post-processing"); FELZ only */
+    int32_t connectivity; /* 4 or 8 (BASELINE.json configs[1], configs[2]) */
+    int32_t variant;      /* GSEG_FELZ | GSEG_HIER | GSEG_SUPERPIX */
+    int32_t max_levels;   /* HIER/SUPERPIX: stop after this many levels; 0 = until one component */
+    int32_t max_rounds;   /* cap on Boruvka rounds (Report p5: 10-20 in practice); 0 = 48 */
+    uint32_t flags;
+} gseg_params;
+
+/* One row per executed Boruvka round (SURVEY.md section 5 "metrics": V_r, E_r per round). */
+typedef struct gseg_round_stat {
+    int64_t n_components; /* components entering the round */
+    int64_t n_edges;      /* live (inter-component) edges entering the round */
+    int64_t n_merged;     /* components merged away by the round */
+    int32_t phase;        /* 0 = predicate / hierarchy round, 1 = min-size round */
+    int32_t reserved;
+} gseg_round_stat;
+
+typedef struct gseg_ctx gseg_ctx;
+
+int gseg_version(void);
+const char *gseg_strerror(int status);
+const char *gseg_last_error(const gseg_ctx *ctx);
+
+/* Replaces: per-branch main() device/scratch set-up.  Allocates every
+ * device buffer for images up to max_w x max_h on CUDA device `device`. */
+int gseg_create(gseg_ctx **out, int device, int max_w, int max_h);
+void gseg_destroy(gseg_ctx *ctx);
+
+/* Run the context's work on a caller-owned CUDA stream (cudaStream_t as void*); NULL = own stream. */
+int gseg_set_stream(gseg_ctx *ctx, void *cuda_stream);
+
+/* Replaces: L3 pre-filter + L2 graph creation + L1 segmentation core of one reference executable
+ * (Report p2 Fig.1; p3 s3.2.1; p2-3 s3.1 steps 1-9; p3-4 s3.2.2; p4 s3.2.4).
+ * rgb: interleaved 8-bit RGB, `stride_bytes` per row (>= 3*w), in host or device memory (mem_kind).
+ * Returns when the partition is complete on the device. */
+int gseg_segment(gseg_ctx *ctx, const uint8_t *rgb, int w, int h, int stride_bytes, int mem_kind,
+                 const gseg_params *params);
+
+/* Asynchronous form: enqueue only (host input must be pinned and stay valid); gseg_wait completes it. */
+int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int h, int stride_bytes, int mem_kind,
+                       const gseg_params *params);
+int gseg_wait(gseg_ctx *ctx);
+
+/* Number of hierarchy levels produced (FELZ: 1).  Replaces: the stored per-round supervertex ids
+ * (Report p4 s3.2.3 par.1). */
+int gseg_num_levels(const gseg_ctx *ctx);
+/* Components at `level` (0-based; -1 = last). */
+int gseg_num_components(const gseg_ctx *ctx, int level);
+
+/* Replaces: L0 hierarchy materialisation, one thread per pixel mapping the previous level's ids
+ * through the stored supervertex ids (Report p4 s3.2.3).  out: w*h int32, row-major, dense ids in
+ * [0, gseg_num_components(level)).  level -1 = last level / the FELZ partition. */
+int gseg_labels(gseg_ctx *ctx, int level, int32_t *out, int mem_kind);
+/* All levels 0..n-1 in one pass (level l at out + l*w*h); n = min(max_levels, gseg_num_levels). */
+int gseg_labels_all(gseg_ctx *ctx, int32_t *out, int max_levels, int mem_kind);
+
+/* Replaces: random colour table + colour image (cuRAND, Report p4 s3.2.3).  out: w*h*3 bytes. */
+int gseg_colorize(gseg_ctx *ctx, int level, uint64_t seed, uint8_t *out_rgb, int mem_kind);
+
+/* Round-0 edge weights in edge-index order idx = (y*w+x)*D + d, D = 2 (E,S) or 4 (E,S,SE,NE);
+ * +inf where the edge does not exist (SUPERPIX: the static edge strength).  For the 1e-6 check. */
+int gseg_weights(gseg_ctx *ctx, float *out, int mem_kind);
+/* Blurred image, 3 planes of w*h floats (R,G,B). */
+int gseg_blurred(gseg_ctx *ctx, float *out, int mem_kind);
+
+/* Per-round statistics of the last run; returns number of rounds (<= cap written). */
+int gseg_stats(const gseg_ctx *ctx, gseg_round_stat *out, int cap);
+
+/* Deterministic synthetic input: w*h*3 bytes into host or device memory. */
+int gseg_synth(gseg_ctx *ctx, uint8_t *out_rgb, int w, int h, uint64_t seed, int mem_kind);
+
+/* Stand-alone primitives of the edge-dedup path (Report p3 s3.2.2
+ * "sort"): in-house onesweep radix sort of 64-bit keys with 32-bit payload, on device memory. */
+int gseg_sort_pairs_u64(gseg_ctx *ctx, uint64_t *keys, uint32_t *vals, int64_t n, int begin_bit, int end_bit);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GSEG_H */

@@ -1,0 +1,59 @@
+"""CPU-only: the C-ABI library builds, loads and exports every symbol include/gseg.h declares, and
+fails loudly (no CPU fallback) when there is no CUDA device."""
+import ctypes as C
+import os
+import re
+
+import pytest
+
+
+def declared_symbols(header):
+    txt = open(header).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(gseg_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_symbols_exported(gseg):
+    L = gseg.load()
+    syms = declared_symbols(gseg.HEADER)
+    assert len(syms) >= 18
+    for s in syms:
+        assert hasattr(L, s), "libgseg.so does not export %s" % s
+
+
+def test_version_and_strerror(gseg):
+    L = gseg.load()
+    assert L.gseg_version() == 100
+    assert L.gseg_strerror(0) == b"ok"
+    assert b"no CPU fallback" in L.gseg_strerror(-2)
+
+
+def test_struct_layout_matches_header(gseg):
+    assert C.sizeof(gseg.Params) == 32
+    assert C.sizeof(gseg.RoundStat) == 32
+
+
+def test_no_gpu_fails_loudly(gseg):
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(gseg.GsegError) as e:
+        gseg.Segmenter(64, 64)
+    assert "no CPU fallback" in str(e.value)
+
+
+def test_bad_create_args(gseg):
+    L = gseg.load()
+    h = C.c_void_p()
+    assert L.gseg_create(C.byref(h), 0, 0, 10) == -1
+    assert L.gseg_create(None, 0, 10, 10) == -1
+
+
+def test_product_does_not_reference_oracle(gseg):
+    """The product path must never route through the oracle."""
+    pkg = os.path.dirname(gseg.__file__)
+    for root, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                txt = open(os.path.join(root, f)).read()
+                assert "liboracle" not in txt and "gseg_oracle" not in txt and "import oracle" not in txt, f

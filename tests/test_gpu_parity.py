@@ -1,0 +1,213 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI (ctypes on libgseg.so), against
+the CPU oracle on the same seeded inputs.  Bar: bit-exact partitions (up to label renaming) and
+bit-exact edge weights (the north-star tolerance is 1e-6 relative; we assert both)."""
+import hashlib
+import os
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(__file__), "golden", "golden_v1.npz")
+
+
+@pytest.fixture(scope="module")
+def seg(gseg):
+    s = gseg.Segmenter(3840, 2160)
+    yield s
+    s.close()
+
+
+def same_partition(oracle, a, b):
+    ca, na = oracle.canon(a)
+    cb, nb = oracle.canon(b)
+    return na == nb and np.array_equal(ca, cb)
+
+
+def check_weights(got, ref):
+    fin = np.isfinite(ref)
+    assert np.array_equal(np.isfinite(got), fin)
+    rel = np.abs(got[fin] - ref[fin]) / np.maximum(np.abs(ref[fin]), 1e-30)
+    assert rel.size == 0 or float(rel.max()) <= 1e-6          # north-star tolerance
+    assert np.array_equal(got.view(np.uint32), ref.view(np.uint32))  # and in fact bit-exact
+
+
+def run_both(gseg, oracle, seg, img, sigma, k, ms, conn, variant, flags=0, max_rounds=0, max_levels=0):
+    h, w, _ = img.shape
+    seg.segment(img, sigma=sigma, k=k, min_size=ms, connectivity=conn, variant=variant, flags=flags,
+                max_rounds=max_rounds, max_levels=max_levels)
+    ref = oracle.pipeline(img, sigma, k, ms, conn, variant, max_rounds=max_rounds or 48,
+                          max_levels=(max_levels or 64) if variant != 0 else 0)
+    return ref
+
+
+def test_synth_generator_matches_oracle(gseg, oracle, seg):
+    for (w, h, seed) in [(320, 240, 1), (130, 70, 7), (1, 1, 3), (1920, 1080, 2)]:
+        assert np.array_equal(seg.synth(w, h, seed), oracle.synth(w, h, seed))
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (1, 7), (7, 1), (2, 2), (5, 3), (17, 13), (64, 48), (257, 129)])
+@pytest.mark.parametrize("conn", [4, 8])
+def test_blur_and_weights_bit_exact(gseg, oracle, seg, w, h, conn):
+    img = oracle.synth(w, h, 100 + w)
+    for sigma in (0.8, 0.0, 1.7):
+        seg.segment(img, sigma=sigma, k=300, min_size=0, connectivity=conn, variant=gseg.FELZ)
+        pl = oracle.blur(img, sigma)
+        assert np.array_equal(seg.blurred().view(np.uint32), pl.view(np.uint32))
+        check_weights(seg.weights(), oracle.edges(pl, conn)[0])
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (1, 7), (7, 1), (2, 2), (5, 3), (17, 13), (64, 48), (257, 129), (320, 240)])
+@pytest.mark.parametrize("conn", [4, 8])
+@pytest.mark.parametrize("flags", [0, 1])
+def test_felz_partition_bit_exact(gseg, oracle, seg, w, h, conn, flags):
+    img = oracle.synth(w, h, 7 * w + h)
+    for k, ms in [(300.0, 20), (30.0, 5), (3.0, 0), (0.0, 4), (5000.0, 1)]:
+        ref = run_both(gseg, oracle, seg, img, 0.8, k, ms, conn, gseg.FELZ, flags)
+        lab = seg.labels()
+        assert same_partition(oracle, lab, ref["labels"]), (w, h, conn, k, ms)
+        assert seg.num_components() == ref["n"]
+        assert lab.min() == 0 and lab.max() == ref["n"] - 1   # dense ids
+        st = seg.stats()
+        assert [tuple(int(x) for x in r[[0, 2, 3]]) for r in ref["stats"]] == [(a, c, d) for a, b, c, d in st]
+        assert [int(r[1]) for r in ref["stats"]][1:] == [b for a, b, c, d in st][1:]
+
+
+@pytest.mark.parametrize("w,h", [(1, 1), (1, 7), (2, 2), (17, 13), (64, 48), (257, 129), (320, 240)])
+@pytest.mark.parametrize("conn", [4, 8])
+@pytest.mark.parametrize("variant", [1, 2])
+@pytest.mark.parametrize("flags", [0, 1])
+def test_hierarchy_levels_bit_exact(gseg, oracle, seg, w, h, conn, variant, flags):
+    img = oracle.synth(w, h, 3 * w + h)
+    ref = run_both(gseg, oracle, seg, img, 0.8, 0.0, 0, conn, variant, flags)
+    assert seg.num_levels() == ref["nlevels"]
+    levels = seg.labels_all()
+    assert len(levels) == ref["nlevels"]
+    for l in range(ref["nlevels"]):
+        assert same_partition(oracle, levels[l], ref["levels"][l]), (variant, l)
+        assert seg.num_components(l) == ref["ncomp"][l]
+        assert np.array_equal(seg.labels(l), levels[l])
+    if ref["nlevels"]:
+        assert np.array_equal(seg.labels(-1), levels[-1])
+    if variant == 2:
+        pl = oracle.blur(img, 0.8)
+        check_weights(seg.weights(), oracle.strength(oracle.sobel(pl), conn))
+
+
+def test_degenerate_images(gseg, oracle, seg):
+    h, w = 45, 67
+    ramp = np.zeros((h, w, 3), np.uint8)
+    ramp[..., 0] = (np.arange(w) * 3 % 256)[None, :]
+    ramp[..., 1] = (np.arange(h) * 5 % 256)[:, None]
+    rng = np.random.default_rng(0)
+    imgs = [np.zeros((h, w, 3), np.uint8), np.full((h, w, 3), 255, np.uint8), ramp,
+            rng.integers(0, 256, (h, w, 3), dtype=np.uint8)]
+    for img in imgs:
+        for conn in (4, 8):
+            for variant, k, ms in [(0, 300.0, 20), (0, 0.0, 0), (1, 0, 0), (2, 0, 0)]:
+                for flags in (0, 1):
+                    ref = run_both(gseg, oracle, seg, img, 0.8, k, ms, conn, variant, flags)
+                    assert same_partition(oracle, seg.labels(), ref["labels"]), (conn, variant, k)
+
+
+def test_round_and_level_caps(gseg, oracle, seg):
+    img = oracle.synth(200, 150, 9)
+    for flags in (0, 1):
+        ref = run_both(gseg, oracle, seg, img, 0.8, 300.0, 20, 4, gseg.FELZ, flags, max_rounds=3)
+        assert same_partition(oracle, seg.labels(), ref["labels"])
+        assert len(seg.stats()) == 3
+        ref = run_both(gseg, oracle, seg, img, 0.8, 0, 0, 8, gseg.HIER, flags, max_levels=4)
+        assert seg.num_levels() == 4 and same_partition(oracle, seg.labels(), ref["labels"])
+
+
+def test_strided_and_device_input(gseg, oracle, seg):
+    import torch
+    img = oracle.synth(150, 90, 4)
+    ref = oracle.pipeline(img, 0.8, 300.0, 20, 8, oracle.FELZ)
+    wide = np.zeros((90, 200, 3), np.uint8)
+    wide[:, :150] = img
+    view = wide[:, :150]           # row stride 600 bytes, 450 used
+    p = seg.params(connectivity=8)
+    seg.w, seg.hh, seg.D = 150, 90, 4
+    import ctypes as C
+    rc = seg.L.gseg_segment(seg.h, C.c_void_p(view.ctypes.data), 150, 90, 600, gseg.MEM_HOST, C.byref(p))
+    assert rc == 0
+    assert same_partition(oracle, seg.labels(), ref["labels"])
+    dimg = torch.from_numpy(img).cuda()
+    seg.segment(dimg, connectivity=8)
+    out = torch.empty((90, 150), dtype=torch.int32, device="cuda")
+    seg.labels(out=out)
+    assert same_partition(oracle, out.cpu().numpy(), ref["labels"])
+    col = seg.colorize()
+    assert col.shape == (90, 150, 3)
+    lab = seg.labels()
+    # same label <-> same colour
+    assert len(np.unique(col.reshape(-1, 3), axis=0)) <= seg.num_components()
+    assert np.array_equal(col[lab == lab[0, 0]], np.broadcast_to(col[0, 0], col[lab == lab[0, 0]].shape))
+
+
+def test_argument_errors(gseg, seg):
+    img = np.zeros((8, 8, 3), np.uint8)
+    for kw in [dict(connectivity=6), dict(variant=5), dict(sigma=40.0), dict(max_rounds=-1)]:
+        with pytest.raises(gseg.GsegError):
+            seg.segment(img, **kw)
+    big = np.zeros((2161, 3840, 3), np.uint8)
+    with pytest.raises(gseg.GsegError):
+        seg.segment(big)
+    seg.segment(img)
+    with pytest.raises(gseg.GsegError):
+        seg.labels(3)
+
+
+def test_golden_fixtures(gseg, oracle, seg):
+    from tests.golden.make_golden import CASES
+    g = np.load(GOLD)
+    for i, (w, h, seed, sigma, k, ms, conn, variant) in enumerate(CASES):
+        if variant == 3:
+            continue  # Kruskal baseline is CPU-only (BASELINE.json configs[0])
+        img = seg.synth(w, h, seed)
+        assert np.array_equal(np.frombuffer(hashlib.sha256(img.tobytes()).digest(), np.uint8), g["c%d_img_sha" % i])
+        seg.segment(img, sigma=sigma, k=k, min_size=ms, connectivity=conn, variant=variant)
+        assert np.array_equal(seg.weights().view(np.uint32), g["c%d_wts_bits" % i])
+        assert np.array_equal(oracle.canon(seg.labels())[0], g["c%d_labels" % i])
+        if variant in (1, 2):
+            lv = seg.labels_all()
+            assert len(lv) == len(g["c%d_levels" % i])
+            for a, b in zip(lv, g["c%d_levels" % i]):
+                assert np.array_equal(oracle.canon(a)[0], b)
+
+
+@pytest.mark.parametrize("w,h,conn,variant,seed", [(1920, 1080, 4, 0, 2), (3840, 2160, 8, 1, 3), (1920, 1080, 8, 2, 1000)])
+def test_full_size_configs(gseg, oracle, seg, w, h, conn, variant, seed):
+    """BASELINE.json configs[1], configs[2] and one image of configs[3] at full size, both schedules."""
+    img = seg.synth(w, h, seed)
+    ref = oracle.pipeline(img, 0.8, 300.0, 20, conn, variant, max_levels=0)
+    for flags in (0, 1):
+        seg.segment(img, sigma=0.8, k=300.0, min_size=20, connectivity=conn, variant=variant, flags=flags)
+        assert same_partition(oracle, seg.labels(), ref["labels"])
+        assert seg.num_components() == ref["n"]
+        # size-independent properties: labels are dense, sizes sum to V, idempotent re-run
+        lab = seg.labels()
+        cnt = np.bincount(lab.reshape(-1))
+        assert cnt.sum() == w * h and cnt.min() > 0 and len(cnt) == seg.num_components()
+        if variant == 0:
+            assert cnt.min() >= 20
+    seg.segment(img, sigma=0.8, k=300.0, min_size=20, connectivity=conn, variant=variant, flags=1)
+    assert np.array_equal(seg.labels(), lab)
+
+
+def test_sort_pairs(gseg, seg):
+    import torch
+    for n, bits in [(1, 64), (1000, 64), (4096, 40), (100003, 64), (3_000_000, 52), (5_000_000, 64)]:
+        g = torch.Generator(device="cuda").manual_seed(n)
+        keys = torch.randint(0, 2 ** 62, (n,), dtype=torch.int64, device="cuda", generator=g)
+        if bits < 64:
+            keys &= (1 << bits) - 1
+        keys[::7] = keys[0]  # duplicates: stability must keep payload order
+        vals = torch.arange(n, dtype=torch.int32, device="cuda")
+        ref_k, ref_i = torch.sort(keys, stable=True)
+        k2, v2 = keys.clone(), vals.clone()
+        seg.sort_pairs(k2.data_ptr(), v2.data_ptr(), n, 0, bits)
+        assert torch.equal(k2, ref_k)
+        assert torch.equal(v2.long(), ref_i)
