@@ -1,0 +1,284 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the segmentation hot path (BASELINE.json metric).
+
+Workload (N = 1): BASELINE.json configs[1] -- Boruvka-MST Felzenszwalb on synthetic 1920x1080 RGB
+images, 4-connected grid, sigma 0.8, k 300, min_size 20.  One "step" = one pass of the whole hot
+path (blur -> edge weights -> Boruvka rounds with predicate -> min-size rounds -> label image) over
+a batch of B distinct synthetic images.  N > 1: one process per GPU, every rank segments its own
+B images per step (images shard, no data-path collective; weak scaling).
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl gseg|reference] [--batch B]
+
+Prints ONE JSON line (rank 0).  `value` = Mpixel/s with the inputs resident in HBM; `e2e` = the same
+through the C-ABI with pinned HOST buffers (H2D image in, D2H label image out inside the timed
+region).  `--impl reference` times the CPU path (oracle port; the reference's own source is not
+mounted) on all host cores.
+"""
+import argparse
+import importlib
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+PKG = "graph-algorithm-image-segmentation-gpgpu_b200"
+
+W, H, CONN, SIGMA, K, MIN_SIZE = 1920, 1080, 4, 0.8, 300.0, 20
+METRIC = "Mpixel/s end-to-end segmentation (1080p, Boruvka-Felzenszwalb, 4-connected)"
+WORKLOAD = "configs[1]: Boruvka-MST Felzenszwalb, synthetic 1920x1080 RGB, 4-connected, sigma=0.8 k=300 min_size=20"
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self.stop_flag, self.proc = index, [], False, None
+
+    def run(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            for line in self.proc.stdout:
+                if self.stop_flag:
+                    break
+                self.rows.append([x.strip() for x in line.split(",")])
+        except Exception:
+            pass
+
+    def finish(self):
+        self.stop_flag = True
+        if self.proc is not None:
+            self.proc.terminate()
+        sm, mx, reasons = [], 0.0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                continue
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def cpu_run(O, imgs, variant, threads):
+    """Segment every image of `imgs` on `threads` host threads with the CPU port; returns seconds."""
+    import numpy as np
+    todo = list(range(len(imgs)))
+    lock = threading.Lock()
+
+    def work():
+        while True:
+            with lock:
+                if not todo:
+                    return
+                i = todo.pop()
+            O.segment(imgs[i], SIGMA, K, MIN_SIZE, CONN, variant)
+
+    t0 = time.perf_counter()
+    ts = [threading.Thread(target=work) for _ in range(threads)]
+    [t.start() for t in ts]
+    [t.join() for t in ts]
+    return time.perf_counter() - t0
+
+
+def reference_arm(args, rank):
+    """The reference's CPU implementation of the path, timed on the host cores.  The reference's
+    source is not mounted (/root/reference holds only README/installation/Report.pdf), so
+    oracle/_ref cannot exist; this is the oracle port of felzenszwalb_Boruvka_cpp semantics
+    (kind = "port"), one image per host thread in flight."""
+    if rank != 0:
+        return
+    from oracle import oracle as O
+    O.build()
+    cores = os.cpu_count() or 1
+    imgs = [O.synth(W, H, 2000 + i) for i in range(cores)]
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        cpu_run(O, imgs[:cores], O.FELZ, cores)
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_run(O, imgs, O.FELZ, cores)
+    ms = t / args.steps * 1e3
+    val = cores * W * H / 1e6 / (ms / 1e3)
+    sample = "%d images of 1920x1080 per step, one per host thread, blur+weights+Boruvka-Felzenszwalb+min-size (oracle port, gcc -O2)" % cores
+    line = {"impl": "reference", "metric": METRIC, "value": round(val, 3), "unit": "Mpixel/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32+u64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_step": cores},
+            "cpu_baseline": {"value": round(val, 3), "unit": "Mpixel/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": round(val, 3), "unit": "Mpixel/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="gseg", choices=["gseg", "reference"])
+    ap.add_argument("--batch", type=int, default=32, help="images per step per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        return reference_arm(args, rank)
+    args.warmup = max(args.warmup, 3)
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    gseg = importlib.import_module(PKG)
+    if rank == 0:
+        gseg.build()
+    if world > 1:
+        dist.barrier()
+    B = args.batch
+    seg = gseg.Segmenter(W, H, device=local_rank)
+    stream = torch.cuda.current_stream()
+    seg.set_stream(stream.cuda_stream)
+    flags = gseg.FLAG_GRAPH
+    kw = dict(sigma=SIGMA, k=K, min_size=MIN_SIZE, connectivity=CONN, variant=gseg.FELZ, flags=flags)
+
+    # inputs resident in HBM: B distinct images = B*6.2 MB (> 126 MB L2 for B >= 21), and every image
+    # rewrites ~0.4 GB of per-context scratch, so nothing of an image survives in L2 until its next use
+    dimgs = torch.empty((B, H, W, 3), dtype=torch.uint8, device="cuda")
+    for i in range(B):
+        seg.synth(W, H, 2000 + rank * B + i, out=dimgs[i])
+    dlab = torch.empty((H, W), dtype=torch.int32, device="cuda")
+    himgs = torch.empty((B, H, W, 3), dtype=torch.uint8).pin_memory()
+    himgs.copy_(dimgs)
+    hlab = torch.empty((H, W), dtype=torch.int32).pin_memory()
+    torch.cuda.synchronize()
+
+    def step_dev():
+        for i in range(B):
+            seg.segment(dimgs[i], **kw)
+            seg.labels(out=dlab)
+
+    def step_e2e():
+        for i in range(B):
+            seg.segment(himgs[i], **kw)
+            seg.labels(out=hlab)
+
+    def timed(fn, steps, warm):
+        for _ in range(warm):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        l0 = seg.launch_count()
+        e0.record(stream)
+        for _ in range(steps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        nl = seg.launch_count() - l0
+        ms = e0.elapsed_time(e1) / steps
+        if world > 1:
+            t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+            dist.barrier()
+        return ms, nl
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.start()
+    ms_dev, launches = timed(step_dev, args.steps, args.warmup)
+    ms_e2e, _ = timed(step_e2e, args.steps, args.warmup)
+    clocks = sampler.finish() if sampler else None
+    pix = world * B * W * H / 1e6
+    value, e2e = pix / (ms_dev / 1e3), pix / (ms_e2e / 1e3)
+
+    # ---- roofline of the dominant kernel: CUDA events around every kernel of the host-driven schedule
+    roof = None
+    if rank == 0:
+        peak, peak_src = peaks()
+        seg.set_profiling(True)
+        kw2 = dict(kw, flags=0)
+        agg = {}
+        nprof = min(B, 8)
+        for i in range(nprof):
+            seg.segment(dimgs[i], **kw2)
+            for name, rnd, ms, by in seg.profile():
+                a = agg.setdefault((name, rnd), [0.0, 0.0])
+                a[0] += ms / nprof
+                a[1] += by / nprof
+        seg.set_profiling(False)
+        tot = sum(v[0] for v in agg.values())
+        (kname, krnd), (kms, kby) = max(agg.items(), key=lambda kv: kv[1][0])
+        achieved = kby / (kms * 1e-3) / 1e9 if kms > 0 else 0.0
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "traffic.json")
+        if os.path.exists(tpath):
+            try:
+                traffic = json.load(open(tpath)).get(kname)
+            except Exception:
+                traffic = None
+        roof = {"bound": "hbm", "kernel": "%s (round %d)" % (kname, krnd), "achieved": round(achieved, 1),
+                "peak": peak, "unit": "GB/s", "frac": round(achieved / peak, 4), "traffic": traffic,
+                "peak_source": peak_src, "algo_bytes_per_launch": round(kby), "us_per_launch": round(kms * 1e3, 2),
+                "share_of_kernel_time": round(kms / tot, 4) if tot else None}
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle as O
+        O.build()
+        cores = os.cpu_count() or 1
+        nimg = cores * 2
+        imgs = [himgs[i % B].numpy() for i in range(nimg)]
+        sec = cpu_run(O, imgs, O.FELZ, cores)
+        cpu = {"value": round(nimg * W * H / 1e6 / sec, 3), "unit": "Mpixel/s", "cores": cores, "kind": "port",
+               "sample": "%d of the bench's own 1920x1080 images on %d host threads (oracle port of the Boruvka-Felzenszwalb "
+                         "CPU path, %.1f s)" % (nimg, cores, sec)}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": round(value, 1), "unit": "Mpixel/s", "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": round(ms_dev, 4), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32+u64", "data": "synthetic",
+                "config": {"workload": WORKLOAD, "batch_per_gpu_per_step": B, "schedule": "cuda-graph",
+                           "l2": "inputs %d MB per GPU (> 126 MB L2) and ~0.4 GB of scratch rewritten per image; no explicit flush"
+                                 % (B * W * H * 3 // 2**20)},
+                "e2e": {"value": round(e2e, 1), "unit": "Mpixel/s", "ms_per_step": round(ms_e2e, 4),
+                        "h2d_bytes_per_step": B * W * H * 3, "d2h_bytes_per_step": B * W * H * 4},
+                "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

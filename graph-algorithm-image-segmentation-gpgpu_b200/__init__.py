@@ -58,6 +58,10 @@ class Params(C.Structure):
                 ("variant", C.c_int32), ("max_levels", C.c_int32), ("max_rounds", C.c_int32), ("flags", C.c_uint32)]
 
 
+class KernelTime(C.Structure):
+    _fields_ = [("name", C.c_char * 24), ("round", C.c_int32), ("ms", C.c_float), ("algo_bytes", C.c_double)]
+
+
 class RoundStat(C.Structure):
     _fields_ = [("n_components", C.c_int64), ("n_edges", C.c_int64), ("n_merged", C.c_int64),
                 ("phase", C.c_int32), ("reserved", C.c_int32)]
@@ -96,6 +100,10 @@ def load():
     L.gseg_blurred.argtypes = [vp, vp, i32]
     L.gseg_stats.argtypes = [vp, C.POINTER(RoundStat), i32]
     L.gseg_synth.argtypes = [vp, vp, i32, i32, u64, i32]
+    L.gseg_set_profiling.argtypes = [vp, i32]
+    L.gseg_profile_read.argtypes = [vp, C.POINTER(KernelTime), i32]
+    L.gseg_launch_count.argtypes = [vp]
+    L.gseg_launch_count.restype = C.c_longlong
     L.gseg_sort_pairs_u64.argtypes = [vp, vp, vp, C.c_int64, i32, i32]
     _lib = L
     return L
@@ -216,6 +224,18 @@ class Segmenter:
         arr = (RoundStat * 64)()
         n = self._ck(self.L.gseg_stats(self.h, arr, 64), "gseg_stats")
         return [(arr[i].n_components, arr[i].n_edges, arr[i].n_merged, arr[i].phase) for i in range(n)]
+
+    def set_profiling(self, on):
+        self._ck(self.L.gseg_set_profiling(self.h, int(on)), "gseg_set_profiling")
+
+    def profile(self):
+        """[(kernel name, round, ms, algorithmic bytes)] of the last host-driven run with profiling on."""
+        arr = (KernelTime * 1024)()
+        n = self._ck(self.L.gseg_profile_read(self.h, arr, 1024), "gseg_profile_read")
+        return [(arr[i].name.decode(), arr[i].round, arr[i].ms, arr[i].algo_bytes) for i in range(n)]
+
+    def launch_count(self):
+        return int(self.L.gseg_launch_count(self.h))
 
     def synth(self, w, h, seed, out=None):
         if out is None:

@@ -13,6 +13,7 @@
 #include "gseg_kernels.cuh"
 #include "gseg_sort.cuh"
 
+#define GSEG_MAXMARK 1024
 #define NSM 148
 #define GRID_CAP (NSM * 8)
 #define PERSIST_GRID (NSM * 4)
@@ -42,6 +43,13 @@ struct gseg_ctx {
     bool valid, pending;
     u32 epoch_next;
     char err[256];
+    // per-kernel profiling (host-driven schedule only) and launch accounting
+    bool profiling;
+    int n_marks;
+    cudaEvent_t ev[GSEG_MAXMARK + 1];
+    const char *mark_name[GSEG_MAXMARK];
+    int mark_round[GSEG_MAXMARK];
+    long long launches, graph_nodes;
     // graph cache
     cudaGraphExec_t gexec;
     int g_w, g_h, g_variant, g_D, g_rounds;
@@ -185,31 +193,65 @@ static int gauss_mask(float sigma, float *mask) {
     return len;
 }
 
+// Called right before every kernel launch: counts it and, when profiling, drops an event so that
+// consecutive events bracket exactly one kernel.
+static inline void mark(gseg_ctx *c, cudaStream_t s, const char *name, int round) {
+    ++c->launches;
+    if (!c->profiling || c->n_marks >= GSEG_MAXMARK) return;
+    if (!c->ev[c->n_marks]) cudaEventCreate(&c->ev[c->n_marks]);
+    cudaEventRecord(c->ev[c->n_marks], s);
+    c->mark_name[c->n_marks] = name;
+    c->mark_round[c->n_marks] = round;
+    ++c->n_marks;
+}
+// Closes the last kernel of a round before the host read-back gap (a nameless mark).
+static inline void mark_end(gseg_ctx *c, cudaStream_t s) {
+    if (!c->profiling || c->n_marks == 0 || c->n_marks >= GSEG_MAXMARK) return;
+    if (!c->ev[c->n_marks]) cudaEventCreate(&c->ev[c->n_marks]);
+    cudaEventRecord(c->ev[c->n_marks], s);
+    c->mark_name[c->n_marks] = nullptr;
+    c->mark_round[c->n_marks] = -1;
+    ++c->n_marks;
+}
+
 // ---- round scheduling --------------------------------------------------------------------------
 template <int VARIANT>
 static void enqueue_round0(gseg_ctx *c, cudaStream_t s) {
     constexpr bool SP = VARIANT == GSEG_SUPERPIX;
     const size_t V = (size_t)c->w * c->h;
     GsegCtl *ctl = c->d_ctl;
+    mark(c, s, "k_init", 0);
     k_init<<<1, 32, 0, s>>>(ctl);
+    mark(c, s, "k_blur_h", 0);
     k_blur_h<<<grid_for(V, NT), NT, 0, s>>>(ctl, c->d_tmp);
+    mark(c, s, "k_blur_v", 0);
     k_blur_v<<<grid_for(3 * V, NT), NT, 0, s>>>(ctl, c->d_tmp, c->d_planes);
     if (SP) {
+        mark(c, s, "k_sobel", 0);
         k_sobel<<<grid_for(V, NT), NT, 0, s>>>(ctl, c->d_planes, c->d_G);
+        mark(c, s, "k_weights", 0);
         k_weights<true><<<grid_for(V, NT), NT, 0, s>>>(ctl, c->d_planes, c->d_G, c->d_wgrid);
     } else {
+        mark(c, s, "k_weights", 0);
         k_weights<false><<<grid_for(V, NT), NT, 0, s>>>(ctl, c->d_planes, c->d_G, c->d_wgrid);
     }
+    mark(c, s, "k_r0_choose", 0);
     k_r0_choose<VARIANT><<<grid_for(V, NT), NT, 0, s>>>(ctl, c->d_wgrid, c->d_planes, c->d_dir0, c->d_wsel);
+    mark(c, s, "k_r0_succ", 0);
     k_r0_succ<SP><<<grid_for(V, NT), NT, 0, s>>>(ctl, c->d_dir0, c->d_succ, c->d_size[1], c->d_int[1], c->d_best[1],
                                                   c->d_csum[1]);
+    mark(c, s, "k_jump", 0);
     k_jump<<<grid_for(V, NT), NT, 0, s>>>(ctl, c->d_succ);
+    mark(c, s, "k_rootscan", 0);
     k_rootscan<<<grid_for(V, TILE_C, PERSIST_GRID), NT, 0, s>>>(ctl, c->d_succ, c->d_rank, c->d_statusC);
+    mark(c, s, "k_relabel", 0);
     k_relabel<true, SP><<<grid_for(V, NT), NT, 0, s>>>(ctl, c->d_succ, c->d_rank, c->d_wsel, nullptr, nullptr, nullptr,
                                                        c->d_planes, c->d_arena, c->d_size[1], c->d_int[1], c->d_csum[1]);
+    mark(c, s, "k_r0_edges", 0);
     k_r0_edges<SP><<<grid_for(V, NT, PERSIST_GRID * 2), NT, 0, s>>>(ctl, c->d_wgrid, c->d_arena, c->d_ea[1], c->d_eb[1],
                                                                     c->d_ew[1], c->d_best[1], c->d_size[1], c->d_csum[1],
                                                                     c->d_statusE);
+    mark(c, s, "k_advance", 0);
     k_advance<<<1, 32, 0, s>>>(ctl);
 }
 
@@ -217,17 +259,23 @@ template <bool SP>
 static void enqueue_round(gseg_ctx *c, cudaStream_t s, int r, size_t Vb, size_t Eb) {
     const int cur = r & 1, nxt = cur ^ 1;
     GsegCtl *ctl = c->d_ctl;
+    mark(c, s, "k_succ", r);
     k_succ<SP><<<grid_for(Vb, NT, PERSIST_GRID), NT, 0, s>>>(ctl, c->d_best[cur], c->d_ea[cur], c->d_eb[cur], c->d_size[cur],
                                                             c->d_int[cur], c->d_succ, c->d_wsel, c->d_size[nxt],
                                                             c->d_int[nxt], c->d_best[nxt], c->d_csum[nxt]);
+    mark(c, s, "k_jump", r);
     k_jump<<<grid_for(Vb, NT, PERSIST_GRID), NT, 0, s>>>(ctl, c->d_succ);
+    mark(c, s, "k_rootscan", r);
     k_rootscan<<<grid_for(Vb, TILE_C, PERSIST_GRID), NT, 0, s>>>(ctl, c->d_succ, c->d_rank, c->d_statusC);
+    mark(c, s, "k_relabel", r);
     k_relabel<false, SP><<<grid_for(Vb, NT, PERSIST_GRID), NT, 0, s>>>(ctl, c->d_succ, c->d_rank, c->d_wsel, c->d_size[cur],
                                                                       c->d_int[cur], c->d_csum[cur], c->d_planes, c->d_arena,
                                                                       c->d_size[nxt], c->d_int[nxt], c->d_csum[nxt]);
+    mark(c, s, "k_edges", r);
     k_edges<SP><<<grid_for(Eb, TILE_E, PERSIST_GRID), NT, 0, s>>>(ctl, c->d_ea[cur], c->d_eb[cur], c->d_ew[cur], c->d_arena,
                                                                  c->d_ea[nxt], c->d_eb[nxt], c->d_ew[nxt], c->d_best[nxt],
                                                                  c->d_size[nxt], c->d_csum[nxt], c->d_statusE);
+    mark(c, s, "k_advance", r);
     k_advance<<<1, 32, 0, s>>>(ctl);
 }
 
@@ -270,6 +318,9 @@ static int build_graph(gseg_ctx *ctx) {
         return GSEG_OK;
     if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }
     cudaGraph_t g = nullptr;
+    const bool prof = ctx->profiling;
+    const long long before = ctx->launches;
+    ctx->profiling = false; // events are meaningless inside a captured graph
     CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
     const size_t V = (size_t)ctx->w * ctx->h, E = V * ctx->D;
     enqueue_round0_v(ctx, ctx->stream);
@@ -279,6 +330,9 @@ static int build_graph(gseg_ctx *ctx) {
         enqueue_round_v(ctx, ctx->stream, r, Vb, E);
     }
     cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+    ctx->profiling = prof;
+    ctx->graph_nodes = ctx->launches - before;
+    ctx->launches = before;
     if (e != cudaSuccess) return fail(ctx, GSEG_E_CUDA, "cudaStreamEndCapture", e);
     e = cudaGraphInstantiate(&ctx->gexec, g, 0);
     cudaGraphDestroy(g);
@@ -340,16 +394,20 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
         if (rc) return rc;
         CK(cudaGraphLaunch(ctx->gexec, ctx->stream));
         CK(cudaGetLastError());
+        ctx->launches += ctx->graph_nodes;
         ctx->pending = true;
         return GSEG_OK;
     }
     // host-driven schedule: one 2 KB read-back per round decides termination and sizes the next grids
+    ctx->n_marks = 0;
     enqueue_round0_v(ctx, ctx->stream);
+    mark_end(ctx, ctx->stream);
     CK(cudaGetLastError());
     int rc = readback(ctx);
     if (rc) return rc;
     for (int r = 1; r < R && ctx->h_ctl->phase != PH_DONE; ++r) {
         enqueue_round_v(ctx, ctx->stream, r, ctx->h_ctl->Vcur, ctx->h_ctl->Ecur);
+        mark_end(ctx, ctx->stream);
         CK(cudaGetLastError());
         rc = readback(ctx);
         if (rc) return rc;
@@ -526,4 +584,58 @@ extern "C" int gseg_sort_pairs_u64(gseg_ctx *ctx, uint64_t *keys, uint32_t *vals
     if (e != cudaSuccess) return fail(ctx, GSEG_E_CUDA, "onesweep_sort_pairs", e);
     CK(cudaStreamSynchronize(ctx->stream));
     return GSEG_OK;
+}
+
+// ---- profiling / accounting ----------------------------------------------------------------------
+extern "C" int gseg_set_profiling(gseg_ctx *ctx, int on) {
+    if (!ctx) return GSEG_E_ARG;
+    ctx->profiling = on != 0;
+    ctx->n_marks = 0;
+    return GSEG_OK;
+}
+
+extern "C" long long gseg_launch_count(const gseg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+
+// Algorithmic bytes of one kernel launch (DESIGN.md "Kernels"): every input array
+// read once, every output written once, gathers and atomics at element size.
+static double algo_bytes(const gseg_ctx *c, const char *name, int r) {
+    const GsegCtl *h = c->h_ctl;
+    const double V0 = (double)c->w * c->h, D = c->D;
+    const double V = r == 0 ? V0 : h->stV[r], E = r == 0 ? 0 : h->stE[r], Vn = h->stVafter[r];
+    const double En = (r + 1 < (int)h->round) ? h->stE[r + 1] : h->Ecur;
+    const bool sp = c->params.variant == GSEG_SUPERPIX;
+    if (!strcmp(name, "k_blur_h")) return 3 * V0 + 12 * V0;
+    if (!strcmp(name, "k_blur_v")) return 12 * V0 + 12 * V0;
+    if (!strcmp(name, "k_sobel")) return 12 * V0 + 4 * V0;
+    if (!strcmp(name, "k_weights")) return (sp ? 4 : 12) * V0 + 4 * D * V0;
+    if (!strcmp(name, "k_r0_choose")) return 4 * D * V0 + (sp ? 12 * V0 : 0) + 5 * V0;
+    if (!strcmp(name, "k_r0_succ")) return V0 + 4 * V0 + 16 * V0 + (sp ? 24 * V0 : 0);
+    if (!strcmp(name, "k_jump")) return 4 * V + 4 * V + 4 * (V - Vn);
+    if (!strcmp(name, "k_rootscan")) return 4 * V + 4 * V;
+    if (!strcmp(name, "k_relabel")) return 4 * V + 4 * V + 4 * V + (r == 0 ? 4 * V : 12 * V) + 8 * V + (sp ? 48 * V : 0);
+    if (!strcmp(name, "k_r0_edges")) return 4 * V0 + 4 * D * V0 + 12 * En + 16 * En;
+    if (!strcmp(name, "k_succ")) return 8 * V + 8 * V + 8 * V + 8 * V + 16 * V + (sp ? 24 * V : 0);
+    if (!strcmp(name, "k_edges")) return 12 * E + 8 * E + 12 * En + 16 * En;
+    return 0;
+}
+
+extern "C" int gseg_profile_read(gseg_ctx *ctx, gseg_kernel_time *out, int cap) {
+    if (!ctx || !ctx->valid) return GSEG_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaStreamSynchronize(ctx->stream));
+    int n = 0;
+    for (int i = 0; i + 1 < ctx->n_marks && n < cap; ++i) {
+        // the closing event of mark i is the next mark's event; nameless marks are read-back gaps
+        if (!ctx->mark_name[i]) continue;
+        float ms = 0.f;
+        if (cudaEventElapsedTime(&ms, ctx->ev[i], ctx->ev[i + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
+        if (out) {
+            snprintf(out[n].name, sizeof(out[n].name), "%s", ctx->mark_name[i]);
+            out[n].round = ctx->mark_round[i];
+            out[n].ms = ms;
+            out[n].algo_bytes = algo_bytes(ctx, ctx->mark_name[i], ctx->mark_round[i]);
+        }
+        ++n;
+    }
+    return n;
 }

@@ -126,6 +126,19 @@ int gseg_stats(const gseg_ctx *ctx, gseg_round_stat *out, int cap);
 /* Deterministic synthetic input: w*h*3 bytes into host or device memory. */
 int gseg_synth(gseg_ctx *ctx, uint8_t *out_rgb, int w, int h, uint64_t seed, int mem_kind);
 
+/* Measurement support (SURVEY.md section 5 "tracing"; section 8d): with profiling on, the host-driven
+ * schedule brackets every kernel with CUDA events on the context's stream. */
+typedef struct gseg_kernel_time {
+    char name[24];
+    int32_t round;
+    float ms;
+    double algo_bytes; /* algorithmic bytes of this launch (DESIGN.md "Kernels") */
+} gseg_kernel_time;
+int gseg_set_profiling(gseg_ctx *ctx, int on);
+int gseg_profile_read(gseg_ctx *ctx, gseg_kernel_time *out, int cap);
+/* Kernels launched by this context since creation (graph replays count their kernel nodes). */
+long long gseg_launch_count(const gseg_ctx *ctx);
+
 /* Stand-alone primitives of the edge-dedup path (Report p3 s3.2.2
  * "sort"): in-house onesweep radix sort of 64-bit keys with 32-bit payload, on device memory. */
 int gseg_sort_pairs_u64(gseg_ctx *ctx, uint64_t *keys, uint32_t *vals, int64_t n, int begin_bit, int end_bit);

@@ -159,7 +159,8 @@ def felz_kruskal(wts, w, h, conn, k, min_size):
 
 
 def boruvka(wts, w, h, conn, variant, k=0.0, min_size=0, max_rounds=64, planes=None, max_levels=0):
-    """Returns dict(labels, levels[list of label images], ncomp[list], stats[rounds x 4], n)."""
+    """Returns dict(labels, levels[list of label images], ncomp[list], stats[rounds x 4], n).
+    max_levels = 0: run until one component and keep no per-level images."""
     V = h * w
     lab = np.empty(V, np.int32)
     lev = np.empty((max(max_levels, 1), V), np.int32)
@@ -168,8 +169,10 @@ def boruvka(wts, w, h, conn, variant, k=0.0, min_size=0, max_rounds=64, planes=N
     fin = C.c_int(0)
     pl = _p(np.ascontiguousarray(planes, np.float32), C.c_float) if planes is not None else None
     nl = lib().orc_boruvka(w, h, conn, variant, _p(wts, C.c_float), k, min_size, max_rounds, pl,
-                           _p(lab, C.c_int32), _p(lev, C.c_int32) if max_levels > 0 else None, max_levels,
-                           _p(nco, C.c_int32), _p(stats, C.c_int64), stats.shape[0], C.byref(fin))
+                           _p(lab, C.c_int32), _p(lev, C.c_int32) if max_levels > 0 else None,
+                           max_levels if max_levels > 0 else 1 << 30,
+                           _p(nco, C.c_int32) if max_levels > 0 else None, _p(stats, C.c_int64), stats.shape[0],
+                           C.byref(fin))
     nst = int(np.count_nonzero(stats[:, 0]))
     nkeep = min(nl, max_levels)
     return dict(labels=lab.reshape(h, w), levels=[lev[i].reshape(h, w) for i in range(nkeep)],
