@@ -204,7 +204,7 @@ def test_sort_pairs(gseg, seg):
         keys = torch.randint(0, 2 ** 62, (n,), dtype=torch.int64, device="cuda", generator=g)
         if bits < 64:
             keys &= (1 << bits) - 1
-        keys[::7] = keys[0]  # duplicates: stability must keep payload order
+        keys[::7] = int(keys[0].item())  # duplicates: stability must keep payload order
         vals = torch.arange(n, dtype=torch.int32, device="cuda")
         ref_k, ref_i = torch.sort(keys, stable=True)
         k2, v2 = keys.clone(), vals.clone()
