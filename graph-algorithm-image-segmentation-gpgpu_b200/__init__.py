@@ -22,7 +22,7 @@ HEADER = os.path.join(_ROOT, "include", "gseg.h")
 
 FELZ, HIER, SUPERPIX = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
-FLAG_GRAPH, FLAG_KEEP_PLANES = 1, 2
+FLAG_HOST_LOOP = 1
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-ffp-contract=off"]
@@ -88,6 +88,7 @@ def load():
     L.gseg_destroy.argtypes = [vp]
     L.gseg_destroy.restype = None
     L.gseg_set_stream.argtypes = [vp, vp]
+    L.gseg_set_tail.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.gseg_segment.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(Params)]
     L.gseg_segment_async.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(Params)]
     L.gseg_wait.argtypes = [vp]
@@ -156,6 +157,9 @@ class Segmenter:
 
     def set_stream(self, cuda_stream_ptr):
         self._ck(self.L.gseg_set_stream(self.h, C.c_void_p(cuda_stream_ptr)), "gseg_set_stream")
+
+    def set_tail(self, max_edges, max_components):
+        self._ck(self.L.gseg_set_tail(self.h, max_edges, max_components), "gseg_set_tail")
 
     def params(self, sigma=0.8, k=300.0, min_size=20, connectivity=4, variant=FELZ, max_levels=0, max_rounds=0,
                flags=0):

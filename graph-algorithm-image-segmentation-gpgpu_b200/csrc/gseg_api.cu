@@ -4,6 +4,7 @@
 // gseg_kernels.cuh and fails with GSEG_E_CUDA when no device is usable.
 #include <cuda_runtime.h>
 #include <limits.h>
+#include <stddef.h>
 #include <math.h>
 #include <stdio.h>
 #include <stdlib.h>
@@ -14,28 +15,40 @@
 #include "gseg_sort.cuh"
 
 #define GSEG_MAXMARK 1024
-#define NSM 148
-#define GRID_CAP (NSM * 8)
-#define PERSIST_GRID (NSM * 4)
+#define GRID_CAP (148 * 8)
+
+// Host-initialised head of GsegCtl (layout-compatible prefix).
+struct GsegHead {
+    GsegRunParams p;
+    RoundState st;
+    u32 Vnext, Enext, error, ticketC, ticketE, doneE;
+};
+static_assert(offsetof(GsegCtl, doneE) == offsetof(GsegHead, doneE), "GsegHead must mirror the head of GsegCtl");
 
 struct gseg_ctx {
     int device, max_w, max_h;
     size_t Vmax;
     cudaStream_t stream, own_stream;
-    uint8_t *d_rgb, *d_dir0;
-    float *d_tmp, *d_planes, *d_G, *d_wgrid, *d_export;
+    uint8_t *d_rgb;
+    float *d_tmp, *d_planes, *d_G, *d_wgrid;
     u32 *d_wsel, *d_succ, *d_rank;
     u64 *d_best[2];
-    u32 *d_size[2], *d_int[2];
+    uint2 *d_attr[2];
     long long *d_csum[2];
-    u32 *d_ea[2], *d_eb[2], *d_ew[2];
+    uint2 *d_eab[2];
+    u32 *d_ew[2];
     u32 *d_arena;
     size_t arena_cap;
     u64 *d_statusC, *d_statusE;
     size_t ntilesC, ntilesE;
     int *d_labels[2];
     GsegCtl *d_ctl, *h_ctl;
-    GsegRunParams *h_params;
+    GsegHead *h_head; // pinned image of the host-initialised head of the control block
+    int num_sms;
+    int tail_cluster;     // CTAs in the tail kernel's cluster (16 non-portable, else 8)
+    u32 tail_E, tail_V;   // hand-over thresholds of the tail kernel
+    int nbig_hint;        // grid-wide rounds to enqueue before the tail (-1: estimate; adapts to the last run)
+    int hint_w, hint_h, hint_variant, hint_conn;
     SortScratch sort;
     // run state
     gseg_params params;
@@ -50,9 +63,6 @@ struct gseg_ctx {
     const char *mark_name[GSEG_MAXMARK];
     int mark_round[GSEG_MAXMARK];
     long long launches, graph_nodes;
-    // graph cache
-    cudaGraphExec_t gexec;
-    int g_w, g_h, g_variant, g_D, g_rounds;
 };
 
 static int fail(gseg_ctx *c, int code, const char *what, cudaError_t e) {
@@ -108,7 +118,6 @@ extern "C" int gseg_create(gseg_ctx **out, int device, int max_w, int max_h) {
     ctx->stream = ctx->own_stream;
     const size_t Vp = V + 64; // slack for vector tails
     if (e == cudaSuccess) e = dalloc(&ctx->d_rgb, 3 * Vp);
-    if (e == cudaSuccess) e = dalloc(&ctx->d_dir0, Vp);
     if (e == cudaSuccess) e = dalloc(&ctx->d_tmp, 3 * Vp);
     if (e == cudaSuccess) e = dalloc(&ctx->d_planes, 3 * Vp);
     if (e == cudaSuccess) e = dalloc(&ctx->d_G, Vp);
@@ -118,19 +127,19 @@ extern "C" int gseg_create(gseg_ctx **out, int device, int max_w, int max_h) {
     if (e == cudaSuccess) e = dalloc(&ctx->d_rank, Vp);
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = dalloc(&ctx->d_best[i], Vp);
-        if (e == cudaSuccess) e = dalloc(&ctx->d_size[i], Vp);
-        if (e == cudaSuccess) e = dalloc(&ctx->d_int[i], Vp);
-        if (e == cudaSuccess) e = dalloc(&ctx->d_ea[i], 4 * Vp);
-        if (e == cudaSuccess) e = dalloc(&ctx->d_eb[i], 4 * Vp);
+        if (e == cudaSuccess) e = dalloc(&ctx->d_attr[i], Vp);
+        if (e == cudaSuccess) e = dalloc(&ctx->d_eab[i], 4 * Vp);
         if (e == cudaSuccess) e = dalloc(&ctx->d_ew[i], 4 * Vp);
         if (e == cudaSuccess) e = dalloc(&ctx->d_labels[i], Vp);
     }
     ctx->arena_cap = 6 * V + 1024;
     if (ctx->arena_cap > 0xFFFFFFF0ull) ctx->arena_cap = 0xFFFFFFF0ull;
     if (e == cudaSuccess) e = dalloc(&ctx->d_arena, ctx->arena_cap);
-    ctx->ntilesC = V / TILE_C + 2;
-    ctx->ntilesE = 4 * V / TILE_E + 2;
-    if (ctx->ntilesE < V / NT + 2) ctx->ntilesE = V / NT + 2;
+    // look-back status words: one per tile of the largest tiling that uses each array
+    ctx->ntilesC = V / (NT * CPT) + 2;
+    const size_t img_tiles = (size_t)((max_w + TW - 1) / TW) * (size_t)((max_h + TH - 1) / TH);
+    if (ctx->ntilesC < img_tiles) ctx->ntilesC = img_tiles;
+    ctx->ntilesE = 4 * (V / (NT * EPT) + 1) + 2;
     if (e == cudaSuccess) e = dalloc(&ctx->d_statusC, ctx->ntilesC);
     if (e == cudaSuccess) e = dalloc(&ctx->d_statusE, ctx->ntilesE);
     if (e == cudaSuccess) e = cudaMemset(ctx->d_statusC, 0, ctx->ntilesC * sizeof(u64));
@@ -138,7 +147,35 @@ extern "C" int gseg_create(gseg_ctx **out, int device, int max_w, int max_h) {
     if (e == cudaSuccess) e = dalloc(&ctx->d_ctl, 1);
     if (e == cudaSuccess) e = cudaMemset(ctx->d_ctl, 0, sizeof(GsegCtl));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_ctl, sizeof(GsegCtl));
-    if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_params, sizeof(GsegRunParams));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_head, sizeof(GsegHead));
+    if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (e == cudaSuccess) {
+        // tail kernel: one thread-block cluster, 16 CTAs when the device can co-schedule that many
+        cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaFuncSetAttribute(k_tail<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+        cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PHASE_E_SMEM(NTT, TAIL_EPT));
+        cudaFuncSetAttribute(k_tail<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PHASE_E_SMEM(NTT, TAIL_EPT));
+        int want = 16;
+        if (const char *ev = getenv("GSEG_TAIL_CLUSTER")) want = atoi(ev);
+        if (want < 1) want = 1;
+        if (want > 16) want = 16;
+        for (; want > 1; want >>= 1) {
+            cudaLaunchConfig_t cfg = {};
+            cudaLaunchAttribute at[1];
+            cfg.gridDim = dim3(want); cfg.blockDim = dim3(NTT); cfg.dynamicSmemBytes = PHASE_E_SMEM(NTT, TAIL_EPT);
+            at[0].id = cudaLaunchAttributeClusterDimension;
+            at[0].val.clusterDim.x = want; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+            cfg.attrs = at; cfg.numAttrs = 1;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, k_tail<true>, &cfg) == cudaSuccess && ncl >= 1) break;
+            cudaGetLastError();
+        }
+        ctx->tail_cluster = want;
+        ctx->tail_E = 256u * 1024u; ctx->tail_V = 64u * 1024u;
+        if (const char *ev = getenv("GSEG_TAIL_E")) ctx->tail_E = (u32)strtoul(ev, nullptr, 10);
+        if (const char *ev = getenv("GSEG_TAIL_V")) ctx->tail_V = (u32)strtoul(ev, nullptr, 10);
+        ctx->nbig_hint = -1;
+    }
     if (e != cudaSuccess) {
         fprintf(stderr, "gseg_create: %s\n", cudaGetErrorString(e));
         gseg_destroy(ctx);
@@ -153,18 +190,17 @@ extern "C" void gseg_destroy(gseg_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
     if (ctx->own_stream) cudaStreamSynchronize(ctx->own_stream);
-    if (ctx->gexec) cudaGraphExecDestroy(ctx->gexec);
-    cudaFree(ctx->d_rgb); cudaFree(ctx->d_dir0); cudaFree(ctx->d_tmp); cudaFree(ctx->d_planes);
-    cudaFree(ctx->d_G); cudaFree(ctx->d_wgrid); cudaFree(ctx->d_export); cudaFree(ctx->d_wsel);
+    cudaFree(ctx->d_rgb); cudaFree(ctx->d_tmp); cudaFree(ctx->d_planes);
+    cudaFree(ctx->d_G); cudaFree(ctx->d_wgrid); cudaFree(ctx->d_wsel);
     cudaFree(ctx->d_succ); cudaFree(ctx->d_rank);
     for (int i = 0; i < 2; ++i) {
-        cudaFree(ctx->d_best[i]); cudaFree(ctx->d_size[i]); cudaFree(ctx->d_int[i]); cudaFree(ctx->d_csum[i]);
-        cudaFree(ctx->d_ea[i]); cudaFree(ctx->d_eb[i]); cudaFree(ctx->d_ew[i]); cudaFree(ctx->d_labels[i]);
+        cudaFree(ctx->d_best[i]); cudaFree(ctx->d_attr[i]); cudaFree(ctx->d_csum[i]);
+        cudaFree(ctx->d_eab[i]); cudaFree(ctx->d_ew[i]); cudaFree(ctx->d_labels[i]);
     }
     cudaFree(ctx->d_arena); cudaFree(ctx->d_statusC); cudaFree(ctx->d_statusE); cudaFree(ctx->d_ctl);
     sort_scratch_free(&ctx->sort);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
-    if (ctx->h_params) cudaFreeHost(ctx->h_params);
+    if (ctx->h_head) cudaFreeHost(ctx->h_head);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     free(ctx);
 }
@@ -173,7 +209,14 @@ extern "C" int gseg_set_stream(gseg_ctx *ctx, void *s) {
     if (!ctx) return GSEG_E_ARG;
     if (ctx->pending) return GSEG_E_STATE;
     ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
-    if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }
+    return GSEG_OK;
+}
+
+extern "C" int gseg_set_tail(gseg_ctx *ctx, uint32_t max_edges, uint32_t max_components) {
+    if (!ctx) return GSEG_E_ARG;
+    if (ctx->pending) return GSEG_E_STATE;
+    ctx->tail_E = max_edges; ctx->tail_V = max_components;
+    ctx->nbig_hint = -1;
     return GSEG_OK;
 }
 
@@ -215,80 +258,117 @@ static inline void mark_end(gseg_ctx *c, cudaStream_t s) {
 }
 
 // ---- round scheduling --------------------------------------------------------------------------
-template <int VARIANT>
+static GsegBufs bufs_of(const gseg_ctx *c) {
+    GsegBufs B;
+    B.planes = c->d_planes; B.G = c->d_G; B.wgrid = c->d_wgrid;
+    B.succ = c->d_succ; B.rank = c->d_rank; B.wsel = c->d_wsel; B.arena = c->d_arena;
+    for (int i = 0; i < 2; ++i) {
+        B.best[i] = c->d_best[i]; B.attr[i] = c->d_attr[i]; B.csum[i] = c->d_csum[i];
+        B.eab[i] = c->d_eab[i]; B.ew[i] = c->d_ew[i];
+    }
+    B.statusC = c->d_statusC; B.statusE = c->d_statusE;
+    return B;
+}
+
+template <int R>
+static size_t blur_smem() { return (size_t)(((TW + 2 * R) * 3 * (TH + 2 * R) + 15) & ~15) + (size_t)3 * (TH + 2 * R) * TW * sizeof(float); }
+template <int R>
+static void launch_blur(gseg_ctx *c, cudaStream_t s, int ntiles) {
+    static bool attr[64] = {false}; // the opt-in is per function and per device
+    if (!attr[c->device & 63]) { cudaFuncSetAttribute(k_blur_tile<R>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)blur_smem<R>()); attr[c->device & 63] = true; }
+    k_blur_tile<R><<<ntiles, NT, blur_smem<R>(), s>>>(c->d_ctl, c->d_planes);
+}
+
+template <int VARIANT, int D>
+static size_t graph_smem() {
+    return (size_t)(3 + D + (VARIANT == GSEG_SUPERPIX ? 1 : 0)) * BH * BW * sizeof(float) + (size_t)(BH - 2) * (BW - 2) + 16;
+}
+template <int VARIANT, int D>
+static void launch_r0_graph(gseg_ctx *c, cudaStream_t s, int ntiles, const GsegBufs &B) {
+    static bool attr[64] = {false};
+    if (!attr[c->device & 63]) { cudaFuncSetAttribute(k_r0_graph<VARIANT, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)graph_smem<VARIANT, D>()); attr[c->device & 63] = true; }
+    k_r0_graph<VARIANT, D><<<ntiles < c->num_sms * 3 ? ntiles : c->num_sms * 3, NT, graph_smem<VARIANT, D>(), s>>>(c->d_ctl, B);
+}
+template <int D, bool SP>
+static void launch_r0_edges(gseg_ctx *c, cudaStream_t s, size_t V, const GsegBufs &B) {
+    const size_t ntiles = (size_t)D * ((V + NT * 8 - 1) / (NT * 8));
+    k_r0_edges<D, SP><<<(int)(ntiles < (size_t)c->num_sms * 4 ? ntiles : (size_t)c->num_sms * 4), NT, 0, s>>>(c->d_ctl, B);
+}
+
+// Round 0: blur -> [sobel] -> fused graph kernel -> relabel -> edge list.  4-5 launches.
 static void enqueue_round0(gseg_ctx *c, cudaStream_t s) {
-    constexpr bool SP = VARIANT == GSEG_SUPERPIX;
     const size_t V = (size_t)c->w * c->h;
-    GsegCtl *ctl = c->d_ctl;
-    mark(c, s, "k_init", 0);
-    k_init<<<1, 32, 0, s>>>(ctl);
-    mark(c, s, "k_blur_h", 0);
-    k_blur_h<<<grid_for(V, NT), NT, 0, s>>>(ctl, c->d_tmp);
-    mark(c, s, "k_blur_v", 0);
-    k_blur_v<<<grid_for(3 * V, NT), NT, 0, s>>>(ctl, c->d_tmp, c->d_planes);
-    if (SP) {
-        mark(c, s, "k_sobel", 0);
-        k_sobel<<<grid_for(V, NT), NT, 0, s>>>(ctl, c->d_planes, c->d_G);
-        mark(c, s, "k_weights", 0);
-        k_weights<true><<<grid_for(V, NT), NT, 0, s>>>(ctl, c->d_planes, c->d_G, c->d_wgrid);
+    const int variant = c->params.variant, D = c->D;
+    const bool sp = variant == GSEG_SUPERPIX;
+    const GsegBufs B = bufs_of(c);
+    const int ntiles = ((c->w + TW - 1) / TW) * ((c->h + TH - 1) / TH);
+    const int R = c->h_head->p.mask_len - 1;
+    if (R >= 1 && R <= 8) {
+        mark(c, s, "k_blur_tile", 0);
+        switch (R) {
+        case 1: launch_blur<1>(c, s, ntiles); break;
+        case 2: launch_blur<2>(c, s, ntiles); break;
+        case 3: launch_blur<3>(c, s, ntiles); break;
+        case 4: launch_blur<4>(c, s, ntiles); break;
+        case 5: launch_blur<5>(c, s, ntiles); break;
+        case 6: launch_blur<6>(c, s, ntiles); break;
+        case 7: launch_blur<7>(c, s, ntiles); break;
+        default: launch_blur<8>(c, s, ntiles); break;
+        }
     } else {
-        mark(c, s, "k_weights", 0);
-        k_weights<false><<<grid_for(V, NT), NT, 0, s>>>(ctl, c->d_planes, c->d_G, c->d_wgrid);
+        mark(c, s, "k_blur_h", 0);
+        k_blur_h<<<grid_for(V, NT), NT, 0, s>>>(c->d_ctl, c->d_tmp);
+        mark(c, s, "k_blur_v", 0);
+        k_blur_v<<<grid_for(3 * V, NT), NT, 0, s>>>(c->d_ctl, c->d_tmp, c->d_planes);
     }
-    mark(c, s, "k_r0_choose", 0);
-    k_r0_choose<VARIANT><<<grid_for(V, NT), NT, 0, s>>>(ctl, c->d_wgrid, c->d_planes, c->d_dir0, c->d_wsel);
-    mark(c, s, "k_r0_succ", 0);
-    k_r0_succ<SP><<<grid_for(V, NT), NT, 0, s>>>(ctl, c->d_dir0, c->d_succ, c->d_size[1], c->d_int[1], c->d_best[1],
-                                                  c->d_csum[1]);
-    mark(c, s, "k_jump", 0);
-    k_jump<<<grid_for(V, NT), NT, 0, s>>>(ctl, c->d_succ);
-    mark(c, s, "k_rootscan", 0);
-    k_rootscan<<<grid_for(V, TILE_C, PERSIST_GRID), NT, 0, s>>>(ctl, c->d_succ, c->d_rank, c->d_statusC);
+    if (sp) {
+        mark(c, s, "k_sobel", 0);
+        k_sobel<<<grid_for(V, NT), NT, 0, s>>>(c->d_ctl, c->d_planes, c->d_G);
+    }
+    mark(c, s, "k_r0_graph", 0);
+    if (variant == GSEG_FELZ) { if (D == 2) launch_r0_graph<GSEG_FELZ, 2>(c, s, ntiles, B); else launch_r0_graph<GSEG_FELZ, 4>(c, s, ntiles, B); }
+    else if (variant == GSEG_HIER) { if (D == 2) launch_r0_graph<GSEG_HIER, 2>(c, s, ntiles, B); else launch_r0_graph<GSEG_HIER, 4>(c, s, ntiles, B); }
+    else { if (D == 2) launch_r0_graph<GSEG_SUPERPIX, 2>(c, s, ntiles, B); else launch_r0_graph<GSEG_SUPERPIX, 4>(c, s, ntiles, B); }
     mark(c, s, "k_relabel", 0);
-    k_relabel<true, SP><<<grid_for(V, NT), NT, 0, s>>>(ctl, c->d_succ, c->d_rank, c->d_wsel, nullptr, nullptr, nullptr,
-                                                       c->d_planes, c->d_arena, c->d_size[1], c->d_int[1], c->d_csum[1]);
+    if (sp) k_relabel<true, true><<<grid_for(V, NT), NT, 0, s>>>(c->d_ctl, B);
+    else k_relabel<true, false><<<grid_for(V, NT), NT, 0, s>>>(c->d_ctl, B);
     mark(c, s, "k_r0_edges", 0);
-    k_r0_edges<SP><<<grid_for(V, NT, PERSIST_GRID * 2), NT, 0, s>>>(ctl, c->d_wgrid, c->d_arena, c->d_ea[1], c->d_eb[1],
-                                                                    c->d_ew[1], c->d_best[1], c->d_size[1], c->d_csum[1],
-                                                                    c->d_statusE);
-    mark(c, s, "k_advance", 0);
-    k_advance<<<1, 32, 0, s>>>(ctl);
+    if (D == 2) { if (sp) launch_r0_edges<2, true>(c, s, V, B); else launch_r0_edges<2, false>(c, s, V, B); }
+    else { if (sp) launch_r0_edges<4, true>(c, s, V, B); else launch_r0_edges<4, false>(c, s, V, B); }
 }
 
-template <bool SP>
+// One grid-wide round r >= 1: 3 launches.  Vb/Eb bound the round's component / edge counts (exact after
+// a read-back in the host-driven schedule, the image's own bounds otherwise); every kernel takes its
+// real sizes from the device-resident round state and surplus blocks exit through the tile tickets.
 static void enqueue_round(gseg_ctx *c, cudaStream_t s, int r, size_t Vb, size_t Eb) {
-    const int cur = r & 1, nxt = cur ^ 1;
-    GsegCtl *ctl = c->d_ctl;
-    mark(c, s, "k_succ", r);
-    k_succ<SP><<<grid_for(Vb, NT, PERSIST_GRID), NT, 0, s>>>(ctl, c->d_best[cur], c->d_ea[cur], c->d_eb[cur], c->d_size[cur],
-                                                            c->d_int[cur], c->d_succ, c->d_wsel, c->d_size[nxt],
-                                                            c->d_int[nxt], c->d_best[nxt], c->d_csum[nxt]);
-    mark(c, s, "k_jump", r);
-    k_jump<<<grid_for(Vb, NT, PERSIST_GRID), NT, 0, s>>>(ctl, c->d_succ);
-    mark(c, s, "k_rootscan", r);
-    k_rootscan<<<grid_for(Vb, TILE_C, PERSIST_GRID), NT, 0, s>>>(ctl, c->d_succ, c->d_rank, c->d_statusC);
+    const bool sp = c->params.variant == GSEG_SUPERPIX;
+    const GsegBufs B = bufs_of(c);
+    const int cap = c->num_sms * 4;
+    mark(c, s, "k_succ_scan", r);
+    if (sp) k_succ_scan<true><<<grid_for(Vb, NT * CPT, cap), NT, 0, s>>>(c->d_ctl, B);
+    else k_succ_scan<false><<<grid_for(Vb, NT * CPT, cap), NT, 0, s>>>(c->d_ctl, B);
     mark(c, s, "k_relabel", r);
-    k_relabel<false, SP><<<grid_for(Vb, NT, PERSIST_GRID), NT, 0, s>>>(ctl, c->d_succ, c->d_rank, c->d_wsel, c->d_size[cur],
-                                                                      c->d_int[cur], c->d_csum[cur], c->d_planes, c->d_arena,
-                                                                      c->d_size[nxt], c->d_int[nxt], c->d_csum[nxt]);
+    if (sp) k_relabel<false, true><<<grid_for(Vb, NT, cap), NT, 0, s>>>(c->d_ctl, B);
+    else k_relabel<false, false><<<grid_for(Vb, NT, cap), NT, 0, s>>>(c->d_ctl, B);
     mark(c, s, "k_edges", r);
-    k_edges<SP><<<grid_for(Eb, TILE_E, PERSIST_GRID), NT, 0, s>>>(ctl, c->d_ea[cur], c->d_eb[cur], c->d_ew[cur], c->d_arena,
-                                                                 c->d_ea[nxt], c->d_eb[nxt], c->d_ew[nxt], c->d_best[nxt],
-                                                                 c->d_size[nxt], c->d_csum[nxt], c->d_statusE);
-    mark(c, s, "k_advance", r);
-    k_advance<<<1, 32, 0, s>>>(ctl);
+    if (sp) k_edges<true><<<grid_for(Eb, NT * EPT, cap), NT, 0, s>>>(c->d_ctl, B);
+    else k_edges<false><<<grid_for(Eb, NT * EPT, cap), NT, 0, s>>>(c->d_ctl, B);
 }
 
-static void enqueue_round0_v(gseg_ctx *c, cudaStream_t s) {
-    switch (c->params.variant) {
-    case GSEG_FELZ: enqueue_round0<GSEG_FELZ>(c, s); break;
-    case GSEG_HIER: enqueue_round0<GSEG_HIER>(c, s); break;
-    default: enqueue_round0<GSEG_SUPERPIX>(c, s); break;
-    }
-}
-static void enqueue_round_v(gseg_ctx *c, cudaStream_t s, int r, size_t Vb, size_t Eb) {
-    if (c->params.variant == GSEG_SUPERPIX) enqueue_round<true>(c, s, r, Vb, Eb);
-    else enqueue_round<false>(c, s, r, Vb, Eb);
+// The tail: one cluster runs every remaining (small) round.
+static cudaError_t enqueue_tail(gseg_ctx *c, cudaStream_t s) {
+    cudaLaunchConfig_t cfg = {};
+    cudaLaunchAttribute at[1];
+    cfg.gridDim = dim3(c->tail_cluster); cfg.blockDim = dim3(NTT);
+    cfg.dynamicSmemBytes = PHASE_E_SMEM(NTT, TAIL_EPT); cfg.stream = s;
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = c->tail_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    GsegCtl *ctl = c->d_ctl;
+    GsegBufs B = bufs_of(c);
+    mark(c, s, "k_tail", -1);
+    if (c->params.variant == GSEG_SUPERPIX) return cudaLaunchKernelEx(&cfg, k_tail<true>, ctl, B);
+    return cudaLaunchKernelEx(&cfg, k_tail<false>, ctl, B);
 }
 
 static int max_rounds_of(const gseg_params *p) {
@@ -306,38 +386,14 @@ static int finish(gseg_ctx *ctx) {
     ctx->pending = false;
     if (ctx->h_ctl->error == DERR_SCAN) return fail(ctx, GSEG_E_INTERNAL, "look-back watchdog", cudaSuccess);
     if (ctx->h_ctl->error == DERR_ARENA) return fail(ctx, GSEG_E_ARENA, "map arena", cudaSuccess);
+    // remember how many grid-wide rounds this kind of image needed before the tail could take over
+    const GsegCtl *h = ctx->h_ctl;
+    int nbig = 0;
+    for (u32 r = 1; r < h->st.round; ++r)
+        if (h->stE[r] > ctx->tail_E || h->stV[r] > ctx->tail_V) nbig = (int)r;
+    ctx->nbig_hint = nbig;
+    ctx->hint_w = ctx->w; ctx->hint_h = ctx->h; ctx->hint_variant = ctx->params.variant; ctx->hint_conn = ctx->params.connectivity;
     ctx->valid = true;
-    return GSEG_OK;
-}
-
-// whole schedule captured once per (w, h, variant, connectivity, max_rounds) and replayed
-static int build_graph(gseg_ctx *ctx) {
-    const int R = max_rounds_of(&ctx->params);
-    if (ctx->gexec && ctx->g_w == ctx->w && ctx->g_h == ctx->h && ctx->g_variant == ctx->params.variant &&
-        ctx->g_D == ctx->D && ctx->g_rounds == R)
-        return GSEG_OK;
-    if (ctx->gexec) { cudaGraphExecDestroy(ctx->gexec); ctx->gexec = nullptr; }
-    cudaGraph_t g = nullptr;
-    const bool prof = ctx->profiling;
-    const long long before = ctx->launches;
-    ctx->profiling = false; // events are meaningless inside a captured graph
-    CK(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-    const size_t V = (size_t)ctx->w * ctx->h, E = V * ctx->D;
-    enqueue_round0_v(ctx, ctx->stream);
-    for (int r = 1; r < R; ++r) {
-        size_t Vb = V;
-        if (ctx->params.variant != GSEG_FELZ) { Vb = V >> (r > 30 ? 30 : r); if (Vb < 1) Vb = 1; }
-        enqueue_round_v(ctx, ctx->stream, r, Vb, E);
-    }
-    cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
-    ctx->profiling = prof;
-    ctx->graph_nodes = ctx->launches - before;
-    ctx->launches = before;
-    if (e != cudaSuccess) return fail(ctx, GSEG_E_CUDA, "cudaStreamEndCapture", e);
-    e = cudaGraphInstantiate(&ctx->gexec, g, 0);
-    cudaGraphDestroy(g);
-    if (e != cudaSuccess) { ctx->gexec = nullptr; return fail(ctx, GSEG_E_CUDA, "cudaGraphInstantiate", e); }
-    ctx->g_w = ctx->w; ctx->g_h = ctx->h; ctx->g_variant = ctx->params.variant; ctx->g_D = ctx->D; ctx->g_rounds = R;
     return GSEG_OK;
 }
 
@@ -347,17 +403,29 @@ static int ensure_csum(gseg_ctx *ctx) {
     return GSEG_OK;
 }
 
+// Grid-wide rounds to enqueue ahead of the tail when nothing is known about the image: live edges
+// shrink by roughly 0.55-0.6x per round on natural and synthetic images (Report.pdf p5: 10-20 rounds).
+static int estimate_nbig(const gseg_ctx *c) {
+    double E = 0.62 * (double)c->w * c->h * c->D, V = 0.3 * (double)c->w * c->h;
+    int n = 0;
+    while ((E > c->tail_E || V > c->tail_V) && n < GSEG_MAXR) { E *= 0.6; V *= 0.27; ++n; }
+    return n;
+}
+
 extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int h, int stride, int mem_kind,
                                   const gseg_params *p) {
     if (!ctx || !rgb || !p) return GSEG_E_ARG;
     if (ctx->pending) return fail(ctx, GSEG_E_STATE, "previous run not waited for", cudaSuccess);
     if (w < 1 || h < 1 || stride < 3 * w) return fail(ctx, GSEG_E_ARG, "image geometry", cudaSuccess);
     if ((size_t)w * h > ctx->Vmax) return fail(ctx, GSEG_E_SIZE, "image exceeds context capacity", cudaSuccess);
+    if ((size_t)((w + TW - 1) / TW) * (size_t)((h + TH - 1) / TH) > ctx->ntilesC)
+        return fail(ctx, GSEG_E_SIZE, "image aspect exceeds context capacity", cudaSuccess);
     if (p->connectivity != 4 && p->connectivity != 8) return fail(ctx, GSEG_E_ARG, "connectivity must be 4 or 8", cudaSuccess);
     if (p->variant < GSEG_FELZ || p->variant > GSEG_SUPERPIX) return fail(ctx, GSEG_E_ARG, "variant", cudaSuccess);
     if (!(p->sigma >= 0.0f) || p->max_levels < 0 || p->max_rounds < 0) return fail(ctx, GSEG_E_ARG, "parameter range", cudaSuccess);
     if (mem_kind != GSEG_MEM_HOST && mem_kind != GSEG_MEM_DEVICE) return fail(ctx, GSEG_E_ARG, "mem_kind", cudaSuccess);
-    GsegRunParams *hp = ctx->h_params;
+    GsegHead *hh = ctx->h_head;
+    GsegRunParams *hp = &hh->p;
     const int len = gauss_mask(p->sigma, hp->mask);
     if (len < 0) return fail(ctx, GSEG_E_ARG, "sigma too large (more than 64 taps)", cudaSuccess);
     CK(cudaSetDevice(ctx->device));
@@ -374,6 +442,7 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
         dstride = 3 * w;
     }
     const int R = max_rounds_of(p);
+    const bool host_loop = (p->flags & GSEG_FLAG_HOST_LOOP) != 0;
     // look-back tags: 2 per round, 30 bits; recycle the tag space long before it wraps
     if (ctx->epoch_next + 2u * GSEG_MAXR + 8u >= (1u << 30)) {
         CK(cudaMemsetAsync(ctx->d_statusC, 0, ctx->ntilesC * sizeof(u64), ctx->stream));
@@ -386,27 +455,38 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
     hp->arena_cap = (u32)ctx->arena_cap;
     hp->epoch_base = ctx->epoch_next;
     hp->mask_len = len;
+    hp->tail_E = host_loop ? 0u : ctx->tail_E;
+    hp->tail_V = host_loop ? 0u : ctx->tail_V;
     ctx->epoch_next += 2u * GSEG_MAXR + 8u;
-    CK(cudaMemcpyAsync(&ctx->d_ctl->p, hp, sizeof(GsegRunParams), cudaMemcpyHostToDevice, ctx->stream));
+    // the whole head of the control block (parameters + round-0 state + tickets) in one copy
+    hh->st.V = (u32)((size_t)w * h); hh->st.E = 0; hh->st.round = 0; hh->st.phase = PH_PRED; hh->st.levels = 0; hh->st.map_off = 0;
+    hh->Vnext = hh->st.V; hh->Enext = 0; hh->error = DERR_NONE; hh->ticketC = 0; hh->ticketE = 0; hh->doneE = 0;
+    CK(cudaMemcpyAsync(ctx->d_ctl, hh, sizeof(GsegHead), cudaMemcpyHostToDevice, ctx->stream));
 
-    if (p->flags & GSEG_FLAG_GRAPH) {
-        int rc = build_graph(ctx);
-        if (rc) return rc;
-        CK(cudaGraphLaunch(ctx->gexec, ctx->stream));
+    ctx->n_marks = 0;
+    enqueue_round0(ctx, ctx->stream);
+    CK(cudaGetLastError());
+    if (!host_loop) {
+        // device-driven schedule: the grid-wide rounds this kind of image is expected to need, then the
+        // tail cluster; no host involvement until gseg_wait (which continues the run if the guess was short)
+        int nbig = ctx->nbig_hint;
+        if (nbig < 0 || ctx->hint_w != w || ctx->hint_h != h || ctx->hint_variant != p->variant ||
+            ctx->hint_conn != p->connectivity)
+            nbig = estimate_nbig(ctx);
+        if (nbig > R - 1) nbig = R - 1;
+        const size_t V = (size_t)w * h;
+        for (int r = 1; r <= nbig; ++r) enqueue_round(ctx, ctx->stream, r, V, V * ctx->D);
         CK(cudaGetLastError());
-        ctx->launches += ctx->graph_nodes;
+        CK(enqueue_tail(ctx, ctx->stream));
         ctx->pending = true;
         return GSEG_OK;
     }
     // host-driven schedule: one 2 KB read-back per round decides termination and sizes the next grids
-    ctx->n_marks = 0;
-    enqueue_round0_v(ctx, ctx->stream);
     mark_end(ctx, ctx->stream);
-    CK(cudaGetLastError());
     int rc = readback(ctx);
     if (rc) return rc;
-    for (int r = 1; r < R && ctx->h_ctl->phase != PH_DONE; ++r) {
-        enqueue_round_v(ctx, ctx->stream, r, ctx->h_ctl->Vcur, ctx->h_ctl->Ecur);
+    for (int r = 1; r < R && ctx->h_ctl->st.phase != PH_DONE; ++r) {
+        enqueue_round(ctx, ctx->stream, r, ctx->h_ctl->st.V, ctx->h_ctl->st.E);
         mark_end(ctx, ctx->stream);
         CK(cudaGetLastError());
         rc = readback(ctx);
@@ -421,6 +501,16 @@ extern "C" int gseg_wait(gseg_ctx *ctx) {
     if (!ctx->pending) return ctx->valid ? GSEG_OK : GSEG_E_STATE;
     CK(cudaSetDevice(ctx->device));
     int rc = readback(ctx);
+    // the guess of grid-wide rounds was short: keep going, two rounds and a tail at a time
+    while (!rc && ctx->h_ctl->st.phase != PH_DONE && ctx->h_ctl->error == DERR_NONE) {
+        const int r = (int)ctx->h_ctl->st.round;
+        enqueue_round(ctx, ctx->stream, r, ctx->h_ctl->st.V, ctx->h_ctl->st.E);
+        enqueue_round(ctx, ctx->stream, r + 1, ctx->h_ctl->st.V, ctx->h_ctl->st.E);
+        cudaError_t e = cudaGetLastError();
+        if (e == cudaSuccess) e = enqueue_tail(ctx, ctx->stream);
+        if (e != cudaSuccess) { ctx->pending = false; return fail(ctx, GSEG_E_CUDA, "continuation launch", e); }
+        rc = readback(ctx);
+    }
     if (rc) { ctx->pending = false; return rc; }
     return finish(ctx);
 }
@@ -434,27 +524,27 @@ extern "C" int gseg_segment(gseg_ctx *ctx, const uint8_t *rgb, int w, int h, int
 
 extern "C" int gseg_num_levels(const gseg_ctx *ctx) {
     if (!ctx || !ctx->valid) return GSEG_E_STATE;
-    return ctx->params.variant == GSEG_FELZ ? 1 : (int)ctx->h_ctl->levels;
+    return ctx->params.variant == GSEG_FELZ ? 1 : (int)ctx->h_ctl->st.levels;
 }
 
 extern "C" int gseg_num_components(const gseg_ctx *ctx, int level) {
     if (!ctx || !ctx->valid) return GSEG_E_STATE;
     const int nl = gseg_num_levels(ctx);
     if (level < 0) level = nl - 1;
-    if (ctx->params.variant == GSEG_FELZ) return level == 0 ? (int)ctx->h_ctl->Vcur : GSEG_E_LEVEL;
-    if (nl == 0 && level == -1) return (int)ctx->h_ctl->Vcur;
+    if (ctx->params.variant == GSEG_FELZ) return level == 0 ? (int)ctx->h_ctl->st.V : GSEG_E_LEVEL;
+    if (nl == 0 && level == -1) return (int)ctx->h_ctl->st.V;
     if (level >= nl) return GSEG_E_LEVEL;
     return (int)ctx->h_ctl->stVafter[level];
 }
 
 static int level_to_round(const gseg_ctx *ctx, int level, int *round) {
-    const int rounds = (int)ctx->h_ctl->round;
+    const int rounds = (int)ctx->h_ctl->st.round;
     if (ctx->params.variant == GSEG_FELZ) {
         if (level != 0 && level != -1) return GSEG_E_LEVEL;
         *round = rounds - 1;
         return GSEG_OK;
     }
-    const int nl = (int)ctx->h_ctl->levels;
+    const int nl = (int)ctx->h_ctl->st.levels;
     if (level < 0) level = nl - 1;
     if (level >= nl && !(nl == 0 && level <= 0)) return GSEG_E_LEVEL;
     if (level < 0) level = 0; // no merging round at all (single pixel): round 0's identity map
@@ -527,14 +617,8 @@ extern "C" int gseg_weights(gseg_ctx *ctx, float *out, int mem_kind) {
     if (!ctx->valid) return GSEG_E_STATE;
     CK(cudaSetDevice(ctx->device));
     const size_t V = (size_t)ctx->w * ctx->h, n = V * ctx->D;
-    float *dst = out;
-    if (mem_kind != GSEG_MEM_DEVICE) {
-        if (!ctx->d_export) CK(dalloc(&ctx->d_export, 4 * (ctx->Vmax + 64)));
-        dst = ctx->d_export;
-    }
-    k_weights_export<<<grid_for(n, NT), NT, 0, ctx->stream>>>(ctx->d_wgrid, (u32)V, ctx->D, dst);
-    CK(cudaGetLastError());
-    if (mem_kind != GSEG_MEM_DEVICE) CK(cudaMemcpyAsync(out, dst, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaMemcpyAsync(out, ctx->d_wgrid, n * sizeof(float),
+                       mem_kind == GSEG_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return GSEG_OK;
 }
@@ -552,7 +636,7 @@ extern "C" int gseg_blurred(gseg_ctx *ctx, float *out, int mem_kind) {
 
 extern "C" int gseg_stats(const gseg_ctx *ctx, gseg_round_stat *out, int cap) {
     if (!ctx || !ctx->valid) return GSEG_E_STATE;
-    const int n = (int)ctx->h_ctl->round;
+    const int n = (int)ctx->h_ctl->st.round;
     for (int i = 0; i < n && i < cap && out; ++i) {
         out[i].n_components = ctx->h_ctl->stV[i];
         out[i].n_edges = i == 0 ? 0 : ctx->h_ctl->stE[i];
@@ -600,22 +684,28 @@ extern "C" long long gseg_launch_count(const gseg_ctx *ctx) { return ctx ? ctx->
 // read once, every output written once, gathers and atomics at element size.
 static double algo_bytes(const gseg_ctx *c, const char *name, int r) {
     const GsegCtl *h = c->h_ctl;
+    if (r < 0) return 0;
     const double V0 = (double)c->w * c->h, D = c->D;
     const double V = r == 0 ? V0 : h->stV[r], E = r == 0 ? 0 : h->stE[r], Vn = h->stVafter[r];
-    const double En = (r + 1 < (int)h->round) ? h->stE[r + 1] : h->Ecur;
+    const double En = (r + 1 < (int)h->st.round) ? h->stE[r + 1] : h->st.E;
     const bool sp = c->params.variant == GSEG_SUPERPIX;
+    const double acc = sp ? 40 : 16; // accumulators per new component: (size, Int) 8 + best 8 [+ 3 colour sums 24]
+    if (!strcmp(name, "k_blur_tile")) return 3 * V0 + 12 * V0;            // u8 image in, 3 fp32 planes out
     if (!strcmp(name, "k_blur_h")) return 3 * V0 + 12 * V0;
     if (!strcmp(name, "k_blur_v")) return 12 * V0 + 12 * V0;
     if (!strcmp(name, "k_sobel")) return 12 * V0 + 4 * V0;
-    if (!strcmp(name, "k_weights")) return (sp ? 4 : 12) * V0 + 4 * D * V0;
-    if (!strcmp(name, "k_r0_choose")) return 4 * D * V0 + (sp ? 12 * V0 : 0) + 5 * V0;
-    if (!strcmp(name, "k_r0_succ")) return V0 + 4 * V0 + 16 * V0 + (sp ? 24 * V0 : 0);
-    if (!strcmp(name, "k_jump")) return 4 * V + 4 * V + 4 * (V - Vn);
-    if (!strcmp(name, "k_rootscan")) return 4 * V + 4 * V;
-    if (!strcmp(name, "k_relabel")) return 4 * V + 4 * V + 4 * V + (r == 0 ? 4 * V : 12 * V) + 8 * V + (sp ? 48 * V : 0);
-    if (!strcmp(name, "k_r0_edges")) return 4 * V0 + 4 * D * V0 + 12 * En + 16 * En;
-    if (!strcmp(name, "k_succ")) return 8 * V + 8 * V + 8 * V + 8 * V + 16 * V + (sp ? 24 * V : 0);
-    if (!strcmp(name, "k_edges")) return 12 * E + 8 * E + 12 * En + 16 * En;
+    // planes (+G) in; D weight planes, successor, chosen weight out; rank + cleared accumulators per root
+    if (!strcmp(name, "k_r0_graph")) return (sp ? 16 : 12) * V0 + 4 * D * V0 + 8 * V0 + (4 + acc) * Vn;
+    // succ in, rank gather, map out, old (size, Int) [+ colour sums] in, wsel of merged in, accumulators updated
+    if (!strcmp(name, "k_relabel"))
+        return 4 * V + 4 * V + 4 * V + (r == 0 ? (sp ? 12 * V : 0) : (sp ? 32 : 8) * V) + 4 * (V - Vn) + (sp ? 32 : 8) * Vn;
+    // per direction plane: map of the pixel and of its neighbour (4 + 4 B per grid edge), weights of survivors,
+    // 12 B per surviving edge out, both ends' min-edge words (8 B each)
+    if (!strcmp(name, "k_r0_edges")) return 8 * D * V0 + 4 * En + 12 * En + 16 * En;
+    // best + chosen edge ends + both sides' (size, Int) + partner's best; succ, wsel out; rank + cleared accumulators
+    if (!strcmp(name, "k_succ_scan")) return 8 * V + 8 * V + 16 * V + 8 * V + 8 * V + (4 + acc) * Vn;
+    // 12 B per edge in, two 4 B map gathers, 12 B per surviving edge out, both ends' min-edge words
+    if (!strcmp(name, "k_edges")) return 12 * E + 8 * E + 12 * En + 16 * En + (sp ? 56 * En : 0);
     return 0;
 }
 

@@ -25,20 +25,43 @@ struct GsegRunParams {
     u32 arena_cap;  // capacity of the supervertex-map arena in u32 entries
     u32 epoch_base; // first look-back tag of this run (monotonic across runs)
     int mask_len;
+    u32 tail_E, tail_V; // a round with E <= tail_E and V <= tail_V runs inside the single-cluster tail kernel
     float mask[GSEG_MAXMASK];
 };
 
-// Device-resident control block: all round-to-round state lives here so that a whole run can be
-// replayed as one CUDA graph without the host reading anything back between rounds (the reference
-// copies a 4-byte flag to the host every round, Report.pdf p5).
+// State of the round about to run.  Lives in GsegCtl between kernels of the host-driven schedule
+// and in registers inside the persistent round kernel.
+struct RoundState {
+    u32 V, E;      // components / live edges entering the round
+    u32 round, phase, levels;
+    u32 map_off;   // arena offset of this round's old->new supervertex map
+};
+
+// Device-resident control block: all round-to-round state lives here, so a whole run needs no host
+// involvement between rounds (the reference copies a 4-byte flag to the host every round,
+// Report.pdf p5).  The host initialises [p .. ticketE] with one H2D copy per run.
 struct GsegCtl {
     GsegRunParams p;
-    u32 Vcur, Ecur;   // components / live edges entering the current round
-    u32 Vnext, Enext; // produced by the component scan / the edge compaction
-    u32 phase, round, levels, error;
+    RoundState st;
+    u32 Vnext, Enext; // produced by the component scan / the edge compaction of the current round
+    u32 error;
     u32 ticketC, ticketE; // dynamic tile tickets of the two look-back scans
-    u32 map_off[GSEG_MAXR + 1]; // arena offset of round r's old->new supervertex map
+    u32 doneE;            // blocks that finished the edge phase (the last one advances the round state)
+    // ---- end of host-initialised head ----
+    u32 map_off[GSEG_MAXR + 1];
     u32 stV[GSEG_MAXR], stE[GSEG_MAXR], stM[GSEG_MAXR], stP[GSEG_MAXR], stVafter[GSEG_MAXR];
+};
+
+// Every device array of a context (both parities of the ping-pong buffers).
+struct GsegBufs {
+    float *planes, *G, *wgrid;
+    u32 *succ, *rank, *wsel, *arena;
+    u64 *best[2];     // per component: min outgoing edge key (weight bits << 32 | edge position)
+    uint2 *attr[2];   // per component: x = size |C|, y = fp32 bits of Int(C)
+    long long *csum[2]; // per component: 3 fixed-point colour sums (superpixel variant)
+    uint2 *eab[2];    // per live edge: the two end components
+    u32 *ew[2];       // per live edge: fp32 bits of the weight (superpixel: of the static strength)
+    u64 *statusC, *statusE;
 };
 
 __device__ __forceinline__ u64 ld_relaxed_u64(const u64 *p) {
@@ -64,16 +87,16 @@ __device__ __forceinline__ u32 warp_incl_scan(u32 v, int lane) {
     return v;
 }
 
-// Exclusive scan of one value per thread over a block of NT threads. s: >= 34 u32 of shared memory.
+// Exclusive scan of one value per thread over a block of NTHR threads. s: >= 34 u32 of shared memory.
 // Leaves the block total in s[32]. Contains two __syncthreads().
-template <int NT>
+template <int NTHR>
 __device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *s) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     u32 inc = warp_incl_scan(v, lane);
     if (lane == 31) s[wid] = inc;
     __syncthreads();
     if (wid == 0) {
-        u32 x = lane < NT / 32 ? s[lane] : 0u;
+        u32 x = lane < NTHR / 32 ? s[lane] : 0u;
         u32 xi = warp_incl_scan(x, lane);
         s[lane] = xi - x;
         if (lane == 31) s[32] = xi;
@@ -131,17 +154,33 @@ __device__ __forceinline__ u32 lookback_prefix(u64 *status, u32 tile, u32 tag, u
     return excl;
 }
 
-// Per-block exclusive offset of `cnt` items inside a globally ordered compaction.
-// Returns this thread's global output offset; s[32] = tile total, s[33] = tile prefix.
-template <int NT>
-__device__ __forceinline__ u32 tile_offset(u32 cnt, u32 tile, u32 tag, u64 *status, u32 *err, u32 *s) {
-    const u32 ex = block_excl_scan<NT>(cnt, s);
+// Block-wide: exclusive offset of `cnt` items inside a globally ordered compaction.
+// Returns this thread's offset INSIDE the tile; afterwards s[32] = tile total, s[33] = tile prefix.
+// Warp 0 runs the look-back; callers may overlap independent work between this call's return and the
+// next __syncthreads(), after which s[33] is valid for everyone.
+template <int NTHR>
+__device__ __forceinline__ u32 tile_scan_begin(u32 cnt, u32 tile, u32 tag, u64 *status, u32 *err, u32 *s) {
+    const u32 ex = block_excl_scan<NTHR>(cnt, s);
     if (threadIdx.x < 32) {
         const u32 pre = lookback_prefix(status, tile, tag, s[32], err);
         if (threadIdx.x == 0) s[33] = pre;
     }
-    __syncthreads();
-    return s[33] + ex;
+    return ex;
 }
 
 __device__ __forceinline__ u64 make_key(u32 wbits, u32 idx) { return ((u64)wbits << 32) | (u64)idx; }
+
+// Segmented min-edge selection: the lanes of a warp that hold edges of
+// the same component `id` agree on the group's minimum key with match/redux warp primitives, and one
+// lane per group issues the 64-bit atomicMin.  `pos` MUST increase with the lane index (it is the
+// edge's position in the output list), so among equal weights the lowest lane holds the minimum.
+// All 32 lanes must call; inactive lanes pass act = false.
+__device__ __forceinline__ void warp_group_min(u64 *best, u32 id, u32 kb, u32 pos, bool act) {
+    const u32 actm = __ballot_sync(0xFFFFFFFFu, act);
+    if (!act) return;
+    const int lane = threadIdx.x & 31;
+    const u32 grp = __match_any_sync(actm, id);
+    const u32 wmin = __reduce_min_sync(grp, kb);
+    const u32 cand = __ballot_sync(actm, kb == wmin) & grp;
+    if (kb == wmin && (cand & ((1u << lane) - 1u)) == 0u) atomicMin(best + id, make_key(kb, pos));
+}

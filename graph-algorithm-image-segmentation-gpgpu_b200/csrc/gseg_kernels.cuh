@@ -1,56 +1,118 @@
 // gseg_kernels.cuh -- every CUDA kernel of the segmentation hot path (sm_100a).
 //
 // Stage map:
-//   a1  k_blur_h / k_blur_v            separable Gaussian pre-filter          Report.pdf p3 s3.2 par.2
-//   a2  k_sobel                        Sobel magnitude (superpixel variant)   Report.pdf p4 s3.2.4
-//   a3  k_weights                      grid edge weights / strengths          Report.pdf p3 s3.2.1, p2 par.1
-//   a4  k_r0_choose, k_edges           min outgoing edge per vertex/component Report.pdf p2-3 s3.1 steps 1-3
-//   a6+a7 k_r0_succ, k_succ            predicate + 2-cycle removal            Report.pdf p3 steps 4-5
-//   a8  k_jump, k_relabel              flatten + size / Int(C) / colour       Report.pdf p3 steps 7-8
-//   a9  k_rootscan                     supervertex renumbering (flag + scan)  Report.pdf p3 s3.2.2
-//   a10 k_r0_edges, k_edges            edge relabel, self-loop drop, stable compaction
-//   a11 k_edges<SUPERPIX>              per-round re-weighting from component means
-//   a12 k_compose, k_compose_all       hierarchy materialisation              Report.pdf p4 s3.2.3
-//   a13 min-size rounds                phase PH_MINSIZE of k_succ             Report.pdf p3 step 6
-//   a14 k_colorize                     random colour per component            Report.pdf p4 s3.2.3
+//   a1  k_blur_tile<R> (k_blur_h/k_blur_v for > 8 taps)  separable Gaussian        Report.pdf p3 s3.2 par.2
+//   a2  k_sobel                        Sobel magnitude (superpixel variant)         Report.pdf p4 s3.2.4
+//   a3+a4+a6+a7+a9 (round 0)  k_r0_graph: edge weights, min edge per pixel, predicate, 2-cycle
+//                                      removal, root renumbering -- one shared-memory tile pass
+//                                                                                   Report.pdf p3 s3.2.1, p2-3 s3.1 steps 1,4,5
+//   a6+a7+a9 phase_S                   predicate + 2-cycle removal + supervertex renumbering
+//   a8  phase_R                        flatten (pointer chase) + size / Int(C) / colour accumulation
+//   a10+a4 k_r0_edges, phase_E         edge relabel, self-loop drop, stable compaction, fused with the
+//                                      next round's segmented min-edge selection (warp match/redux)
+//   a11 phase_E<SUPERPIX>              per-round re-weighting from component means
+//   a12 k_compose*                     hierarchy materialisation                    Report.pdf p4 s3.2.3
+//   a13 min-size rounds                phase PH_MINSIZE of phase_S                  Report.pdf p3 step 6
+//   a14 k_colorize                     random colour per component                  Report.pdf p4 s3.2.3
+//   --  k_tail                         persistent single-cluster kernel: every round whose graph is small
+//                                      runs inside one launch with cluster barriers, instead of the
+//                                      reference's per-round host loop (Report.pdf p3 "Dynamic
+//                                      parallelism", p5 "4 bytes copied back per iteration")
 //
 // Float contract: every fp32 product, sum, quotient and square root on the weight path is a
 // separately rounded IEEE operation (__fmul_rn/__fadd_rn/__fsub_rn/__fdiv_rn/__fsqrt_rn) in the
 // order DESIGN.md "Semantics" states; ptxas never contracts these intrinsics into FMAs, so weights
 // are bit-identical to the CPU oracle and the total edge order (weight bits, edge index) is too.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "gseg_device.cuh"
 
-#define NT 256
-#define TILE_E (NT * 4) // edges per tile of the edge compaction
-#define TILE_C (NT * 8) // components per tile of the root scan
+namespace cg = cooperative_groups;
 
-__device__ __constant__ int c_DX[4] = {1, 0, 1, 1};
-__device__ __constant__ int c_DY[4] = {0, 1, 1, -1};
+#define NT 256   // threads per block of the grid-wide kernels
+#define NTT 1024 // threads per block of the single-cluster tail kernel
+#define CPT 4    // components per thread of phase S (tile = NTH * CPT)
+#define EPT 8    // edges per thread of phase E (tile = NTH * EPT)
 
-// ------------------------------------------------------------------------------------------------
-// run set-up
-// ------------------------------------------------------------------------------------------------
-__global__ void k_init(GsegCtl *ctl) {
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
-        const u32 V = (u32)ctl->p.w * (u32)ctl->p.h;
-        ctl->Vcur = V;
-        ctl->Ecur = 0;
-        ctl->Vnext = V;
-        ctl->Enext = 0;
-        ctl->phase = PH_PRED;
-        ctl->round = 0;
-        ctl->levels = 0;
-        ctl->error = DERR_NONE;
-        ctl->ticketC = 0;
-        ctl->ticketE = 0;
-        ctl->map_off[0] = 0;
-    }
-}
+// round-0 image tiles
+#define TW 64
+#define TH 32
+#define BW (TW + 4)
+#define BH (TH + 4)
+
+__constant__ int c_DX[4] = {1, 0, 1, 1};
+__constant__ int c_DY[4] = {0, 1, 1, -1};
 
 // ------------------------------------------------------------------------------------------------
 // a1: separable Gaussian, clamped borders.  u8 interleaved RGB -> 3 fp32 planes.
+// Tile kernel: (TW+2R) x (TH+2R) input bytes -> shared; horizontal pass into shared; vertical pass
+// to global.  Each thread produces 8 outputs along the filter direction from 8+2R register-held
+// taps, so shared memory is read ~2x per output instead of (2R+1)x.
 // ------------------------------------------------------------------------------------------------
+template <int R>
+__global__ void __launch_bounds__(NT) k_blur_tile(const GsegCtl *__restrict__ ctl, float *__restrict__ planes) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr int IW = TW + 2 * R, IH = TH + 2 * R, IWB = IW * 3;
+    constexpr int IBYTES = (IWB * IH + 15) & ~15;
+    uint8_t *sI = smem_raw;                                  // [IH][IW*3]
+    float *sH = reinterpret_cast<float *>(smem_raw + IBYTES); // [3][IH][TW]
+    const int w = ctl->p.w, h = ctl->p.h, stride = ctl->p.stride;
+    const uint8_t *__restrict__ rgb = ctl->p.rgb;
+    float m[R + 1];
+#pragma unroll
+    for (int i = 0; i <= R; ++i) m[i] = ctl->p.mask[i];
+    const int ntx = (w + TW - 1) / TW;
+    const int x0 = (blockIdx.x % ntx) * TW, y0 = (blockIdx.x / ntx) * TH;
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int r = wid; r < IH; r += NT / 32) {
+        const int gy = min(max(y0 - R + r, 0), h - 1);
+        const uint8_t *row = rgb + (size_t)gy * stride;
+        for (int o = lane; o < IWB; o += 32) {
+            const int px = o / 3, ch = o - px * 3;
+            const int gx = min(max(x0 - R + px, 0), w - 1);
+            sI[r * IWB + o] = row[3 * gx + ch];
+        }
+    }
+    __syncthreads();
+    for (int item = threadIdx.x; item < IH * 3 * (TW / 8); item += NT) {
+        const int g = item % (TW / 8), ch = (item / (TW / 8)) % 3, r = item / (3 * (TW / 8));
+        float v[8 + 2 * R];
+        const uint8_t *src = sI + r * IWB + (g * 8) * 3 + ch;
+#pragma unroll
+        for (int j = 0; j < 8 + 2 * R; ++j) v[j] = (float)src[3 * j];
+        float *dst = sH + (ch * IH + r) * TW + g * 8;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float s = __fmul_rn(m[0], v[R + j]);
+#pragma unroll
+            for (int i = 1; i <= R; ++i) s = __fadd_rn(s, __fmul_rn(m[i], __fadd_rn(v[R + j - i], v[R + j + i])));
+            dst[j] = s;
+        }
+    }
+    __syncthreads();
+    const u32 V = (u32)w * (u32)h;
+    for (int item = threadIdx.x; item < TW * 3 * (TH / 8); item += NT) {
+        const int c = item % TW, ch = (item / TW) % 3, rg = item / (3 * TW);
+        const int gx = x0 + c;
+        if (gx >= w) continue;
+        float v[8 + 2 * R];
+        const float *src = sH + (ch * IH + rg * 8) * TW + c;
+#pragma unroll
+        for (int j = 0; j < 8 + 2 * R; ++j) v[j] = src[j * TW];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            const int gy = y0 + rg * 8 + j;
+            if (gy >= h) break;
+            float s = __fmul_rn(m[0], v[R + j]);
+#pragma unroll
+            for (int i = 1; i <= R; ++i) s = __fadd_rn(s, __fmul_rn(m[i], __fadd_rn(v[R + j - i], v[R + j + i])));
+            planes[(size_t)ch * V + (size_t)gy * w + gx] = s;
+        }
+    }
+}
+
+// general-sigma fallback (more than 8 one-sided taps)
 __global__ void __launch_bounds__(NT) k_blur_h(const GsegCtl *__restrict__ ctl, float *__restrict__ tmp) {
     const int w = ctl->p.w, h = ctl->p.h, stride = ctl->p.stride, len = ctl->p.mask_len;
     const uint8_t *__restrict__ rgb = ctl->p.rgb;
@@ -71,7 +133,6 @@ __global__ void __launch_bounds__(NT) k_blur_h(const GsegCtl *__restrict__ ctl, 
         }
     }
 }
-
 __global__ void __launch_bounds__(NT) k_blur_v(const GsegCtl *__restrict__ ctl, const float *__restrict__ tmp,
                                                float *__restrict__ planes) {
     const int w = ctl->p.w, h = ctl->p.h, len = ctl->p.mask_len;
@@ -116,32 +177,6 @@ __global__ void __launch_bounds__(NT) k_sobel(const GsegCtl *__restrict__ ctl, c
     }
 }
 
-// a3: grid edge weights, plane-major wgrid[d*V + p]; +inf where the edge does not exist.
-__device__ __forceinline__ float l2rgb(const float *pl, u32 V, u32 p, u32 q) {
-    const float dr = __fsub_rn(pl[p], pl[q]), dg = __fsub_rn(pl[V + p], pl[V + q]),
-                db = __fsub_rn(pl[2 * V + p], pl[2 * V + q]);
-    const float s = __fadd_rn(__fadd_rn(__fmul_rn(dr, dr), __fmul_rn(dg, dg)), __fmul_rn(db, db));
-    return __fsqrt_rn(s);
-}
-template <bool STRENGTH>
-__global__ void __launch_bounds__(NT) k_weights(const GsegCtl *__restrict__ ctl, const float *__restrict__ planes,
-                                                const float *__restrict__ G, float *__restrict__ wgrid) {
-    const int w = ctl->p.w, h = ctl->p.h, D = ctl->p.D;
-    const u32 V = (u32)w * (u32)h;
-    for (u32 p = blockIdx.x * NT + threadIdx.x; p < V; p += gridDim.x * NT) {
-        const int y = p / w, x = p - y * w;
-        for (int d = 0; d < D; ++d) {
-            const int xx = x + c_DX[d], yy = y + c_DY[d];
-            float v = __int_as_float(GSEG_INF_BITS);
-            if (xx < w && yy < h && yy >= 0) {
-                const u32 q = (u32)yy * w + xx;
-                v = STRENGTH ? __fmul_rn(0.5f, __fadd_rn(G[p], G[q])) : l2rgb(planes, V, p, q);
-            }
-            wgrid[(size_t)d * V + p] = v;
-        }
-    }
-}
-
 // 24.8 fixed-point colour of a pixel and the superpixel round weight.
 __device__ __forceinline__ int fx8(float v) { return __float2int_rn(__fmul_rn(v, 256.0f)); }
 __device__ __forceinline__ float mean_dist(const long long *ca, u32 sa, const long long *cb, u32 sb) {
@@ -153,380 +188,181 @@ __device__ __forceinline__ float mean_dist(const long long *ca, u32 sa, const lo
     return __fsqrt_rn(s);
 }
 
-// ------------------------------------------------------------------------------------------------
-// Round 0 on the implicit grid: every pixel is its own component, so the minimum outgoing edge is
-// a pure stencil over its <= 2D incident edges (no atomics).  dir codes: 0..3 own edge (E,S,SE,NE),
-// 4..7 the reverse (W,N,NW,SW); 255 = none / rejected by the predicate.
-// ------------------------------------------------------------------------------------------------
-template <int VARIANT>
-__global__ void __launch_bounds__(NT) k_r0_choose(const GsegCtl *__restrict__ ctl, const float *__restrict__ wgrid,
-                                                  const float *__restrict__ planes, uint8_t *__restrict__ dir0,
-                                                  u32 *__restrict__ wsel) {
-    const int w = ctl->p.w, h = ctl->p.h, D = ctl->p.D;
-    const u32 V = (u32)w * (u32)h;
-    for (u32 p = blockIdx.x * NT + threadIdx.x; p < V; p += gridDim.x * NT) {
-        const int y = p / w, x = p - y * w;
-        u64 best = GSEG_KEY_NONE;
-        int bdir = 255;
-        long long cp[3];
-        if (VARIANT == GSEG_SUPERPIX) {
-            cp[0] = fx8(planes[p]); cp[1] = fx8(planes[V + p]); cp[2] = fx8(planes[2 * V + p]);
-        }
-        for (int d = 0; d < 2 * D; ++d) {
-            const int dd = d < D ? d : d - D;
-            const int sgn = d < D ? 1 : -1;
-            const int xx = x + sgn * c_DX[dd], yy = y + sgn * c_DY[dd];
-            if (xx < 0 || xx >= w || yy < 0 || yy >= h) continue;
-            const u32 q = (u32)yy * w + xx;
-            const u32 owner = d < D ? p : q; // the pixel whose edge list holds this edge
-            float wv = wgrid[(size_t)dd * V + owner];
-            if (VARIANT == GSEG_SUPERPIX) {
-                long long cq[3] = {fx8(planes[q]), fx8(planes[V + q]), fx8(planes[2 * V + q])};
-                wv = __fmul_rn(wv, mean_dist(cp, 1u, cq, 1u));
-            }
-            const u64 key = make_key(__float_as_uint(wv), owner * (u32)D + (u32)dd);
-            if (key < best) { best = key; bdir = d < D ? dd : dd + 4; }
-        }
-        u32 wb = 0;
-        if (bdir != 255) {
-            wb = (u32)(best >> 32);
-            if (VARIANT == GSEG_FELZ) {
-                // Int = 0, |C| = 1 on both sides: thr = 0 + k/1
-                const float thr = __fadd_rn(0.0f, __fdiv_rn(ctl->p.k, 1.0f));
-                if (!(__uint_as_float(wb) <= thr)) bdir = 255;
-            }
-        }
-        dir0[p] = (uint8_t)bdir;
-        wsel[p] = wb;
-    }
-}
-
-__device__ __forceinline__ u32 dir_neighbor(u32 p, int dir, int w) {
-    const int dd = dir & 3, sgn = dir < 4 ? 1 : -1;
-    return (u32)((int)p + sgn * (c_DY[dd] * w + c_DX[dd]));
-}
-
-// successor with 2-cycle removal; also clears the next round's accumulators.
-template <bool SUPERPIX>
-__global__ void __launch_bounds__(NT) k_r0_succ(const GsegCtl *__restrict__ ctl, const uint8_t *__restrict__ dir0,
-                                                u32 *__restrict__ succ, u32 *__restrict__ size_n,
-                                                u32 *__restrict__ int_n, u64 *__restrict__ best_n,
-                                                long long *__restrict__ csum_n) {
-    const int w = ctl->p.w;
-    const u32 V = (u32)w * (u32)ctl->p.h;
-    for (u32 p = blockIdx.x * NT + threadIdx.x; p < V; p += gridDim.x * NT) {
-        const int d = dir0[p];
-        u32 s = p;
-        if (d != 255) {
-            const u32 q = dir_neighbor(p, d, w);
-            s = (dir0[q] == (d ^ 4) && p < q) ? p : q;
-        }
-        succ[p] = s;
-        size_n[p] = 0;
-        int_n[p] = 0;
-        best_n[p] = GSEG_KEY_NONE;
-        if (SUPERPIX) { csum_n[3 * (size_t)p] = 0; csum_n[3 * (size_t)p + 1] = 0; csum_n[3 * (size_t)p + 2] = 0; }
-    }
+// component-mean distance from the global accumulators (written by atomics in phase R: read at L2)
+__device__ __forceinline__ float mean_dist_g(const long long *csum, const uint2 *attr, u32 a, u32 b) {
+    long long ca[3] = {__ldcg(csum + 3 * (size_t)a), __ldcg(csum + 3 * (size_t)a + 1), __ldcg(csum + 3 * (size_t)a + 2)};
+    long long cb[3] = {__ldcg(csum + 3 * (size_t)b), __ldcg(csum + 3 * (size_t)b + 1), __ldcg(csum + 3 * (size_t)b + 2)};
+    return mean_dist(ca, __ldcg(&attr[a].x), cb, __ldcg(&attr[b].x));
 }
 
 // ------------------------------------------------------------------------------------------------
-// a8: flatten the merge forest in place.  Every value ever stored in succ[] is an ancestor of its
-// slot and roots never change, so concurrent chasing with in-place compression is race-benign.
+// Round 0 on the implicit grid (every pixel is its own component): one tile pass does
+//   edge weights (a3) -> per-pixel minimum incident edge (a4; a pure stencil, no atomics) ->
+//   predicate (a7) -> 2-cycle removal (a6) -> root flags + look-back scan = new ids (a9).
+// Blurred halo: 2 pixels (the 2-cycle test needs the neighbour's choice, which needs the neighbour's
+// neighbours).  dir codes: 0..3 own edge (E,S,SE,NE), 4..7 the reverse (W,N,NW,SW); 255 = none.
+// Edge index (the tie-break of every comparison) = d*V + p, direction-major.
+// New component ids are assigned in tile order (any bijection is valid: ids only name components).
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) k_jump(const GsegCtl *__restrict__ ctl, u32 *succ) {
-    if (ctl->phase == PH_DONE) return;
-    const u32 V = ctl->Vcur;
-    for (u32 c = blockIdx.x * NT + threadIdx.x; c < V; c += gridDim.x * NT) {
-        u32 s = ld_relaxed_u32(succ + c);
-        if (s == c) continue;
-        for (;;) {
-            const u32 ss = ld_relaxed_u32(succ + s);
-            if (ss == s) break;
-            s = ss;
-        }
-        succ[c] = s;
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// a9: roots -> dense new ids in root-index order (flag + single-pass look-back scan).
-// rank[c] = number of roots below c.  Total -> ctl->Vnext.
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(NT) k_rootscan(GsegCtl *ctl, const u32 *__restrict__ succ, u32 *__restrict__ rank,
-                                                 u64 *status) {
-    if (ctl->phase == PH_DONE) return;
+template <int VARIANT, int D>
+__global__ void __launch_bounds__(NT) k_r0_graph(GsegCtl *ctl, GsegBufs B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr bool SP = VARIANT == GSEG_SUPERPIX;
+    float *sP = reinterpret_cast<float *>(smem_raw);   // [3][BH][BW] blurred colour
+    float *sW = sP + 3 * BH * BW;                      // [D][BH][BW] own-edge key weights
+    float *sG = sW + D * BH * BW;                      // [BH][BW] Sobel (SP only)
+    uint8_t *sDir = reinterpret_cast<uint8_t *>(sG + (SP ? BH * BW : 0)); // [BH-2][BW-2] choices of tile + halo 1
     __shared__ u32 s_scan[34];
     __shared__ u32 s_tile;
-    const u32 V = ctl->Vcur;
-    const u32 ntiles = (V + TILE_C - 1) / TILE_C;
-    const u32 tag = ctl->p.epoch_base + ctl->round * 2u + 1u;
+    const int w = ctl->p.w, h = ctl->p.h;
+    const u32 V = (u32)w * (u32)h;
+    const int ntx = (w + TW - 1) / TW, nty = (h + TH - 1) / TH;
+    const u32 ntiles = (u32)ntx * (u32)nty;
+    const u32 tag = ctl->p.epoch_base + 1u;
+    const float kthr = __fadd_rn(0.0f, __fdiv_rn(ctl->p.k, 1.0f)); // Int = 0, |C| = 1 on both sides
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ticketE = 0;
     for (;;) {
         if (threadIdx.x == 0) s_tile = atomicAdd(&ctl->ticketC, 1u);
         __syncthreads();
         const u32 tile = s_tile;
-        if (tile >= ntiles) {
-            if (tile == 0 && threadIdx.x == 0) ctl->Vnext = 0;
-            break;
-        }
-        const u32 base = tile * TILE_C + threadIdx.x * 8;
-        u32 f[8], cnt = 0;
-        if (base + 7 < V) {
-            const uint4 a = *reinterpret_cast<const uint4 *>(succ + base);
-            const uint4 b = *reinterpret_cast<const uint4 *>(succ + base + 4);
-            f[0] = a.x == base; f[1] = a.y == base + 1; f[2] = a.z == base + 2; f[3] = a.w == base + 3;
-            f[4] = b.x == base + 4; f[5] = b.y == base + 5; f[6] = b.z == base + 6; f[7] = b.w == base + 7;
-        } else {
-#pragma unroll
-            for (int j = 0; j < 8; ++j) f[j] = (base + j < V) ? (succ[base + j] == base + j) : 0u;
-        }
-#pragma unroll
-        for (int j = 0; j < 8; ++j) cnt += f[j];
-        u32 off = tile_offset<NT>(cnt, tile, tag, status, &ctl->error, s_scan);
-        if (tile == ntiles - 1 && threadIdx.x == 0) ctl->Vnext = s_scan[33] + s_scan[32];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) {
-            if (base + j < V) rank[base + j] = off;
-            off += f[j];
+        if (tile >= ntiles) break;
+        const int x0 = (int)(tile % ntx) * TW, y0 = (int)(tile / ntx) * TH;
+        // 1. blurred halo tile
+        for (int i = threadIdx.x; i < BH * BW; i += NT) {
+            const int r = i / BW, c = i - r * BW;
+            const int gx = x0 - 2 + c, gy = y0 - 2 + r;
+            float v0 = 0.f, v1 = 0.f, v2 = 0.f, g = 0.f;
+            if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
+                const u32 p = (u32)gy * w + gx;
+                v0 = B.planes[p]; v1 = B.planes[V + p]; v2 = B.planes[2 * V + p];
+                if (SP) g = B.G[p];
+            }
+            sP[i] = v0; sP[BH * BW + i] = v1; sP[2 * BH * BW + i] = v2;
+            if (SP) sG[i] = g;
         }
         __syncthreads();
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// a8: old id -> new id map, and accumulation of size / Int(C) / colour sums into the new ids.
-// R0: components are pixels (size 1, Int 0, colour = the pixel's fixed-point colour).
-// ------------------------------------------------------------------------------------------------
-template <bool R0, bool SUPERPIX>
-__global__ void __launch_bounds__(NT) k_relabel(const GsegCtl *__restrict__ ctl, const u32 *__restrict__ succ,
-                                                const u32 *__restrict__ rank, const u32 *__restrict__ wsel,
-                                                const u32 *__restrict__ size_c, const u32 *__restrict__ int_c,
-                                                const long long *__restrict__ csum_c, const float *__restrict__ planes,
-                                                u32 *__restrict__ arena, u32 *__restrict__ size_n,
-                                                u32 *__restrict__ int_n, long long *__restrict__ csum_n) {
-    if (ctl->phase == PH_DONE) return;
-    const u32 V = ctl->Vcur;
-    u32 *map = arena + ctl->map_off[ctl->round];
-    const u32 V0 = (u32)ctl->p.w * (u32)ctl->p.h;
-    for (u32 c = blockIdx.x * NT + threadIdx.x; c < V; c += gridDim.x * NT) {
-        const u32 r = succ[c];
-        const u32 m = rank[r];
-        map[c] = m;
-        atomicAdd(size_n + m, R0 ? 1u : size_c[c]);
-        u32 iv = R0 ? 0u : int_c[c];
-        if (r != c) iv = max(iv, wsel[c]);
-        if (iv) atomicMax(int_n + m, iv);
-        if (SUPERPIX) {
-            long long v0, v1, v2;
-            if (R0) { v0 = fx8(planes[c]); v1 = fx8(planes[V0 + c]); v2 = fx8(planes[2 * V0 + c]); }
-            else { v0 = csum_c[3 * (size_t)c]; v1 = csum_c[3 * (size_t)c + 1]; v2 = csum_c[3 * (size_t)c + 2]; }
-            atomicAdd((u64 *)(csum_n + 3 * (size_t)m), (u64)v0);
-            atomicAdd((u64 *)(csum_n + 3 * (size_t)m + 1), (u64)v1);
-            atomicAdd((u64 *)(csum_n + 3 * (size_t)m + 2), (u64)v2);
-        }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// a10 (round 0): grid edges -> explicit list of inter-component edges, in edge-index order (stable),
-// fused with next round's per-component minimum (key = weight bits << 32 | position in the list;
-// stable compaction keeps list order == edge-index order, so position is the same tie-break).
-// One thread per pixel; a tile is NT pixels.
-// ------------------------------------------------------------------------------------------------
-template <bool SUPERPIX>
-__global__ void __launch_bounds__(NT) k_r0_edges(GsegCtl *ctl, const float *__restrict__ wgrid,
-                                                 const u32 *__restrict__ arena, u32 *__restrict__ oa,
-                                                 u32 *__restrict__ ob, u32 *__restrict__ ow, u64 *best_n,
-                                                 const u32 *__restrict__ size_n, const long long *__restrict__ csum_n,
-                                                 u64 *status) {
-    if (ctl->phase == PH_DONE) return;
-    __shared__ u32 s_scan[34];
-    __shared__ u32 s_tile;
-    const int w = ctl->p.w, h = ctl->p.h, D = ctl->p.D;
-    const u32 V = (u32)w * (u32)h;
-    const u32 *__restrict__ map = arena; // map_off[0] == 0
-    const u32 ntiles = (V + NT - 1) / NT;
-    const u32 tag = ctl->p.epoch_base + ctl->round * 2u + 2u;
-    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ticketC = 0;
-    for (;;) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(&ctl->ticketE, 1u);
-        __syncthreads();
-        const u32 tile = s_tile;
-        if (tile >= ntiles) {
-            if (tile == 0 && threadIdx.x == 0) ctl->Enext = 0;
-            break;
-        }
-        const u32 p = tile * NT + threadIdx.x;
-        u32 a = 0, b[4], wv[4], cnt = 0;
-        bool keep[4] = {false, false, false, false};
-        if (p < V) {
-            const int y = p / w, x = p - y * w;
-            a = map[p];
+        // 2. own-edge weights of every halo-tile pixel (inf where an end is outside the image/halo)
+        for (int i = threadIdx.x; i < BH * BW; i += NT) {
+            const int r = i / BW, c = i - r * BW;
+            const int gx = x0 - 2 + c, gy = y0 - 2 + r;
+            const bool in = gx >= 0 && gx < w && gy >= 0 && gy < h;
+            const float p0 = sP[i], p1 = sP[BH * BW + i], p2 = sP[2 * BH * BW + i];
+#pragma unroll
             for (int d = 0; d < D; ++d) {
-                const int xx = x + c_DX[d], yy = y + c_DY[d];
-                if (xx < w && yy < h && yy >= 0) {
-                    b[d] = map[(u32)yy * w + xx];
-                    if (b[d] != a) {
-                        keep[d] = true;
-                        wv[d] = __float_as_uint(wgrid[(size_t)d * V + p]);
-                        ++cnt;
+                const int dx = d == 1 ? 0 : 1, dy = d == 0 ? 0 : (d == 3 ? -1 : 1);
+                const int rr = r + dy, cc = c + dx;
+                float wv = __int_as_float(GSEG_INF_BITS);
+                if (in && rr >= 0 && rr < BH && cc < BW && gx + dx < w && gy + dy < h && gy + dy >= 0) {
+                    const int j = rr * BW + cc;
+                    if (SP) {
+                        long long ca[3] = {fx8(p0), fx8(p1), fx8(p2)};
+                        long long cb[3] = {fx8(sP[j]), fx8(sP[BH * BW + j]), fx8(sP[2 * BH * BW + j])};
+                        wv = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(sG[i], sG[j])), mean_dist(ca, 1u, cb, 1u));
+                    } else {
+                        const float dr = __fsub_rn(p0, sP[j]), dg = __fsub_rn(p1, sP[BH * BW + j]),
+                                    db = __fsub_rn(p2, sP[2 * BH * BW + j]);
+                        wv = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dr, dr), __fmul_rn(dg, dg)), __fmul_rn(db, db)));
                     }
                 }
+                sW[d * BH * BW + i] = wv;
             }
         }
-        u32 pos = tile_offset<NT>(cnt, tile, tag, status, &ctl->error, s_scan);
-        if (tile == ntiles - 1 && threadIdx.x == 0) ctl->Enext = s_scan[33] + s_scan[32];
-        for (int d = 0; d < D; ++d) {
-            if (!keep[d]) continue;
-            oa[pos] = a; ob[pos] = b[d]; ow[pos] = wv[d];
-            u32 kb = wv[d];
-            if (SUPERPIX)
-                kb = __float_as_uint(__fmul_rn(__uint_as_float(wv[d]),
-                                               mean_dist(csum_n + 3 * (size_t)a, size_n[a], csum_n + 3 * (size_t)b[d], size_n[b[d]])));
-            const u64 key = make_key(kb, pos);
-            atomicMin(best_n + a, key);
-            atomicMin(best_n + b[d], key);
-            ++pos;
-        }
         __syncthreads();
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// a6+a7 (rounds >= 1): each component's choice under the predicate / min-size rule, 2-cycle removal.
-// ------------------------------------------------------------------------------------------------
-struct RoundView {
-    const u64 *best;
-    const u32 *ea, *eb, *size, *Int;
-    float k;
-    int min_size, variant;
-    u32 phase;
-};
-__device__ __forceinline__ u32 comp_choice(const RoundView &v, u32 c, u32 *wbits_out) {
-    const u64 key = v.best[c];
-    if (key == GSEG_KEY_NONE) return c;
-    const u32 pos = (u32)key, wb = (u32)(key >> 32);
-    const u32 a = v.ea[pos], b = v.eb[pos];
-    const u32 other = a == c ? b : a;
-    bool ok;
-    if (v.variant != GSEG_FELZ) ok = true;
-    else if (v.phase == PH_PRED) {
-        const float wt = __uint_as_float(wb);
-        const float ta = __fadd_rn(__uint_as_float(v.Int[a]), __fdiv_rn(v.k, __uint2float_rn(v.size[a])));
-        const float tb = __fadd_rn(__uint_as_float(v.Int[b]), __fdiv_rn(v.k, __uint2float_rn(v.size[b])));
-        ok = wt <= ta && wt <= tb;
-    } else ok = v.size[c] < (u32)v.min_size;
-    *wbits_out = wb;
-    return ok ? other : c;
-}
-
-template <bool SUPERPIX>
-__global__ void __launch_bounds__(NT) k_succ(const GsegCtl *__restrict__ ctl, const u64 *__restrict__ best,
-                                             const u32 *__restrict__ ea, const u32 *__restrict__ eb,
-                                             const u32 *__restrict__ size_c, const u32 *__restrict__ int_c,
-                                             u32 *__restrict__ succ, u32 *__restrict__ wsel, u32 *__restrict__ size_n,
-                                             u32 *__restrict__ int_n, u64 *__restrict__ best_n,
-                                             long long *__restrict__ csum_n) {
-    if (ctl->phase == PH_DONE) return;
-    const u32 V = ctl->Vcur;
-    RoundView v;
-    v.best = best; v.ea = ea; v.eb = eb; v.size = size_c; v.Int = int_c;
-    v.k = ctl->p.k; v.min_size = ctl->p.min_size; v.variant = ctl->p.variant; v.phase = ctl->phase;
-    for (u32 c = blockIdx.x * NT + threadIdx.x; c < V; c += gridDim.x * NT) {
-        u32 wb = 0, wb2;
-        u32 s = comp_choice(v, c, &wb);
-        if (s != c) {
-            const u32 t = comp_choice(v, s, &wb2);
-            if (t == c && c < s) s = c;
-        }
-        succ[c] = s;
-        wsel[c] = wb;
-        size_n[c] = 0;
-        int_n[c] = 0;
-        best_n[c] = GSEG_KEY_NONE;
-        if (SUPERPIX) { csum_n[3 * (size_t)c] = 0; csum_n[3 * (size_t)c + 1] = 0; csum_n[3 * (size_t)c + 2] = 0; }
-    }
-}
-
-// ------------------------------------------------------------------------------------------------
-// a10 (rounds >= 1): relabel edge ends through this round's map, drop self-loops, stable compaction,
-// fused with next round's per-component minimum.  4 consecutive edges per thread.
-// ------------------------------------------------------------------------------------------------
-template <bool SUPERPIX>
-__global__ void __launch_bounds__(NT) k_edges(GsegCtl *ctl, const u32 *__restrict__ ea, const u32 *__restrict__ eb,
-                                              const u32 *__restrict__ ew, const u32 *__restrict__ arena,
-                                              u32 *__restrict__ oa, u32 *__restrict__ ob, u32 *__restrict__ ow,
-                                              u64 *best_n, const u32 *__restrict__ size_n,
-                                              const long long *__restrict__ csum_n, u64 *status) {
-    if (ctl->phase == PH_DONE) return;
-    __shared__ u32 s_scan[34];
-    __shared__ u32 s_tile;
-    const u32 E = ctl->Ecur;
-    const u32 *__restrict__ map = arena + ctl->map_off[ctl->round];
-    const u32 ntiles = (E + TILE_E - 1) / TILE_E;
-    const u32 tag = ctl->p.epoch_base + ctl->round * 2u + 2u;
-    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ticketC = 0;
-    for (;;) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(&ctl->ticketE, 1u);
-        __syncthreads();
-        const u32 tile = s_tile;
-        if (tile >= ntiles) {
-            if (tile == 0 && threadIdx.x == 0) ctl->Enext = 0;
-            break;
-        }
-        const u32 base = tile * TILE_E + threadIdx.x * 4;
-        u32 a[4], b[4], wv[4], cnt = 0;
-        bool keep[4];
-        if (base + 3 < E) {
-            const uint4 va = *reinterpret_cast<const uint4 *>(ea + base);
-            const uint4 vb = *reinterpret_cast<const uint4 *>(eb + base);
-            const uint4 vw = *reinterpret_cast<const uint4 *>(ew + base);
-            a[0] = va.x; a[1] = va.y; a[2] = va.z; a[3] = va.w;
-            b[0] = vb.x; b[1] = vb.y; b[2] = vb.z; b[3] = vb.w;
-            wv[0] = vw.x; wv[1] = vw.y; wv[2] = vw.z; wv[3] = vw.w;
+        // 3. choice of every pixel of tile + 1-pixel halo
+        for (int i = threadIdx.x; i < (BH - 2) * (BW - 2); i += NT) {
+            const int r = i / (BW - 2) + 1, c = i % (BW - 2) + 1;
+            const int gx = x0 - 2 + c, gy = y0 - 2 + r;
+            int bdir = 255;
+            if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
+                const u32 p = (u32)gy * w + gx;
+                u64 best = GSEG_KEY_NONE;
 #pragma unroll
-            for (int j = 0; j < 4; ++j) { a[j] = map[a[j]]; b[j] = map[b[j]]; keep[j] = a[j] != b[j]; cnt += keep[j]; }
-        } else {
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-                keep[j] = false;
-                if (base + j < E) {
-                    a[j] = map[ea[base + j]]; b[j] = map[eb[base + j]]; wv[j] = ew[base + j];
-                    keep[j] = a[j] != b[j];
-                    cnt += keep[j];
+                for (int d = 0; d < D; ++d) {
+                    const int dx = d == 1 ? 0 : 1, dy = d == 0 ? 0 : (d == 3 ? -1 : 1);
+                    const u32 wo = __float_as_uint(sW[d * BH * BW + r * BW + c]);
+                    if (wo != GSEG_INF_BITS) {
+                        const u64 key = make_key(wo, (u32)d * V + p);
+                        if (key < best) { best = key; bdir = d; }
+                    }
+                    if (gx - dx >= 0 && gy - dy >= 0 && gy - dy < h) { // the edge owned by the opposite neighbour
+                        const u32 wr = __float_as_uint(sW[d * BH * BW + (r - dy) * BW + (c - dx)]);
+                        const u32 q = (u32)((int)p - dy * w - dx);
+                        const u64 key = make_key(wr, (u32)d * V + q);
+                        if (wr != GSEG_INF_BITS && key < best) { best = key; bdir = d + 4; }
+                    }
                 }
+                if (VARIANT == GSEG_FELZ && bdir != 255 && !(__uint_as_float((u32)(best >> 32)) <= kthr)) bdir = 255;
             }
+            sDir[(r - 1) * (BW - 2) + (c - 1)] = (uint8_t)bdir;
         }
-        u32 pos = tile_offset<NT>(cnt, tile, tag, status, &ctl->error, s_scan);
-        if (tile == ntiles - 1 && threadIdx.x == 0) ctl->Enext = s_scan[33] + s_scan[32];
+        __syncthreads();
+        // 4. successor (2-cycle removal), outputs, root flags.  Thread: column t%64, rows (t/64)*8 + j.
+        const int c = (int)(threadIdx.x % TW), rg = (int)(threadIdx.x / TW) * 8;
+        const int gx = x0 + c;
+        u32 flags = 0, cnt = 0;
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-            if (!keep[j]) continue;
-            oa[pos] = a[j]; ob[pos] = b[j]; ow[pos] = wv[j];
-            u32 kb = wv[j];
-            if (SUPERPIX)
-                kb = __float_as_uint(__fmul_rn(__uint_as_float(wv[j]),
-                                               mean_dist(csum_n + 3 * (size_t)a[j], size_n[a[j]], csum_n + 3 * (size_t)b[j], size_n[b[j]])));
-            const u64 key = make_key(kb, pos);
-            atomicMin(best_n + a[j], key);
-            atomicMin(best_n + b[j], key);
-            ++pos;
+        for (int j = 0; j < 8; ++j) {
+            const int gy = y0 + rg + j;
+            if (gx >= w || gy >= h) continue;
+            const u32 p = (u32)gy * w + gx;
+            const int r1 = rg + j + 1, c1 = c + 1; // coordinates in sDir
+            const int d = sDir[r1 * (BW - 2) + c1];
+            u32 s = p, wb = 0;
+            if (d != 255) {
+                const int dd = d & 3, sgn = d < 4 ? 1 : -1;
+                const int dx = sgn * (dd == 1 ? 0 : 1), dy = sgn * (dd == 0 ? 0 : (dd == 3 ? -1 : 1));
+                const u32 q = (u32)((int)p + dy * w + dx);
+                const int dq = sDir[(r1 + dy) * (BW - 2) + (c1 + dx)];
+                s = (dq == (d ^ 4) && p < q) ? p : q;
+                // weight of the chosen edge, from its owner's slot
+                const int ro = d < 4 ? r1 + 1 : r1 + 1 + dy, co = d < 4 ? c1 + 1 : c1 + 1 + dx;
+                wb = __float_as_uint(sW[dd * BH * BW + ro * BW + co]);
+            }
+            B.succ[p] = s;
+            B.wsel[p] = wb;
+#pragma unroll
+            for (int dd = 0; dd < D; ++dd) {
+                float wv = sW[dd * BH * BW + (r1 + 1) * BW + (c1 + 1)];
+                if (SP && __float_as_uint(wv) != GSEG_INF_BITS) {
+                    const int dx = dd == 1 ? 0 : 1, dy = dd == 0 ? 0 : (dd == 3 ? -1 : 1);
+                    wv = __fmul_rn(0.5f, __fadd_rn(sG[(r1 + 1) * BW + c1 + 1], sG[(r1 + 1 + dy) * BW + c1 + 1 + dx]));
+                }
+                B.wgrid[(size_t)dd * V + p] = wv;
+            }
+            if (s == p) { flags |= 1u << j; ++cnt; }
+        }
+        // 5. new ids of the roots, in tile order
+        const u32 ex = tile_scan_begin<NT>(cnt, tile, tag, B.statusC, &ctl->error, s_scan);
+        __syncthreads();
+        const u32 pre = s_scan[33], total = s_scan[32];
+        if (tile == ntiles - 1 && threadIdx.x == 0) ctl->Vnext = pre + total;
+        u32 id = pre + ex;
+#pragma unroll
+        for (int j = 0; j < 8; ++j)
+            if (flags & (1u << j)) B.rank[(u32)(y0 + rg + j) * w + gx] = id++;
+        // the tile owns the new ids [pre, pre + total): clear their accumulators for phase R / E
+        for (u32 i = threadIdx.x; i < total; i += NT) {
+            const u32 n = pre + i;
+            B.attr[1][n] = make_uint2(0u, 0u); B.best[1][n] = GSEG_KEY_NONE;
+            if (SP) { B.csum[1][3 * (size_t)n] = 0; B.csum[1][3 * (size_t)n + 1] = 0; B.csum[1][3 * (size_t)n + 2] = 0; }
         }
         __syncthreads();
     }
 }
 
 // ------------------------------------------------------------------------------------------------
-// End-of-round bookkeeping: statistics, phase machine, arena accounting.  One thread.
+// Round state helpers.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_advance(GsegCtl *ctl) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    if (ctl->phase == PH_DONE) return;
-    const u32 r = ctl->round;
-    const u32 V = ctl->Vcur, Vn = ctl->Vnext, merged = V - Vn;
-    ctl->stV[r] = V; ctl->stE[r] = ctl->Ecur; ctl->stM[r] = merged; ctl->stP[r] = ctl->phase; ctl->stVafter[r] = Vn;
+__device__ __forceinline__ bool in_tail(const GsegCtl *ctl, const RoundState &st) {
+    return st.round >= 1u && st.E <= ctl->p.tail_E && st.V <= ctl->p.tail_V;
+}
+
+// End-of-round bookkeeping: statistics, phase machine, arena accounting.  Every thread can run it
+// redundantly on its private copy of the state; `writer` alone records it in the control block.
+__device__ __forceinline__ void advance_state(GsegCtl *ctl, RoundState &st, u32 Vn, u32 En, bool writer) {
+    const u32 r = st.round, V = st.V, merged = V - Vn;
     const int variant = ctl->p.variant;
-    u32 phase = ctl->phase, levels = ctl->levels;
+    u32 phase = st.phase, levels = st.levels;
     if (merged == 0) {
         if (variant == GSEG_FELZ && phase == PH_PRED && ctl->p.min_size > 1) phase = PH_MINSIZE;
         else phase = PH_DONE;
@@ -534,15 +370,380 @@ __global__ void k_advance(GsegCtl *ctl) {
         ++levels;
         if (variant != GSEG_FELZ && (Vn <= 1u || (int)levels >= ctl->p.max_levels)) phase = PH_DONE;
     }
-    const u32 next_off = ctl->map_off[r] + V;
-    ctl->map_off[r + 1] = next_off;
-    ctl->round = r + 1;
-    ctl->levels = levels;
-    ctl->Vcur = Vn;
-    ctl->Ecur = ctl->Enext;
+    const u32 next_off = st.map_off + V;
     if ((int)(r + 1) >= ctl->p.max_rounds) phase = PH_DONE;
-    if (phase != PH_DONE && (u64)next_off + (u64)Vn > (u64)ctl->p.arena_cap) { ctl->error = DERR_ARENA; phase = PH_DONE; }
-    ctl->phase = phase;
+    bool arena_err = false;
+    if (phase != PH_DONE && (u64)next_off + (u64)Vn > (u64)ctl->p.arena_cap) { arena_err = true; phase = PH_DONE; }
+    if (writer) {
+        ctl->stV[r] = V; ctl->stE[r] = st.E; ctl->stM[r] = merged; ctl->stP[r] = st.phase; ctl->stVafter[r] = Vn;
+        ctl->map_off[r] = st.map_off;
+        ctl->map_off[r + 1] = next_off;
+        if (arena_err) ctl->error = DERR_ARENA;
+    }
+    st.round = r + 1; st.levels = levels; st.V = Vn; st.E = En; st.phase = phase; st.map_off = next_off;
+    if (writer) ctl->st = st;
+}
+
+// Grid-wide kernels: the last block to finish the edge phase advances the round state.
+__device__ __forceinline__ void last_block_advance(GsegCtl *ctl, const RoundState &st) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&ctl->doneE, 1u) == gridDim.x - 1u) {
+            __threadfence();
+            ctl->doneE = 0;
+            RoundState s2 = st;
+            advance_state(ctl, s2, ld_relaxed_u32(&ctl->Vnext), ld_relaxed_u32(&ctl->Enext), true);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a8: flatten + relabel + accumulate.  Chases succ[] to the root (in-place compression is
+// race-benign: every value ever stored in a slot is an ancestor of that slot and roots never
+// change), maps the component to its root's new id and adds size / Int(C) / colour sums.  Lanes of
+// a warp that map to the same new component combine their contributions with match/redux first.
+// R0: components are pixels (size 1, Int 0, colour = the pixel's fixed-point colour).
+// ------------------------------------------------------------------------------------------------
+template <int NTH, bool R0, bool SP>
+__device__ __forceinline__ void phase_R(const GsegCtl *ctl, const GsegBufs &B, const RoundState &st) {
+    const int cur = st.round & 1, nxt = cur ^ 1;
+    const u32 V = st.V, Vr = (V + 31u) & ~31u;
+    u32 *map = B.arena + st.map_off;
+    const u32 V0 = (u32)ctl->p.w * (u32)ctl->p.h;
+    const int lane = threadIdx.x & 31;
+    for (u32 c = blockIdx.x * NTH + threadIdx.x; c < Vr; c += gridDim.x * NTH) {
+        const bool act = c < V;
+        const u32 actm = __ballot_sync(0xFFFFFFFFu, act);
+        if (!act) continue;
+        u32 r = ld_relaxed_u32(B.succ + c);
+        if (r != c) {
+            for (;;) {
+                const u32 rr = ld_relaxed_u32(B.succ + r);
+                if (rr == r) break;
+                r = rr;
+            }
+            B.succ[c] = r;
+        }
+        const u32 m = __ldcg(B.rank + r);
+        map[c] = m;
+        u32 sz = 1u, iv = 0u;
+        if (!R0) { const uint2 at = __ldcg(B.attr[cur] + c); sz = at.x; iv = at.y; }
+        if (r != c) iv = max(iv, __ldcg(B.wsel + c));
+        const u32 grp = __match_any_sync(actm, m);
+        const u32 ssum = __reduce_add_sync(grp, sz);
+        const u32 imax = __reduce_max_sync(grp, iv);
+        if ((grp & ((1u << lane) - 1u)) == 0u) {
+            atomicAdd(&B.attr[nxt][m].x, ssum);
+            if (imax) atomicMax(&B.attr[nxt][m].y, imax);
+        }
+        if (SP) {
+            long long v0, v1, v2;
+            if (R0) { v0 = fx8(B.planes[c]); v1 = fx8(B.planes[V0 + c]); v2 = fx8(B.planes[2 * V0 + c]); }
+            else {
+                v0 = __ldcg(B.csum[cur] + 3 * (size_t)c); v1 = __ldcg(B.csum[cur] + 3 * (size_t)c + 1);
+                v2 = __ldcg(B.csum[cur] + 3 * (size_t)c + 2);
+            }
+            atomicAdd((u64 *)(B.csum[nxt] + 3 * (size_t)m), (u64)v0);
+            atomicAdd((u64 *)(B.csum[nxt] + 3 * (size_t)m + 1), (u64)v1);
+            atomicAdd((u64 *)(B.csum[nxt] + 3 * (size_t)m + 2), (u64)v2);
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Shared tail of the two edge compactions: the tile's surviving edges sit in shared memory in
+// stable order; write them out coalesced at [pre, pre+total) and fold them into the next round's
+// per-component minimum.  Key = weight bits << 32 | position in the new list (stable compaction
+// keeps list order == edge-index order, so position is the same tie-break as the edge index).
+// ------------------------------------------------------------------------------------------------
+template <int NTH, bool SP>
+__device__ __forceinline__ void emit_edges(const GsegBufs &B, int nxt, u32 pre, u32 total, const uint2 *s_ab,
+                                           const u32 *s_w) {
+    uint2 *oab = B.eab[nxt];
+    u32 *ow = B.ew[nxt];
+    u64 *best = B.best[nxt];
+    const u32 rounded = (total + 31u) & ~31u;
+    for (u32 j = threadIdx.x; j < rounded; j += NTH) {
+        const bool act = j < total;
+        uint2 ab = make_uint2(0u, 0u);
+        u32 kb = 0u;
+        const u32 pos = pre + j;
+        if (act) {
+            ab = s_ab[j];
+            const u32 wv = s_w[j];
+            oab[pos] = ab; ow[pos] = wv;
+            kb = wv;
+            if (SP) kb = __float_as_uint(__fmul_rn(__uint_as_float(wv), mean_dist_g(B.csum[nxt], B.attr[nxt], ab.x, ab.y)));
+        }
+        warp_group_min(best, ab.x, kb, pos, act);
+        warp_group_min(best, ab.y, kb, pos, act);
+    }
+}
+
+// a10 (round 0): grid edges -> explicit list of inter-component edges, in edge-index order
+// (direction-major: all E edges in pixel order, then S, SE, NE).  A tile is one direction x PPT*NT
+// consecutive pixels; PPT consecutive pixels per thread.
+template <int D, bool SP>
+__global__ void __launch_bounds__(NT) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
+    constexpr int PPT = 8, TILE_P = NT * PPT;
+    __shared__ __align__(16) uint2 s_ab[TILE_P];
+    __shared__ u32 s_w[TILE_P];
+    __shared__ u32 s_scan[34];
+    __shared__ u32 s_tile;
+    const RoundState st = ctl->st; // round 0
+    const int w = ctl->p.w, h = ctl->p.h;
+    const u32 V = (u32)w * (u32)h;
+    const u32 *__restrict__ map = B.arena; // round 0's map sits at arena offset 0
+    const u32 tpd = (V + TILE_P - 1) / TILE_P, ntiles = tpd * (u32)D;
+    const u32 tag = ctl->p.epoch_base + 2u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ticketC = 0;
+    for (;;) {
+        if (threadIdx.x == 0) s_tile = atomicAdd(&ctl->ticketE, 1u);
+        __syncthreads();
+        const u32 tile = s_tile;
+        if (tile >= ntiles) break;
+        const int d = (int)(tile / tpd);
+        const int dx = d == 1 ? 0 : 1, dy = d == 0 ? 0 : (d == 3 ? -1 : 1);
+        const int off = dy * w + dx;
+        const u32 p0 = (tile - (u32)d * tpd) * TILE_P + threadIdx.x * PPT;
+        u32 a[PPT], b[PPT], keep = 0, cnt = 0;
+        int y = (int)(p0 / (u32)w), x = (int)(p0 - (u32)y * (u32)w);
+#pragma unroll
+        for (int j = 0; j < PPT; ++j) {
+            const u32 p = p0 + j;
+            if (p < V && x + dx < w && y + dy < h && y + dy >= 0) {
+                a[j] = map[p];
+                b[j] = map[(u32)((int)p + off)];
+                if (a[j] != b[j]) { keep |= 1u << j; ++cnt; }
+            }
+            if (++x == w) { x = 0; ++y; }
+        }
+        const u32 ex = tile_scan_begin<NT>(cnt, tile, tag, B.statusE, &ctl->error, s_scan);
+        // stage survivors in stable order while warp 0 finishes the look-back
+        u32 o = ex;
+        const float *wg = B.wgrid + (size_t)d * V + p0;
+#pragma unroll
+        for (int j = 0; j < PPT; ++j)
+            if (keep & (1u << j)) {
+                s_ab[o] = make_uint2(a[j], b[j]);
+                s_w[o] = __float_as_uint(wg[j]);
+                ++o;
+            }
+        __syncthreads();
+        const u32 pre = s_scan[33], total = s_scan[32];
+        if (tile == ntiles - 1 && threadIdx.x == 0) ctl->Enext = pre + total;
+        emit_edges<NT, SP>(B, 1, pre, total, s_ab, s_w);
+        __syncthreads();
+    }
+    last_block_advance(ctl, st);
+}
+
+// ------------------------------------------------------------------------------------------------
+// a6+a7+a9 (rounds >= 1): each component's choice under the predicate / min-size rule, 2-cycle
+// removal, root flags + look-back scan = new ids; the tile clears the accumulators of its new ids.
+// ------------------------------------------------------------------------------------------------
+struct RoundView {
+    const u64 *best;
+    const uint2 *eab, *attr;
+    float k;
+    int min_size, variant;
+    u32 phase;
+};
+__device__ __forceinline__ u32 comp_choice(const RoundView &v, u32 c, u32 *wbits_out) {
+    const u64 key = __ldcg(v.best + c);
+    if (key == GSEG_KEY_NONE) return c;
+    const u32 pos = (u32)key, wb = (u32)(key >> 32);
+    const uint2 ab = __ldcg(v.eab + pos);
+    const u32 other = ab.x == c ? ab.y : ab.x;
+    bool ok;
+    if (v.variant != GSEG_FELZ) ok = true;
+    else if (v.phase == PH_PRED) {
+        const float wt = __uint_as_float(wb);
+        const uint2 ta = __ldcg(v.attr + ab.x), tb = __ldcg(v.attr + ab.y);
+        const float fa = __fadd_rn(__uint_as_float(ta.y), __fdiv_rn(v.k, __uint2float_rn(ta.x)));
+        const float fb = __fadd_rn(__uint_as_float(tb.y), __fdiv_rn(v.k, __uint2float_rn(tb.x)));
+        ok = wt <= fa && wt <= fb;
+    } else ok = __ldcg(&v.attr[c].x) < (u32)v.min_size;
+    *wbits_out = wb;
+    return ok ? other : c;
+}
+
+template <int NTH, bool SP>
+__device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, u32 *s_scan, u32 *s_tile) {
+    constexpr u32 TILE_C = NTH * CPT;
+    const int cur = st.round & 1, nxt = cur ^ 1;
+    const u32 V = st.V;
+    const u32 ntiles = (V + TILE_C - 1) / TILE_C;
+    const u32 tag = ctl->p.epoch_base + st.round * 2u + 1u;
+    RoundView v;
+    v.best = B.best[cur]; v.eab = B.eab[cur]; v.attr = B.attr[cur];
+    v.k = ctl->p.k; v.min_size = ctl->p.min_size; v.variant = ctl->p.variant; v.phase = st.phase;
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ticketE = 0;
+    for (;;) {
+        if (threadIdx.x == 0) *s_tile = atomicAdd(&ctl->ticketC, 1u);
+        __syncthreads();
+        const u32 tile = *s_tile;
+        if (tile >= ntiles) break;
+        const u32 base = tile * TILE_C + threadIdx.x * CPT;
+        u32 flags = 0, cnt = 0;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            const u32 c = base + j;
+            if (c >= V) break;
+            u32 wb = 0, wb2;
+            u32 s = comp_choice(v, c, &wb);
+            if (s != c) {
+                const u32 t = comp_choice(v, s, &wb2);
+                if (t == c && c < s) s = c;
+            }
+            B.succ[c] = s;
+            B.wsel[c] = wb;
+            if (s == c) { flags |= 1u << j; ++cnt; }
+        }
+        const u32 ex = tile_scan_begin<NTH>(cnt, tile, tag, B.statusC, &ctl->error, s_scan);
+        __syncthreads();
+        const u32 pre = s_scan[33], total = s_scan[32];
+        if (tile == ntiles - 1 && threadIdx.x == 0) ctl->Vnext = pre + total;
+        u32 id = pre + ex;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j)
+            if (flags & (1u << j)) B.rank[base + j] = id++;
+        for (u32 i = threadIdx.x; i < total; i += NTH) {
+            const u32 n = pre + i;
+            B.attr[nxt][n] = make_uint2(0u, 0u); B.best[nxt][n] = GSEG_KEY_NONE;
+            if (SP) { B.csum[nxt][3 * (size_t)n] = 0; B.csum[nxt][3 * (size_t)n + 1] = 0; B.csum[nxt][3 * (size_t)n + 2] = 0; }
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------------------
+// a10 (rounds >= 1): relabel edge ends through this round's map, drop self-loops, stable compaction,
+// fused with next round's per-component minimum.  EPN consecutive edges per thread.
+// smem: NTH*EPN x (uint2 + u32) staging.
+// ------------------------------------------------------------------------------------------------
+template <int NTH, int EPN, bool SP>
+__device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, unsigned char *smem_raw,
+                                        u32 *s_scan, u32 *s_tile) {
+    constexpr u32 TILE_E = NTH * EPN;
+    const int cur = st.round & 1, nxt = cur ^ 1;
+    uint2 *s_ab = reinterpret_cast<uint2 *>(smem_raw);
+    u32 *s_w = reinterpret_cast<u32 *>(s_ab + TILE_E);
+    const u32 E = st.E;
+    const uint2 *eab = B.eab[cur];
+    const u32 *ew = B.ew[cur];
+    const u32 *map = B.arena + st.map_off;
+    const u32 ntiles = (E + TILE_E - 1) / TILE_E;
+    const u32 tag = ctl->p.epoch_base + st.round * 2u + 2u;
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        ctl->ticketC = 0;
+        if (ntiles == 0) ctl->Enext = 0;
+    }
+    for (;;) {
+        if (threadIdx.x == 0) *s_tile = atomicAdd(&ctl->ticketE, 1u);
+        __syncthreads();
+        const u32 tile = *s_tile;
+        if (tile >= ntiles) break;
+        const u32 base = tile * TILE_E + threadIdx.x * EPN;
+        u32 a[EPN], b[EPN], wv[EPN], keep = 0, cnt = 0;
+        if (base + EPN - 1 < E) {
+#pragma unroll
+            for (int q = 0; q < EPN / 2; ++q) {
+                const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(eab + base) + q);
+                a[2 * q] = v.x; b[2 * q] = v.y; a[2 * q + 1] = v.z; b[2 * q + 1] = v.w;
+            }
+#pragma unroll
+            for (int q = 0; q < EPN / 4; ++q) {
+                const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(ew + base) + q);
+                wv[4 * q] = v.x; wv[4 * q + 1] = v.y; wv[4 * q + 2] = v.z; wv[4 * q + 3] = v.w;
+            }
+#pragma unroll
+            for (int j = 0; j < EPN; ++j) {
+                a[j] = __ldcg(map + a[j]); b[j] = __ldcg(map + b[j]);
+                if (a[j] != b[j]) { keep |= 1u << j; ++cnt; }
+            }
+        } else {
+#pragma unroll
+            for (int j = 0; j < EPN; ++j)
+                if (base + j < E) {
+                    const uint2 ab = __ldcg(eab + base + j);
+                    a[j] = __ldcg(map + ab.x); b[j] = __ldcg(map + ab.y);
+                    wv[j] = __ldcg(ew + base + j);
+                    if (a[j] != b[j]) { keep |= 1u << j; ++cnt; }
+                }
+        }
+        const u32 ex = tile_scan_begin<NTH>(cnt, tile, tag, B.statusE, &ctl->error, s_scan);
+        u32 o = ex;
+#pragma unroll
+        for (int j = 0; j < EPN; ++j)
+            if (keep & (1u << j)) { s_ab[o] = make_uint2(a[j], b[j]); s_w[o] = wv[j]; ++o; }
+        __syncthreads();
+        const u32 pre = s_scan[33], total = s_scan[32];
+        if (tile == ntiles - 1 && threadIdx.x == 0) ctl->Enext = pre + total;
+        emit_edges<NTH, SP>(B, nxt, pre, total, s_ab, s_w);
+        __syncthreads();
+    }
+}
+#define PHASE_E_SMEM(NTH, EPN) ((size_t)(NTH) * (EPN) * (sizeof(uint2) + sizeof(u32)))
+
+// ---- grid-wide schedule: one kernel per phase ---------------------------------------------------
+// Every kernel sizes itself from the device-resident round state, so the host enqueues rounds without
+// reading anything back; kernels of rounds that are not needed (done / handed to the tail) exit at once.
+template <bool R0, bool SP>
+__global__ void __launch_bounds__(NT) k_relabel(const GsegCtl *ctl, GsegBufs B) {
+    const RoundState st = ctl->st;
+    if (st.phase == PH_DONE || in_tail(ctl, st)) return;
+    phase_R<NT, R0, SP>(ctl, B, st);
+}
+template <bool SP>
+__global__ void __launch_bounds__(NT) k_succ_scan(GsegCtl *ctl, GsegBufs B) {
+    __shared__ u32 s_scan[34];
+    __shared__ u32 s_tile;
+    const RoundState st = ctl->st;
+    if (st.phase == PH_DONE || in_tail(ctl, st)) return;
+    phase_S<NT, SP>(ctl, B, st, s_scan, &s_tile);
+}
+template <bool SP>
+__global__ void __launch_bounds__(NT) k_edges(GsegCtl *ctl, GsegBufs B) {
+    __shared__ __align__(16) unsigned char smem_e[PHASE_E_SMEM(NT, EPT)];
+    __shared__ u32 s_scan[34];
+    __shared__ u32 s_tile;
+    const RoundState st = ctl->st;
+    if (st.phase == PH_DONE || in_tail(ctl, st)) return;
+    phase_E<NT, EPT, SP>(ctl, B, st, smem_e, s_scan, &s_tile);
+    last_block_advance(ctl, st);
+}
+
+// ---- tail schedule: every small round inside one launch of a single thread-block cluster -----------
+// Loops S | R | E with three cluster barriers per round until the phase machine says done or the
+// graph is (unexpectedly) too large for the tail.  Replaces the reference's host loop with its per-round
+// 4-byte read-back and its dynamic-parallelism orchestration kernel (Report.pdf p3, p5).  A cluster is
+// co-scheduled by hardware, so tails of different images run side by side on disjoint SMs.
+#define TAIL_EPT 4
+template <bool SP>
+__global__ void __launch_bounds__(NTT, 1) k_tail(GsegCtl *ctl, GsegBufs B) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    __shared__ u32 s_scan[34];
+    __shared__ u32 s_tile;
+    cg::cluster_group cl = cg::this_cluster();
+    const bool writer = blockIdx.x == 0 && threadIdx.x == 0;
+    RoundState st = ctl->st;
+    cl.sync(); // everyone holds the entry state before the writer may replace it
+    while (st.phase != PH_DONE && in_tail(ctl, st)) {
+        phase_S<NTT, SP>(ctl, B, st, s_scan, &s_tile);
+        __threadfence();
+        cl.sync();
+        const u32 Vn = ld_relaxed_u32(&ctl->Vnext);
+        phase_R<NTT, false, SP>(ctl, B, st);
+        __threadfence();
+        cl.sync();
+        phase_E<NTT, TAIL_EPT, SP>(ctl, B, st, smem_raw, s_scan, &s_tile);
+        __threadfence();
+        cl.sync();
+        const u32 En = ld_relaxed_u32(&ctl->Enext);
+        advance_state(ctl, st, Vn, En, writer);
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -583,15 +784,6 @@ __global__ void __launch_bounds__(NT) k_colorize(const int *__restrict__ labels,
         out[3 * (size_t)p] = (uint8_t)(hsh & 255);
         out[3 * (size_t)p + 1] = (uint8_t)((hsh >> 8) & 255);
         out[3 * (size_t)p + 2] = (uint8_t)((hsh >> 16) & 255);
-    }
-}
-
-// plane-major grid weights -> edge-index order (gseg_weights)
-__global__ void __launch_bounds__(NT) k_weights_export(const float *__restrict__ wgrid, u32 V, int D,
-                                                       float *__restrict__ out) {
-    for (u32 t = blockIdx.x * NT + threadIdx.x; t < V * (u32)D; t += gridDim.x * NT) {
-        const u32 p = t / D, d = t - p * D;
-        out[t] = wgrid[(size_t)d * V + p];
     }
 }
 

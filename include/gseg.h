@@ -37,8 +37,11 @@ extern "C" {
 #define GSEG_MEM_DEVICE 1
 
 /* flags */
-#define GSEG_FLAG_GRAPH 1u      /* replay the whole round schedule as one CUDA graph (no per-round host sync) */
-#define GSEG_FLAG_KEEP_PLANES 2u /* keep blurred planes / weights readable after the call (gseg_blurred/weights) */
+#define GSEG_FLAG_HOST_LOOP 1u /* host-driven schedule: one kernel per phase and a read-back per round (the
+                                  reference's "ab conventional" driver, Report p3); used for per-kernel timing.
+                                  Default (0): the device-resident round state drives every kernel, the host
+                                  enqueues the whole run without reading anything back, and all small rounds
+                                  run inside one persistent thread-block-cluster kernel. */
 
 typedef enum gseg_status {
     GSEG_OK = 0,
@@ -86,6 +89,11 @@ void gseg_destroy(gseg_ctx *ctx);
 /* Run the context's work on a caller-owned CUDA stream (cudaStream_t as void*); NULL = own stream. */
 int gseg_set_stream(gseg_ctx *ctx, void *cuda_stream);
 
+/* Scheduling knob (no effect on results): a Boruvka round whose graph has at most max_edges live edges
+ * and max_components components runs inside the single-cluster tail kernel instead of grid-wide
+ * kernels.  (0, 0) disables the tail.  Defaults: 262144 edges, 65536 components. */
+int gseg_set_tail(gseg_ctx *ctx, uint32_t max_edges, uint32_t max_components);
+
 /* Replaces: L3 pre-filter + L2 graph creation + L1 segmentation core of one reference executable
  * (Report p2 Fig.1; p3 s3.2.1; p2-3 s3.1 steps 1-9; p3-4 s3.2.2; p4 s3.2.4).
  * rgb: interleaved 8-bit RGB, `stride_bytes` per row (>= 3*w), in host or device memory (mem_kind).
@@ -114,7 +122,7 @@ int gseg_labels_all(gseg_ctx *ctx, int32_t *out, int max_levels, int mem_kind);
 /* Replaces: random colour table + colour image (cuRAND, Report p4 s3.2.3).  out: w*h*3 bytes. */
 int gseg_colorize(gseg_ctx *ctx, int level, uint64_t seed, uint8_t *out_rgb, int mem_kind);
 
-/* Round-0 edge weights in edge-index order idx = (y*w+x)*D + d, D = 2 (E,S) or 4 (E,S,SE,NE);
+/* Round-0 edge weights in edge-index order idx = d*w*h + (y*w+x), d in 0..D-1, D = 2 (E,S) or 4 (E,S,SE,NE);
  * +inf where the edge does not exist (SUPERPIX: the static edge strength).  For the 1e-6 check. */
 int gseg_weights(gseg_ctx *ctx, float *out, int mem_kind);
 /* Blurred image, 3 planes of w*h floats (R,G,B). */

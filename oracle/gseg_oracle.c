@@ -161,9 +161,11 @@ void orc_sobel(const float *planes, int w, int h, float *G) {
 }
 
 /* ------------------------------------------------------------------------------------------------
- * Grid graph.  Edge index idx = p*D + d, p = y*w + x, D = 2 (4-connected: E,S) or 4 (8-connected:
- * E,S,SE,NE -- the F&H `segment` construction order).  Absent edges carry +inf.  This index is the
- * tie-break of every comparison ("ties broken by edge index", BASELINE.json north_star).
+ * Grid graph.  Edge index idx = d*V + p (direction-major), p = y*w + x, V = w*h, D = 2
+ * (4-connected: E,S) or 4 (8-connected: E,S,SE,NE -- the F&H `segment` neighbour set).  Absent
+ * edges carry +inf.  This index is the tie-break of every comparison ("ties broken by edge index",
+ * BASELINE.json north_star); which fixed numbering is used is a free choice ([D]) because the
+ * reference's own std::sort leaves the order of equal weights unspecified.
  * ---------------------------------------------------------------------------------------------- */
 static const int DX[4] = {1, 0, 1, 1};
 static const int DY[4] = {0, 1, 1, -1};
@@ -188,8 +190,8 @@ int64_t orc_edges(const float *planes, int w, int h, int conn, float *wts) {
             size_t p = (size_t)y * w + x;
             for (int d = 0; d < D; ++d) {
                 int xx = x + DX[d], yy = y + DY[d];
-                if (xx < 0 || xx >= w || yy < 0 || yy >= h) { wts[p * D + d] = INFINITY; continue; }
-                wts[p * D + d] = l2rgb(planes, V, p, (size_t)yy * w + xx);
+                if (xx < 0 || xx >= w || yy < 0 || yy >= h) { wts[(size_t)d * V + p] = INFINITY; continue; }
+                wts[(size_t)d * V + p] = l2rgb(planes, V, p, (size_t)yy * w + xx);
                 ++n;
             }
         }
@@ -199,14 +201,15 @@ int64_t orc_edges(const float *planes, int w, int h, int conn, float *wts) {
 /* Superpixel static edge strength: mean Sobel magnitude of the two end pixels ([D]). */
 void orc_strength(const float *G, int w, int h, int conn, float *str) {
     int D = dirs_of(conn);
+    size_t V = (size_t)w * h;
     for (int y = 0; y < h; ++y)
         for (int x = 0; x < w; ++x) {
             size_t p = (size_t)y * w + x;
             for (int d = 0; d < D; ++d) {
                 int xx = x + DX[d], yy = y + DY[d];
-                if (xx < 0 || xx >= w || yy < 0 || yy >= h) { str[p * D + d] = INFINITY; continue; }
+                if (xx < 0 || xx >= w || yy < 0 || yy >= h) { str[(size_t)d * V + p] = INFINITY; continue; }
                 float s = G[p] + G[(size_t)yy * w + xx];
-                str[p * D + d] = 0.5f * s;
+                str[(size_t)d * V + p] = 0.5f * s;
             }
         }
 }
@@ -262,7 +265,7 @@ int orc_felz_kruskal(int w, int h, int conn, const float *wts, float k, int min_
     for (size_t i = 0; i < n; ++i) {
         uint32_t idx = (uint32_t)keys[i];
         float wt = bitsf((uint32_t)(keys[i] >> 32));
-        int32_t p = (int32_t)(idx / D); int d = (int)(idx % D);
+        int d = (int)(idx / V); int32_t p = (int32_t)(idx % V);
         int32_t q = p + DY[d] * w + DX[d];
         int32_t a = uf_find(u, p), b = uf_find(u, q);
         if (a != b && wt <= thr[a] && wt <= thr[b]) {
@@ -273,7 +276,7 @@ int orc_felz_kruskal(int w, int h, int conn, const float *wts, float k, int min_
     }
     for (size_t i = 0; i < n; ++i) {
         uint32_t idx = (uint32_t)keys[i];
-        int32_t p = (int32_t)(idx / D); int d = (int)(idx % D);
+        int d = (int)(idx / V); int32_t p = (int32_t)(idx % V);
         int32_t q = p + DY[d] * w + DX[d];
         int32_t a = uf_find(u, p), b = uf_find(u, q);
         if (a != b && (u[a].size < min_size || u[b].size < min_size)) uf_join(u, a, b);
@@ -339,7 +342,7 @@ int orc_boruvka(int w, int h, int conn, int variant, const float *wts, float k, 
         size_t nl2 = 0;
         for (size_t i = 0; i < nlive; ++i) {
             uint32_t idx = live[i];
-            int32_t p = (int32_t)(idx / D); int d = (int)(idx % D);
+            int d = (int)(idx / V); int32_t p = (int32_t)(idx % V);
             int32_t q = p + DY[d] * w + DX[d];
             int32_t a = comp[p], b = comp[q];
             if (a == b) continue;
@@ -367,7 +370,7 @@ int orc_boruvka(int w, int h, int conn, int variant, const float *wts, float k, 
             if (best[c] == KEY_NONE) continue;
             uint32_t idx = (uint32_t)best[c];
             float wt = bitsf((uint32_t)(best[c] >> 32));
-            int32_t p = (int32_t)(idx / D); int d = (int)(idx % D);
+            int d = (int)(idx / V); int32_t p = (int32_t)(idx % V);
             int32_t q = p + DY[d] * w + DX[d];
             int32_t a = comp[p], b = comp[q];
             int32_t other = a == c ? b : a;

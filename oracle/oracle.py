@@ -130,7 +130,7 @@ def sobel(planes):
 
 
 def edges(planes, conn):
-    """Edge weights in edge-index order idx = p*D + d; +inf where the edge does not exist."""
+    """Edge weights in edge-index order idx = d*V + p; +inf where the edge does not exist."""
     _, h, w = planes.shape
     D = 4 if conn == 8 else 2
     wts = np.empty(h * w * D, np.float32)

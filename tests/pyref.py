@@ -40,7 +40,7 @@ def blur(img, sigma):
 
 
 def edge_list(planes, conn):
-    """[(wbits, idx, p, q)] for existing edges, idx = p*D + d."""
+    """[(wbits, idx, p, q)] for existing edges, idx = d*V + p (direction-major)."""
     _, h, w = planes.shape
     D = 4 if conn == 8 else 2
     es = []
@@ -56,8 +56,8 @@ def edge_list(planes, conn):
                     db = planes[2, y, x] - planes[2, yy, xx]
                     s = F(F(dr * dr) + F(dg * dg)) + F(db * db)
                     wt = np.sqrt(F(s))
-                    wts[p * D + d] = wt
-                    es.append((int(F(wt).view(np.uint32)), p * D + d, p, yy * w + xx))
+                    wts[d * h * w + p] = wt
+                    es.append((int(F(wt).view(np.uint32)), d * h * w + p, p, yy * w + xx))
     return es, wts
 
 

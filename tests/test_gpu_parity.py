@@ -95,6 +95,25 @@ def test_hierarchy_levels_bit_exact(gseg, oracle, seg, w, h, conn, variant, flag
         check_weights(seg.weights(), oracle.strength(oracle.sobel(pl), conn))
 
 
+@pytest.mark.parametrize("tail", [(0, 0), (1000, 100), (1 << 30, 1 << 30)])
+def test_schedules_agree(gseg, oracle, tail):
+    """The tail hand-over thresholds change the schedule (grid-wide rounds, host continuation after a
+    short guess, everything in the tail cluster), never the result."""
+    s = gseg.Segmenter(640, 480)
+    try:
+        s.set_tail(*tail)
+        for (w, h, seed, conn, variant) in [(320, 240, 11, 8, 0), (333, 211, 12, 4, 0), (320, 240, 13, 4, 1),
+                                            (200, 150, 14, 8, 2), (640, 480, 15, 8, 0)]:
+            img = oracle.synth(w, h, seed)
+            ref = oracle.pipeline(img, 0.8, 300.0, 20, conn, variant, max_levels=0)
+            for rep in range(2):  # second run uses the adapted round guess
+                s.segment(img, sigma=0.8, k=300.0, min_size=20, connectivity=conn, variant=variant)
+                assert same_partition(oracle, s.labels(), ref["labels"]), (tail, w, h, conn, variant, rep)
+                assert [tuple(int(x) for x in r[[0, 2, 3]]) for r in ref["stats"]] == [(a, c, d) for a, b, c, d in s.stats()]
+    finally:
+        s.close()
+
+
 def test_degenerate_images(gseg, oracle, seg):
     h, w = 45, 67
     ramp = np.zeros((h, w, 3), np.uint8)

@@ -31,7 +31,7 @@ seg.synth(w, h, 2, out=dimg)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 kw = dict(sigma=0.8, k=300.0, min_size=20, connectivity=conn, variant=variant)
 
-for flags, name in [(0, "host-driven"), (1, "graph")]:
+for flags, name in [(1, "host-driven"), (0, "persistent")]:
     for _ in range(3):
         seg.segment(dimg, flags=flags, **kw)
     ts = []
@@ -52,7 +52,7 @@ NREP = 5
 for rep in range(NREP):
     flush.zero_()
     torch.cuda.synchronize()
-    seg.segment(dimg, flags=0, **kw)
+    seg.segment(dimg, flags=1, **kw)
     for name, rnd, ms, by in seg.profile():
         key = (name, rnd)
         a = agg.setdefault(key, [0.0, by])
