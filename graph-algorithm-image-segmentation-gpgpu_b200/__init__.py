@@ -64,7 +64,8 @@ class KernelTime(C.Structure):
 
 class RoundStat(C.Structure):
     _fields_ = [("n_components", C.c_int64), ("n_edges", C.c_int64), ("n_merged", C.c_int64),
-                ("phase", C.c_int32), ("reserved", C.c_int32)]
+                ("phase", C.c_int32), ("in_tail", C.c_int32), ("us_end", C.c_float), ("us_S", C.c_float),
+                ("us_R", C.c_float), ("us_E", C.c_float)]
 
 
 _lib = None
@@ -228,6 +229,12 @@ class Segmenter:
         arr = (RoundStat * 64)()
         n = self._ck(self.L.gseg_stats(self.h, arr, 64), "gseg_stats")
         return [(arr[i].n_components, arr[i].n_edges, arr[i].n_merged, arr[i].phase) for i in range(n)]
+
+    def timeline(self):
+        """Device timeline of the last run: [(round, in_tail, us_end, us_S, us_R, us_E)]."""
+        arr = (RoundStat * 64)()
+        n = self._ck(self.L.gseg_stats(self.h, arr, 64), "gseg_stats")
+        return [(i, arr[i].in_tail, arr[i].us_end, arr[i].us_S, arr[i].us_R, arr[i].us_E) for i in range(n)]
 
     def set_profiling(self, on):
         self._ck(self.L.gseg_set_profiling(self.h, int(on)), "gseg_set_profiling")

@@ -47,6 +47,7 @@ struct gseg_ctx {
     int num_sms;
     int tail_cluster;     // CTAs in the tail kernel's cluster (16 non-portable, else 8)
     u32 tail_E, tail_V;   // hand-over thresholds of the tail kernel
+    u32 run_tail_E, run_tail_V; // thresholds the last run used
     int nbig_hint;        // grid-wide rounds to enqueue before the tail (-1: estimate; adapts to the last run)
     int hint_w, hint_h, hint_variant, hint_conn;
     SortScratch sort;
@@ -210,6 +211,11 @@ extern "C" int gseg_set_stream(gseg_ctx *ctx, void *s) {
     if (ctx->pending) return GSEG_E_STATE;
     ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
     return GSEG_OK;
+}
+
+extern "C" int gseg_debug_ts(const gseg_ctx *ctx, unsigned long long *out) {
+    for (int i = 0; i < 24; ++i) out[i] = ctx->h_ctl->dbg[i];
+    return 0;
 }
 
 extern "C" int gseg_set_tail(gseg_ctx *ctx, uint32_t max_edges, uint32_t max_components) {
@@ -422,7 +428,7 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
         return fail(ctx, GSEG_E_SIZE, "image aspect exceeds context capacity", cudaSuccess);
     if (p->connectivity != 4 && p->connectivity != 8) return fail(ctx, GSEG_E_ARG, "connectivity must be 4 or 8", cudaSuccess);
     if (p->variant < GSEG_FELZ || p->variant > GSEG_SUPERPIX) return fail(ctx, GSEG_E_ARG, "variant", cudaSuccess);
-    if (!(p->sigma >= 0.0f) || p->max_levels < 0 || p->max_rounds < 0) return fail(ctx, GSEG_E_ARG, "parameter range", cudaSuccess);
+    if (!(p->sigma >= 0.0f) || p->max_levels < 0 || p->max_rounds < 0 || p->min_size < 0 || !(p->k >= 0.0f)) return fail(ctx, GSEG_E_ARG, "parameter range", cudaSuccess);
     if (mem_kind != GSEG_MEM_HOST && mem_kind != GSEG_MEM_DEVICE) return fail(ctx, GSEG_E_ARG, "mem_kind", cudaSuccess);
     GsegHead *hh = ctx->h_head;
     GsegRunParams *hp = &hh->p;
@@ -455,8 +461,8 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
     hp->arena_cap = (u32)ctx->arena_cap;
     hp->epoch_base = ctx->epoch_next;
     hp->mask_len = len;
-    hp->tail_E = host_loop ? 0u : ctx->tail_E;
-    hp->tail_V = host_loop ? 0u : ctx->tail_V;
+    hp->tail_E = ctx->run_tail_E = host_loop ? 0u : ctx->tail_E;
+    hp->tail_V = ctx->run_tail_V = host_loop ? 0u : ctx->tail_V;
     ctx->epoch_next += 2u * GSEG_MAXR + 8u;
     // the whole head of the control block (parameters + round-0 state + tickets) in one copy
     hh->st.V = (u32)((size_t)w * h); hh->st.E = 0; hh->st.round = 0; hh->st.phase = PH_PRED; hh->st.levels = 0; hh->st.map_off = 0;
@@ -642,7 +648,14 @@ extern "C" int gseg_stats(const gseg_ctx *ctx, gseg_round_stat *out, int cap) {
         out[i].n_edges = i == 0 ? 0 : ctx->h_ctl->stE[i];
         out[i].n_merged = ctx->h_ctl->stM[i];
         out[i].phase = (int32_t)ctx->h_ctl->stP[i];
-        out[i].reserved = 0;
+        const GsegCtl *hc = ctx->h_ctl;
+        const bool tail = i >= 1 && hc->t_begin[i] >= hc->t_start && hc->t_begin[i] <= hc->t_end[i] &&
+                          hc->stE[i] <= ctx->run_tail_E && hc->stV[i] <= ctx->run_tail_V;
+        out[i].in_tail = tail ? 1 : 0;
+        out[i].us_end = (float)((double)(hc->t_end[i] - hc->t_start) * 1e-3);
+        out[i].us_S = tail ? (float)((double)(hc->t_S[i] - hc->t_begin[i]) * 1e-3) : 0.f;
+        out[i].us_R = tail ? (float)((double)(hc->t_R[i] - hc->t_S[i]) * 1e-3) : 0.f;
+        out[i].us_E = tail ? (float)((double)(hc->t_end[i] - hc->t_R[i]) * 1e-3) : 0.f;
     }
     return n;
 }

@@ -50,6 +50,10 @@ struct GsegCtl {
     // ---- end of host-initialised head ----
     u32 map_off[GSEG_MAXR + 1];
     u32 stV[GSEG_MAXR], stE[GSEG_MAXR], stM[GSEG_MAXR], stP[GSEG_MAXR], stVafter[GSEG_MAXR];
+    // device timeline (globaltimer, ns): start of the round-0 graph kernel; end of every round; tail rounds
+    // also record the ends of their S and R phases and their start
+    u64 dbg[24];
+    u64 t_start, t_end[GSEG_MAXR], t_begin[GSEG_MAXR], t_S[GSEG_MAXR], t_R[GSEG_MAXR];
 };
 
 // Every device array of a context (both parities of the ping-pong buffers).
@@ -76,6 +80,12 @@ __device__ __forceinline__ u32 ld_relaxed_u32(const u32 *p) {
     u32 v;
     asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     return v;
+}
+
+__device__ __forceinline__ u64 globaltimer_ns() {
+    u64 t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
 }
 
 __device__ __forceinline__ u32 warp_incl_scan(u32 v, int lane) {
@@ -170,17 +180,57 @@ __device__ __forceinline__ u32 tile_scan_begin(u32 cnt, u32 tile, u32 tag, u64 *
 
 __device__ __forceinline__ u64 make_key(u32 wbits, u32 idx) { return ((u64)wbits << 32) | (u64)idx; }
 
-// Segmented min-edge selection: the lanes of a warp that hold edges of
-// the same component `id` agree on the group's minimum key with match/redux warp primitives, and one
-// lane per group issues the 64-bit atomicMin.  `pos` MUST increase with the lane index (it is the
-// edge's position in the output list), so among equal weights the lowest lane holds the minimum.
-// All 32 lanes must call; inactive lanes pass act = false.
-__device__ __forceinline__ void warp_group_min(u64 *best, u32 id, u32 kb, u32 pos, bool act) {
-    const u32 actm = __ballot_sync(0xFFFFFFFFu, act);
-    if (!act) return;
+// Segmented min-edge selection by warp shuffles: consecutive lanes that
+// hold edges of the same component `id` form a run; a fixed 5-step segmented min leaves the run's
+// minimum key in its first lane, which alone issues the 64-bit atomicMin.  Edge lists are in
+// edge-index order, so a component's edges come in long runs (a row segment of a component, a stretch
+// of boundary between two components) and the number of atomics falls with the run length.
+// `pos` MUST increase with the lane index (it is the edge's position in the output list), so among
+// equal weights the lower lane already holds the minimum.  All 32 lanes must call.
+template <bool FILTER>
+__device__ __forceinline__ void warp_run_min(u64 *best, u32 id, u32 kb, u32 pos, bool act) {
     const int lane = threadIdx.x & 31;
-    const u32 grp = __match_any_sync(actm, id);
-    const u32 wmin = __reduce_min_sync(grp, kb);
-    const u32 cand = __ballot_sync(actm, kb == wmin) & grp;
-    if (kb == wmin && (cand & ((1u << lane) - 1u)) == 0u) atomicMin(best + id, make_key(kb, pos));
+    const u32 pid = __shfl_up_sync(0xFFFFFFFFu, id, 1);
+    const u32 actm = __ballot_sync(0xFFFFFFFFu, act);
+    const bool head = lane == 0 || pid != id || !((actm >> (lane - 1)) & 1u);
+    const u32 heads = __ballot_sync(0xFFFFFFFFu, head || !act);
+    if (!act) kb = 0xFFFFFFFFu;
+    // lanes [lane, end) belong to this lane's run, end = next head above this lane
+    const u32 above = heads & ~((2u << lane) - 1u);
+    const int end = above ? __ffs(above) - 1 : 32;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 okb = __shfl_down_sync(0xFFFFFFFFu, kb, o);
+        const u32 opos = __shfl_down_sync(0xFFFFFFFFu, pos, o);
+        if (lane + o < end && okb < kb) { kb = okb; pos = opos; }
+    }
+    if (head && act) {
+        const u64 key = make_key(kb, pos);
+        // FILTER (components with many edges each): the running minimum only ever decreases, so a key that
+        // is not below the value read now can never win; skipping it spares the L2 a same-address atomic
+        if (!FILTER || key < ld_relaxed_u64(best + id)) atomicMin(best + id, key);
+    }
+}
+
+// Same run structure for the size / Int(C) accumulation of phase R: the run's first lane adds the
+// run's total size and takes the run's maximum Int.  All 32 lanes must call.
+__device__ __forceinline__ void warp_run_accumulate(uint2 *attr, u32 id, u32 sz, u32 iv, bool act) {
+    const int lane = threadIdx.x & 31;
+    const u32 pid = __shfl_up_sync(0xFFFFFFFFu, id, 1);
+    const u32 actm = __ballot_sync(0xFFFFFFFFu, act);
+    const bool head = lane == 0 || pid != id || !((actm >> (lane - 1)) & 1u);
+    const u32 heads = __ballot_sync(0xFFFFFFFFu, head || !act);
+    if (!act) { sz = 0u; iv = 0u; }
+    const u32 above = heads & ~((2u << lane) - 1u);
+    const int end = above ? __ffs(above) - 1 : 32;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const u32 osz = __shfl_down_sync(0xFFFFFFFFu, sz, o);
+        const u32 oiv = __shfl_down_sync(0xFFFFFFFFu, iv, o);
+        if (lane + o < end) { sz += osz; iv = max(iv, oiv); }
+    }
+    if (head && act) {
+        atomicAdd(&attr[id].x, sz);
+        if (iv) atomicMax(&attr[id].y, iv);
+    }
 }

@@ -9,7 +9,7 @@
 //   a6+a7+a9 phase_S                   predicate + 2-cycle removal + supervertex renumbering
 //   a8  phase_R                        flatten (pointer chase) + size / Int(C) / colour accumulation
 //   a10+a4 k_r0_edges, phase_E         edge relabel, self-loop drop, stable compaction, fused with the
-//                                      next round's segmented min-edge selection (warp match/redux)
+//                                      next round's segmented min-edge selection (warp-shuffle run minima)
 //   a11 phase_E<SUPERPIX>              per-round re-weighting from component means
 //   a12 k_compose*                     hierarchy materialisation                    Report.pdf p4 s3.2.3
 //   a13 min-size rounds                phase PH_MINSIZE of phase_S                  Report.pdf p3 step 6
@@ -220,7 +220,7 @@ __global__ void __launch_bounds__(NT) k_r0_graph(GsegCtl *ctl, GsegBufs B) {
     const u32 ntiles = (u32)ntx * (u32)nty;
     const u32 tag = ctl->p.epoch_base + 1u;
     const float kthr = __fadd_rn(0.0f, __fdiv_rn(ctl->p.k, 1.0f)); // Int = 0, |C| = 1 on both sides
-    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ticketE = 0;
+    if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->ticketE = 0; ctl->t_start = globaltimer_ns(); }
     for (;;) {
         if (threadIdx.x == 0) s_tile = atomicAdd(&ctl->ticketC, 1u);
         __syncthreads();
@@ -378,6 +378,7 @@ __device__ __forceinline__ void advance_state(GsegCtl *ctl, RoundState &st, u32 
         ctl->stV[r] = V; ctl->stE[r] = st.E; ctl->stM[r] = merged; ctl->stP[r] = st.phase; ctl->stVafter[r] = Vn;
         ctl->map_off[r] = st.map_off;
         ctl->map_off[r + 1] = next_off;
+        ctl->t_end[r] = globaltimer_ns();
         if (arena_err) ctl->error = DERR_ARENA;
     }
     st.round = r + 1; st.levels = levels; st.V = Vn; st.E = En; st.phase = phase; st.map_off = next_off;
@@ -401,8 +402,8 @@ __device__ __forceinline__ void last_block_advance(GsegCtl *ctl, const RoundStat
 // ------------------------------------------------------------------------------------------------
 // a8: flatten + relabel + accumulate.  Chases succ[] to the root (in-place compression is
 // race-benign: every value ever stored in a slot is an ancestor of that slot and roots never
-// change), maps the component to its root's new id and adds size / Int(C) / colour sums.  Lanes of
-// a warp that map to the same new component combine their contributions with match/redux first.
+// change), maps the component to its root's new id and adds size / Int(C) / colour sums.  Consecutive
+// lanes that map to the same new component combine their contributions by warp shuffles first.
 // R0: components are pixels (size 1, Int 0, colour = the pixel's fixed-point colour).
 // ------------------------------------------------------------------------------------------------
 template <int NTH, bool R0, bool SP>
@@ -411,33 +412,26 @@ __device__ __forceinline__ void phase_R(const GsegCtl *ctl, const GsegBufs &B, c
     const u32 V = st.V, Vr = (V + 31u) & ~31u;
     u32 *map = B.arena + st.map_off;
     const u32 V0 = (u32)ctl->p.w * (u32)ctl->p.h;
-    const int lane = threadIdx.x & 31;
     for (u32 c = blockIdx.x * NTH + threadIdx.x; c < Vr; c += gridDim.x * NTH) {
         const bool act = c < V;
-        const u32 actm = __ballot_sync(0xFFFFFFFFu, act);
-        if (!act) continue;
-        u32 r = ld_relaxed_u32(B.succ + c);
-        if (r != c) {
-            for (;;) {
-                const u32 rr = ld_relaxed_u32(B.succ + r);
-                if (rr == r) break;
-                r = rr;
+        u32 m = 0u, sz = 1u, iv = 0u;
+        if (act) {
+            u32 r = ld_relaxed_u32(B.succ + c);
+            if (r != c) {
+                for (;;) {
+                    const u32 rr = ld_relaxed_u32(B.succ + r);
+                    if (rr == r) break;
+                    r = rr;
+                }
+                B.succ[c] = r;
             }
-            B.succ[c] = r;
+            m = __ldcg(B.rank + r);
+            map[c] = m;
+            if (!R0) { const uint2 at = __ldcg(B.attr[cur] + c); sz = at.x; iv = at.y; }
+            if (r != c) iv = max(iv, __ldcg(B.wsel + c));
         }
-        const u32 m = __ldcg(B.rank + r);
-        map[c] = m;
-        u32 sz = 1u, iv = 0u;
-        if (!R0) { const uint2 at = __ldcg(B.attr[cur] + c); sz = at.x; iv = at.y; }
-        if (r != c) iv = max(iv, __ldcg(B.wsel + c));
-        const u32 grp = __match_any_sync(actm, m);
-        const u32 ssum = __reduce_add_sync(grp, sz);
-        const u32 imax = __reduce_max_sync(grp, iv);
-        if ((grp & ((1u << lane) - 1u)) == 0u) {
-            atomicAdd(&B.attr[nxt][m].x, ssum);
-            if (imax) atomicMax(&B.attr[nxt][m].y, imax);
-        }
-        if (SP) {
+        warp_run_accumulate(B.attr[nxt], m, sz, iv, act);
+        if (SP && act) {
             long long v0, v1, v2;
             if (R0) { v0 = fx8(B.planes[c]); v1 = fx8(B.planes[V0 + c]); v2 = fx8(B.planes[2 * V0 + c]); }
             else {
@@ -457,9 +451,12 @@ __device__ __forceinline__ void phase_R(const GsegCtl *ctl, const GsegBufs &B, c
 // per-component minimum.  Key = weight bits << 32 | position in the new list (stable compaction
 // keeps list order == edge-index order, so position is the same tie-break as the edge index).
 // ------------------------------------------------------------------------------------------------
-template <int NTH, bool SP>
+#ifdef GSEG_DEBUG_TS
+__device__ u64 *g_dbg_unused;
+#endif
+template <int NTH, bool SP, bool FILTER>
 __device__ __forceinline__ void emit_edges(const GsegBufs &B, int nxt, u32 pre, u32 total, const uint2 *s_ab,
-                                           const u32 *s_w) {
+                                           const u32 *s_w, u64 *g_dbg = nullptr) {
     uint2 *oab = B.eab[nxt];
     u32 *ow = B.ew[nxt];
     u64 *best = B.best[nxt];
@@ -476,8 +473,17 @@ __device__ __forceinline__ void emit_edges(const GsegBufs &B, int nxt, u32 pre, 
             kb = wv;
             if (SP) kb = __float_as_uint(__fmul_rn(__uint_as_float(wv), mean_dist_g(B.csum[nxt], B.attr[nxt], ab.x, ab.y)));
         }
-        warp_group_min(best, ab.x, kb, pos, act);
-        warp_group_min(best, ab.y, kb, pos, act);
+#ifdef GSEG_DEBUG_TS
+        if (g_dbg && threadIdx.x == 0) g_dbg[8 + 3 * (j / NTH)] = globaltimer_ns();
+#endif
+        warp_run_min<FILTER>(best, ab.x, kb, pos, act);
+#ifdef GSEG_DEBUG_TS
+        if (g_dbg && threadIdx.x == 0) g_dbg[9 + 3 * (j / NTH)] = globaltimer_ns();
+#endif
+        warp_run_min<FILTER>(best, ab.y, kb, pos, act);
+#ifdef GSEG_DEBUG_TS
+        if (g_dbg && threadIdx.x == 0) g_dbg[10 + 3 * (j / NTH)] = globaltimer_ns();
+#endif
     }
 }
 
@@ -533,7 +539,7 @@ __global__ void __launch_bounds__(NT) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
         __syncthreads();
         const u32 pre = s_scan[33], total = s_scan[32];
         if (tile == ntiles - 1 && threadIdx.x == 0) ctl->Enext = pre + total;
-        emit_edges<NT, SP>(B, 1, pre, total, s_ab, s_w);
+        emit_edges<NT, SP, false>(B, 1, pre, total, s_ab, s_w);
         __syncthreads();
     }
     last_block_advance(ctl, st);
@@ -543,32 +549,6 @@ __global__ void __launch_bounds__(NT) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
 // a6+a7+a9 (rounds >= 1): each component's choice under the predicate / min-size rule, 2-cycle
 // removal, root flags + look-back scan = new ids; the tile clears the accumulators of its new ids.
 // ------------------------------------------------------------------------------------------------
-struct RoundView {
-    const u64 *best;
-    const uint2 *eab, *attr;
-    float k;
-    int min_size, variant;
-    u32 phase;
-};
-__device__ __forceinline__ u32 comp_choice(const RoundView &v, u32 c, u32 *wbits_out) {
-    const u64 key = __ldcg(v.best + c);
-    if (key == GSEG_KEY_NONE) return c;
-    const u32 pos = (u32)key, wb = (u32)(key >> 32);
-    const uint2 ab = __ldcg(v.eab + pos);
-    const u32 other = ab.x == c ? ab.y : ab.x;
-    bool ok;
-    if (v.variant != GSEG_FELZ) ok = true;
-    else if (v.phase == PH_PRED) {
-        const float wt = __uint_as_float(wb);
-        const uint2 ta = __ldcg(v.attr + ab.x), tb = __ldcg(v.attr + ab.y);
-        const float fa = __fadd_rn(__uint_as_float(ta.y), __fdiv_rn(v.k, __uint2float_rn(ta.x)));
-        const float fb = __fadd_rn(__uint_as_float(tb.y), __fdiv_rn(v.k, __uint2float_rn(tb.x)));
-        ok = wt <= fa && wt <= fb;
-    } else ok = __ldcg(&v.attr[c].x) < (u32)v.min_size;
-    *wbits_out = wb;
-    return ok ? other : c;
-}
-
 template <int NTH, bool SP>
 __device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, u32 *s_scan, u32 *s_tile) {
     constexpr u32 TILE_C = NTH * CPT;
@@ -576,9 +556,12 @@ __device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const R
     const u32 V = st.V;
     const u32 ntiles = (V + TILE_C - 1) / TILE_C;
     const u32 tag = ctl->p.epoch_base + st.round * 2u + 1u;
-    RoundView v;
-    v.best = B.best[cur]; v.eab = B.eab[cur]; v.attr = B.attr[cur];
-    v.k = ctl->p.k; v.min_size = ctl->p.min_size; v.variant = ctl->p.variant; v.phase = st.phase;
+    const u64 *best = B.best[cur];
+    const uint2 *eab = B.eab[cur], *attr = B.attr[cur];
+    const float kk = ctl->p.k;
+    const u32 min_size = (u32)ctl->p.min_size, phase = st.phase;
+    const bool pred = ctl->p.variant == GSEG_FELZ && phase == PH_PRED;
+    const bool msz = ctl->p.variant == GSEG_FELZ && phase == PH_MINSIZE;
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ticketE = 0;
     for (;;) {
         if (threadIdx.x == 0) *s_tile = atomicAdd(&ctl->ticketC, 1u);
@@ -586,16 +569,49 @@ __device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const R
         const u32 tile = *s_tile;
         if (tile >= ntiles) break;
         const u32 base = tile * TILE_C + threadIdx.x * CPT;
+        // Three dependent gathers per component, each stage issued for all CPT components at once:
+        //   best[c] -> ends of that edge -> {attributes of both ends, best[] of the other end}.
+        // The other end s picks c back iff best[s] is this very edge (a lighter edge at s would also be
+        // incident to ... s only, and the predicate is symmetric), which is the 2-cycle test.
+        u64 key[CPT], key2[CPT];
+        uint2 ab[CPT], ta[CPT], tb[CPT];
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) key[j] = base + j < V ? __ldcg(best + base + j) : GSEG_KEY_NONE;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) ab[j] = key[j] != GSEG_KEY_NONE ? __ldcg(eab + (u32)key[j]) : make_uint2(0u, 0u);
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            key2[j] = GSEG_KEY_NONE; ta[j] = tb[j] = make_uint2(1u, 0u);
+            if (key[j] != GSEG_KEY_NONE) {
+                const u32 c = base + j, other = ab[j].x == c ? ab[j].y : ab[j].x;
+                key2[j] = __ldcg(best + other);
+                if (pred || msz) { ta[j] = __ldcg(attr + ab[j].x); tb[j] = __ldcg(attr + ab[j].y); }
+            }
+        }
         u32 flags = 0, cnt = 0;
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
             const u32 c = base + j;
             if (c >= V) break;
-            u32 wb = 0, wb2;
-            u32 s = comp_choice(v, c, &wb);
-            if (s != c) {
-                const u32 t = comp_choice(v, s, &wb2);
-                if (t == c && c < s) s = c;
+            u32 s = c, wb = 0u;
+            if (key[j] != GSEG_KEY_NONE) {
+                wb = (u32)(key[j] >> 32);
+                const bool c_is_a = ab[j].x == c;
+                const u32 other = c_is_a ? ab[j].y : ab[j].x;
+                bool ok = true, other_ok = true;
+                if (pred) {
+                    const float wt = __uint_as_float(wb);
+                    const float fa = __fadd_rn(__uint_as_float(ta[j].y), __fdiv_rn(kk, __uint2float_rn(ta[j].x)));
+                    const float fb = __fadd_rn(__uint_as_float(tb[j].y), __fdiv_rn(kk, __uint2float_rn(tb[j].x)));
+                    ok = wt <= fa && wt <= fb;
+                } else if (msz) {
+                    ok = (c_is_a ? ta[j].x : tb[j].x) < min_size;
+                    other_ok = (c_is_a ? tb[j].x : ta[j].x) < min_size;
+                }
+                if (ok) {
+                    s = other;
+                    if (key2[j] == key[j] && other_ok && c < other) s = c; // 2-cycle: the lower id stays root
+                }
             }
             B.succ[c] = s;
             B.wsel[c] = wb;
@@ -624,8 +640,8 @@ __device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const R
 // smem: NTH*EPN x (uint2 + u32) staging.
 // ------------------------------------------------------------------------------------------------
 template <int NTH, int EPN, bool SP>
-__device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, unsigned char *smem_raw,
-                                        u32 *s_scan, u32 *s_tile) {
+__device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, u32 Vnext,
+                                        unsigned char *smem_raw, u32 *s_scan, u32 *s_tile) {
     constexpr u32 TILE_E = NTH * EPN;
     const int cur = st.round & 1, nxt = cur ^ 1;
     uint2 *s_ab = reinterpret_cast<uint2 *>(smem_raw);
@@ -636,14 +652,27 @@ __device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const R
     const u32 *map = B.arena + st.map_off;
     const u32 ntiles = (E + TILE_E - 1) / TILE_E;
     const u32 tag = ctl->p.epoch_base + st.round * 2u + 2u;
+    const bool filter = (E >> 3) > Vnext; // more than ~16 edge ends per surviving component
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         ctl->ticketC = 0;
         if (ntiles == 0) ctl->Enext = 0;
     }
+#ifdef GSEG_DEBUG_TS
+    bool dbg = false;
+    int di = 0;
+#define DTS() do { if (dbg && di < 16) ctl->dbg[di++] = globaltimer_ns(); } while (0)
+#else
+#define DTS() do {} while (0)
+#endif
+    DTS();
     for (;;) {
         if (threadIdx.x == 0) *s_tile = atomicAdd(&ctl->ticketE, 1u);
         __syncthreads();
         const u32 tile = *s_tile;
+#ifdef GSEG_DEBUG_TS
+        if (NTH == NTT && tile == 0 && threadIdx.x == 0) dbg = true;
+#endif
+        DTS();
         if (tile >= ntiles) break;
         const u32 base = tile * TILE_E + threadIdx.x * EPN;
         u32 a[EPN], b[EPN], wv[EPN], keep = 0, cnt = 0;
@@ -673,17 +702,27 @@ __device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const R
                     if (a[j] != b[j]) { keep |= 1u << j; ++cnt; }
                 }
         }
+        DTS();
         const u32 ex = tile_scan_begin<NTH>(cnt, tile, tag, B.statusE, &ctl->error, s_scan);
         u32 o = ex;
 #pragma unroll
         for (int j = 0; j < EPN; ++j)
             if (keep & (1u << j)) { s_ab[o] = make_uint2(a[j], b[j]); s_w[o] = wv[j]; ++o; }
         __syncthreads();
+        DTS();
         const u32 pre = s_scan[33], total = s_scan[32];
         if (tile == ntiles - 1 && threadIdx.x == 0) ctl->Enext = pre + total;
-        emit_edges<NTH, SP>(B, nxt, pre, total, s_ab, s_w);
+#ifdef GSEG_DEBUG_TS
+        u64 *dp = dbg ? ctl->dbg : nullptr;
+#else
+        u64 *dp = nullptr;
+#endif
+        if (filter) emit_edges<NTH, SP, true>(B, nxt, pre, total, s_ab, s_w, dp);
+        else emit_edges<NTH, SP, false>(B, nxt, pre, total, s_ab, s_w, dp);
         __syncthreads();
+        DTS();
     }
+    DTS();
 }
 #define PHASE_E_SMEM(NTH, EPN) ((size_t)(NTH) * (EPN) * (sizeof(uint2) + sizeof(u32)))
 
@@ -711,7 +750,7 @@ __global__ void __launch_bounds__(NT) k_edges(GsegCtl *ctl, GsegBufs B) {
     __shared__ u32 s_tile;
     const RoundState st = ctl->st;
     if (st.phase == PH_DONE || in_tail(ctl, st)) return;
-    phase_E<NT, EPT, SP>(ctl, B, st, smem_e, s_scan, &s_tile);
+    phase_E<NT, EPT, SP>(ctl, B, st, ctl->Vnext, smem_e, s_scan, &s_tile);
     last_block_advance(ctl, st);
 }
 
@@ -731,16 +770,28 @@ __global__ void __launch_bounds__(NTT, 1) k_tail(GsegCtl *ctl, GsegBufs B) {
     RoundState st = ctl->st;
     cl.sync(); // everyone holds the entry state before the writer may replace it
     while (st.phase != PH_DONE && in_tail(ctl, st)) {
+        if (writer) ctl->t_begin[st.round] = globaltimer_ns();
         phase_S<NTT, SP>(ctl, B, st, s_scan, &s_tile);
         __threadfence();
         cl.sync();
+        if (writer) ctl->t_S[st.round] = globaltimer_ns();
         const u32 Vn = ld_relaxed_u32(&ctl->Vnext);
         phase_R<NTT, false, SP>(ctl, B, st);
         __threadfence();
         cl.sync();
-        phase_E<NTT, TAIL_EPT, SP>(ctl, B, st, smem_raw, s_scan, &s_tile);
+        if (writer) ctl->t_R[st.round] = globaltimer_ns();
+        phase_E<NTT, TAIL_EPT, SP>(ctl, B, st, Vn, smem_raw, s_scan, &s_tile);
+#ifdef GSEG_DEBUG_TS
+        if (writer) ctl->dbg[16] = globaltimer_ns();
+#endif
         __threadfence();
+#ifdef GSEG_DEBUG_TS
+        if (writer) ctl->dbg[17] = globaltimer_ns();
+#endif
         cl.sync();
+#ifdef GSEG_DEBUG_TS
+        if (writer) ctl->dbg[18] = globaltimer_ns();
+#endif
         const u32 En = ld_relaxed_u32(&ctl->Enext);
         advance_state(ctl, st, Vn, En, writer);
     }

@@ -72,7 +72,9 @@ typedef struct gseg_round_stat {
     int64_t n_edges;      /* live (inter-component) edges entering the round */
     int64_t n_merged;     /* components merged away by the round */
     int32_t phase;        /* 0 = predicate / hierarchy round, 1 = min-size round */
-    int32_t reserved;
+    int32_t in_tail;      /* 1 when the round ran inside the single-cluster tail kernel */
+    float us_end;         /* device clock at the end of the round, microseconds since round 0's graph kernel started */
+    float us_S, us_R, us_E; /* tail rounds: duration of the choose/scan, flatten and edge phases (else 0) */
 } gseg_round_stat;
 
 typedef struct gseg_ctx gseg_ctx;

@@ -44,6 +44,11 @@ for flags, name in [(1, "host-driven"), (0, "persistent")]:
     P("%-12s wall ms/image (L2 flushed): min %.3f med %.3f  -> %.1f Mpixel/s (med)" %
       (name, min(ts), sorted(ts)[len(ts) // 2], w * h / 1e3 / sorted(ts)[len(ts) // 2]))
 P("rounds:", seg.stats())
+P("device timeline of the device-driven run (us since round-0 graph kernel start):")
+prev = 0.0
+for (r, tail, end, us, ur, ue) in seg.timeline():
+    P("  round %2d %s end %8.1f  dur %7.1f   S %6.1f R %6.1f E %6.1f" % (r, "tail" if tail else "grid", end, end - prev, us, ur, ue))
+    prev = end
 P("components:", seg.num_components(), "levels:", seg.num_levels(), "launches so far:", seg.launch_count())
 
 seg.set_profiling(True)
