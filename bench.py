@@ -168,7 +168,9 @@ def main():
     S = max(1, min(args.contexts, B))
     # S independent contexts, each with its own CUDA stream: the small late Boruvka rounds of one image
     # (a single thread-block cluster) overlap the grid-wide early rounds of the next images
-    segs = [gseg.Segmenter(W, H, device=local_rank) for _ in range(S)]
+    batch = importlib.import_module(PKG + ".batch")
+    pool = batch.ContextPool(gseg, W, H, device=local_rank, contexts=S)
+    segs = pool.segs
     seg = segs[0]
     stream = torch.cuda.current_stream()
     kw = dict(sigma=SIGMA, k=K, min_size=MIN_SIZE, connectivity=CONN, variant=gseg.FELZ, flags=0)
@@ -185,13 +187,7 @@ def main():
     torch.cuda.synchronize()
 
     def run_batch(imgs, labs):
-        for base in range(0, B, S):
-            n = min(S, B - base)
-            for j in range(n):
-                segs[j].segment(imgs[base + j], wait=False, **kw)
-            for j in range(n):
-                segs[j].wait()
-                segs[j].labels(out=labs[j])
+        pool.run(imgs, lambda i, sg: sg.labels(out=labs[i % S]), **kw)
 
     def step_dev():
         run_batch(dimgs, dlab)

@@ -567,6 +567,7 @@ extern "C" int gseg_labels(gseg_ctx *ctx, int level, int32_t *out, int mem_kind)
     CK(cudaSetDevice(ctx->device));
     const size_t V = (size_t)ctx->w * ctx->h;
     int *dst = mem_kind == GSEG_MEM_DEVICE ? out : ctx->d_labels[0];
+    ++ctx->launches;
     k_compose<<<grid_for(V, NT), NT, 0, ctx->stream>>>(ctx->d_ctl, ctx->d_arena, round, dst);
     CK(cudaGetLastError());
     if (mem_kind != GSEG_MEM_DEVICE)
@@ -589,6 +590,7 @@ extern "C" int gseg_labels_all(gseg_ctx *ctx, int32_t *out, int max_levels, int 
     const int *prev = nullptr;
     for (int l = 0; l < nl; ++l) {
         int *dst = mem_kind == GSEG_MEM_DEVICE ? out + (size_t)l * V : ctx->d_labels[l & 1];
+        ++ctx->launches;
         if (l == 0) k_compose<<<grid_for(V, NT), NT, 0, ctx->stream>>>(ctx->d_ctl, ctx->d_arena, 0, dst);
         else k_compose_step<<<grid_for(V, NT), NT, 0, ctx->stream>>>(ctx->d_ctl, ctx->d_arena, l, prev, dst);
         if (mem_kind != GSEG_MEM_DEVICE)
@@ -608,9 +610,11 @@ extern "C" int gseg_colorize(gseg_ctx *ctx, int level, uint64_t seed, uint8_t *o
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     const size_t V = (size_t)ctx->w * ctx->h;
+    ++ctx->launches;
     k_compose<<<grid_for(V, NT), NT, 0, ctx->stream>>>(ctx->d_ctl, ctx->d_arena, round, ctx->d_labels[0]);
     // d_tmp is free after the run; 3V bytes fit easily
     uint8_t *dst = mem_kind == GSEG_MEM_DEVICE ? out : (uint8_t *)ctx->d_tmp;
+    ++ctx->launches;
     k_colorize<<<grid_for(V, NT), NT, 0, ctx->stream>>>(ctx->d_labels[0], (u32)V, seed, dst);
     CK(cudaGetLastError());
     if (mem_kind != GSEG_MEM_DEVICE) CK(cudaMemcpyAsync(out, dst, 3 * V, cudaMemcpyDeviceToHost, ctx->stream));
@@ -667,6 +671,7 @@ extern "C" int gseg_synth(gseg_ctx *ctx, uint8_t *out, int w, int h, uint64_t se
     CK(cudaSetDevice(ctx->device));
     const size_t V = (size_t)w * h;
     uint8_t *dst = mem_kind == GSEG_MEM_DEVICE ? out : ctx->d_rgb;
+    ++ctx->launches;
     k_synth<<<grid_for(V, NT), NT, 0, ctx->stream>>>(dst, w, h, seed);
     CK(cudaGetLastError());
     if (mem_kind != GSEG_MEM_DEVICE) CK(cudaMemcpyAsync(out, dst, 3 * V, cudaMemcpyDeviceToHost, ctx->stream));

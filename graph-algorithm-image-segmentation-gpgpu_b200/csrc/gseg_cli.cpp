@@ -1,0 +1,170 @@
+// gseg_cli.cpp -- C++ host program over the C-ABI of include/gseg.h.
+//
+// Mirrors the command line of the reference's executables as far as it is known: the report's CPU
+// baseline is Felzenszwalb's `segment sigma k min input(ppm) output(ppm)` (Report.pdf p4 "Baseline",
+// ref [23]); the GPU branches take the same parameters plus the hierarchy level (BASELINE.json
+// north_star) and time 20 iterations excluding disk I/O (Report.pdf p4 s4.1).  No compute happens in
+// this file: it parses arguments, reads/writes PPM and calls libgseg.so.
+//
+//   gseg [options] sigma k min_size input.ppm output.ppm
+//     --variant felz|hier|superpix   reference branch semantics (default felz)
+//     --conn 4|8                     grid connectivity (default 8, as in `segment`)
+//     --level L                      hierarchy level to write (hier/superpix; default last)
+//     --labels FILE                  also write the label image as raw little-endian int32, row-major
+//     --synth WxH:SEED               ignore input.ppm, segment the deterministic synthetic image
+//     --iters N                      timing loop: N runs after 2 warm-ups, mean +- std (excludes I/O)
+//     --device D                     CUDA device ordinal
+#include <chrono>
+#include <cmath>
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "gseg.h"
+
+static bool read_ppm(const char *path, std::vector<uint8_t> &px, int &w, int &h) {
+    FILE *f = fopen(path, "rb");
+    if (!f) return false;
+    auto token = [&](char *buf, size_t n) -> bool { // next whitespace-delimited header token, '#' comments skipped
+        int c = fgetc(f);
+        for (;;) {
+            while (c == ' ' || c == '\t' || c == '\n' || c == '\r') c = fgetc(f);
+            if (c == '#') { while (c != '\n' && c != EOF) c = fgetc(f); continue; }
+            break;
+        }
+        size_t i = 0;
+        while (c != EOF && c != ' ' && c != '\t' && c != '\n' && c != '\r' && i + 1 < n) { buf[i++] = (char)c; c = fgetc(f); }
+        buf[i] = 0;
+        return i > 0;
+    };
+    char t[64];
+    bool ok = token(t, sizeof t) && !strcmp(t, "P6");
+    int maxv = 0;
+    ok = ok && token(t, sizeof t) && (w = atoi(t)) > 0;
+    ok = ok && token(t, sizeof t) && (h = atoi(t)) > 0;
+    ok = ok && token(t, sizeof t) && (maxv = atoi(t)) > 0 && maxv < 256;
+    if (ok) {
+        px.resize((size_t)w * h * 3);
+        ok = fread(px.data(), 1, px.size(), f) == px.size();
+    }
+    fclose(f);
+    return ok;
+}
+
+static bool write_ppm(const char *path, const std::vector<uint8_t> &px, int w, int h) {
+    FILE *f = fopen(path, "wb");
+    if (!f) return false;
+    fprintf(f, "P6\n%d %d\n255\n", w, h);
+    const bool ok = fwrite(px.data(), 1, px.size(), f) == px.size();
+    fclose(f);
+    return ok;
+}
+
+static int usage() {
+    fprintf(stderr,
+            "usage: gseg [--variant felz|hier|superpix] [--conn 4|8] [--level L] [--labels FILE]\n"
+            "            [--synth WxH:SEED] [--iters N] [--device D] sigma k min_size input.ppm output.ppm\n");
+    return 2;
+}
+
+int main(int argc, char **argv) {
+    gseg_params p;
+    memset(&p, 0, sizeof p);
+    p.connectivity = 8;
+    p.variant = GSEG_FELZ;
+    int level = -1, iters = 0, device = 0, sw = 0, sh = 0;
+    unsigned long long sseed = 0;
+    const char *labels_path = nullptr;
+    std::vector<const char *> pos;
+    for (int i = 1; i < argc; ++i) {
+        std::string a = argv[i];
+        auto need = [&](const char *name) -> const char * {
+            if (i + 1 >= argc) { fprintf(stderr, "gseg: %s needs a value\n", name); exit(2); }
+            return argv[++i];
+        };
+        if (a == "--variant") {
+            std::string v = need("--variant");
+            if (v == "felz") p.variant = GSEG_FELZ;
+            else if (v == "hier") p.variant = GSEG_HIER;
+            else if (v == "superpix") p.variant = GSEG_SUPERPIX;
+            else return usage();
+        } else if (a == "--conn") p.connectivity = atoi(need("--conn"));
+        else if (a == "--level") level = atoi(need("--level"));
+        else if (a == "--labels") labels_path = need("--labels");
+        else if (a == "--iters") iters = atoi(need("--iters"));
+        else if (a == "--device") device = atoi(need("--device"));
+        else if (a == "--synth") {
+            if (sscanf(need("--synth"), "%dx%d:%llu", &sw, &sh, &sseed) != 3 || sw < 1 || sh < 1) return usage();
+        } else if (a.size() > 2 && a[0] == '-' && a[1] == '-') return usage();
+        else pos.push_back(argv[i]);
+    }
+    if (pos.size() != 5) return usage();
+    p.sigma = (float)atof(pos[0]);
+    p.k = (float)atof(pos[1]);
+    p.min_size = atoi(pos[2]);
+    const char *in_path = pos[3], *out_path = pos[4];
+
+    std::vector<uint8_t> img;
+    int w = sw, h = sh;
+    if (!sw && !read_ppm(in_path, img, w, h)) {
+        fprintf(stderr, "gseg: cannot read binary PPM (P6, maxval < 256) from %s\n", in_path);
+        return 1;
+    }
+    gseg_ctx *ctx = nullptr;
+    int rc = gseg_create(&ctx, device, w, h);
+    if (rc) { fprintf(stderr, "gseg: gseg_create: %s\n", gseg_strerror(rc)); return 1; }
+    if (sw) {
+        img.resize((size_t)w * h * 3);
+        rc = gseg_synth(ctx, img.data(), w, h, sseed, GSEG_MEM_HOST);
+        if (rc) { fprintf(stderr, "gseg: gseg_synth: %s\n", gseg_strerror(rc)); return 1; }
+    }
+    auto run = [&]() { return gseg_segment(ctx, img.data(), w, h, 3 * w, GSEG_MEM_HOST, &p); };
+    rc = run();
+    if (rc) { fprintf(stderr, "gseg: gseg_segment: %s (%s)\n", gseg_strerror(rc), gseg_last_error(ctx)); return 1; }
+    if (iters > 0) { // the reference's timing loop: same input, disk I/O excluded (Report.pdf p4 s4.1)
+        run();
+        std::vector<double> ms;
+        for (int i = 0; i < iters; ++i) {
+            const auto t0 = std::chrono::steady_clock::now();
+            rc = run();
+            const auto t1 = std::chrono::steady_clock::now();
+            if (rc) { fprintf(stderr, "gseg: gseg_segment: %s\n", gseg_strerror(rc)); return 1; }
+            ms.push_back(std::chrono::duration<double, std::milli>(t1 - t0).count());
+        }
+        double mean = 0, var = 0;
+        for (double v : ms) mean += v;
+        mean /= ms.size();
+        for (double v : ms) var += (v - mean) * (v - mean);
+        printf("time_ms mean %.4f std %.4f over %d runs (%dx%d, H2D copy included) = %.1f Mpixel/s\n", mean,
+               std::sqrt(var / ms.size()), iters, w, h, (double)w * h / 1e3 / mean);
+    }
+    const int nlev = gseg_num_levels(ctx);
+    if (p.variant != GSEG_FELZ && level >= nlev) {
+        fprintf(stderr, "gseg: level %d out of range, %d levels produced\n", level, nlev);
+        return 1;
+    }
+    const int ncomp = gseg_num_components(ctx, p.variant == GSEG_FELZ ? -1 : level);
+    std::vector<uint8_t> out((size_t)w * h * 3);
+    rc = gseg_colorize(ctx, p.variant == GSEG_FELZ ? -1 : level, 1, out.data(), GSEG_MEM_HOST);
+    if (rc) { fprintf(stderr, "gseg: gseg_colorize: %s\n", gseg_strerror(rc)); return 1; }
+    if (!write_ppm(out_path, out, w, h)) { fprintf(stderr, "gseg: cannot write %s\n", out_path); return 1; }
+    if (labels_path) {
+        std::vector<int32_t> lab((size_t)w * h);
+        rc = gseg_labels(ctx, p.variant == GSEG_FELZ ? -1 : level, lab.data(), GSEG_MEM_HOST);
+        if (rc) { fprintf(stderr, "gseg: gseg_labels: %s\n", gseg_strerror(rc)); return 1; }
+        FILE *f = fopen(labels_path, "wb");
+        if (!f || fwrite(lab.data(), sizeof(int32_t), lab.size(), f) != lab.size()) {
+            fprintf(stderr, "gseg: cannot write %s\n", labels_path);
+            return 1;
+        }
+        fclose(f);
+    }
+    printf("got %d components", ncomp); // `segment` prints "got %d components"
+    if (p.variant != GSEG_FELZ) printf(" at level %d of %d", level < 0 ? nlev - 1 : level, nlev);
+    printf("\n");
+    gseg_destroy(ctx);
+    return 0;
+}

@@ -57,3 +57,16 @@ def test_product_does_not_reference_oracle(gseg):
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 txt = open(os.path.join(root, f)).read()
                 assert "liboracle" not in txt and "gseg_oracle" not in txt and "import oracle" not in txt, f
+
+
+def test_cli_builds_and_fails_loudly_without_gpu(gseg, tmp_path):
+    """The C++ host program is built with the library; without a CUDA device it must refuse, not fall back."""
+    import subprocess
+    assert os.path.exists(gseg.CLI_PATH)
+    r = subprocess.run([gseg.CLI_PATH], capture_output=True, text=True)
+    assert r.returncode == 2 and "usage: gseg" in r.stderr
+    import torch
+    if not torch.cuda.is_available():
+        r = subprocess.run([gseg.CLI_PATH, "--synth", "64x48:1", "0.8", "300", "20", "-", str(tmp_path / "o.ppm")],
+                           capture_output=True, text=True)
+        assert r.returncode == 1 and "no CPU fallback" in r.stderr

@@ -230,3 +230,30 @@ def test_sort_pairs(gseg, seg):
         seg.sort_pairs(k2.data_ptr(), v2.data_ptr(), n, 0, bits)
         assert torch.equal(k2, ref_k)
         assert torch.equal(v2.long(), ref_i)
+
+
+def test_cli_ppm_roundtrip(gseg, oracle, tmp_path):
+    """The C++ CLI (segment-style argv, PPM in, random-colour PPM + raw labels out) against the oracle."""
+    import subprocess
+    w, h = 160, 120
+    img = oracle.synth(w, h, 21)
+    inp, outp, labp = tmp_path / "in.ppm", tmp_path / "out.ppm", tmp_path / "lab.bin"
+    with open(inp, "wb") as f:
+        f.write(b"P6\n# synthetic\n%d %d\n255\n" % (w, h))
+        f.write(img.tobytes())
+    r = subprocess.run([gseg.CLI_PATH, "--labels", str(labp), "0.8", "300", "20", str(inp), str(outp)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ref = oracle.pipeline(img, 0.8, 300.0, 20, 8, oracle.FELZ)
+    assert "got %d components" % ref["n"] in r.stdout
+    lab = np.fromfile(labp, np.int32).reshape(h, w)
+    assert same_partition(oracle, lab, ref["labels"])
+    data = open(outp, "rb").read()
+    assert data.startswith(b"P6\n%d %d\n255\n" % (w, h)) and len(data) == len(b"P6\n%d %d\n255\n" % (w, h)) + w * h * 3
+    # hierarchy level through the CLI, synthetic input generated on the device
+    r = subprocess.run([gseg.CLI_PATH, "--variant", "hier", "--conn", "4", "--level", "2", "--synth", "%dx%d:21" % (w, h),
+                        "--labels", str(labp), "--iters", "2", "0.8", "0", "0", "-", str(outp)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    ref = oracle.pipeline(img, 0.8, 0.0, 0, 4, oracle.HIER, max_levels=64)
+    assert same_partition(oracle, np.fromfile(labp, np.int32).reshape(h, w), ref["levels"][2])
+    assert "time_ms mean" in r.stdout
