@@ -16,7 +16,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
-LIB_PATH = os.path.join(_HERE, "libgseg.so")
+LIB_PATH = os.environ.get("GSEG_LIB") or os.path.join(_HERE, "libgseg.so")
 CLI_PATH = os.path.join(_HERE, "gseg")
 HEADER = os.path.join(_ROOT, "include", "gseg.h")
 

@@ -44,7 +44,8 @@ struct gseg_ctx {
     int *d_labels[2];
     GsegCtl *d_ctl, *h_ctl;
     GsegHead *h_head; // pinned image of the host-initialised head of the control block
-    int num_sms;
+    int num_sms, occ_mult;
+    u32 filter_shift;
     int tail_cluster;     // CTAs in the tail kernel's cluster (16 non-portable, else 8)
     u32 tail_E, tail_V;   // hand-over thresholds of the tail kernel
     u32 run_tail_E, run_tail_V; // thresholds the last run used
@@ -137,10 +138,10 @@ extern "C" int gseg_create(gseg_ctx **out, int device, int max_w, int max_h) {
     if (ctx->arena_cap > 0xFFFFFFF0ull) ctx->arena_cap = 0xFFFFFFF0ull;
     if (e == cudaSuccess) e = dalloc(&ctx->d_arena, ctx->arena_cap);
     // look-back status words: one per tile of the largest tiling that uses each array
-    ctx->ntilesC = V / (NT * CPT) + 2;
+    ctx->ntilesC = V / (32 * CPT) + 2;
     const size_t img_tiles = (size_t)((max_w + TW - 1) / TW) * (size_t)((max_h + TH - 1) / TH);
     if (ctx->ntilesC < img_tiles) ctx->ntilesC = img_tiles;
-    ctx->ntilesE = 4 * (V / (NT * EPT) + 1) + 2;
+    ctx->ntilesE = 4 * (V / (32 * 4) + 1) + 2; // warp tiles of >= 128 edges
     if (e == cudaSuccess) e = dalloc(&ctx->d_statusC, ctx->ntilesC);
     if (e == cudaSuccess) e = dalloc(&ctx->d_statusE, ctx->ntilesE);
     if (e == cudaSuccess) e = cudaMemset(ctx->d_statusC, 0, ctx->ntilesC * sizeof(u64));
@@ -154,8 +155,6 @@ extern "C" int gseg_create(gseg_ctx **out, int device, int max_w, int max_h) {
         // tail kernel: one thread-block cluster, 16 CTAs when the device can co-schedule that many
         cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         cudaFuncSetAttribute(k_tail<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
-        cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PHASE_E_SMEM(NTT, TAIL_EPT));
-        cudaFuncSetAttribute(k_tail<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)PHASE_E_SMEM(NTT, TAIL_EPT));
         int want = 16;
         if (const char *ev = getenv("GSEG_TAIL_CLUSTER")) want = atoi(ev);
         if (want < 1) want = 1;
@@ -163,7 +162,7 @@ extern "C" int gseg_create(gseg_ctx **out, int device, int max_w, int max_h) {
         for (; want > 1; want >>= 1) {
             cudaLaunchConfig_t cfg = {};
             cudaLaunchAttribute at[1];
-            cfg.gridDim = dim3(want); cfg.blockDim = dim3(NTT); cfg.dynamicSmemBytes = PHASE_E_SMEM(NTT, TAIL_EPT);
+            cfg.gridDim = dim3(want); cfg.blockDim = dim3(NTT); cfg.dynamicSmemBytes = 0;
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = want; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
@@ -176,6 +175,10 @@ extern "C" int gseg_create(gseg_ctx **out, int device, int max_w, int max_h) {
         if (const char *ev = getenv("GSEG_TAIL_E")) ctx->tail_E = (u32)strtoul(ev, nullptr, 10);
         if (const char *ev = getenv("GSEG_TAIL_V")) ctx->tail_V = (u32)strtoul(ev, nullptr, 10);
         ctx->nbig_hint = -1;
+        ctx->occ_mult = 4;
+        if (const char *ev = getenv("GSEG_OCC_MULT")) ctx->occ_mult = atoi(ev) > 0 ? atoi(ev) : 4;
+        ctx->filter_shift = 6;
+        if (const char *ev = getenv("GSEG_FILTER_SHIFT")) ctx->filter_shift = (u32)atoi(ev);
     }
     if (e != cudaSuccess) {
         fprintf(stderr, "gseg_create: %s\n", cudaGetErrorString(e));
@@ -213,8 +216,8 @@ extern "C" int gseg_set_stream(gseg_ctx *ctx, void *s) {
     return GSEG_OK;
 }
 
-extern "C" int gseg_debug_ts(const gseg_ctx *ctx, unsigned long long *out) {
-    for (int i = 0; i < 24; ++i) out[i] = ctx->h_ctl->dbg[i];
+extern "C" int gseg_debug_seg(const gseg_ctx *ctx, unsigned long long *out) {
+    for (int i = 0; i < 8; ++i) out[i] = ctx->h_ctl->seg[i];
     return 0;
 }
 
@@ -293,12 +296,12 @@ template <int VARIANT, int D>
 static void launch_r0_graph(gseg_ctx *c, cudaStream_t s, int ntiles, const GsegBufs &B) {
     static bool attr[64] = {false};
     if (!attr[c->device & 63]) { cudaFuncSetAttribute(k_r0_graph<VARIANT, D>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)graph_smem<VARIANT, D>()); attr[c->device & 63] = true; }
-    k_r0_graph<VARIANT, D><<<ntiles < c->num_sms * 3 ? ntiles : c->num_sms * 3, NT, graph_smem<VARIANT, D>(), s>>>(c->d_ctl, B);
+    k_r0_graph<VARIANT, D><<<ntiles < c->num_sms * c->occ_mult ? ntiles : c->num_sms * c->occ_mult, NT, graph_smem<VARIANT, D>(), s>>>(c->d_ctl, B);
 }
 template <int D, bool SP>
 static void launch_r0_edges(gseg_ctx *c, cudaStream_t s, size_t V, const GsegBufs &B) {
-    const size_t ntiles = (size_t)D * ((V + NT * 8 - 1) / (NT * 8));
-    k_r0_edges<D, SP><<<(int)(ntiles < (size_t)c->num_sms * 4 ? ntiles : (size_t)c->num_sms * 4), NT, 0, s>>>(c->d_ctl, B);
+    const size_t ntiles = ((size_t)D * ((V + 255) / 256) + NT / 32 - 1) / (NT / 32); // blocks that cover all warp tiles
+    k_r0_edges<D, SP><<<(int)(ntiles < (size_t)c->num_sms * c->occ_mult ? ntiles : (size_t)c->num_sms * c->occ_mult), NT, 0, s>>>(c->d_ctl, B);
 }
 
 // Round 0: blur -> [sobel] -> fused graph kernel -> relabel -> edge list.  4-5 launches.
@@ -349,7 +352,7 @@ static void enqueue_round0(gseg_ctx *c, cudaStream_t s) {
 static void enqueue_round(gseg_ctx *c, cudaStream_t s, int r, size_t Vb, size_t Eb) {
     const bool sp = c->params.variant == GSEG_SUPERPIX;
     const GsegBufs B = bufs_of(c);
-    const int cap = c->num_sms * 4;
+    const int cap = c->num_sms * c->occ_mult;
     mark(c, s, "k_succ_scan", r);
     if (sp) k_succ_scan<true><<<grid_for(Vb, NT * CPT, cap), NT, 0, s>>>(c->d_ctl, B);
     else k_succ_scan<false><<<grid_for(Vb, NT * CPT, cap), NT, 0, s>>>(c->d_ctl, B);
@@ -366,7 +369,7 @@ static cudaError_t enqueue_tail(gseg_ctx *c, cudaStream_t s) {
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
     cfg.gridDim = dim3(c->tail_cluster); cfg.blockDim = dim3(NTT);
-    cfg.dynamicSmemBytes = PHASE_E_SMEM(NTT, TAIL_EPT); cfg.stream = s;
+    cfg.dynamicSmemBytes = 0; cfg.stream = s;
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = c->tail_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
@@ -461,6 +464,8 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
     hp->arena_cap = (u32)ctx->arena_cap;
     hp->epoch_base = ctx->epoch_next;
     hp->mask_len = len;
+    hp->filter_shift = ctx->filter_shift;
+    hp->dbg_flags = getenv("GSEG_DBG_FLAGS") ? (u32)atoi(getenv("GSEG_DBG_FLAGS")) : 0u;
     hp->tail_E = ctx->run_tail_E = host_loop ? 0u : ctx->tail_E;
     hp->tail_V = ctx->run_tail_V = host_loop ? 0u : ctx->tail_V;
     ctx->epoch_next += 2u * GSEG_MAXR + 8u;
@@ -468,6 +473,9 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
     hh->st.V = (u32)((size_t)w * h); hh->st.E = 0; hh->st.round = 0; hh->st.phase = PH_PRED; hh->st.levels = 0; hh->st.map_off = 0;
     hh->Vnext = hh->st.V; hh->Enext = 0; hh->error = DERR_NONE; hh->ticketC = 0; hh->ticketE = 0; hh->doneE = 0;
     CK(cudaMemcpyAsync(ctx->d_ctl, hh, sizeof(GsegHead), cudaMemcpyHostToDevice, ctx->stream));
+#ifdef GSEG_PROF_SEG
+    CK(cudaMemsetAsync(&ctx->d_ctl->seg[0], 0, sizeof(u64) * 8, ctx->stream));
+#endif
 
     ctx->n_marks = 0;
     enqueue_round0(ctx, ctx->stream);

@@ -25,6 +25,8 @@ struct GsegRunParams {
     u32 arena_cap;  // capacity of the supervertex-map arena in u32 entries
     u32 epoch_base; // first look-back tag of this run (monotonic across runs)
     int mask_len;
+    u32 dbg_flags;      // timing ablations (GSEG_DBG_FLAGS): 1 no look-back, 2 static tiles, 4 no emit, 8 no run-min
+    u32 filter_shift;   // read-before-atomic filter when (E >> filter_shift) > surviving components
     u32 tail_E, tail_V; // a round with E <= tail_E and V <= tail_V runs inside the single-cluster tail kernel
     float mask[GSEG_MAXMASK];
 };
@@ -52,7 +54,7 @@ struct GsegCtl {
     u32 stV[GSEG_MAXR], stE[GSEG_MAXR], stM[GSEG_MAXR], stP[GSEG_MAXR], stVafter[GSEG_MAXR];
     // device timeline (globaltimer, ns): start of the round-0 graph kernel; end of every round; tail rounds
     // also record the ends of their S and R phases and their start
-    u64 dbg[24];
+    u64 seg[8];
     u64 t_start, t_end[GSEG_MAXR], t_begin[GSEG_MAXR], t_S[GSEG_MAXR], t_R[GSEG_MAXR];
 };
 
@@ -151,6 +153,9 @@ __device__ __forceinline__ u32 lookback_prefix(u64 *status, u32 tile, u32 tag, u
                 if (lane == 0) *err = DERR_SCAN;
                 return excl;
             }
+            // back off: thousands of warps polling the few cache lines at the scan frontier would queue up
+            // in one L2 slice and delay every other access behind them
+            __nanosleep(spins < 8u ? 200u : 1000u);
             continue;
         }
         u32 v = lane <= first ? (u32)s : 0u;
@@ -208,7 +213,11 @@ __device__ __forceinline__ void warp_run_min(u64 *best, u32 id, u32 kb, u32 pos,
         const u64 key = make_key(kb, pos);
         // FILTER (components with many edges each): the running minimum only ever decreases, so a key that
         // is not below the value read now can never win; skipping it spares the L2 a same-address atomic
+#ifndef GSEG_EXP_NO_ATOMIC
         if (!FILTER || key < ld_relaxed_u64(best + id)) atomicMin(best + id, key);
+#else
+        if (key == 12345ull) best[id] = key;
+#endif
     }
 }
 

@@ -32,8 +32,8 @@ namespace cg = cooperative_groups;
 
 #define NT 256   // threads per block of the grid-wide kernels
 #define NTT 1024 // threads per block of the single-cluster tail kernel
-#define CPT 4    // components per thread of phase S (tile = NTH * CPT)
-#define EPT 8    // edges per thread of phase E (tile = NTH * EPT)
+#define CPT 4    // rows of 32 components per warp tile of phase S
+#define EPT 8    // rows of 32 edges per warp tile of phase E
 
 // round-0 image tiles
 #define TW 64
@@ -446,57 +446,38 @@ __device__ __forceinline__ void phase_R(const GsegCtl *ctl, const GsegBufs &B, c
 }
 
 // ------------------------------------------------------------------------------------------------
-// Shared tail of the two edge compactions: the tile's surviving edges sit in shared memory in
-// stable order; write them out coalesced at [pre, pre+total) and fold them into the next round's
-// per-component minimum.  Key = weight bits << 32 | position in the new list (stable compaction
-// keeps list order == edge-index order, so position is the same tie-break as the edge index).
+// Shared tail of the two edge compactions.  A warp tile is ROWS rows of 32 consecutive list entries
+// (row j, lane l = entry base + 32 j + l): every load, gather and store of a row touches consecutive
+// addresses, and component ids of neighbouring entries are close, so a gather instruction needs a few
+// 128-byte lines instead of 32 (the L1 wavefront rate, not HBM, bounds these kernels).  The keep-ballot
+// of each row gives every survivor its stable output position without a shuffle scan:
+//     pos = tile prefix + survivors in earlier rows + survivors in lower lanes of this row.
+// emit_row writes one row's survivors and folds them into the next round's per-component minimum.
+// Key = weight bits << 32 | position in the new list (stable compaction keeps list order == edge-index
+// order, so position is the same tie-break as the edge index).
 // ------------------------------------------------------------------------------------------------
-#ifdef GSEG_DEBUG_TS
-__device__ u64 *g_dbg_unused;
-#endif
-template <int NTH, bool SP, bool FILTER>
-__device__ __forceinline__ void emit_edges(const GsegBufs &B, int nxt, u32 pre, u32 total, const uint2 *s_ab,
-                                           const u32 *s_w, u64 *g_dbg = nullptr) {
-    uint2 *oab = B.eab[nxt];
-    u32 *ow = B.ew[nxt];
-    u64 *best = B.best[nxt];
-    const u32 rounded = (total + 31u) & ~31u;
-    for (u32 j = threadIdx.x; j < rounded; j += NTH) {
-        const bool act = j < total;
-        uint2 ab = make_uint2(0u, 0u);
-        u32 kb = 0u;
-        const u32 pos = pre + j;
-        if (act) {
-            ab = s_ab[j];
-            const u32 wv = s_w[j];
-            oab[pos] = ab; ow[pos] = wv;
-            kb = wv;
-            if (SP) kb = __float_as_uint(__fmul_rn(__uint_as_float(wv), mean_dist_g(B.csum[nxt], B.attr[nxt], ab.x, ab.y)));
-        }
-#ifdef GSEG_DEBUG_TS
-        if (g_dbg && threadIdx.x == 0) g_dbg[8 + 3 * (j / NTH)] = globaltimer_ns();
-#endif
-        warp_run_min<FILTER>(best, ab.x, kb, pos, act);
-#ifdef GSEG_DEBUG_TS
-        if (g_dbg && threadIdx.x == 0) g_dbg[9 + 3 * (j / NTH)] = globaltimer_ns();
-#endif
-        warp_run_min<FILTER>(best, ab.y, kb, pos, act);
-#ifdef GSEG_DEBUG_TS
-        if (g_dbg && threadIdx.x == 0) g_dbg[10 + 3 * (j / NTH)] = globaltimer_ns();
-#endif
+template <bool SP, bool FILTER>
+__device__ __forceinline__ void emit_row(const GsegBufs &B, int nxt, u32 pos, bool act, u32 a, u32 b, u32 wv) {
+    u32 kb = wv;
+    if (act) {
+        B.eab[nxt][pos] = make_uint2(a, b);
+        B.ew[nxt][pos] = wv;
+        if (SP) kb = __float_as_uint(__fmul_rn(__uint_as_float(wv), mean_dist_g(B.csum[nxt], B.attr[nxt], a, b)));
     }
+    warp_run_min<FILTER>(B.best[nxt], a, kb, pos, act);
+    warp_run_min<FILTER>(B.best[nxt], b, kb, pos, act);
 }
 
 // a10 (round 0): grid edges -> explicit list of inter-component edges, in edge-index order
-// (direction-major: all E edges in pixel order, then S, SE, NE).  A tile is one direction x PPT*NT
-// consecutive pixels; PPT consecutive pixels per thread.
+// (direction-major: all E edges in pixel order, then S, SE, NE).  Every WARP owns its tiles: a tile is
+// one direction x 32*ROWS consecutive pixels, handed out by an atomic ticket; the warp counts its
+// survivors, takes its global offset from a warp-granular decoupled look-back and emits row by row.
+// There is no shared memory and no block-wide barrier in the loop.
 template <int D, bool SP>
 __global__ void __launch_bounds__(NT) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
-    constexpr int PPT = 8, TILE_P = NT * PPT;
-    __shared__ __align__(16) uint2 s_ab[TILE_P];
-    __shared__ u32 s_w[TILE_P];
-    __shared__ u32 s_scan[34];
-    __shared__ u32 s_tile;
+    constexpr int ROWS = 8, TILE_P = 32 * ROWS;
+    const int lane = threadIdx.x & 31;
+    const u32 lt = (1u << lane) - 1u;
     const RoundState st = ctl->st; // round 0
     const int w = ctl->p.w, h = ctl->p.h;
     const u32 V = (u32)w * (u32)h;
@@ -504,43 +485,52 @@ __global__ void __launch_bounds__(NT) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
     const u32 tpd = (V + TILE_P - 1) / TILE_P, ntiles = tpd * (u32)D;
     const u32 tag = ctl->p.epoch_base + 2u;
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ticketC = 0;
+    const u32 dbgf = ctl->p.dbg_flags;
+    u32 stile = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
     for (;;) {
-        if (threadIdx.x == 0) s_tile = atomicAdd(&ctl->ticketE, 1u);
-        __syncthreads();
-        const u32 tile = s_tile;
+        u32 tile = 0;
+        if (dbgf & 2u) { tile = stile; stile += gridDim.x * (NT / 32); }
+        else {
+            if (lane == 0) tile = atomicAdd(&ctl->ticketE, 1u);
+            tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
+        }
         if (tile >= ntiles) break;
         const int d = (int)(tile / tpd);
         const int dx = d == 1 ? 0 : 1, dy = d == 0 ? 0 : (d == 3 ? -1 : 1);
         const int off = dy * w + dx;
-        const u32 p0 = (tile - (u32)d * tpd) * TILE_P + threadIdx.x * PPT;
-        u32 a[PPT], b[PPT], keep = 0, cnt = 0;
+        const u32 p0 = (tile - (u32)d * tpd) * TILE_P + lane;
+        u32 a[ROWS], b[ROWS], m[ROWS];
         int y = (int)(p0 / (u32)w), x = (int)(p0 - (u32)y * (u32)w);
 #pragma unroll
-        for (int j = 0; j < PPT; ++j) {
-            const u32 p = p0 + j;
+        for (int j = 0; j < ROWS; ++j) {
+            const u32 p = p0 + 32u * j;
+            bool keep = false;
+            a[j] = b[j] = 0u;
             if (p < V && x + dx < w && y + dy < h && y + dy >= 0) {
                 a[j] = map[p];
                 b[j] = map[(u32)((int)p + off)];
-                if (a[j] != b[j]) { keep |= 1u << j; ++cnt; }
+                keep = a[j] != b[j];
             }
-            if (++x == w) { x = 0; ++y; }
+            m[j] = __ballot_sync(0xFFFFFFFFu, keep);
+            x += 32;
+            while (x >= w) { x -= w; ++y; }
         }
-        const u32 ex = tile_scan_begin<NT>(cnt, tile, tag, B.statusE, &ctl->error, s_scan);
-        // stage survivors in stable order while warp 0 finishes the look-back
-        u32 o = ex;
-        const float *wg = B.wgrid + (size_t)d * V + p0;
+        u32 total = 0;
 #pragma unroll
-        for (int j = 0; j < PPT; ++j)
-            if (keep & (1u << j)) {
-                s_ab[o] = make_uint2(a[j], b[j]);
-                s_w[o] = __float_as_uint(wg[j]);
-                ++o;
-            }
-        __syncthreads();
-        const u32 pre = s_scan[33], total = s_scan[32];
-        if (tile == ntiles - 1 && threadIdx.x == 0) ctl->Enext = pre + total;
-        emit_edges<NT, SP, false>(B, 1, pre, total, s_ab, s_w);
-        __syncthreads();
+        for (int j = 0; j < ROWS; ++j) total += __popc(m[j]);
+        const u32 pre = (dbgf & 1u) ? tile * TILE_P : lookback_prefix(B.statusE, tile, tag, total, &ctl->error);
+        if (tile == ntiles - 1 && lane == 0) ctl->Enext = pre + total;
+        const float *wg = B.wgrid + (size_t)d * V + p0;
+        u32 rowoff = pre;
+        if (dbgf & 4u) continue;
+#pragma unroll
+        for (int j = 0; j < ROWS; ++j) {
+            if (m[j] == 0u) continue; // warp-uniform
+            const bool act = (m[j] >> lane) & 1u;
+            const u32 wv = act ? __float_as_uint(wg[32 * j]) : 0u;
+            emit_row<SP, false>(B, 1, rowoff + __popc(m[j] & lt), act, a[j], b[j], wv);
+            rowoff += __popc(m[j]);
+        }
     }
     last_block_advance(ctl, st);
 }
@@ -549,9 +539,11 @@ __global__ void __launch_bounds__(NT) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
 // a6+a7+a9 (rounds >= 1): each component's choice under the predicate / min-size rule, 2-cycle
 // removal, root flags + look-back scan = new ids; the tile clears the accumulators of its new ids.
 // ------------------------------------------------------------------------------------------------
-template <int NTH, bool SP>
-__device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, u32 *s_scan, u32 *s_tile) {
-    constexpr u32 TILE_C = NTH * CPT;
+template <bool SP>
+__device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const RoundState &st) {
+    constexpr u32 TILE_C = 32 * CPT; // components per warp tile: CPT rows of 32 consecutive ids
+    const int lane = threadIdx.x & 31;
+    const u32 lt = (1u << lane) - 1u;
     const int cur = st.round & 1, nxt = cur ^ 1;
     const u32 V = st.V;
     const u32 ntiles = (V + TILE_C - 1) / TILE_C;
@@ -564,167 +556,142 @@ __device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const R
     const bool msz = ctl->p.variant == GSEG_FELZ && phase == PH_MINSIZE;
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ticketE = 0;
     for (;;) {
-        if (threadIdx.x == 0) *s_tile = atomicAdd(&ctl->ticketC, 1u);
-        __syncthreads();
-        const u32 tile = *s_tile;
+        u32 tile = 0;
+        if (lane == 0) tile = atomicAdd(&ctl->ticketC, 1u);
+        tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
         if (tile >= ntiles) break;
-        const u32 base = tile * TILE_C + threadIdx.x * CPT;
-        // Three dependent gathers per component, each stage issued for all CPT components at once:
+        const u32 base = tile * TILE_C + lane;
+        // Three dependent gathers per component, each stage issued for all CPT rows at once:
         //   best[c] -> ends of that edge -> {attributes of both ends, best[] of the other end}.
-        // The other end s picks c back iff best[s] is this very edge (a lighter edge at s would also be
-        // incident to ... s only, and the predicate is symmetric), which is the 2-cycle test.
+        // The other end s picks c back iff best[s] is this very edge (a lighter edge at s cannot lead to
+        // c, or it would be c's minimum too; the predicate is symmetric): that is the 2-cycle test.
         u64 key[CPT], key2[CPT];
         uint2 ab[CPT], ta[CPT], tb[CPT];
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) key[j] = base + j < V ? __ldcg(best + base + j) : GSEG_KEY_NONE;
+        for (int j = 0; j < CPT; ++j) key[j] = base + 32u * j < V ? __ldcg(best + base + 32u * j) : GSEG_KEY_NONE;
 #pragma unroll
         for (int j = 0; j < CPT; ++j) ab[j] = key[j] != GSEG_KEY_NONE ? __ldcg(eab + (u32)key[j]) : make_uint2(0u, 0u);
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
             key2[j] = GSEG_KEY_NONE; ta[j] = tb[j] = make_uint2(1u, 0u);
             if (key[j] != GSEG_KEY_NONE) {
-                const u32 c = base + j, other = ab[j].x == c ? ab[j].y : ab[j].x;
+                const u32 c = base + 32u * j, other = ab[j].x == c ? ab[j].y : ab[j].x;
                 key2[j] = __ldcg(best + other);
                 if (pred || msz) { ta[j] = __ldcg(attr + ab[j].x); tb[j] = __ldcg(attr + ab[j].y); }
             }
         }
-        u32 flags = 0, cnt = 0;
+        u32 m[CPT], total = 0;
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
-            const u32 c = base + j;
-            if (c >= V) break;
-            u32 s = c, wb = 0u;
-            if (key[j] != GSEG_KEY_NONE) {
-                wb = (u32)(key[j] >> 32);
-                const bool c_is_a = ab[j].x == c;
-                const u32 other = c_is_a ? ab[j].y : ab[j].x;
-                bool ok = true, other_ok = true;
-                if (pred) {
-                    const float wt = __uint_as_float(wb);
-                    const float fa = __fadd_rn(__uint_as_float(ta[j].y), __fdiv_rn(kk, __uint2float_rn(ta[j].x)));
-                    const float fb = __fadd_rn(__uint_as_float(tb[j].y), __fdiv_rn(kk, __uint2float_rn(tb[j].x)));
-                    ok = wt <= fa && wt <= fb;
-                } else if (msz) {
-                    ok = (c_is_a ? ta[j].x : tb[j].x) < min_size;
-                    other_ok = (c_is_a ? tb[j].x : ta[j].x) < min_size;
+            const u32 c = base + 32u * j;
+            bool root = false;
+            if (c < V) {
+                u32 s = c, wb = 0u;
+                if (key[j] != GSEG_KEY_NONE) {
+                    wb = (u32)(key[j] >> 32);
+                    const bool c_is_a = ab[j].x == c;
+                    const u32 other = c_is_a ? ab[j].y : ab[j].x;
+                    bool ok = true, other_ok = true;
+                    if (pred) {
+                        const float wt = __uint_as_float(wb);
+                        const float fa = __fadd_rn(__uint_as_float(ta[j].y), __fdiv_rn(kk, __uint2float_rn(ta[j].x)));
+                        const float fb = __fadd_rn(__uint_as_float(tb[j].y), __fdiv_rn(kk, __uint2float_rn(tb[j].x)));
+                        ok = wt <= fa && wt <= fb;
+                    } else if (msz) {
+                        ok = (c_is_a ? ta[j].x : tb[j].x) < min_size;
+                        other_ok = (c_is_a ? tb[j].x : ta[j].x) < min_size;
+                    }
+                    if (ok) {
+                        s = other;
+                        if (key2[j] == key[j] && other_ok && c < other) s = c; // 2-cycle: the lower id stays root
+                    }
                 }
-                if (ok) {
-                    s = other;
-                    if (key2[j] == key[j] && other_ok && c < other) s = c; // 2-cycle: the lower id stays root
-                }
+                B.succ[c] = s;
+                B.wsel[c] = wb;
+                root = s == c;
             }
-            B.succ[c] = s;
-            B.wsel[c] = wb;
-            if (s == c) { flags |= 1u << j; ++cnt; }
+            m[j] = __ballot_sync(0xFFFFFFFFu, root);
+            total += __popc(m[j]);
         }
-        const u32 ex = tile_scan_begin<NTH>(cnt, tile, tag, B.statusC, &ctl->error, s_scan);
-        __syncthreads();
-        const u32 pre = s_scan[33], total = s_scan[32];
-        if (tile == ntiles - 1 && threadIdx.x == 0) ctl->Vnext = pre + total;
-        u32 id = pre + ex;
+        const u32 pre = lookback_prefix(B.statusC, tile, tag, total, &ctl->error);
+        if (tile == ntiles - 1 && lane == 0) ctl->Vnext = pre + total;
+        u32 rowoff = pre;
 #pragma unroll
-        for (int j = 0; j < CPT; ++j)
-            if (flags & (1u << j)) B.rank[base + j] = id++;
-        for (u32 i = threadIdx.x; i < total; i += NTH) {
+        for (int j = 0; j < CPT; ++j) {
+            if ((m[j] >> lane) & 1u) B.rank[base + 32u * j] = rowoff + __popc(m[j] & lt);
+            rowoff += __popc(m[j]);
+        }
+        // the tile owns the new ids [pre, pre + total): clear their accumulators for phase R / E
+        for (u32 i = lane; i < total; i += 32u) {
             const u32 n = pre + i;
             B.attr[nxt][n] = make_uint2(0u, 0u); B.best[nxt][n] = GSEG_KEY_NONE;
             if (SP) { B.csum[nxt][3 * (size_t)n] = 0; B.csum[nxt][3 * (size_t)n + 1] = 0; B.csum[nxt][3 * (size_t)n + 2] = 0; }
         }
-        __syncthreads();
     }
 }
 
 // ------------------------------------------------------------------------------------------------
 // a10 (rounds >= 1): relabel edge ends through this round's map, drop self-loops, stable compaction,
-// fused with next round's per-component minimum.  EPN consecutive edges per thread.
-// smem: NTH*EPN x (uint2 + u32) staging.
+// fused with next round's per-component minimum.  Warp tiles of EPN rows x 32 edges (see emit_row); no
+// shared memory, no block-wide barrier.
 // ------------------------------------------------------------------------------------------------
-template <int NTH, int EPN, bool SP>
-__device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, u32 Vnext,
-                                        unsigned char *smem_raw, u32 *s_scan, u32 *s_tile) {
-    constexpr u32 TILE_E = NTH * EPN;
+template <int EPN, bool SP>
+__device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, u32 Vnext) {
+    constexpr u32 TILE_E = 32 * EPN;
+    const int lane = threadIdx.x & 31;
+    const u32 lt = (1u << lane) - 1u;
     const int cur = st.round & 1, nxt = cur ^ 1;
-    uint2 *s_ab = reinterpret_cast<uint2 *>(smem_raw);
-    u32 *s_w = reinterpret_cast<u32 *>(s_ab + TILE_E);
     const u32 E = st.E;
     const uint2 *eab = B.eab[cur];
     const u32 *ew = B.ew[cur];
     const u32 *map = B.arena + st.map_off;
     const u32 ntiles = (E + TILE_E - 1) / TILE_E;
     const u32 tag = ctl->p.epoch_base + st.round * 2u + 2u;
-    const bool filter = (E >> 3) > Vnext; // more than ~16 edge ends per surviving component
+    const bool filter = (E >> ctl->p.filter_shift) > Vnext; // many edge ends per surviving component
     if (blockIdx.x == 0 && threadIdx.x == 0) {
         ctl->ticketC = 0;
         if (ntiles == 0) ctl->Enext = 0;
     }
-#ifdef GSEG_DEBUG_TS
-    bool dbg = false;
-    int di = 0;
-#define DTS() do { if (dbg && di < 16) ctl->dbg[di++] = globaltimer_ns(); } while (0)
-#else
-#define DTS() do {} while (0)
-#endif
-    DTS();
     for (;;) {
-        if (threadIdx.x == 0) *s_tile = atomicAdd(&ctl->ticketE, 1u);
-        __syncthreads();
-        const u32 tile = *s_tile;
-#ifdef GSEG_DEBUG_TS
-        if (NTH == NTT && tile == 0 && threadIdx.x == 0) dbg = true;
-#endif
-        DTS();
+        u32 tile = 0;
+        if (lane == 0) tile = atomicAdd(&ctl->ticketE, 1u);
+        tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
         if (tile >= ntiles) break;
-        const u32 base = tile * TILE_E + threadIdx.x * EPN;
-        u32 a[EPN], b[EPN], wv[EPN], keep = 0, cnt = 0;
-        if (base + EPN - 1 < E) {
+        const u32 base = tile * TILE_E + lane;
+        u32 a[EPN], b[EPN], wv[EPN], m[EPN];
 #pragma unroll
-            for (int q = 0; q < EPN / 2; ++q) {
-                const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(eab + base) + q);
-                a[2 * q] = v.x; b[2 * q] = v.y; a[2 * q + 1] = v.z; b[2 * q + 1] = v.w;
-            }
-#pragma unroll
-            for (int q = 0; q < EPN / 4; ++q) {
-                const uint4 v = __ldcg(reinterpret_cast<const uint4 *>(ew + base) + q);
-                wv[4 * q] = v.x; wv[4 * q + 1] = v.y; wv[4 * q + 2] = v.z; wv[4 * q + 3] = v.w;
-            }
-#pragma unroll
-            for (int j = 0; j < EPN; ++j) {
-                a[j] = __ldcg(map + a[j]); b[j] = __ldcg(map + b[j]);
-                if (a[j] != b[j]) { keep |= 1u << j; ++cnt; }
-            }
-        } else {
-#pragma unroll
-            for (int j = 0; j < EPN; ++j)
-                if (base + j < E) {
-                    const uint2 ab = __ldcg(eab + base + j);
-                    a[j] = __ldcg(map + ab.x); b[j] = __ldcg(map + ab.y);
-                    wv[j] = __ldcg(ew + base + j);
-                    if (a[j] != b[j]) { keep |= 1u << j; ++cnt; }
-                }
+        for (int j = 0; j < EPN; ++j) {
+            const u32 e = base + 32u * j;
+            uint2 ab = make_uint2(0u, 0u);
+            wv[j] = 0u;
+            if (e < E) { ab = __ldcg(eab + e); wv[j] = __ldcg(ew + e); }
+            a[j] = ab.x; b[j] = ab.y;
         }
-        DTS();
-        const u32 ex = tile_scan_begin<NTH>(cnt, tile, tag, B.statusE, &ctl->error, s_scan);
-        u32 o = ex;
+        u32 total = 0;
 #pragma unroll
-        for (int j = 0; j < EPN; ++j)
-            if (keep & (1u << j)) { s_ab[o] = make_uint2(a[j], b[j]); s_w[o] = wv[j]; ++o; }
-        __syncthreads();
-        DTS();
-        const u32 pre = s_scan[33], total = s_scan[32];
-        if (tile == ntiles - 1 && threadIdx.x == 0) ctl->Enext = pre + total;
-#ifdef GSEG_DEBUG_TS
-        u64 *dp = dbg ? ctl->dbg : nullptr;
-#else
-        u64 *dp = nullptr;
-#endif
-        if (filter) emit_edges<NTH, SP, true>(B, nxt, pre, total, s_ab, s_w, dp);
-        else emit_edges<NTH, SP, false>(B, nxt, pre, total, s_ab, s_w, dp);
-        __syncthreads();
-        DTS();
+        for (int j = 0; j < EPN; ++j) {
+            bool keep = false;
+            if (base + 32u * j < E) {
+                a[j] = __ldcg(map + a[j]); b[j] = __ldcg(map + b[j]);
+                keep = a[j] != b[j];
+            }
+            m[j] = __ballot_sync(0xFFFFFFFFu, keep);
+            total += __popc(m[j]);
+        }
+        const u32 pre = lookback_prefix(B.statusE, tile, tag, total, &ctl->error);
+        if (tile == ntiles - 1 && lane == 0) ctl->Enext = pre + total;
+        u32 rowoff = pre;
+#pragma unroll
+        for (int j = 0; j < EPN; ++j) {
+            if (m[j] == 0u) continue; // warp-uniform
+            const bool act = (m[j] >> lane) & 1u;
+            const u32 pos = rowoff + __popc(m[j] & lt);
+            if (filter) emit_row<SP, true>(B, nxt, pos, act, a[j], b[j], wv[j]);
+            else emit_row<SP, false>(B, nxt, pos, act, a[j], b[j], wv[j]);
+            rowoff += __popc(m[j]);
+        }
     }
-    DTS();
 }
-#define PHASE_E_SMEM(NTH, EPN) ((size_t)(NTH) * (EPN) * (sizeof(uint2) + sizeof(u32)))
 
 // ---- grid-wide schedule: one kernel per phase ---------------------------------------------------
 // Every kernel sizes itself from the device-resident round state, so the host enqueues rounds without
@@ -737,20 +704,15 @@ __global__ void __launch_bounds__(NT) k_relabel(const GsegCtl *ctl, GsegBufs B) 
 }
 template <bool SP>
 __global__ void __launch_bounds__(NT) k_succ_scan(GsegCtl *ctl, GsegBufs B) {
-    __shared__ u32 s_scan[34];
-    __shared__ u32 s_tile;
     const RoundState st = ctl->st;
     if (st.phase == PH_DONE || in_tail(ctl, st)) return;
-    phase_S<NT, SP>(ctl, B, st, s_scan, &s_tile);
+    phase_S<SP>(ctl, B, st);
 }
 template <bool SP>
 __global__ void __launch_bounds__(NT) k_edges(GsegCtl *ctl, GsegBufs B) {
-    __shared__ __align__(16) unsigned char smem_e[PHASE_E_SMEM(NT, EPT)];
-    __shared__ u32 s_scan[34];
-    __shared__ u32 s_tile;
     const RoundState st = ctl->st;
     if (st.phase == PH_DONE || in_tail(ctl, st)) return;
-    phase_E<NT, EPT, SP>(ctl, B, st, ctl->Vnext, smem_e, s_scan, &s_tile);
+    phase_E<EPT, SP>(ctl, B, st, ctl->Vnext);
     last_block_advance(ctl, st);
 }
 
@@ -762,16 +724,13 @@ __global__ void __launch_bounds__(NT) k_edges(GsegCtl *ctl, GsegBufs B) {
 #define TAIL_EPT 4
 template <bool SP>
 __global__ void __launch_bounds__(NTT, 1) k_tail(GsegCtl *ctl, GsegBufs B) {
-    extern __shared__ __align__(16) unsigned char smem_raw[];
-    __shared__ u32 s_scan[34];
-    __shared__ u32 s_tile;
     cg::cluster_group cl = cg::this_cluster();
     const bool writer = blockIdx.x == 0 && threadIdx.x == 0;
     RoundState st = ctl->st;
     cl.sync(); // everyone holds the entry state before the writer may replace it
     while (st.phase != PH_DONE && in_tail(ctl, st)) {
         if (writer) ctl->t_begin[st.round] = globaltimer_ns();
-        phase_S<NTT, SP>(ctl, B, st, s_scan, &s_tile);
+        phase_S<SP>(ctl, B, st);
         __threadfence();
         cl.sync();
         if (writer) ctl->t_S[st.round] = globaltimer_ns();
@@ -780,18 +739,9 @@ __global__ void __launch_bounds__(NTT, 1) k_tail(GsegCtl *ctl, GsegBufs B) {
         __threadfence();
         cl.sync();
         if (writer) ctl->t_R[st.round] = globaltimer_ns();
-        phase_E<NTT, TAIL_EPT, SP>(ctl, B, st, Vn, smem_raw, s_scan, &s_tile);
-#ifdef GSEG_DEBUG_TS
-        if (writer) ctl->dbg[16] = globaltimer_ns();
-#endif
+        phase_E<TAIL_EPT, SP>(ctl, B, st, Vn);
         __threadfence();
-#ifdef GSEG_DEBUG_TS
-        if (writer) ctl->dbg[17] = globaltimer_ns();
-#endif
         cl.sync();
-#ifdef GSEG_DEBUG_TS
-        if (writer) ctl->dbg[18] = globaltimer_ns();
-#endif
         const u32 En = ld_relaxed_u32(&ctl->Enext);
         advance_state(ctl, st, Vn, En, writer);
     }
