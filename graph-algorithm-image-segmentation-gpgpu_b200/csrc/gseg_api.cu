@@ -36,7 +36,7 @@ struct gseg_ctx {
     uint2 *d_attr[2];
     long long *d_csum[2];
     uint2 *d_eab[2];
-    u32 *d_ew[2];
+    u32 *d_ew[2], *d_pcnt[2];
     u32 *d_arena;
     size_t arena_cap;
     u64 *d_statusC, *d_statusE;
@@ -47,7 +47,7 @@ struct gseg_ctx {
     int num_sms, occ_mult;
     u32 filter_shift;
     int tail_cluster;     // CTAs in the tail kernel's cluster (16 non-portable, else 8)
-    u32 tail_E, tail_V;   // hand-over thresholds of the tail kernel
+    u32 tail_E, tail_V, tail_P; // hand-over thresholds of the tail kernel
     u32 run_tail_E, run_tail_V; // thresholds the last run used
     int nbig_hint;        // grid-wide rounds to enqueue before the tail (-1: estimate; adapts to the last run)
     int hint_w, hint_h, hint_variant, hint_conn;
@@ -132,6 +132,7 @@ extern "C" int gseg_create(gseg_ctx **out, int device, int max_w, int max_h) {
         if (e == cudaSuccess) e = dalloc(&ctx->d_attr[i], Vp);
         if (e == cudaSuccess) e = dalloc(&ctx->d_eab[i], 4 * Vp);
         if (e == cudaSuccess) e = dalloc(&ctx->d_ew[i], 4 * Vp);
+        if (e == cudaSuccess) e = dalloc(&ctx->d_pcnt[i], 4 * (V / GSEG_PAGE + 1) + 2);
         if (e == cudaSuccess) e = dalloc(&ctx->d_labels[i], Vp);
     }
     ctx->arena_cap = 6 * V + 1024;
@@ -141,7 +142,7 @@ extern "C" int gseg_create(gseg_ctx **out, int device, int max_w, int max_h) {
     ctx->ntilesC = V / (32 * CPT) + 2;
     const size_t img_tiles = (size_t)((max_w + TW - 1) / TW) * (size_t)((max_h + TH - 1) / TH);
     if (ctx->ntilesC < img_tiles) ctx->ntilesC = img_tiles;
-    ctx->ntilesE = 4 * (V / (32 * 4) + 1) + 2; // warp tiles of >= 128 edges
+    ctx->ntilesE = 4 * (V / GSEG_PAGE + 1) + 2; // pages of the edge list
     if (e == cudaSuccess) e = dalloc(&ctx->d_statusC, ctx->ntilesC);
     if (e == cudaSuccess) e = dalloc(&ctx->d_statusE, ctx->ntilesE);
     if (e == cudaSuccess) e = cudaMemset(ctx->d_statusC, 0, ctx->ntilesC * sizeof(u64));
@@ -171,7 +172,8 @@ extern "C" int gseg_create(gseg_ctx **out, int device, int max_w, int max_h) {
             cudaGetLastError();
         }
         ctx->tail_cluster = want;
-        ctx->tail_E = 256u * 1024u; ctx->tail_V = 64u * 1024u;
+        ctx->tail_E = 256u * 1024u; ctx->tail_V = 64u * 1024u; ctx->tail_P = 2048u;
+        if (const char *ev = getenv("GSEG_TAIL_P")) ctx->tail_P = (u32)strtoul(ev, nullptr, 10);
         if (const char *ev = getenv("GSEG_TAIL_E")) ctx->tail_E = (u32)strtoul(ev, nullptr, 10);
         if (const char *ev = getenv("GSEG_TAIL_V")) ctx->tail_V = (u32)strtoul(ev, nullptr, 10);
         ctx->nbig_hint = -1;
@@ -199,7 +201,7 @@ extern "C" void gseg_destroy(gseg_ctx *ctx) {
     cudaFree(ctx->d_succ); cudaFree(ctx->d_rank);
     for (int i = 0; i < 2; ++i) {
         cudaFree(ctx->d_best[i]); cudaFree(ctx->d_attr[i]); cudaFree(ctx->d_csum[i]);
-        cudaFree(ctx->d_eab[i]); cudaFree(ctx->d_ew[i]); cudaFree(ctx->d_labels[i]);
+        cudaFree(ctx->d_eab[i]); cudaFree(ctx->d_ew[i]); cudaFree(ctx->d_pcnt[i]); cudaFree(ctx->d_labels[i]);
     }
     cudaFree(ctx->d_arena); cudaFree(ctx->d_statusC); cudaFree(ctx->d_statusE); cudaFree(ctx->d_ctl);
     sort_scratch_free(&ctx->sort);
@@ -214,11 +216,6 @@ extern "C" int gseg_set_stream(gseg_ctx *ctx, void *s) {
     if (ctx->pending) return GSEG_E_STATE;
     ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
     return GSEG_OK;
-}
-
-extern "C" int gseg_debug_seg(const gseg_ctx *ctx, unsigned long long *out) {
-    for (int i = 0; i < 8; ++i) out[i] = ctx->h_ctl->seg[i];
-    return 0;
 }
 
 extern "C" int gseg_set_tail(gseg_ctx *ctx, uint32_t max_edges, uint32_t max_components) {
@@ -273,7 +270,7 @@ static GsegBufs bufs_of(const gseg_ctx *c) {
     B.succ = c->d_succ; B.rank = c->d_rank; B.wsel = c->d_wsel; B.arena = c->d_arena;
     for (int i = 0; i < 2; ++i) {
         B.best[i] = c->d_best[i]; B.attr[i] = c->d_attr[i]; B.csum[i] = c->d_csum[i];
-        B.eab[i] = c->d_eab[i]; B.ew[i] = c->d_ew[i];
+        B.eab[i] = c->d_eab[i]; B.ew[i] = c->d_ew[i]; B.pcnt[i] = c->d_pcnt[i];
     }
     B.statusC = c->d_statusC; B.statusE = c->d_statusE;
     return B;
@@ -300,7 +297,7 @@ static void launch_r0_graph(gseg_ctx *c, cudaStream_t s, int ntiles, const GsegB
 }
 template <int D, bool SP>
 static void launch_r0_edges(gseg_ctx *c, cudaStream_t s, size_t V, const GsegBufs &B) {
-    const size_t ntiles = ((size_t)D * ((V + 255) / 256) + NT / 32 - 1) / (NT / 32); // blocks that cover all warp tiles
+    const size_t ntiles = ((size_t)D * ((V + GSEG_PAGE - 1) / GSEG_PAGE) + NT / 32 - 1) / (NT / 32); // blocks that cover all pages
     k_r0_edges<D, SP><<<(int)(ntiles < (size_t)c->num_sms * c->occ_mult ? ntiles : (size_t)c->num_sms * c->occ_mult), NT, 0, s>>>(c->d_ctl, B);
 }
 
@@ -349,7 +346,7 @@ static void enqueue_round0(gseg_ctx *c, cudaStream_t s) {
 // One grid-wide round r >= 1: 3 launches.  Vb/Eb bound the round's component / edge counts (exact after
 // a read-back in the host-driven schedule, the image's own bounds otherwise); every kernel takes its
 // real sizes from the device-resident round state and surplus blocks exit through the tile tickets.
-static void enqueue_round(gseg_ctx *c, cudaStream_t s, int r, size_t Vb, size_t Eb) {
+static void enqueue_round(gseg_ctx *c, cudaStream_t s, int r, size_t Vb, size_t Pb) {
     const bool sp = c->params.variant == GSEG_SUPERPIX;
     const GsegBufs B = bufs_of(c);
     const int cap = c->num_sms * c->occ_mult;
@@ -360,8 +357,8 @@ static void enqueue_round(gseg_ctx *c, cudaStream_t s, int r, size_t Vb, size_t 
     if (sp) k_relabel<false, true><<<grid_for(Vb, NT, cap), NT, 0, s>>>(c->d_ctl, B);
     else k_relabel<false, false><<<grid_for(Vb, NT, cap), NT, 0, s>>>(c->d_ctl, B);
     mark(c, s, "k_edges", r);
-    if (sp) k_edges<true><<<grid_for(Eb, NT * EPT, cap), NT, 0, s>>>(c->d_ctl, B);
-    else k_edges<false><<<grid_for(Eb, NT * EPT, cap), NT, 0, s>>>(c->d_ctl, B);
+    if (sp) k_edges<true><<<grid_for(Pb, NT / 32, cap), NT, 0, s>>>(c->d_ctl, B);
+    else k_edges<false><<<grid_for(Pb, NT / 32, cap), NT, 0, s>>>(c->d_ctl, B);
 }
 
 // The tail: one cluster runs every remaining (small) round.
@@ -399,7 +396,7 @@ static int finish(gseg_ctx *ctx) {
     const GsegCtl *h = ctx->h_ctl;
     int nbig = 0;
     for (u32 r = 1; r < h->st.round; ++r)
-        if (h->stE[r] > ctx->tail_E || h->stV[r] > ctx->tail_V) nbig = (int)r;
+        if (!h->stTail[r]) nbig = (int)r;
     ctx->nbig_hint = nbig;
     ctx->hint_w = ctx->w; ctx->hint_h = ctx->h; ctx->hint_variant = ctx->params.variant; ctx->hint_conn = ctx->params.connectivity;
     ctx->valid = true;
@@ -468,14 +465,12 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
     hp->dbg_flags = getenv("GSEG_DBG_FLAGS") ? (u32)atoi(getenv("GSEG_DBG_FLAGS")) : 0u;
     hp->tail_E = ctx->run_tail_E = host_loop ? 0u : ctx->tail_E;
     hp->tail_V = ctx->run_tail_V = host_loop ? 0u : ctx->tail_V;
+    hp->tail_P = ctx->tail_P;
     ctx->epoch_next += 2u * GSEG_MAXR + 8u;
     // the whole head of the control block (parameters + round-0 state + tickets) in one copy
-    hh->st.V = (u32)((size_t)w * h); hh->st.E = 0; hh->st.round = 0; hh->st.phase = PH_PRED; hh->st.levels = 0; hh->st.map_off = 0;
+    hh->st.V = (u32)((size_t)w * h); hh->st.E = 0; hh->st.round = 0; hh->st.phase = PH_PRED; hh->st.levels = 0; hh->st.map_off = 0; hh->st.P = 0; hh->st.dense = 0;
     hh->Vnext = hh->st.V; hh->Enext = 0; hh->error = DERR_NONE; hh->ticketC = 0; hh->ticketE = 0; hh->doneE = 0;
     CK(cudaMemcpyAsync(ctx->d_ctl, hh, sizeof(GsegHead), cudaMemcpyHostToDevice, ctx->stream));
-#ifdef GSEG_PROF_SEG
-    CK(cudaMemsetAsync(&ctx->d_ctl->seg[0], 0, sizeof(u64) * 8, ctx->stream));
-#endif
 
     ctx->n_marks = 0;
     enqueue_round0(ctx, ctx->stream);
@@ -489,7 +484,7 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
             nbig = estimate_nbig(ctx);
         if (nbig > R - 1) nbig = R - 1;
         const size_t V = (size_t)w * h;
-        for (int r = 1; r <= nbig; ++r) enqueue_round(ctx, ctx->stream, r, V, V * ctx->D);
+        for (int r = 1; r <= nbig; ++r) enqueue_round(ctx, ctx->stream, r, V, (size_t)ctx->D * (V / GSEG_PAGE + 1));
         CK(cudaGetLastError());
         CK(enqueue_tail(ctx, ctx->stream));
         ctx->pending = true;
@@ -500,7 +495,7 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
     int rc = readback(ctx);
     if (rc) return rc;
     for (int r = 1; r < R && ctx->h_ctl->st.phase != PH_DONE; ++r) {
-        enqueue_round(ctx, ctx->stream, r, ctx->h_ctl->st.V, ctx->h_ctl->st.E);
+        enqueue_round(ctx, ctx->stream, r, ctx->h_ctl->st.V, ctx->h_ctl->st.P);
         mark_end(ctx, ctx->stream);
         CK(cudaGetLastError());
         rc = readback(ctx);
@@ -518,8 +513,8 @@ extern "C" int gseg_wait(gseg_ctx *ctx) {
     // the guess of grid-wide rounds was short: keep going, two rounds and a tail at a time
     while (!rc && ctx->h_ctl->st.phase != PH_DONE && ctx->h_ctl->error == DERR_NONE) {
         const int r = (int)ctx->h_ctl->st.round;
-        enqueue_round(ctx, ctx->stream, r, ctx->h_ctl->st.V, ctx->h_ctl->st.E);
-        enqueue_round(ctx, ctx->stream, r + 1, ctx->h_ctl->st.V, ctx->h_ctl->st.E);
+        enqueue_round(ctx, ctx->stream, r, ctx->h_ctl->st.V, ctx->h_ctl->st.P);
+        enqueue_round(ctx, ctx->stream, r + 1, ctx->h_ctl->st.V, ctx->h_ctl->st.P);
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = enqueue_tail(ctx, ctx->stream);
         if (e != cudaSuccess) { ctx->pending = false; return fail(ctx, GSEG_E_CUDA, "continuation launch", e); }
@@ -661,8 +656,7 @@ extern "C" int gseg_stats(const gseg_ctx *ctx, gseg_round_stat *out, int cap) {
         out[i].n_merged = ctx->h_ctl->stM[i];
         out[i].phase = (int32_t)ctx->h_ctl->stP[i];
         const GsegCtl *hc = ctx->h_ctl;
-        const bool tail = i >= 1 && hc->t_begin[i] >= hc->t_start && hc->t_begin[i] <= hc->t_end[i] &&
-                          hc->stE[i] <= ctx->run_tail_E && hc->stV[i] <= ctx->run_tail_V;
+        const bool tail = hc->stTail[i] != 0;
         out[i].in_tail = tail ? 1 : 0;
         out[i].us_end = (float)((double)(hc->t_end[i] - hc->t_start) * 1e-3);
         out[i].us_S = tail ? (float)((double)(hc->t_S[i] - hc->t_begin[i]) * 1e-3) : 0.f;

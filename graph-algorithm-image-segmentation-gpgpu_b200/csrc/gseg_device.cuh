@@ -12,6 +12,7 @@ typedef unsigned long long u64;
 #define GSEG_INF_BITS 0x7F800000u
 #define GSEG_MAXR 64 /* hard cap on rounds per run */
 #define GSEG_MAXMASK 64
+#define GSEG_PAGE 256u /* slots per page of the edge list = one warp tile (8 rows of 32) */
 
 enum { PH_PRED = 0, PH_MINSIZE = 1, PH_DONE = 2 };
 enum { DERR_NONE = 0, DERR_SCAN = 1, DERR_ARENA = 2 };
@@ -27,7 +28,7 @@ struct GsegRunParams {
     int mask_len;
     u32 dbg_flags;      // timing ablations (GSEG_DBG_FLAGS): 1 no look-back, 2 static tiles, 4 no emit, 8 no run-min
     u32 filter_shift;   // read-before-atomic filter when (E >> filter_shift) > surviving components
-    u32 tail_E, tail_V; // a round with E <= tail_E and V <= tail_V runs inside the single-cluster tail kernel
+    u32 tail_E, tail_V, tail_P; // a round with E <= tail_E, V <= tail_V and P <= tail_P runs inside the single-cluster tail kernel
     float mask[GSEG_MAXMASK];
 };
 
@@ -37,6 +38,8 @@ struct RoundState {
     u32 V, E;      // components / live edges entering the round
     u32 round, phase, levels;
     u32 map_off;   // arena offset of this round's old->new supervertex map
+    u32 P;         // pages (GSEG_PAGE slots each) of the current edge list
+    u32 dense;     // 1: the list is dense (page t holds min(GSEG_PAGE, E - t*GSEG_PAGE) edges); 0: pcnt[] holds the counts
 };
 
 // Device-resident control block: all round-to-round state lives here, so a whole run needs no host
@@ -52,9 +55,9 @@ struct GsegCtl {
     // ---- end of host-initialised head ----
     u32 map_off[GSEG_MAXR + 1];
     u32 stV[GSEG_MAXR], stE[GSEG_MAXR], stM[GSEG_MAXR], stP[GSEG_MAXR], stVafter[GSEG_MAXR];
+    u32 stTail[GSEG_MAXR], stPages[GSEG_MAXR]; // 1 when the round ran in the tail kernel; pages of its edge list
     // device timeline (globaltimer, ns): start of the round-0 graph kernel; end of every round; tail rounds
     // also record the ends of their S and R phases and their start
-    u64 seg[8];
     u64 t_start, t_end[GSEG_MAXR], t_begin[GSEG_MAXR], t_S[GSEG_MAXR], t_R[GSEG_MAXR];
 };
 
@@ -67,6 +70,7 @@ struct GsegBufs {
     long long *csum[2]; // per component: 3 fixed-point colour sums (superpixel variant)
     uint2 *eab[2];    // per live edge: the two end components
     u32 *ew[2];       // per live edge: fp32 bits of the weight (superpixel: of the static strength)
+    u32 *pcnt[2];     // per page of the edge list: live edges in the page (unless the list is dense)
     u64 *statusC, *statusE;
 };
 
@@ -181,6 +185,29 @@ __device__ __forceinline__ u32 tile_scan_begin(u32 cnt, u32 tile, u32 tag, u64 *
         if (threadIdx.x == 0) s[33] = pre;
     }
     return ex;
+}
+
+// Block-granular ordered offsets for warps that each hold one count: the warps of a block exchange
+// their counts through shared memory, warp 0 scans them and runs ONE decoupled look-back for the block
+// (so the scan has gridDim participants, not gridDim x warps: short look-back walks), and every warp
+// gets the global exclusive offset of its items.  Contains two __syncthreads(); sh: >= 66 u32.
+// Returns the block's inclusive end (prefix + block total) in *block_end.
+__device__ __forceinline__ u32 block_ordered_offset(u32 warp_total, u32 btile, u32 tag, u64 *status, u32 *err, u32 *sh,
+                                                    u32 *block_end) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    if (lane == 0) sh[wid] = warp_total;
+    __syncthreads();
+    if (wid == 0) {
+        const u32 v = lane < nwarp ? sh[lane] : 0u;
+        const u32 inc = warp_incl_scan(v, lane);
+        const u32 tot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        const u32 pre = lookback_prefix(status, btile, tag, tot, err);
+        sh[32 + lane] = pre + inc - v;
+        if (lane == 0) sh[64] = pre + tot;
+    }
+    __syncthreads();
+    *block_end = sh[64];
+    return sh[32 + wid];
 }
 
 __device__ __forceinline__ u64 make_key(u32 wbits, u32 idx) { return ((u64)wbits << 32) | (u64)idx; }

@@ -33,7 +33,6 @@ namespace cg = cooperative_groups;
 #define NT 256   // threads per block of the grid-wide kernels
 #define NTT 1024 // threads per block of the single-cluster tail kernel
 #define CPT 4    // rows of 32 components per warp tile of phase S
-#define EPT 8    // rows of 32 edges per warp tile of phase E
 
 // round-0 image tiles
 #define TW 64
@@ -354,12 +353,13 @@ __global__ void __launch_bounds__(NT) k_r0_graph(GsegCtl *ctl, GsegBufs B) {
 // Round state helpers.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool in_tail(const GsegCtl *ctl, const RoundState &st) {
-    return st.round >= 1u && st.E <= ctl->p.tail_E && st.V <= ctl->p.tail_V;
+    return st.round >= 1u && st.E <= ctl->p.tail_E && st.V <= ctl->p.tail_V && st.P <= ctl->p.tail_P;
 }
 
 // End-of-round bookkeeping: statistics, phase machine, arena accounting.  Every thread can run it
 // redundantly on its private copy of the state; `writer` alone records it in the control block.
-__device__ __forceinline__ void advance_state(GsegCtl *ctl, RoundState &st, u32 Vn, u32 En, bool writer) {
+__device__ __forceinline__ void advance_state(GsegCtl *ctl, RoundState &st, u32 Vn, u32 En, bool dense_out, bool writer,
+                                              u32 tail_flag = 0u) {
     const u32 r = st.round, V = st.V, merged = V - Vn;
     const int variant = ctl->p.variant;
     u32 phase = st.phase, levels = st.levels;
@@ -375,6 +375,7 @@ __device__ __forceinline__ void advance_state(GsegCtl *ctl, RoundState &st, u32 
     bool arena_err = false;
     if (phase != PH_DONE && (u64)next_off + (u64)Vn > (u64)ctl->p.arena_cap) { arena_err = true; phase = PH_DONE; }
     if (writer) {
+        ctl->stTail[r] = tail_flag; ctl->stPages[r] = st.P;
         ctl->stV[r] = V; ctl->stE[r] = st.E; ctl->stM[r] = merged; ctl->stP[r] = st.phase; ctl->stVafter[r] = Vn;
         ctl->map_off[r] = st.map_off;
         ctl->map_off[r + 1] = next_off;
@@ -382,11 +383,13 @@ __device__ __forceinline__ void advance_state(GsegCtl *ctl, RoundState &st, u32 
         if (arena_err) ctl->error = DERR_ARENA;
     }
     st.round = r + 1; st.levels = levels; st.V = Vn; st.E = En; st.phase = phase; st.map_off = next_off;
+    if (dense_out) { st.P = (En + GSEG_PAGE - 1u) / GSEG_PAGE; st.dense = 1u; } else st.dense = 0u; // else: same pages
     if (writer) ctl->st = st;
 }
 
-// Grid-wide kernels: the last block to finish the edge phase advances the round state.
-__device__ __forceinline__ void last_block_advance(GsegCtl *ctl, const RoundState &st) {
+// Grid-wide kernels: the last block to finish the edge phase advances the round state.  `esum` = this
+// block's count of emitted edges (added to the round's total first).
+__device__ __forceinline__ void last_block_advance(GsegCtl *ctl, const RoundState &st, bool dense_out) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -394,9 +397,16 @@ __device__ __forceinline__ void last_block_advance(GsegCtl *ctl, const RoundStat
             __threadfence();
             ctl->doneE = 0;
             RoundState s2 = st;
-            advance_state(ctl, s2, ld_relaxed_u32(&ctl->Vnext), ld_relaxed_u32(&ctl->Enext), true);
+            advance_state(ctl, s2, ld_relaxed_u32(&ctl->Vnext), ld_relaxed_u32(&ctl->Enext), dense_out, true);
+            ctl->Enext = 0; // the next edge phase accumulates its count from zero
         }
     }
+}
+
+// Whether this round's edge phase re-packs the list densely (ordered look-back scan) instead of keeping
+// every page in place: when the pages are on average less than a quarter full.
+__device__ __forceinline__ bool want_dense_out(const RoundState &st) {
+    return (unsigned long long)st.P * GSEG_PAGE > 4ull * st.E;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -468,37 +478,37 @@ __device__ __forceinline__ void emit_row(const GsegBufs &B, int nxt, u32 pos, bo
     warp_run_min<FILTER>(B.best[nxt], b, kb, pos, act);
 }
 
-// a10 (round 0): grid edges -> explicit list of inter-component edges, in edge-index order
-// (direction-major: all E edges in pixel order, then S, SE, NE).  Every WARP owns its tiles: a tile is
-// one direction x 32*ROWS consecutive pixels, handed out by an atomic ticket; the warp counts its
-// survivors, takes its global offset from a warp-granular decoupled look-back and emits row by row.
-// There is no shared memory and no block-wide barrier in the loop.
+// a10 (round 0): grid edges -> paged list of inter-component edges, in edge-index order
+// (direction-major: all E edges in pixel order, then S, SE, NE).
+//
+// PAGED EDGE LIST.  The list is a sequence of pages of GSEG_PAGE = 256 slots; page t holds pcnt[t]
+// live edges at slots [256 t, 256 t + pcnt[t]).  List order = page order, then slot order, so the slot
+// index of an edge is still a strictly increasing function of its edge index and serves as the
+// tie-break.  Compaction is page-local: one warp turns page t of the input into page t of the output
+// (8 rows of 32, survivors ranked by row ballots), so the hot kernels need NO global ordered scan, no
+// tile tickets, no look-back and no barrier: every warp streams through its pages independently.
+// (The decoupled look-back this replaces cost 35-40 % of these kernels: with ~4700 warps starting
+// together, each look-back walks back through thousands of not-yet-resolved predecessors.)  Only when
+// the pages have become sparse (< 1/4 full) does one round re-pack the list densely with the ordered
+// scan; by then the list is small.
 template <int D, bool SP>
 __global__ void __launch_bounds__(NT) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
-    constexpr int ROWS = 8, TILE_P = 32 * ROWS;
+    constexpr int ROWS = GSEG_PAGE / 32;
     const int lane = threadIdx.x & 31;
     const u32 lt = (1u << lane) - 1u;
     const RoundState st = ctl->st; // round 0
     const int w = ctl->p.w, h = ctl->p.h;
     const u32 V = (u32)w * (u32)h;
     const u32 *__restrict__ map = B.arena; // round 0's map sits at arena offset 0
-    const u32 tpd = (V + TILE_P - 1) / TILE_P, ntiles = tpd * (u32)D;
-    const u32 tag = ctl->p.epoch_base + 2u;
+    const u32 tpd = (V + GSEG_PAGE - 1) / GSEG_PAGE, ntiles = tpd * (u32)D;
+    const u32 nw = gridDim.x * (NT / 32);
+    u32 esum = 0;
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ticketC = 0;
-    const u32 dbgf = ctl->p.dbg_flags;
-    u32 stile = blockIdx.x * (NT / 32) + (threadIdx.x >> 5);
-    for (;;) {
-        u32 tile = 0;
-        if (dbgf & 2u) { tile = stile; stile += gridDim.x * (NT / 32); }
-        else {
-            if (lane == 0) tile = atomicAdd(&ctl->ticketE, 1u);
-            tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
-        }
-        if (tile >= ntiles) break;
+    for (u32 tile = blockIdx.x * (NT / 32) + (threadIdx.x >> 5); tile < ntiles; tile += nw) {
         const int d = (int)(tile / tpd);
         const int dx = d == 1 ? 0 : 1, dy = d == 0 ? 0 : (d == 3 ? -1 : 1);
         const int off = dy * w + dx;
-        const u32 p0 = (tile - (u32)d * tpd) * TILE_P + lane;
+        const u32 p0 = (tile - (u32)d * tpd) * GSEG_PAGE + lane;
         u32 a[ROWS], b[ROWS], m[ROWS];
         int y = (int)(p0 / (u32)w), x = (int)(p0 - (u32)y * (u32)w);
 #pragma unroll
@@ -518,11 +528,10 @@ __global__ void __launch_bounds__(NT) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
         u32 total = 0;
 #pragma unroll
         for (int j = 0; j < ROWS; ++j) total += __popc(m[j]);
-        const u32 pre = (dbgf & 1u) ? tile * TILE_P : lookback_prefix(B.statusE, tile, tag, total, &ctl->error);
-        if (tile == ntiles - 1 && lane == 0) ctl->Enext = pre + total;
+        if (lane == 0) B.pcnt[1][tile] = total;
+        esum += total;
         const float *wg = B.wgrid + (size_t)d * V + p0;
-        u32 rowoff = pre;
-        if (dbgf & 4u) continue;
+        u32 rowoff = tile * GSEG_PAGE;
 #pragma unroll
         for (int j = 0; j < ROWS; ++j) {
             if (m[j] == 0u) continue; // warp-uniform
@@ -532,7 +541,10 @@ __global__ void __launch_bounds__(NT) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
             rowoff += __popc(m[j]);
         }
     }
-    last_block_advance(ctl, st);
+    if (lane == 0 && esum) atomicAdd(&ctl->Enext, esum);
+    RoundState s0 = st;
+    s0.P = ntiles;
+    last_block_advance(ctl, s0, false);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -540,13 +552,14 @@ __global__ void __launch_bounds__(NT) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
 // removal, root flags + look-back scan = new ids; the tile clears the accumulators of its new ids.
 // ------------------------------------------------------------------------------------------------
 template <bool SP>
-__device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const RoundState &st) {
-    constexpr u32 TILE_C = 32 * CPT; // components per warp tile: CPT rows of 32 consecutive ids
-    const int lane = threadIdx.x & 31;
+__device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, u32 *sh) {
+    constexpr u32 TILE_C = 32 * CPT; // components per warp: CPT rows of 32 consecutive ids
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     const u32 lt = (1u << lane) - 1u;
     const int cur = st.round & 1, nxt = cur ^ 1;
     const u32 V = st.V;
-    const u32 ntiles = (V + TILE_C - 1) / TILE_C;
+    const u32 nwt = (V + TILE_C - 1) / TILE_C;            // warp tiles
+    const u32 ntiles = (nwt + nwarp - 1) / nwarp;         // block tiles = look-back participants
     const u32 tag = ctl->p.epoch_base + st.round * 2u + 1u;
     const u64 *best = B.best[cur];
     const uint2 *eab = B.eab[cur], *attr = B.attr[cur];
@@ -556,10 +569,11 @@ __device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const R
     const bool msz = ctl->p.variant == GSEG_FELZ && phase == PH_MINSIZE;
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ticketE = 0;
     for (;;) {
-        u32 tile = 0;
-        if (lane == 0) tile = atomicAdd(&ctl->ticketC, 1u);
-        tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
-        if (tile >= ntiles) break;
+        if (threadIdx.x == 0) sh[65] = atomicAdd(&ctl->ticketC, 1u);
+        __syncthreads();
+        const u32 btile = sh[65];
+        if (btile >= ntiles) break;
+        const u32 tile = btile * nwarp + wid; // may lie beyond the last warp tile: then every row is empty
         const u32 base = tile * TILE_C + lane;
         // Three dependent gathers per component, each stage issued for all CPT rows at once:
         //   best[c] -> ends of that edge -> {attributes of both ends, best[] of the other end}.
@@ -613,8 +627,9 @@ __device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const R
             m[j] = __ballot_sync(0xFFFFFFFFu, root);
             total += __popc(m[j]);
         }
-        const u32 pre = lookback_prefix(B.statusC, tile, tag, total, &ctl->error);
-        if (tile == ntiles - 1 && lane == 0) ctl->Vnext = pre + total;
+        u32 bend;
+        const u32 pre = block_ordered_offset(total, btile, tag, B.statusC, &ctl->error, sh, &bend);
+        if (btile == ntiles - 1 && threadIdx.x == 0) ctl->Vnext = bend;
         u32 rowoff = pre;
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
@@ -631,58 +646,74 @@ __device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const R
 }
 
 // ------------------------------------------------------------------------------------------------
-// a10 (rounds >= 1): relabel edge ends through this round's map, drop self-loops, stable compaction,
-// fused with next round's per-component minimum.  Warp tiles of EPN rows x 32 edges (see emit_row); no
-// shared memory, no block-wide barrier.
+// a10 (rounds >= 1): relabel edge ends through this round's map, drop self-loops, page-local stable
+// compaction (see k_r0_edges), fused with next round's per-component minimum.  One warp per page.
+// dense_out: the round that re-packs a sparse list: pages are handed out by ticket and every page takes
+// its output offset from a warp-granular decoupled look-back.
 // ------------------------------------------------------------------------------------------------
-template <int EPN, bool SP>
-__device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, u32 Vnext) {
-    constexpr u32 TILE_E = 32 * EPN;
+template <bool SP>
+__device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, u32 Vnext, u32 *sh) {
+    constexpr int ROWS = GSEG_PAGE / 32;
     const int lane = threadIdx.x & 31;
     const u32 lt = (1u << lane) - 1u;
     const int cur = st.round & 1, nxt = cur ^ 1;
-    const u32 E = st.E;
+    const u32 E = st.E, P = st.P;
     const uint2 *eab = B.eab[cur];
     const u32 *ew = B.ew[cur];
+    const u32 *pc = B.pcnt[cur];
     const u32 *map = B.arena + st.map_off;
-    const u32 ntiles = (E + TILE_E - 1) / TILE_E;
     const u32 tag = ctl->p.epoch_base + st.round * 2u + 2u;
     const bool filter = (E >> ctl->p.filter_shift) > Vnext; // many edge ends per surviving component
-    if (blockIdx.x == 0 && threadIdx.x == 0) {
-        ctl->ticketC = 0;
-        if (ntiles == 0) ctl->Enext = 0;
-    }
+    const bool dense_in = st.dense != 0u, dense_out = want_dense_out(st);
+    if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ticketC = 0;
+    const u32 nwarp = blockDim.x >> 5, nw = gridDim.x * nwarp;
+    const u32 nbt = (P + nwarp - 1) / nwarp; // dense_out: block tiles of nwarp consecutive pages
+    u32 page = blockIdx.x * nwarp + (threadIdx.x >> 5), btile = 0;
+    u32 esum = 0;
     for (;;) {
-        u32 tile = 0;
-        if (lane == 0) tile = atomicAdd(&ctl->ticketE, 1u);
-        tile = __shfl_sync(0xFFFFFFFFu, tile, 0);
-        if (tile >= ntiles) break;
-        const u32 base = tile * TILE_E + lane;
-        u32 a[EPN], b[EPN], wv[EPN], m[EPN];
+        if (dense_out) {
+            if (threadIdx.x == 0) sh[65] = atomicAdd(&ctl->ticketE, 1u);
+            __syncthreads();
+            btile = sh[65];
+            if (btile >= nbt) break;
+            page = btile * nwarp + (threadIdx.x >> 5); // may lie beyond the last page: then it is empty
+        } else if (page >= P) break;
+        u32 c = 0u;
+        if (page < P) {
+            if (dense_in) c = page * GSEG_PAGE < E ? min(GSEG_PAGE, E - page * GSEG_PAGE) : 0u;
+            else c = __ldcg(pc + page);
+        }
+        const u32 base = page * GSEG_PAGE + lane;
+        u32 a[ROWS], b[ROWS], wv[ROWS], m[ROWS];
 #pragma unroll
-        for (int j = 0; j < EPN; ++j) {
-            const u32 e = base + 32u * j;
+        for (int j = 0; j < ROWS; ++j) {
             uint2 ab = make_uint2(0u, 0u);
             wv[j] = 0u;
-            if (e < E) { ab = __ldcg(eab + e); wv[j] = __ldcg(ew + e); }
+            if (32u * j + lane < c) { ab = __ldcg(eab + base + 32u * j); wv[j] = __ldcg(ew + base + 32u * j); }
             a[j] = ab.x; b[j] = ab.y;
         }
         u32 total = 0;
 #pragma unroll
-        for (int j = 0; j < EPN; ++j) {
+        for (int j = 0; j < ROWS; ++j) {
             bool keep = false;
-            if (base + 32u * j < E) {
+            if (32u * j + lane < c) {
                 a[j] = __ldcg(map + a[j]); b[j] = __ldcg(map + b[j]);
                 keep = a[j] != b[j];
             }
             m[j] = __ballot_sync(0xFFFFFFFFu, keep);
             total += __popc(m[j]);
         }
-        const u32 pre = lookback_prefix(B.statusE, tile, tag, total, &ctl->error);
-        if (tile == ntiles - 1 && lane == 0) ctl->Enext = pre + total;
-        u32 rowoff = pre;
+        u32 rowoff;
+        if (dense_out) {
+            u32 bend;
+            rowoff = block_ordered_offset(total, btile, tag, B.statusE, &ctl->error, sh, &bend);
+        } else {
+            rowoff = page * GSEG_PAGE;
+            if (lane == 0) B.pcnt[nxt][page] = total;
+        }
+        esum += total;
 #pragma unroll
-        for (int j = 0; j < EPN; ++j) {
+        for (int j = 0; j < ROWS; ++j) {
             if (m[j] == 0u) continue; // warp-uniform
             const bool act = (m[j] >> lane) & 1u;
             const u32 pos = rowoff + __popc(m[j] & lt);
@@ -690,7 +721,9 @@ __device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const R
             else emit_row<SP, false>(B, nxt, pos, act, a[j], b[j], wv[j]);
             rowoff += __popc(m[j]);
         }
+        if (!dense_out) page += nw;
     }
+    if (lane == 0 && esum) atomicAdd(&ctl->Enext, esum);
 }
 
 // ---- grid-wide schedule: one kernel per phase ---------------------------------------------------
@@ -704,16 +737,18 @@ __global__ void __launch_bounds__(NT) k_relabel(const GsegCtl *ctl, GsegBufs B) 
 }
 template <bool SP>
 __global__ void __launch_bounds__(NT) k_succ_scan(GsegCtl *ctl, GsegBufs B) {
+    __shared__ u32 sh[66];
     const RoundState st = ctl->st;
     if (st.phase == PH_DONE || in_tail(ctl, st)) return;
-    phase_S<SP>(ctl, B, st);
+    phase_S<SP>(ctl, B, st, sh);
 }
 template <bool SP>
 __global__ void __launch_bounds__(NT) k_edges(GsegCtl *ctl, GsegBufs B) {
+    __shared__ u32 sh[66];
     const RoundState st = ctl->st;
     if (st.phase == PH_DONE || in_tail(ctl, st)) return;
-    phase_E<EPT, SP>(ctl, B, st, ctl->Vnext);
-    last_block_advance(ctl, st);
+    phase_E<SP>(ctl, B, st, ctl->Vnext, sh);
+    last_block_advance(ctl, st, want_dense_out(st));
 }
 
 // ---- tail schedule: every small round inside one launch of a single thread-block cluster -----------
@@ -721,29 +756,30 @@ __global__ void __launch_bounds__(NT) k_edges(GsegCtl *ctl, GsegBufs B) {
 // graph is (unexpectedly) too large for the tail.  Replaces the reference's host loop with its per-round
 // 4-byte read-back and its dynamic-parallelism orchestration kernel (Report.pdf p3, p5).  A cluster is
 // co-scheduled by hardware, so tails of different images run side by side on disjoint SMs.
-#define TAIL_EPT 4
 template <bool SP>
 __global__ void __launch_bounds__(NTT, 1) k_tail(GsegCtl *ctl, GsegBufs B) {
+    __shared__ u32 sh[66];
     cg::cluster_group cl = cg::this_cluster();
     const bool writer = blockIdx.x == 0 && threadIdx.x == 0;
     RoundState st = ctl->st;
     cl.sync(); // everyone holds the entry state before the writer may replace it
     while (st.phase != PH_DONE && in_tail(ctl, st)) {
         if (writer) ctl->t_begin[st.round] = globaltimer_ns();
-        phase_S<SP>(ctl, B, st);
+        phase_S<SP>(ctl, B, st, sh);
         __threadfence();
         cl.sync();
-        if (writer) ctl->t_S[st.round] = globaltimer_ns();
+        if (writer) { ctl->t_S[st.round] = globaltimer_ns(); ctl->Enext = 0; } // everyone has read last round's count
         const u32 Vn = ld_relaxed_u32(&ctl->Vnext);
+        const bool dense_out = want_dense_out(st);
         phase_R<NTT, false, SP>(ctl, B, st);
         __threadfence();
         cl.sync();
         if (writer) ctl->t_R[st.round] = globaltimer_ns();
-        phase_E<TAIL_EPT, SP>(ctl, B, st, Vn);
+        phase_E<SP>(ctl, B, st, Vn, sh);
         __threadfence();
         cl.sync();
         const u32 En = ld_relaxed_u32(&ctl->Enext);
-        advance_state(ctl, st, Vn, En, writer);
+        advance_state(ctl, st, Vn, En, dense_out, writer, 1u);
     }
 }
 
