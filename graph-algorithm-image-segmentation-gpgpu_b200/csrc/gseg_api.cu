@@ -277,7 +277,7 @@ static GsegBufs bufs_of(const gseg_ctx *c) {
 }
 
 template <int R>
-static size_t blur_smem() { return (size_t)(((TW + 2 * R) * 3 * (TH + 2 * R) + 15) & ~15) + (size_t)3 * (TH + 2 * R) * TW * sizeof(float); }
+static size_t blur_smem() { return (size_t)3 * (TH + 2 * R) * (BLUR_PF(R) + BLUR_PH) * sizeof(float); }
 template <int R>
 static void launch_blur(gseg_ctx *c, cudaStream_t s, int ntiles) {
     static bool attr[64] = {false}; // the opt-in is per function and per device

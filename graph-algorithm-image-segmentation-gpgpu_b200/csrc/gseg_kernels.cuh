@@ -45,17 +45,21 @@ __constant__ int c_DY[4] = {0, 1, 1, -1};
 
 // ------------------------------------------------------------------------------------------------
 // a1: separable Gaussian, clamped borders.  u8 interleaved RGB -> 3 fp32 planes.
-// Tile kernel: (TW+2R) x (TH+2R) input bytes -> shared; horizontal pass into shared; vertical pass
-// to global.  Each thread produces 8 outputs along the filter direction from 8+2R register-held
-// taps, so shared memory is read ~2x per output instead of (2R+1)x.
+// Tile kernel: (TW+2R) x (TH+2R) input pixels -> fp32 planes in shared memory (32-bit loads of the
+// interleaved bytes where the tile is interior and 4-byte aligned); horizontal pass, shared -> shared;
+// vertical pass -> global.  Each thread produces 8 outputs along the filter direction from 8+2R
+// register-held taps (2 shared loads per output instead of 2R+1).  Lanes run ACROSS the filter
+// direction (over rows in the horizontal pass, over columns in the vertical pass) and the shared row
+// pitches are odd, so every shared access of a warp is bank-conflict free.
 // ------------------------------------------------------------------------------------------------
+#define BLUR_PF(R) ((TW + 2 * (R)) | 1)  // pitch of the staged input planes
+#define BLUR_PH (TW + 1)                 // pitch of the horizontally filtered planes
 template <int R>
 __global__ void __launch_bounds__(NT) k_blur_tile(const GsegCtl *__restrict__ ctl, float *__restrict__ planes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    constexpr int IW = TW + 2 * R, IH = TH + 2 * R, IWB = IW * 3;
-    constexpr int IBYTES = (IWB * IH + 15) & ~15;
-    uint8_t *sI = smem_raw;                                  // [IH][IW*3]
-    float *sH = reinterpret_cast<float *>(smem_raw + IBYTES); // [3][IH][TW]
+    constexpr int IW = TW + 2 * R, IH = TH + 2 * R, PF = BLUR_PF(R), PH = BLUR_PH;
+    float *sF = reinterpret_cast<float *>(smem_raw); // [3][IH][PF] input as fp32
+    float *sH = sF + 3 * IH * PF;                    // [3][IH][PH] after the horizontal pass
     const int w = ctl->p.w, h = ctl->p.h, stride = ctl->p.stride;
     const uint8_t *__restrict__ rgb = ctl->p.rgb;
     float m[R + 1];
@@ -63,24 +67,45 @@ __global__ void __launch_bounds__(NT) k_blur_tile(const GsegCtl *__restrict__ ct
     for (int i = 0; i <= R; ++i) m[i] = ctl->p.mask[i];
     const int ntx = (w + TW - 1) / TW;
     const int x0 = (blockIdx.x % ntx) * TW, y0 = (blockIdx.x / ntx) * TH;
-    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-    for (int r = wid; r < IH; r += NT / 32) {
+    // 1. stage: 4 pixels (12 bytes) per item
+    const bool fast = x0 - R >= 0 && x0 - R + IW <= w && (stride & 3) == 0 && ((3 * (x0 - R)) & 3) == 0 &&
+                      (reinterpret_cast<size_t>(rgb) & 3) == 0 && (IW & 3) == 0;
+    constexpr int G4 = (IW + 3) / 4;
+    for (int item = threadIdx.x; item < IH * G4; item += NT) {
+        const int r = item / G4, g = item - r * G4;
         const int gy = min(max(y0 - R + r, 0), h - 1);
         const uint8_t *row = rgb + (size_t)gy * stride;
-        for (int o = lane; o < IWB; o += 32) {
-            const int px = o / 3, ch = o - px * 3;
-            const int gx = min(max(x0 - R + px, 0), w - 1);
-            sI[r * IWB + o] = row[3 * gx + ch];
+        float *d0 = sF + r * PF + 4 * g;
+        if (fast) {
+            const uint32_t *wp = reinterpret_cast<const uint32_t *>(row + 3 * (x0 - R) + 12 * g);
+            const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
+            const uint32_t b[12] = {w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, w0 >> 24,
+                                    w1 & 255u, (w1 >> 8) & 255u, (w1 >> 16) & 255u, w1 >> 24,
+                                    w2 & 255u, (w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24};
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) d0[ch * IH * PF + q] = (float)b[3 * q + ch];
+        } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                const int px = 4 * g + q;
+                if (px >= IW) break;
+                const int gx = min(max(x0 - R + px, 0), w - 1);
+#pragma unroll
+                for (int ch = 0; ch < 3; ++ch) d0[ch * IH * PF + q] = (float)row[3 * gx + ch];
+            }
         }
     }
     __syncthreads();
-    for (int item = threadIdx.x; item < IH * 3 * (TW / 8); item += NT) {
-        const int g = item % (TW / 8), ch = (item / (TW / 8)) % 3, r = item / (3 * (TW / 8));
+    // 2. horizontal pass: item = (channel, 8-column group, row); consecutive lanes take consecutive rows
+    for (int item = threadIdx.x; item < 3 * (TW / 8) * IH; item += NT) {
+        const int r = item % IH, g = (item / IH) % (TW / 8), ch = item / (IH * (TW / 8));
         float v[8 + 2 * R];
-        const uint8_t *src = sI + r * IWB + (g * 8) * 3 + ch;
+        const float *src = sF + (ch * IH + r) * PF + g * 8;
 #pragma unroll
-        for (int j = 0; j < 8 + 2 * R; ++j) v[j] = (float)src[3 * j];
-        float *dst = sH + (ch * IH + r) * TW + g * 8;
+        for (int j = 0; j < 8 + 2 * R; ++j) v[j] = src[j];
+        float *dst = sH + (ch * IH + r) * PH + g * 8;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             float s = __fmul_rn(m[0], v[R + j]);
@@ -90,15 +115,16 @@ __global__ void __launch_bounds__(NT) k_blur_tile(const GsegCtl *__restrict__ ct
         }
     }
     __syncthreads();
+    // 3. vertical pass: item = (channel, 8-row group, column); consecutive lanes take consecutive columns
     const u32 V = (u32)w * (u32)h;
     for (int item = threadIdx.x; item < TW * 3 * (TH / 8); item += NT) {
         const int c = item % TW, ch = (item / TW) % 3, rg = item / (3 * TW);
         const int gx = x0 + c;
         if (gx >= w) continue;
         float v[8 + 2 * R];
-        const float *src = sH + (ch * IH + rg * 8) * TW + c;
+        const float *src = sH + (ch * IH + rg * 8) * PH + c;
 #pragma unroll
-        for (int j = 0; j < 8 + 2 * R; ++j) v[j] = src[j * TW];
+        for (int j = 0; j < 8 + 2 * R; ++j) v[j] = src[j * PH];
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
             const int gy = y0 + rg * 8 + j;
