@@ -140,7 +140,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="gseg", choices=["gseg", "reference"])
     ap.add_argument("--batch", type=int, default=32, help="images per step per GPU")
-    ap.add_argument("--contexts", type=int, default=4, help="gseg contexts (one CUDA stream each) in flight per GPU")
+    ap.add_argument("--contexts", type=int, default=8, help="gseg contexts (one CUDA stream each) in flight per GPU")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

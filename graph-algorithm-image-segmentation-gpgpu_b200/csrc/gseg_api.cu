@@ -21,9 +21,9 @@
 struct GsegHead {
     GsegRunParams p;
     RoundState st;
-    u32 Vnext, Enext, error, ticketC, ticketE, doneE;
+    u32 Vnext, Enext, error, ticketC, ticketE, doneE, Eacc[GSEG_MAXR + 1];
 };
-static_assert(offsetof(GsegCtl, doneE) == offsetof(GsegHead, doneE), "GsegHead must mirror the head of GsegCtl");
+static_assert(offsetof(GsegCtl, Eacc) == offsetof(GsegHead, Eacc), "GsegHead must mirror the head of GsegCtl");
 
 struct gseg_ctx {
     int device, max_w, max_h;
@@ -36,13 +36,14 @@ struct gseg_ctx {
     uint2 *d_attr[2];
     long long *d_csum[2];
     uint2 *d_eab[2];
-    u32 *d_ew[2], *d_pcnt[2];
+    u32 *d_ew[2], *d_pcnt[2], *d_poff[2], *d_pscan;
     u32 *d_arena;
     size_t arena_cap;
     u64 *d_statusC, *d_statusE;
     size_t ntilesC, ntilesE;
     int *d_labels[2];
-    GsegCtl *d_ctl, *h_ctl;
+    GsegCtl *d_ctl, *h_ctl, *h_peek;
+    cudaStream_t peek_stream;
     GsegHead *h_head; // pinned image of the host-initialised head of the control block
     int num_sms, occ_mult;
     u32 filter_shift;
@@ -133,8 +134,10 @@ extern "C" int gseg_create(gseg_ctx **out, int device, int max_w, int max_h) {
         if (e == cudaSuccess) e = dalloc(&ctx->d_eab[i], 4 * Vp);
         if (e == cudaSuccess) e = dalloc(&ctx->d_ew[i], 4 * Vp);
         if (e == cudaSuccess) e = dalloc(&ctx->d_pcnt[i], 4 * (V / GSEG_PAGE + 1) + 2);
+        if (e == cudaSuccess) e = dalloc(&ctx->d_poff[i], 4 * (V / GSEG_PAGE + 1) + 2);
         if (e == cudaSuccess) e = dalloc(&ctx->d_labels[i], Vp);
     }
+    if (e == cudaSuccess) e = dalloc(&ctx->d_pscan, 4 * (V / GSEG_PAGE + 1) + 8);
     ctx->arena_cap = 6 * V + 1024;
     if (ctx->arena_cap > 0xFFFFFFF0ull) ctx->arena_cap = 0xFFFFFFF0ull;
     if (e == cudaSuccess) e = dalloc(&ctx->d_arena, ctx->arena_cap);
@@ -151,6 +154,8 @@ extern "C" int gseg_create(gseg_ctx **out, int device, int max_w, int max_h) {
     if (e == cudaSuccess) e = cudaMemset(ctx->d_ctl, 0, sizeof(GsegCtl));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_ctl, sizeof(GsegCtl));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_head, sizeof(GsegHead));
+    if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_peek, sizeof(GsegCtl));
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->peek_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) {
         // tail kernel: one thread-block cluster, 16 CTAs when the device can co-schedule that many
@@ -172,7 +177,7 @@ extern "C" int gseg_create(gseg_ctx **out, int device, int max_w, int max_h) {
             cudaGetLastError();
         }
         ctx->tail_cluster = want;
-        ctx->tail_E = 256u * 1024u; ctx->tail_V = 64u * 1024u; ctx->tail_P = 2048u;
+        ctx->tail_E = 256u * 1024u; ctx->tail_V = 64u * 1024u; ctx->tail_P = 4096u;
         if (const char *ev = getenv("GSEG_TAIL_P")) ctx->tail_P = (u32)strtoul(ev, nullptr, 10);
         if (const char *ev = getenv("GSEG_TAIL_E")) ctx->tail_E = (u32)strtoul(ev, nullptr, 10);
         if (const char *ev = getenv("GSEG_TAIL_V")) ctx->tail_V = (u32)strtoul(ev, nullptr, 10);
@@ -201,12 +206,14 @@ extern "C" void gseg_destroy(gseg_ctx *ctx) {
     cudaFree(ctx->d_succ); cudaFree(ctx->d_rank);
     for (int i = 0; i < 2; ++i) {
         cudaFree(ctx->d_best[i]); cudaFree(ctx->d_attr[i]); cudaFree(ctx->d_csum[i]);
-        cudaFree(ctx->d_eab[i]); cudaFree(ctx->d_ew[i]); cudaFree(ctx->d_pcnt[i]); cudaFree(ctx->d_labels[i]);
+        cudaFree(ctx->d_eab[i]); cudaFree(ctx->d_ew[i]); cudaFree(ctx->d_pcnt[i]); cudaFree(ctx->d_poff[i]); cudaFree(ctx->d_labels[i]);
     }
-    cudaFree(ctx->d_arena); cudaFree(ctx->d_statusC); cudaFree(ctx->d_statusE); cudaFree(ctx->d_ctl);
+    cudaFree(ctx->d_pscan); cudaFree(ctx->d_arena); cudaFree(ctx->d_statusC); cudaFree(ctx->d_statusE); cudaFree(ctx->d_ctl);
     sort_scratch_free(&ctx->sort);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
     if (ctx->h_head) cudaFreeHost(ctx->h_head);
+    if (ctx->h_peek) cudaFreeHost(ctx->h_peek);
+    if (ctx->peek_stream) cudaStreamDestroy(ctx->peek_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     free(ctx);
 }
@@ -215,6 +222,24 @@ extern "C" int gseg_set_stream(gseg_ctx *ctx, void *s) {
     if (!ctx) return GSEG_E_ARG;
     if (ctx->pending) return GSEG_E_STATE;
     ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
+    return GSEG_OK;
+}
+
+// Debug aid: copy device state on a separate stream while a run is (possibly) stuck.
+// out: st (8 words), Vnext, Enext, error, ticketC, ticketE, doneE, Eacc[0..9], then 32 words each of
+// pscan, pcnt[0], pcnt[1], poff[0], poff[1], dbgw.
+extern "C" int gseg_debug_peek(gseg_ctx *ctx, unsigned int *out_words) {
+    if (!ctx) return GSEG_E_ARG;
+    cudaSetDevice(ctx->device);
+    GsegCtl *tmp = ctx->h_peek;
+    cudaMemcpyAsync(tmp, ctx->d_ctl, sizeof(GsegCtl), cudaMemcpyDeviceToHost, ctx->peek_stream);
+    cudaStreamSynchronize(ctx->peek_stream);
+    const unsigned int *w = (const unsigned int *)&tmp->st;
+    for (int i = 0; i < 24; ++i) out_words[i] = w[i];
+    u32 *srcs[5] = {ctx->d_pscan, ctx->d_pcnt[0], ctx->d_pcnt[1], ctx->d_poff[0], ctx->d_poff[1]};
+    for (int k = 0; k < 5; ++k) cudaMemcpyAsync(out_words + 24 + 32 * k, srcs[k], 32 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->peek_stream);
+    cudaStreamSynchronize(ctx->peek_stream);
+    for (int i = 0; i < 64; ++i) out_words[24 + 160 + i] = tmp->dbgw[i];
     return GSEG_OK;
 }
 
@@ -270,9 +295,9 @@ static GsegBufs bufs_of(const gseg_ctx *c) {
     B.succ = c->d_succ; B.rank = c->d_rank; B.wsel = c->d_wsel; B.arena = c->d_arena;
     for (int i = 0; i < 2; ++i) {
         B.best[i] = c->d_best[i]; B.attr[i] = c->d_attr[i]; B.csum[i] = c->d_csum[i];
-        B.eab[i] = c->d_eab[i]; B.ew[i] = c->d_ew[i]; B.pcnt[i] = c->d_pcnt[i];
+        B.eab[i] = c->d_eab[i]; B.ew[i] = c->d_ew[i]; B.pcnt[i] = c->d_pcnt[i]; B.poff[i] = c->d_poff[i];
     }
-    B.statusC = c->d_statusC; B.statusE = c->d_statusE;
+    B.statusC = c->d_statusC; B.statusE = c->d_statusE; B.pscan = c->d_pscan;
     return B;
 }
 
@@ -350,6 +375,8 @@ static void enqueue_round(gseg_ctx *c, cudaStream_t s, int r, size_t Vb, size_t 
     const bool sp = c->params.variant == GSEG_SUPERPIX;
     const GsegBufs B = bufs_of(c);
     const int cap = c->num_sms * c->occ_mult;
+    mark(c, s, "k_page_scan", r);
+    k_page_scan<<<1, 1024, 0, s>>>(c->d_ctl, B);
     mark(c, s, "k_succ_scan", r);
     if (sp) k_succ_scan<true><<<grid_for(Vb, NT * CPT, cap), NT, 0, s>>>(c->d_ctl, B);
     else k_succ_scan<false><<<grid_for(Vb, NT * CPT, cap), NT, 0, s>>>(c->d_ctl, B);
@@ -392,6 +419,7 @@ static int finish(gseg_ctx *ctx) {
     ctx->pending = false;
     if (ctx->h_ctl->error == DERR_SCAN) return fail(ctx, GSEG_E_INTERNAL, "look-back watchdog", cudaSuccess);
     if (ctx->h_ctl->error == DERR_ARENA) return fail(ctx, GSEG_E_ARENA, "map arena", cudaSuccess);
+    if (ctx->h_ctl->error == DERR_CHASE) return fail(ctx, GSEG_E_INTERNAL, "successor cycle", cudaSuccess);
     // remember how many grid-wide rounds this kind of image needed before the tail could take over
     const GsegCtl *h = ctx->h_ctl;
     int nbig = 0;
@@ -468,8 +496,9 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
     hp->tail_P = ctx->tail_P;
     ctx->epoch_next += 2u * GSEG_MAXR + 8u;
     // the whole head of the control block (parameters + round-0 state + tickets) in one copy
-    hh->st.V = (u32)((size_t)w * h); hh->st.E = 0; hh->st.round = 0; hh->st.phase = PH_PRED; hh->st.levels = 0; hh->st.map_off = 0; hh->st.P = 0; hh->st.dense = 0;
+    hh->st.V = (u32)((size_t)w * h); hh->st.E = 0; hh->st.round = 0; hh->st.phase = PH_PRED; hh->st.levels = 0; hh->st.map_off = 0; hh->st.P = 0; hh->st.cap = 0;
     hh->Vnext = hh->st.V; hh->Enext = 0; hh->error = DERR_NONE; hh->ticketC = 0; hh->ticketE = 0; hh->doneE = 0;
+    memset(hh->Eacc, 0, sizeof(hh->Eacc));
     CK(cudaMemcpyAsync(ctx->d_ctl, hh, sizeof(GsegHead), cudaMemcpyHostToDevice, ctx->stream));
 
     ctx->n_marks = 0;

@@ -15,7 +15,7 @@ typedef unsigned long long u64;
 #define GSEG_PAGE 256u /* slots per page of the edge list = one warp tile (8 rows of 32) */
 
 enum { PH_PRED = 0, PH_MINSIZE = 1, PH_DONE = 2 };
-enum { DERR_NONE = 0, DERR_SCAN = 1, DERR_ARENA = 2 };
+enum { DERR_NONE = 0, DERR_SCAN = 1, DERR_ARENA = 2, DERR_CHASE = 3 };
 
 // Parameters of one run; filled by the host in pinned memory and copied into GsegCtl::p.
 struct GsegRunParams {
@@ -34,12 +34,12 @@ struct GsegRunParams {
 
 // State of the round about to run.  Lives in GsegCtl between kernels of the host-driven schedule
 // and in registers inside the persistent round kernel.
-struct RoundState {
+struct RoundState { // 8 x u32, read field by field by load_state()
     u32 V, E;      // components / live edges entering the round
     u32 round, phase, levels;
     u32 map_off;   // arena offset of this round's old->new supervertex map
-    u32 P;         // pages (GSEG_PAGE slots each) of the current edge list
-    u32 dense;     // 1: the list is dense (page t holds min(GSEG_PAGE, E - t*GSEG_PAGE) edges); 0: pcnt[] holds the counts
+    u32 P;         // pages of the current edge list
+    u32 cap;       // total slot capacity of those pages (sum of the page capacities)
 };
 
 // Device-resident control block: all round-to-round state lives here, so a whole run needs no host
@@ -48,16 +48,18 @@ struct RoundState {
 struct GsegCtl {
     GsegRunParams p;
     RoundState st;
-    u32 Vnext, Enext; // produced by the component scan / the edge compaction of the current round
+    u32 Vnext, Enext; // Vnext: produced by the component scan of the current round (Enext: unused, kept for layout)
     u32 error;
     u32 ticketC, ticketE; // dynamic tile tickets of the two look-back scans
     u32 doneE;            // blocks that finished the edge phase (the last one advances the round state)
+    u32 Eacc[GSEG_MAXR + 1]; // Eacc[r]: edges emitted by round r's edge phase (zeroed by the host; never reset on the device)
     // ---- end of host-initialised head ----
     u32 map_off[GSEG_MAXR + 1];
     u32 stV[GSEG_MAXR], stE[GSEG_MAXR], stM[GSEG_MAXR], stP[GSEG_MAXR], stVafter[GSEG_MAXR];
     u32 stTail[GSEG_MAXR], stPages[GSEG_MAXR]; // 1 when the round ran in the tail kernel; pages of its edge list
     // device timeline (globaltimer, ns): start of the round-0 graph kernel; end of every round; tail rounds
     // also record the ends of their S and R phases and their start
+    u32 dbgw[64]; // debug trace
     u64 t_start, t_end[GSEG_MAXR], t_begin[GSEG_MAXR], t_S[GSEG_MAXR], t_R[GSEG_MAXR];
 };
 
@@ -70,7 +72,9 @@ struct GsegBufs {
     long long *csum[2]; // per component: 3 fixed-point colour sums (superpixel variant)
     uint2 *eab[2];    // per live edge: the two end components
     u32 *ew[2];       // per live edge: fp32 bits of the weight (superpixel: of the static strength)
-    u32 *pcnt[2];     // per page of the edge list: live edges in the page (unless the list is dense)
+    u32 *pcnt[2];     // per page of the edge list: live edges in the page
+    u32 *poff[2];     // per page: first slot of the page in eab/ew
+    u32 *pscan;       // exclusive scan of pcnt[cur] (re-pack rounds only)
     u64 *statusC, *statusE;
 };
 

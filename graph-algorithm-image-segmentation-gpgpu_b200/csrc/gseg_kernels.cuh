@@ -384,7 +384,7 @@ __device__ __forceinline__ bool in_tail(const GsegCtl *ctl, const RoundState &st
 
 // End-of-round bookkeeping: statistics, phase machine, arena accounting.  Every thread can run it
 // redundantly on its private copy of the state; `writer` alone records it in the control block.
-__device__ __forceinline__ void advance_state(GsegCtl *ctl, RoundState &st, u32 Vn, u32 En, bool dense_out, bool writer,
+__device__ __forceinline__ void advance_state(GsegCtl *ctl, RoundState &st, u32 Vn, u32 En, bool repack, bool writer,
                                               u32 tail_flag = 0u) {
     const u32 r = st.round, V = st.V, merged = V - Vn;
     const int variant = ctl->p.variant;
@@ -408,14 +408,22 @@ __device__ __forceinline__ void advance_state(GsegCtl *ctl, RoundState &st, u32 
         ctl->t_end[r] = globaltimer_ns();
         if (arena_err) ctl->error = DERR_ARENA;
     }
+    if (repack) { st.P = (st.P + 3u) / 4u; st.cap = st.E; } // re-pack round: 4 pages -> 1, capacity = the edges that entered it
     st.round = r + 1; st.levels = levels; st.V = Vn; st.E = En; st.phase = phase; st.map_off = next_off;
-    if (dense_out) { st.P = (En + GSEG_PAGE - 1u) / GSEG_PAGE; st.dense = 1u; } else st.dense = 0u; // else: same pages
     if (writer) ctl->st = st;
+}
+
+__device__ __forceinline__ RoundState load_state(const GsegCtl *ctl) {
+    RoundState st;
+    const u32 *p = reinterpret_cast<const u32 *>(&ctl->st);
+    st.V = ld_relaxed_u32(p + 0); st.E = ld_relaxed_u32(p + 1); st.round = ld_relaxed_u32(p + 2); st.phase = ld_relaxed_u32(p + 3);
+    st.levels = ld_relaxed_u32(p + 4); st.map_off = ld_relaxed_u32(p + 5); st.P = ld_relaxed_u32(p + 6); st.cap = ld_relaxed_u32(p + 7);
+    return st;
 }
 
 // Grid-wide kernels: the last block to finish the edge phase advances the round state.  `esum` = this
 // block's count of emitted edges (added to the round's total first).
-__device__ __forceinline__ void last_block_advance(GsegCtl *ctl, const RoundState &st, bool dense_out) {
+__device__ __forceinline__ void last_block_advance(GsegCtl *ctl, const RoundState &st, bool repack) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -423,16 +431,41 @@ __device__ __forceinline__ void last_block_advance(GsegCtl *ctl, const RoundStat
             __threadfence();
             ctl->doneE = 0;
             RoundState s2 = st;
-            advance_state(ctl, s2, ld_relaxed_u32(&ctl->Vnext), ld_relaxed_u32(&ctl->Enext), dense_out, true);
-            ctl->Enext = 0; // the next edge phase accumulates its count from zero
+            advance_state(ctl, s2, ld_relaxed_u32(&ctl->Vnext), ld_relaxed_u32(&ctl->Eacc[st.round]), repack, true);
         }
     }
 }
 
-// Whether this round's edge phase re-packs the list densely (ordered look-back scan) instead of keeping
-// every page in place: when the pages are on average less than a quarter full.
-__device__ __forceinline__ bool want_dense_out(const RoundState &st) {
-    return (unsigned long long)st.P * GSEG_PAGE > 4ull * st.E;
+// Whether this round's edge phase re-packs the list: when the pages are on average less than a quarter
+// full.  A re-pack round merges every 4 consecutive pages into one and writes the new pages back to
+// back at the offsets of an exclusive scan of the INPUT page counts (known before the round starts, so
+// the scan is a tiny separate step, not a look-back inside the hot kernel).
+__device__ __forceinline__ bool want_repack(const RoundState &st) {
+    return st.P >= 4u && 4ull * st.E < (unsigned long long)st.cap;
+}
+
+// Exclusive scan of the page counts by ONE block (any block size that is a multiple of 32, <= 1024).
+// s: >= 34 u32 of shared memory.
+__device__ __forceinline__ void block_scan_pages(const u32 *pcnt, u32 P, u32 *pscan, u32 *s) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    u32 carry = 0;
+    for (u32 base = 0; base < P; base += blockDim.x) {
+        const u32 i = base + threadIdx.x;
+        const u32 v = i < P ? __ldcg(pcnt + i) : 0u;
+        const u32 inc = warp_incl_scan(v, lane);
+        if (lane == 31) s[wid] = inc;
+        __syncthreads();
+        if (wid == 0) {
+            const u32 x = lane < nwarp ? s[lane] : 0u;
+            const u32 xi = warp_incl_scan(x, lane);
+            s[lane] = xi - x;
+            if (lane == 31) s[32] = xi;
+        }
+        __syncthreads();
+        if (i < P) pscan[i] = carry + s[wid] + inc - v;
+        carry += s[32];
+        __syncthreads();
+    }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -454,10 +487,12 @@ __device__ __forceinline__ void phase_R(const GsegCtl *ctl, const GsegBufs &B, c
         if (act) {
             u32 r = ld_relaxed_u32(B.succ + c);
             if (r != c) {
+                u32 steps = 0;
                 for (;;) {
                     const u32 rr = ld_relaxed_u32(B.succ + r);
                     if (rr == r) break;
                     r = rr;
+                    if (++steps > V) { ((GsegCtl *)ctl)->error = DERR_CHASE; break; } // a cycle can only come from a bug: fail, do not hang
                 }
                 B.succ[c] = r;
             }
@@ -554,7 +589,7 @@ __global__ void __launch_bounds__(NT) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
         u32 total = 0;
 #pragma unroll
         for (int j = 0; j < ROWS; ++j) total += __popc(m[j]);
-        if (lane == 0) B.pcnt[1][tile] = total;
+        if (lane == 0) { B.pcnt[1][tile] = total; B.poff[1][tile] = tile * GSEG_PAGE; }
         esum += total;
         const float *wg = B.wgrid + (size_t)d * V + p0;
         u32 rowoff = tile * GSEG_PAGE;
@@ -567,9 +602,9 @@ __global__ void __launch_bounds__(NT) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
             rowoff += __popc(m[j]);
         }
     }
-    if (lane == 0 && esum) atomicAdd(&ctl->Enext, esum);
+    if (lane == 0 && esum) atomicAdd(&ctl->Eacc[0], esum);
     RoundState s0 = st;
-    s0.P = ntiles;
+    s0.P = ntiles; s0.cap = ntiles * GSEG_PAGE;
     last_block_advance(ctl, s0, false);
 }
 
@@ -673,12 +708,12 @@ __device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const R
 
 // ------------------------------------------------------------------------------------------------
 // a10 (rounds >= 1): relabel edge ends through this round's map, drop self-loops, page-local stable
-// compaction (see k_r0_edges), fused with next round's per-component minimum.  One warp per page.
-// dense_out: the round that re-packs a sparse list: pages are handed out by ticket and every page takes
-// its output offset from a warp-granular decoupled look-back.
+// compaction (see k_r0_edges), fused with next round's per-component minimum.  One warp per output
+// page: normally page t -> page t in place; in a re-pack round pages 4g..4g+3 -> page g at
+// pscan[4g].  No tickets, no look-back, no barriers.
 // ------------------------------------------------------------------------------------------------
 template <bool SP>
-__device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, u32 Vnext, u32 *sh) {
+__device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, u32 Vnext) {
     constexpr int ROWS = GSEG_PAGE / 32;
     const int lane = threadIdx.x & 31;
     const u32 lt = (1u << lane) - 1u;
@@ -686,70 +721,59 @@ __device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const R
     const u32 E = st.E, P = st.P;
     const uint2 *eab = B.eab[cur];
     const u32 *ew = B.ew[cur];
-    const u32 *pc = B.pcnt[cur];
+    const u32 *pc = B.pcnt[cur], *po = B.poff[cur];
     const u32 *map = B.arena + st.map_off;
-    const u32 tag = ctl->p.epoch_base + st.round * 2u + 2u;
     const bool filter = (E >> ctl->p.filter_shift) > Vnext; // many edge ends per surviving component
-    const bool dense_in = st.dense != 0u, dense_out = want_dense_out(st);
+    const bool repack = want_repack(st);
+    const u32 G = repack ? 4u : 1u, ngroups = repack ? (P + 3u) / 4u : P;
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ticketC = 0;
     const u32 nwarp = blockDim.x >> 5, nw = gridDim.x * nwarp;
-    const u32 nbt = (P + nwarp - 1) / nwarp; // dense_out: block tiles of nwarp consecutive pages
-    u32 page = blockIdx.x * nwarp + (threadIdx.x >> 5), btile = 0;
     u32 esum = 0;
-    for (;;) {
-        if (dense_out) {
-            if (threadIdx.x == 0) sh[65] = atomicAdd(&ctl->ticketE, 1u);
-            __syncthreads();
-            btile = sh[65];
-            if (btile >= nbt) break;
-            page = btile * nwarp + (threadIdx.x >> 5); // may lie beyond the last page: then it is empty
-        } else if (page >= P) break;
-        u32 c = 0u;
-        if (page < P) {
-            if (dense_in) c = page * GSEG_PAGE < E ? min(GSEG_PAGE, E - page * GSEG_PAGE) : 0u;
-            else c = __ldcg(pc + page);
-        }
-        const u32 base = page * GSEG_PAGE + lane;
-        u32 a[ROWS], b[ROWS], wv[ROWS], m[ROWS];
+    for (u32 g = blockIdx.x * nwarp + (threadIdx.x >> 5); g < ngroups; g += nw) {
+        const u32 out_base = repack ? __ldcg(B.pscan + 4u * g) : __ldcg(po + g);
+        u32 written = 0;
+        for (u32 k = 0; k < G; ++k) {
+            const u32 page = G * g + k;
+            if (page >= P) break;
+            const u32 cnt = __ldcg(pc + page), in_base = __ldcg(po + page);
+            for (u32 c0 = 0; c0 < cnt; c0 += GSEG_PAGE) { // pages merged by a re-pack can exceed one 8-row tile
+                const u32 c = cnt - c0, base = in_base + c0 + lane;
+                u32 a[ROWS], b[ROWS], wv[ROWS], m[ROWS];
 #pragma unroll
-        for (int j = 0; j < ROWS; ++j) {
-            uint2 ab = make_uint2(0u, 0u);
-            wv[j] = 0u;
-            if (32u * j + lane < c) { ab = __ldcg(eab + base + 32u * j); wv[j] = __ldcg(ew + base + 32u * j); }
-            a[j] = ab.x; b[j] = ab.y;
-        }
-        u32 total = 0;
+                for (int j = 0; j < ROWS; ++j) {
+                    uint2 ab = make_uint2(0u, 0u);
+                    wv[j] = 0u;
+                    if (32u * j + lane < c) { ab = __ldcg(eab + base + 32u * j); wv[j] = __ldcg(ew + base + 32u * j); }
+                    a[j] = ab.x; b[j] = ab.y;
+                }
+                u32 total = 0;
 #pragma unroll
-        for (int j = 0; j < ROWS; ++j) {
-            bool keep = false;
-            if (32u * j + lane < c) {
-                a[j] = __ldcg(map + a[j]); b[j] = __ldcg(map + b[j]);
-                keep = a[j] != b[j];
+                for (int j = 0; j < ROWS; ++j) {
+                    bool keep = false;
+                    if (32u * j + lane < c) {
+                        a[j] = __ldcg(map + a[j]); b[j] = __ldcg(map + b[j]);
+                        keep = a[j] != b[j];
+                    }
+                    m[j] = __ballot_sync(0xFFFFFFFFu, keep);
+                    total += __popc(m[j]);
+                }
+                u32 rowoff = out_base + written;
+#pragma unroll
+                for (int j = 0; j < ROWS; ++j) {
+                    if (m[j] == 0u) continue; // warp-uniform
+                    const bool act = (m[j] >> lane) & 1u;
+                    const u32 pos = rowoff + __popc(m[j] & lt);
+                    if (filter) emit_row<SP, true>(B, nxt, pos, act, a[j], b[j], wv[j]);
+                    else emit_row<SP, false>(B, nxt, pos, act, a[j], b[j], wv[j]);
+                    rowoff += __popc(m[j]);
+                }
+                written += total;
             }
-            m[j] = __ballot_sync(0xFFFFFFFFu, keep);
-            total += __popc(m[j]);
         }
-        u32 rowoff;
-        if (dense_out) {
-            u32 bend;
-            rowoff = block_ordered_offset(total, btile, tag, B.statusE, &ctl->error, sh, &bend);
-        } else {
-            rowoff = page * GSEG_PAGE;
-            if (lane == 0) B.pcnt[nxt][page] = total;
-        }
-        esum += total;
-#pragma unroll
-        for (int j = 0; j < ROWS; ++j) {
-            if (m[j] == 0u) continue; // warp-uniform
-            const bool act = (m[j] >> lane) & 1u;
-            const u32 pos = rowoff + __popc(m[j] & lt);
-            if (filter) emit_row<SP, true>(B, nxt, pos, act, a[j], b[j], wv[j]);
-            else emit_row<SP, false>(B, nxt, pos, act, a[j], b[j], wv[j]);
-            rowoff += __popc(m[j]);
-        }
-        if (!dense_out) page += nw;
+        if (lane == 0) { B.pcnt[nxt][g] = written; B.poff[nxt][g] = out_base; }
+        esum += written;
     }
-    if (lane == 0 && esum) atomicAdd(&ctl->Enext, esum);
+    if (lane == 0 && esum) atomicAdd(&ctl->Eacc[st.round], esum);
 }
 
 // ---- grid-wide schedule: one kernel per phase ---------------------------------------------------
@@ -761,6 +785,13 @@ __global__ void __launch_bounds__(NT) k_relabel(const GsegCtl *ctl, GsegBufs B) 
     if (st.phase == PH_DONE || in_tail(ctl, st)) return;
     phase_R<NT, R0, SP>(ctl, B, st);
 }
+// Re-pack rounds only: the scan of the page counts the edge phase will place its output by.
+__global__ void __launch_bounds__(1024) k_page_scan(const GsegCtl *ctl, GsegBufs B) {
+    __shared__ u32 s[34];
+    const RoundState st = ctl->st;
+    if (st.phase == PH_DONE || in_tail(ctl, st) || !want_repack(st)) return;
+    block_scan_pages(B.pcnt[st.round & 1], st.P, B.pscan, s);
+}
 template <bool SP>
 __global__ void __launch_bounds__(NT) k_succ_scan(GsegCtl *ctl, GsegBufs B) {
     __shared__ u32 sh[66];
@@ -770,11 +801,10 @@ __global__ void __launch_bounds__(NT) k_succ_scan(GsegCtl *ctl, GsegBufs B) {
 }
 template <bool SP>
 __global__ void __launch_bounds__(NT) k_edges(GsegCtl *ctl, GsegBufs B) {
-    __shared__ u32 sh[66];
     const RoundState st = ctl->st;
     if (st.phase == PH_DONE || in_tail(ctl, st)) return;
-    phase_E<SP>(ctl, B, st, ctl->Vnext, sh);
-    last_block_advance(ctl, st, want_dense_out(st));
+    phase_E<SP>(ctl, B, st, ctl->Vnext);
+    last_block_advance(ctl, st, want_repack(st));
 }
 
 // ---- tail schedule: every small round inside one launch of a single thread-block cluster -----------
@@ -787,25 +817,31 @@ __global__ void __launch_bounds__(NTT, 1) k_tail(GsegCtl *ctl, GsegBufs B) {
     __shared__ u32 sh[66];
     cg::cluster_group cl = cg::this_cluster();
     const bool writer = blockIdx.x == 0 && threadIdx.x == 0;
-    RoundState st = ctl->st;
+    RoundState st = load_state(ctl);
     cl.sync(); // everyone holds the entry state before the writer may replace it
     while (st.phase != PH_DONE && in_tail(ctl, st)) {
         if (writer) ctl->t_begin[st.round] = globaltimer_ns();
+        const bool repack = want_repack(st);
+        if (repack && blockIdx.x == gridDim.x - 1) block_scan_pages(B.pcnt[st.round & 1], st.P, B.pscan, sh);
         phase_S<SP>(ctl, B, st, sh);
         __threadfence();
         cl.sync();
-        if (writer) { ctl->t_S[st.round] = globaltimer_ns(); ctl->Enext = 0; } // everyone has read last round's count
+        if (writer) ctl->t_S[st.round] = globaltimer_ns();
         const u32 Vn = ld_relaxed_u32(&ctl->Vnext);
-        const bool dense_out = want_dense_out(st);
         phase_R<NTT, false, SP>(ctl, B, st);
         __threadfence();
         cl.sync();
         if (writer) ctl->t_R[st.round] = globaltimer_ns();
-        phase_E<SP>(ctl, B, st, Vn, sh);
+        phase_E<SP>(ctl, B, st, Vn);
         __threadfence();
         cl.sync();
-        const u32 En = ld_relaxed_u32(&ctl->Enext);
-        advance_state(ctl, st, Vn, En, dense_out, writer, 1u);
+        // One thread advances the round state and publishes it; everybody re-reads it after a fourth
+        // barrier.  (Every thread advancing a private copy saves the barrier, but then a thousand copies
+        // of the phase machine have to stay bit-identical for the barriers to match up.)
+        if (writer) advance_state(ctl, st, Vn, ld_relaxed_u32(&ctl->Eacc[st.round]), repack, true, 1u);
+        __threadfence();
+        cl.sync();
+        st = load_state(ctl);
     }
 }
 
