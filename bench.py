@@ -187,7 +187,7 @@ def main():
     torch.cuda.synchronize()
 
     def run_batch(imgs, labs):
-        pool.run(imgs, lambda i, sg: sg.labels(out=labs[i % S]), **kw)
+        pool.run(imgs, lambda i, sg: sg.labels(out=labs[i % S], wait=False), **kw)
 
     def step_dev():
         run_batch(dimgs, dlab)
@@ -238,6 +238,7 @@ def main():
     if rank == 0:
         peak, peak_src = peaks()
         seg.set_profiling(True)
+        seg.set_blocks_per_sm(4)  # per-kernel timing of one context alone: the single-context grid size
         kw2 = dict(kw, flags=gseg.FLAG_HOST_LOOP)
         agg = {}
         nprof = min(B, 8)

@@ -65,7 +65,7 @@ class KernelTime(C.Structure):
 class RoundStat(C.Structure):
     _fields_ = [("n_components", C.c_int64), ("n_edges", C.c_int64), ("n_merged", C.c_int64),
                 ("phase", C.c_int32), ("in_tail", C.c_int32), ("us_end", C.c_float), ("us_S", C.c_float),
-                ("us_R", C.c_float), ("us_E", C.c_float)]
+                ("us_R", C.c_float), ("us_E", C.c_float), ("n_pages", C.c_int32), ("reserved", C.c_int32)]
 
 
 _lib = None
@@ -90,12 +90,15 @@ def load():
     L.gseg_destroy.restype = None
     L.gseg_set_stream.argtypes = [vp, vp]
     L.gseg_set_tail.argtypes = [vp, C.c_uint32, C.c_uint32]
+    L.gseg_set_blocks_per_sm.argtypes = [vp, i32]
     L.gseg_segment.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(Params)]
     L.gseg_segment_async.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(Params)]
     L.gseg_wait.argtypes = [vp]
     L.gseg_num_levels.argtypes = [vp]
     L.gseg_num_components.argtypes = [vp, i32]
     L.gseg_labels.argtypes = [vp, i32, vp, i32]
+    L.gseg_labels_async.argtypes = [vp, i32, vp, i32]
+    L.gseg_sync.argtypes = [vp]
     L.gseg_labels_all.argtypes = [vp, vp, i32, i32]
     L.gseg_colorize.argtypes = [vp, i32, u64, vp, i32]
     L.gseg_weights.argtypes = [vp, vp, i32]
@@ -162,6 +165,9 @@ class Segmenter:
     def set_tail(self, max_edges, max_components):
         self._ck(self.L.gseg_set_tail(self.h, max_edges, max_components), "gseg_set_tail")
 
+    def set_blocks_per_sm(self, blocks):
+        self._ck(self.L.gseg_set_blocks_per_sm(self.h, blocks), "gseg_set_blocks_per_sm")
+
     def params(self, sigma=0.8, k=300.0, min_size=20, connectivity=4, variant=FELZ, max_levels=0, max_rounds=0,
                flags=0):
         return Params(sigma, k, min_size, connectivity, variant, max_levels, max_rounds, flags)
@@ -193,12 +199,18 @@ class Segmenter:
     def num_components(self, level=-1):
         return self._ck(self.L.gseg_num_components(self.h, level), "gseg_num_components")
 
-    def labels(self, level=-1, out=None):
+    def labels(self, level=-1, out=None, wait=True):
+        """Label image of a level.  wait=False only enqueues it (out must be a CUDA tensor or pinned
+        host memory); sync() or any later synchronous call completes it."""
         if out is None:
             out = np.empty((self.hh, self.w), np.int32)
         ptr, kind = _ptr(out)
-        self._ck(self.L.gseg_labels(self.h, level, C.c_void_p(ptr), kind), "gseg_labels")
+        fn = self.L.gseg_labels if wait else self.L.gseg_labels_async
+        self._ck(fn(self.h, level, C.c_void_p(ptr), kind), "gseg_labels")
         return out
+
+    def sync(self):
+        self._ck(self.L.gseg_sync(self.h), "gseg_sync")
 
     def labels_all(self, max_levels=64, out=None):
         n = min(max_levels, self.num_levels())
@@ -234,7 +246,7 @@ class Segmenter:
         """Device timeline of the last run: [(round, in_tail, us_end, us_S, us_R, us_E)]."""
         arr = (RoundStat * 64)()
         n = self._ck(self.L.gseg_stats(self.h, arr, 64), "gseg_stats")
-        return [(i, arr[i].in_tail, arr[i].us_end, arr[i].us_S, arr[i].us_R, arr[i].us_E) for i in range(n)]
+        return [(i, arr[i].in_tail, arr[i].us_end, arr[i].us_S, arr[i].us_R, arr[i].us_E, arr[i].n_pages) for i in range(n)]
 
     def set_profiling(self, on):
         self._ck(self.L.gseg_set_profiling(self.h, int(on)), "gseg_set_profiling")

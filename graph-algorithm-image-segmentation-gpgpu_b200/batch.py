@@ -23,6 +23,9 @@ class ContextPool:
     def __init__(self, gseg, max_w, max_h, device=0, contexts=4):
         self.gseg = gseg
         self.segs = [gseg.Segmenter(max_w, max_h, device=device) for _ in range(max(1, contexts))]
+        if len(self.segs) >= 4:  # many contexts in flight: size each grid for 2 blocks per SM so kernels overlap
+            for s in self.segs:
+                s.set_blocks_per_sm(2)
 
     def close(self):
         for s in self.segs:
@@ -31,7 +34,8 @@ class ContextPool:
 
     def run(self, images, on_result, **params):
         """Segment every image of `images`; `on_result(i, segmenter)` is called once image i is complete
-        (read its labels there).  Returns the number of images processed."""
+        (read its labels there; `segmenter.labels(out=..., wait=False)` keeps the copy-out asynchronous: it
+        is ordered before the context's next image and completed before run() returns)."""
         S = len(self.segs)
         n = len(images)
         for base in range(0, n, S):
@@ -41,6 +45,8 @@ class ContextPool:
             for j in range(m):
                 self.segs[j].wait()
                 on_result(base + j, self.segs[j])
+        for s in self.segs:
+            s.sync()
         return n
 
 

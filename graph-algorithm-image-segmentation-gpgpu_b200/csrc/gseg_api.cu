@@ -120,6 +120,7 @@ extern "C" int gseg_create(gseg_ctx **out, int device, int max_w, int max_h) {
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     ctx->stream = ctx->own_stream;
     const size_t Vp = V + 64; // slack for vector tails
+    const size_t Eslots = 4 * ((V + GSEG_PAGE - 1) / GSEG_PAGE + 1) * GSEG_PAGE;
     if (e == cudaSuccess) e = dalloc(&ctx->d_rgb, 3 * Vp);
     if (e == cudaSuccess) e = dalloc(&ctx->d_tmp, 3 * Vp);
     if (e == cudaSuccess) e = dalloc(&ctx->d_planes, 3 * Vp);
@@ -131,8 +132,9 @@ extern "C" int gseg_create(gseg_ctx **out, int device, int max_w, int max_h) {
     for (int i = 0; i < 2 && e == cudaSuccess; ++i) {
         e = dalloc(&ctx->d_best[i], Vp);
         if (e == cudaSuccess) e = dalloc(&ctx->d_attr[i], Vp);
-        if (e == cudaSuccess) e = dalloc(&ctx->d_eab[i], 4 * Vp);
-        if (e == cudaSuccess) e = dalloc(&ctx->d_ew[i], 4 * Vp);
+        // paged edge list: up to 4 directions x ceil(V / page) pages of GSEG_PAGE slots
+        if (e == cudaSuccess) e = dalloc(&ctx->d_eab[i], Eslots);
+        if (e == cudaSuccess) e = dalloc(&ctx->d_ew[i], Eslots);
         if (e == cudaSuccess) e = dalloc(&ctx->d_pcnt[i], 4 * (V / GSEG_PAGE + 1) + 2);
         if (e == cudaSuccess) e = dalloc(&ctx->d_poff[i], 4 * (V / GSEG_PAGE + 1) + 2);
         if (e == cudaSuccess) e = dalloc(&ctx->d_labels[i], Vp);
@@ -248,6 +250,13 @@ extern "C" int gseg_set_tail(gseg_ctx *ctx, uint32_t max_edges, uint32_t max_com
     if (ctx->pending) return GSEG_E_STATE;
     ctx->tail_E = max_edges; ctx->tail_V = max_components;
     ctx->nbig_hint = -1;
+    return GSEG_OK;
+}
+
+extern "C" int gseg_set_blocks_per_sm(gseg_ctx *ctx, int blocks) {
+    if (!ctx || blocks < 1 || blocks > 8) return GSEG_E_ARG;
+    if (ctx->pending) return GSEG_E_STATE;
+    ctx->occ_mult = blocks;
     return GSEG_OK;
 }
 
@@ -376,7 +385,7 @@ static void enqueue_round(gseg_ctx *c, cudaStream_t s, int r, size_t Vb, size_t 
     const GsegBufs B = bufs_of(c);
     const int cap = c->num_sms * c->occ_mult;
     mark(c, s, "k_page_scan", r);
-    k_page_scan<<<1, 1024, 0, s>>>(c->d_ctl, B);
+    k_page_scan<<<(int)((Pb + 1023) / 1024 < 64 ? (Pb + 1023) / 1024 : 64), 1024, 0, s>>>(c->d_ctl, B);
     mark(c, s, "k_succ_scan", r);
     if (sp) k_succ_scan<true><<<grid_for(Vb, NT * CPT, cap), NT, 0, s>>>(c->d_ctl, B);
     else k_succ_scan<false><<<grid_for(Vb, NT * CPT, cap), NT, 0, s>>>(c->d_ctl, B);
@@ -496,7 +505,7 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
     hp->tail_P = ctx->tail_P;
     ctx->epoch_next += 2u * GSEG_MAXR + 8u;
     // the whole head of the control block (parameters + round-0 state + tickets) in one copy
-    hh->st.V = (u32)((size_t)w * h); hh->st.E = 0; hh->st.round = 0; hh->st.phase = PH_PRED; hh->st.levels = 0; hh->st.map_off = 0; hh->st.P = 0; hh->st.cap = 0;
+    hh->st.V = (u32)((size_t)w * h); hh->st.E = 0; hh->st.round = 0; hh->st.phase = PH_PRED; hh->st.levels = 0; hh->st.map_off = 0; hh->st.P = 0; hh->st.pad = 0;
     hh->Vnext = hh->st.V; hh->Enext = 0; hh->error = DERR_NONE; hh->ticketC = 0; hh->ticketE = 0; hh->doneE = 0;
     memset(hh->Eacc, 0, sizeof(hh->Eacc));
     CK(cudaMemcpyAsync(ctx->d_ctl, hh, sizeof(GsegHead), cudaMemcpyHostToDevice, ctx->stream));
@@ -590,7 +599,7 @@ static int level_to_round(const gseg_ctx *ctx, int level, int *round) {
     return GSEG_OK;
 }
 
-extern "C" int gseg_labels(gseg_ctx *ctx, int level, int32_t *out, int mem_kind) {
+extern "C" int gseg_labels_async(gseg_ctx *ctx, int level, int32_t *out, int mem_kind) {
     if (!ctx || !out) return GSEG_E_ARG;
     if (!ctx->valid) return GSEG_E_STATE;
     int round;
@@ -604,8 +613,20 @@ extern "C" int gseg_labels(gseg_ctx *ctx, int level, int32_t *out, int mem_kind)
     CK(cudaGetLastError());
     if (mem_kind != GSEG_MEM_DEVICE)
         CK(cudaMemcpyAsync(out, dst, V * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+    return GSEG_OK;
+}
+
+extern "C" int gseg_sync(gseg_ctx *ctx) {
+    if (!ctx) return GSEG_E_ARG;
+    CK(cudaSetDevice(ctx->device));
     CK(cudaStreamSynchronize(ctx->stream));
     return GSEG_OK;
+}
+
+extern "C" int gseg_labels(gseg_ctx *ctx, int level, int32_t *out, int mem_kind) {
+    int rc = gseg_labels_async(ctx, level, out, mem_kind);
+    if (rc) return rc;
+    return gseg_sync(ctx);
 }
 
 extern "C" int gseg_labels_all(gseg_ctx *ctx, int32_t *out, int max_levels, int mem_kind) {
@@ -687,6 +708,7 @@ extern "C" int gseg_stats(const gseg_ctx *ctx, gseg_round_stat *out, int cap) {
         const GsegCtl *hc = ctx->h_ctl;
         const bool tail = hc->stTail[i] != 0;
         out[i].in_tail = tail ? 1 : 0;
+        out[i].n_pages = (int32_t)hc->stPages[i]; out[i].reserved = 0;
         out[i].us_end = (float)((double)(hc->t_end[i] - hc->t_start) * 1e-3);
         out[i].us_S = tail ? (float)((double)(hc->t_S[i] - hc->t_begin[i]) * 1e-3) : 0.f;
         out[i].us_R = tail ? (float)((double)(hc->t_R[i] - hc->t_S[i]) * 1e-3) : 0.f;

@@ -39,7 +39,7 @@ struct RoundState { // 8 x u32, read field by field by load_state()
     u32 round, phase, levels;
     u32 map_off;   // arena offset of this round's old->new supervertex map
     u32 P;         // pages of the current edge list
-    u32 cap;       // total slot capacity of those pages (sum of the page capacities)
+    u32 pad;       // (keeps the struct at 8 words)
 };
 
 // Device-resident control block: all round-to-round state lives here, so a whole run needs no host
@@ -224,7 +224,7 @@ __device__ __forceinline__ u64 make_key(u32 wbits, u32 idx) { return ((u64)wbits
 // `pos` MUST increase with the lane index (it is the edge's position in the output list), so among
 // equal weights the lower lane already holds the minimum.  All 32 lanes must call.
 template <bool FILTER>
-__device__ __forceinline__ void warp_run_min(u64 *best, u32 id, u32 kb, u32 pos, bool act) {
+__device__ __forceinline__ void warp_run_min(u64 *best, u32 id, u32 kb, u32 pos, bool act, u32 cur_hi) {
     const int lane = threadIdx.x & 31;
     const u32 pid = __shfl_up_sync(0xFFFFFFFFu, id, 1);
     const u32 actm = __ballot_sync(0xFFFFFFFFu, act);
@@ -244,11 +244,7 @@ __device__ __forceinline__ void warp_run_min(u64 *best, u32 id, u32 kb, u32 pos,
         const u64 key = make_key(kb, pos);
         // FILTER (components with many edges each): the running minimum only ever decreases, so a key that
         // is not below the value read now can never win; skipping it spares the L2 a same-address atomic
-#ifndef GSEG_EXP_NO_ATOMIC
         if (!FILTER || key < ld_relaxed_u64(best + id)) atomicMin(best + id, key);
-#else
-        if (key == 12345ull) best[id] = key;
-#endif
     }
 }
 

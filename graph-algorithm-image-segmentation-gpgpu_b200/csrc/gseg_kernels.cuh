@@ -384,7 +384,7 @@ __device__ __forceinline__ bool in_tail(const GsegCtl *ctl, const RoundState &st
 
 // End-of-round bookkeeping: statistics, phase machine, arena accounting.  Every thread can run it
 // redundantly on its private copy of the state; `writer` alone records it in the control block.
-__device__ __forceinline__ void advance_state(GsegCtl *ctl, RoundState &st, u32 Vn, u32 En, bool repack, bool writer,
+__device__ __forceinline__ void advance_state(GsegCtl *ctl, RoundState &st, u32 Vn, u32 En, u32 G, bool writer,
                                               u32 tail_flag = 0u) {
     const u32 r = st.round, V = st.V, merged = V - Vn;
     const int variant = ctl->p.variant;
@@ -408,7 +408,7 @@ __device__ __forceinline__ void advance_state(GsegCtl *ctl, RoundState &st, u32 
         ctl->t_end[r] = globaltimer_ns();
         if (arena_err) ctl->error = DERR_ARENA;
     }
-    if (repack) { st.P = (st.P + 3u) / 4u; st.cap = st.E; } // re-pack round: 4 pages -> 1, capacity = the edges that entered it
+    st.P = (st.P + G - 1u) / G; // the edge phase merged G pages into one
     st.round = r + 1; st.levels = levels; st.V = Vn; st.E = En; st.phase = phase; st.map_off = next_off;
     if (writer) ctl->st = st;
 }
@@ -417,13 +417,13 @@ __device__ __forceinline__ RoundState load_state(const GsegCtl *ctl) {
     RoundState st;
     const u32 *p = reinterpret_cast<const u32 *>(&ctl->st);
     st.V = ld_relaxed_u32(p + 0); st.E = ld_relaxed_u32(p + 1); st.round = ld_relaxed_u32(p + 2); st.phase = ld_relaxed_u32(p + 3);
-    st.levels = ld_relaxed_u32(p + 4); st.map_off = ld_relaxed_u32(p + 5); st.P = ld_relaxed_u32(p + 6); st.cap = ld_relaxed_u32(p + 7);
+    st.levels = ld_relaxed_u32(p + 4); st.map_off = ld_relaxed_u32(p + 5); st.P = ld_relaxed_u32(p + 6); st.pad = 0u;
     return st;
 }
 
 // Grid-wide kernels: the last block to finish the edge phase advances the round state.  `esum` = this
 // block's count of emitted edges (added to the round's total first).
-__device__ __forceinline__ void last_block_advance(GsegCtl *ctl, const RoundState &st, bool repack) {
+__device__ __forceinline__ void last_block_advance(GsegCtl *ctl, const RoundState &st, u32 G) {
     __syncthreads();
     if (threadIdx.x == 0) {
         __threadfence();
@@ -431,17 +431,24 @@ __device__ __forceinline__ void last_block_advance(GsegCtl *ctl, const RoundStat
             __threadfence();
             ctl->doneE = 0;
             RoundState s2 = st;
-            advance_state(ctl, s2, ld_relaxed_u32(&ctl->Vnext), ld_relaxed_u32(&ctl->Eacc[st.round]), repack, true);
+            advance_state(ctl, s2, ld_relaxed_u32(&ctl->Vnext), ld_relaxed_u32(&ctl->Eacc[st.round]), G, true);
         }
     }
 }
 
-// Whether this round's edge phase re-packs the list: when the pages are on average less than a quarter
-// full.  A re-pack round merges every 4 consecutive pages into one and writes the new pages back to
-// back at the offsets of an exclusive scan of the INPUT page counts (known before the round starts, so
-// the scan is a tiny separate step, not a look-back inside the hot kernel).
-__device__ __forceinline__ bool want_repack(const RoundState &st) {
-    return st.P >= 4u && 4ull * st.E < (unsigned long long)st.cap;
+// Pages of the edge list merged into one by this round's edge phase.  Pages start full-ish and lose
+// ~45 % of their edges per round; whenever the average page holds fewer than 128 edges the round merges
+// G = 2, 4, 8 or 16 consecutive pages into one (so that a merged page receives <= ~256 edges and P keeps
+// tracking E / ~150).  The merged pages are written back to back at the offsets of an exclusive scan of
+// the INPUT page counts (known before the round starts, so the scan is a tiny separate step, not a
+// look-back inside the hot kernel).
+__device__ __forceinline__ u32 group_size(const RoundState &st) {
+    if (st.P < 2u) return 1u;
+    const u32 avg = st.E / st.P; // edges per page entering the round
+    if (avg >= 128u) return 1u;
+    u32 G = 2u;
+    while (G < 16u && (unsigned long long)(2u * G) * avg <= GSEG_PAGE) G *= 2u;
+    return G;
 }
 
 // Exclusive scan of the page counts by ONE block (any block size that is a multiple of 32, <= 1024).
@@ -528,15 +535,16 @@ __device__ __forceinline__ void phase_R(const GsegCtl *ctl, const GsegBufs &B, c
 // order, so position is the same tie-break as the edge index).
 // ------------------------------------------------------------------------------------------------
 template <bool SP, bool FILTER>
-__device__ __forceinline__ void emit_row(const GsegBufs &B, int nxt, u32 pos, bool act, u32 a, u32 b, u32 wv) {
+__device__ __forceinline__ void emit_row(const GsegBufs &B, int nxt, u32 pos, bool act, u32 a, u32 b, u32 wv,
+                                         u32 fa = 0xFFFFFFFFu, u32 fb = 0xFFFFFFFFu) {
     u32 kb = wv;
     if (act) {
         B.eab[nxt][pos] = make_uint2(a, b);
         B.ew[nxt][pos] = wv;
         if (SP) kb = __float_as_uint(__fmul_rn(__uint_as_float(wv), mean_dist_g(B.csum[nxt], B.attr[nxt], a, b)));
     }
-    warp_run_min<FILTER>(B.best[nxt], a, kb, pos, act);
-    warp_run_min<FILTER>(B.best[nxt], b, kb, pos, act);
+    warp_run_min<FILTER>(B.best[nxt], a, kb, pos, act, fa);
+    warp_run_min<FILTER>(B.best[nxt], b, kb, pos, act, fb);
 }
 
 // a10 (round 0): grid edges -> paged list of inter-component edges, in edge-index order
@@ -604,8 +612,8 @@ __global__ void __launch_bounds__(NT) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
     }
     if (lane == 0 && esum) atomicAdd(&ctl->Eacc[0], esum);
     RoundState s0 = st;
-    s0.P = ntiles; s0.cap = ntiles * GSEG_PAGE;
-    last_block_advance(ctl, s0, false);
+    s0.P = ntiles;
+    last_block_advance(ctl, s0, 1u);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -709,8 +717,9 @@ __device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const R
 // ------------------------------------------------------------------------------------------------
 // a10 (rounds >= 1): relabel edge ends through this round's map, drop self-loops, page-local stable
 // compaction (see k_r0_edges), fused with next round's per-component minimum.  One warp per output
-// page: normally page t -> page t in place; in a re-pack round pages 4g..4g+3 -> page g at
-// pscan[4g].  No tickets, no look-back, no barriers.
+// page = G consecutive input pages read as one virtual page (lanes 0..G-1 hold the counts and offsets
+// of the G pages, a 4-step shuffle search maps a virtual slot to its page).  G = 1: page t -> page t in
+// place; G > 1: the output page g starts at pscan[G g].  No tickets, no look-back, no barriers.
 // ------------------------------------------------------------------------------------------------
 template <bool SP>
 __device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, u32 Vnext) {
@@ -724,51 +733,74 @@ __device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const R
     const u32 *pc = B.pcnt[cur], *po = B.poff[cur];
     const u32 *map = B.arena + st.map_off;
     const bool filter = (E >> ctl->p.filter_shift) > Vnext; // many edge ends per surviving component
-    const bool repack = want_repack(st);
-    const u32 G = repack ? 4u : 1u, ngroups = repack ? (P + 3u) / 4u : P;
+    const u32 G = group_size(st), ngroups = (P + G - 1u) / G;
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ticketC = 0;
     const u32 nwarp = blockDim.x >> 5, nw = gridDim.x * nwarp;
     u32 esum = 0;
     for (u32 g = blockIdx.x * nwarp + (threadIdx.x >> 5); g < ngroups; g += nw) {
-        const u32 out_base = repack ? __ldcg(B.pscan + 4u * g) : __ldcg(po + g);
+        u32 mycnt = 0u, myoff = 0u;
+        if ((u32)lane < G && G * g + lane < P) { mycnt = __ldcg(pc + G * g + lane); myoff = __ldcg(po + G * g + lane); }
+        const u32 incl = warp_incl_scan(mycnt, lane);
+        const u32 excl = incl - mycnt, cnt = __shfl_sync(0xFFFFFFFFu, incl, 31);
+        const u32 out_base = G > 1u ? __ldcg(B.pscan + G * g) : __shfl_sync(0xFFFFFFFFu, myoff, 0);
         u32 written = 0;
-        for (u32 k = 0; k < G; ++k) {
-            const u32 page = G * g + k;
-            if (page >= P) break;
-            const u32 cnt = __ldcg(pc + page), in_base = __ldcg(po + page);
-            for (u32 c0 = 0; c0 < cnt; c0 += GSEG_PAGE) { // pages merged by a re-pack can exceed one 8-row tile
-                const u32 c = cnt - c0, base = in_base + c0 + lane;
-                u32 a[ROWS], b[ROWS], wv[ROWS], m[ROWS];
+        for (u32 c0 = 0; c0 < cnt; c0 += GSEG_PAGE) { // a virtual page can exceed one 8-row tile
+            u32 a[ROWS], b[ROWS], wv[ROWS], m[ROWS];
 #pragma unroll
-                for (int j = 0; j < ROWS; ++j) {
-                    uint2 ab = make_uint2(0u, 0u);
-                    wv[j] = 0u;
-                    if (32u * j + lane < c) { ab = __ldcg(eab + base + 32u * j); wv[j] = __ldcg(ew + base + 32u * j); }
-                    a[j] = ab.x; b[j] = ab.y;
-                }
-                u32 total = 0;
+            for (int j = 0; j < ROWS; ++j) {
+                const u32 i = c0 + 32u * j + lane;
+                u32 k = 0u; // input page of virtual slot i: the last page whose first slot is <= i
+                if (G > 1u) {
 #pragma unroll
-                for (int j = 0; j < ROWS; ++j) {
-                    bool keep = false;
-                    if (32u * j + lane < c) {
-                        a[j] = __ldcg(map + a[j]); b[j] = __ldcg(map + b[j]);
-                        keep = a[j] != b[j];
+                    for (u32 step = 8u; step; step >>= 1) {
+                        const u32 e = __shfl_sync(0xFFFFFFFFu, excl, (int)(k + step));
+                        if (k + step < G && e <= i) k += step;
                     }
-                    m[j] = __ballot_sync(0xFFFFFFFFu, keep);
-                    total += __popc(m[j]);
                 }
-                u32 rowoff = out_base + written;
+                const u32 src = __shfl_sync(0xFFFFFFFFu, myoff, (int)k) + (i - __shfl_sync(0xFFFFFFFFu, excl, (int)k));
+                uint2 ab = make_uint2(0u, 0u);
+                wv[j] = 0u;
+                if (i < cnt) { ab = __ldcg(eab + src); wv[j] = __ldcg(ew + src); }
+                a[j] = ab.x; b[j] = ab.y;
+            }
+            u32 total = 0;
+#pragma unroll
+            for (int j = 0; j < ROWS; ++j) {
+                bool keep = false;
+                if (c0 + 32u * j + lane < cnt) {
+                    a[j] = __ldcg(map + a[j]); b[j] = __ldcg(map + b[j]);
+                    keep = a[j] != b[j];
+                }
+                m[j] = __ballot_sync(0xFFFFFFFFu, keep);
+                total += __popc(m[j]);
+            }
+            u32 rowoff = out_base + written;
+            if (filter) {
+                // weights of the current minima of both ends, for all rows at once (one round trip)
+                u32 fa[ROWS], fb[ROWS];
+                const u32 *bhi = reinterpret_cast<const u32 *>(B.best[nxt]) + 1; // high word = weight bits
+#pragma unroll
+                for (int j = 0; j < ROWS; ++j) {
+                    fa[j] = fb[j] = 0xFFFFFFFFu;
+                    if ((m[j] >> lane) & 1u) { fa[j] = ld_relaxed_u32(bhi + 2 * (size_t)a[j]); fb[j] = ld_relaxed_u32(bhi + 2 * (size_t)b[j]); }
+                }
 #pragma unroll
                 for (int j = 0; j < ROWS; ++j) {
                     if (m[j] == 0u) continue; // warp-uniform
                     const bool act = (m[j] >> lane) & 1u;
-                    const u32 pos = rowoff + __popc(m[j] & lt);
-                    if (filter) emit_row<SP, true>(B, nxt, pos, act, a[j], b[j], wv[j]);
-                    else emit_row<SP, false>(B, nxt, pos, act, a[j], b[j], wv[j]);
+                    emit_row<SP, true>(B, nxt, rowoff + __popc(m[j] & lt), act, a[j], b[j], wv[j], fa[j], fb[j]);
                     rowoff += __popc(m[j]);
                 }
-                written += total;
+            } else {
+#pragma unroll
+                for (int j = 0; j < ROWS; ++j) {
+                    if (m[j] == 0u) continue; // warp-uniform
+                    const bool act = (m[j] >> lane) & 1u;
+                    emit_row<SP, false>(B, nxt, rowoff + __popc(m[j] & lt), act, a[j], b[j], wv[j]);
+                    rowoff += __popc(m[j]);
+                }
             }
+            written += total;
         }
         if (lane == 0) { B.pcnt[nxt][g] = written; B.poff[nxt][g] = out_base; }
         esum += written;
@@ -785,12 +817,30 @@ __global__ void __launch_bounds__(NT) k_relabel(const GsegCtl *ctl, GsegBufs B) 
     if (st.phase == PH_DONE || in_tail(ctl, st)) return;
     phase_R<NT, R0, SP>(ctl, B, st);
 }
-// Re-pack rounds only: the scan of the page counts the edge phase will place its output by.
-__global__ void __launch_bounds__(1024) k_page_scan(const GsegCtl *ctl, GsegBufs B) {
-    __shared__ u32 s[34];
+// Merging rounds only: the exclusive scan of the page counts the edge phase places its output by.
+// Blocks take chunks of 1024 counts by ticket; chunk prefixes come from a block-granular look-back.
+__global__ void __launch_bounds__(1024) k_page_scan(GsegCtl *ctl, GsegBufs B) {
+    __shared__ u32 s[68];
     const RoundState st = ctl->st;
-    if (st.phase == PH_DONE || in_tail(ctl, st) || !want_repack(st)) return;
-    block_scan_pages(B.pcnt[st.round & 1], st.P, B.pscan, s);
+    if (st.phase == PH_DONE || in_tail(ctl, st) || group_size(st) == 1u) return;
+    const u32 P = st.P, nchunks = (P + 1023u) / 1024u;
+    const u32 tag = ctl->p.epoch_base + st.round * 2u + 2u;
+    const u32 *pc = B.pcnt[st.round & 1];
+    const int lane = threadIdx.x & 31;
+    for (;;) {
+        if (threadIdx.x == 0) s[67] = atomicAdd(&ctl->ticketE, 1u);
+        __syncthreads();
+        const u32 chunk = s[67];
+        if (chunk >= nchunks) break;
+        const u32 i = chunk * 1024u + threadIdx.x;
+        const u32 v = i < P ? __ldcg(pc + i) : 0u;
+        const u32 inc = warp_incl_scan(v, lane);
+        const u32 wtot = __shfl_sync(0xFFFFFFFFu, inc, 31);
+        u32 bend;
+        const u32 wpre = block_ordered_offset(wtot, chunk, tag, B.statusE, &ctl->error, s, &bend);
+        if (i < P) B.pscan[i] = wpre + inc - v;
+        __syncthreads();
+    }
 }
 template <bool SP>
 __global__ void __launch_bounds__(NT) k_succ_scan(GsegCtl *ctl, GsegBufs B) {
@@ -804,7 +854,7 @@ __global__ void __launch_bounds__(NT) k_edges(GsegCtl *ctl, GsegBufs B) {
     const RoundState st = ctl->st;
     if (st.phase == PH_DONE || in_tail(ctl, st)) return;
     phase_E<SP>(ctl, B, st, ctl->Vnext);
-    last_block_advance(ctl, st, want_repack(st));
+    last_block_advance(ctl, st, group_size(st));
 }
 
 // ---- tail schedule: every small round inside one launch of a single thread-block cluster -----------
@@ -821,8 +871,8 @@ __global__ void __launch_bounds__(NTT, 1) k_tail(GsegCtl *ctl, GsegBufs B) {
     cl.sync(); // everyone holds the entry state before the writer may replace it
     while (st.phase != PH_DONE && in_tail(ctl, st)) {
         if (writer) ctl->t_begin[st.round] = globaltimer_ns();
-        const bool repack = want_repack(st);
-        if (repack && blockIdx.x == gridDim.x - 1) block_scan_pages(B.pcnt[st.round & 1], st.P, B.pscan, sh);
+        const u32 G = group_size(st);
+        if (G > 1u && blockIdx.x == gridDim.x - 1) block_scan_pages(B.pcnt[st.round & 1], st.P, B.pscan, sh);
         phase_S<SP>(ctl, B, st, sh);
         __threadfence();
         cl.sync();
@@ -838,7 +888,7 @@ __global__ void __launch_bounds__(NTT, 1) k_tail(GsegCtl *ctl, GsegBufs B) {
         // One thread advances the round state and publishes it; everybody re-reads it after a fourth
         // barrier.  (Every thread advancing a private copy saves the barrier, but then a thousand copies
         // of the phase machine have to stay bit-identical for the barriers to match up.)
-        if (writer) advance_state(ctl, st, Vn, ld_relaxed_u32(&ctl->Eacc[st.round]), repack, true, 1u);
+        if (writer) advance_state(ctl, st, Vn, ld_relaxed_u32(&ctl->Eacc[st.round]), G, true, 1u);
         __threadfence();
         cl.sync();
         st = load_state(ctl);

@@ -75,6 +75,8 @@ typedef struct gseg_round_stat {
     int32_t in_tail;      /* 1 when the round ran inside the single-cluster tail kernel */
     float us_end;         /* device clock at the end of the round, microseconds since round 0's graph kernel started */
     float us_S, us_R, us_E; /* tail rounds: duration of the choose/scan, flatten and edge phases (else 0) */
+    int32_t n_pages;      /* pages of the edge list entering the round */
+    int32_t reserved;
 } gseg_round_stat;
 
 typedef struct gseg_ctx gseg_ctx;
@@ -95,6 +97,10 @@ int gseg_set_stream(gseg_ctx *ctx, void *cuda_stream);
  * and max_components components runs inside the single-cluster tail kernel instead of grid-wide
  * kernels.  (0, 0) disables the tail.  Defaults: 262144 edges, 65536 components. */
 int gseg_set_tail(gseg_ctx *ctx, uint32_t max_edges, uint32_t max_components);
+
+/* Scheduling knob (no effect on results): resident blocks per SM the grid-wide kernels are sized for
+ * (1..8, default 4).  With several contexts in flight per GPU, 2 leaves room for their kernels to overlap. */
+int gseg_set_blocks_per_sm(gseg_ctx *ctx, int blocks);
 
 /* Replaces: L3 pre-filter + L2 graph creation + L1 segmentation core of one reference executable
  * (Report p2 Fig.1; p3 s3.2.1; p2-3 s3.1 steps 1-9; p3-4 s3.2.2; p4 s3.2.4).
@@ -118,6 +124,11 @@ int gseg_num_components(const gseg_ctx *ctx, int level);
  * through the stored supervertex ids (Report p4 s3.2.3).  out: w*h int32, row-major, dense ids in
  * [0, gseg_num_components(level)).  level -1 = last level / the FELZ partition. */
 int gseg_labels(gseg_ctx *ctx, int level, int32_t *out, int mem_kind);
+/* Asynchronous form of gseg_labels: enqueues the materialisation (and the copy to pinned host memory) on
+ * the context's stream and returns; gseg_sync (or any later synchronous call) completes it. */
+int gseg_labels_async(gseg_ctx *ctx, int level, int32_t *out, int mem_kind);
+int gseg_sync(gseg_ctx *ctx);
+
 /* All levels 0..n-1 in one pass (level l at out + l*w*h); n = min(max_levels, gseg_num_levels). */
 int gseg_labels_all(gseg_ctx *ctx, int32_t *out, int max_levels, int mem_kind);
 

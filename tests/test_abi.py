@@ -30,7 +30,7 @@ def test_version_and_strerror(gseg):
 
 def test_struct_layout_matches_header(gseg):
     assert C.sizeof(gseg.Params) == 32
-    assert C.sizeof(gseg.RoundStat) == 48
+    assert C.sizeof(gseg.RoundStat) == 56
 
 
 def test_no_gpu_fails_loudly(gseg):

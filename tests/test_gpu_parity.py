@@ -114,6 +114,29 @@ def test_schedules_agree(gseg, oracle, tail):
         s.close()
 
 
+def test_context_pool_async_labels(gseg, oracle):
+    """batch.ContextPool: several contexts in flight, asynchronous label copy-out into pinned host memory."""
+    import importlib
+    import torch
+    batch = importlib.import_module(gseg.__name__ + ".batch")
+    pool = batch.ContextPool(gseg, 200, 150, contexts=4)
+    try:
+        imgs = [torch.from_numpy(oracle.synth(200, 150, 300 + i)).pin_memory() for i in range(10)]
+        out = torch.empty((10, 150, 200), dtype=torch.int32).pin_memory()
+        ncomp = [0] * 10
+
+        def got(i, sg):
+            ncomp[i] = sg.num_components()
+            sg.labels(out=out[i], wait=False)
+
+        assert pool.run(imgs, got, sigma=0.8, k=300.0, min_size=20, connectivity=8, variant=gseg.FELZ) == 10
+        for i in range(10):
+            ref = oracle.pipeline(imgs[i].numpy(), 0.8, 300.0, 20, 8, oracle.FELZ)
+            assert ncomp[i] == ref["n"] and same_partition(oracle, out[i].numpy(), ref["labels"])
+    finally:
+        pool.close()
+
+
 def test_degenerate_images(gseg, oracle, seg):
     h, w = 45, 67
     ramp = np.zeros((h, w, 3), np.uint8)

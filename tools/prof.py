@@ -46,8 +46,8 @@ for flags, name in [(1, "host-driven"), (0, "persistent")]:
 P("rounds:", seg.stats())
 P("device timeline of the device-driven run (us since round-0 graph kernel start):")
 prev = 0.0
-for (r, tail, end, us, ur, ue) in seg.timeline():
-    P("  round %2d %s end %8.1f  dur %7.1f   S %6.1f R %6.1f E %6.1f" % (r, "tail" if tail else "grid", end, end - prev, us, ur, ue))
+for (r, tail, end, us, ur, ue, npg) in seg.timeline():
+    P("  round %2d %s end %8.1f  dur %7.1f   S %6.1f R %6.1f E %6.1f   pages %6d" % (r, "tail" if tail else "grid", end, end - prev, us, ur, ue, npg))
     prev = end
 P("components:", seg.num_components(), "levels:", seg.num_levels(), "launches so far:", seg.launch_count())
 
