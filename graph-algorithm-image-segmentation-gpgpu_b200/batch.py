@@ -38,13 +38,18 @@ class ContextPool:
         is ordered before the context's next image and completed before run() returns)."""
         S = len(self.segs)
         n = len(images)
-        for base in range(0, n, S):
-            m = min(S, n - base)
-            for j in range(m):
-                self.segs[j].segment(images[base + j], wait=False, **params)
-            for j in range(m):
+        pending = [-1] * S  # image index in flight on each context
+        # rolling pipeline: a context gets its next image as soon as its previous one is complete, so S - 1
+        # images stay in flight while the host waits for the oldest
+        for i in range(n + S):
+            j = i % S
+            if pending[j] >= 0:
                 self.segs[j].wait()
-                on_result(base + j, self.segs[j])
+                on_result(pending[j], self.segs[j])
+                pending[j] = -1
+            if i < n:
+                self.segs[j].segment(images[i], wait=False, **params)
+                pending[j] = i
         for s in self.segs:
             s.sync()
         return n
