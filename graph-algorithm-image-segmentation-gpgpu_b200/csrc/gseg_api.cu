@@ -21,7 +21,7 @@
 struct GsegHead {
     GsegRunParams p;
     RoundState st;
-    u32 Vnext, Enext, error, ticketC, ticketE, doneE, Eacc[GSEG_MAXR + 1];
+    u32 Vnext, error, ticketC, ticketE, doneE, Eacc[GSEG_MAXR + 1];
 };
 static_assert(offsetof(GsegCtl, Eacc) == offsetof(GsegHead, Eacc), "GsegHead must mirror the head of GsegCtl");
 
@@ -42,8 +42,7 @@ struct gseg_ctx {
     u64 *d_statusC, *d_statusE;
     size_t ntilesC, ntilesE;
     int *d_labels[2];
-    GsegCtl *d_ctl, *h_ctl, *h_peek;
-    cudaStream_t peek_stream;
+    GsegCtl *d_ctl, *h_ctl;
     GsegHead *h_head; // pinned image of the host-initialised head of the control block
     int num_sms, occ_mult;
     u32 filter_shift;
@@ -156,8 +155,6 @@ extern "C" int gseg_create(gseg_ctx **out, int device, int max_w, int max_h) {
     if (e == cudaSuccess) e = cudaMemset(ctx->d_ctl, 0, sizeof(GsegCtl));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_ctl, sizeof(GsegCtl));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_head, sizeof(GsegHead));
-    if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_peek, sizeof(GsegCtl));
-    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->peek_stream, cudaStreamNonBlocking);
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
     if (e == cudaSuccess) {
         // tail kernel: one thread-block cluster, 16 CTAs when the device can co-schedule that many
@@ -214,8 +211,6 @@ extern "C" void gseg_destroy(gseg_ctx *ctx) {
     sort_scratch_free(&ctx->sort);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
     if (ctx->h_head) cudaFreeHost(ctx->h_head);
-    if (ctx->h_peek) cudaFreeHost(ctx->h_peek);
-    if (ctx->peek_stream) cudaStreamDestroy(ctx->peek_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     free(ctx);
 }
@@ -224,24 +219,6 @@ extern "C" int gseg_set_stream(gseg_ctx *ctx, void *s) {
     if (!ctx) return GSEG_E_ARG;
     if (ctx->pending) return GSEG_E_STATE;
     ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
-    return GSEG_OK;
-}
-
-// Debug aid: copy device state on a separate stream while a run is (possibly) stuck.
-// out: st (8 words), Vnext, Enext, error, ticketC, ticketE, doneE, Eacc[0..9], then 32 words each of
-// pscan, pcnt[0], pcnt[1], poff[0], poff[1], dbgw.
-extern "C" int gseg_debug_peek(gseg_ctx *ctx, unsigned int *out_words) {
-    if (!ctx) return GSEG_E_ARG;
-    cudaSetDevice(ctx->device);
-    GsegCtl *tmp = ctx->h_peek;
-    cudaMemcpyAsync(tmp, ctx->d_ctl, sizeof(GsegCtl), cudaMemcpyDeviceToHost, ctx->peek_stream);
-    cudaStreamSynchronize(ctx->peek_stream);
-    const unsigned int *w = (const unsigned int *)&tmp->st;
-    for (int i = 0; i < 24; ++i) out_words[i] = w[i];
-    u32 *srcs[5] = {ctx->d_pscan, ctx->d_pcnt[0], ctx->d_pcnt[1], ctx->d_poff[0], ctx->d_poff[1]};
-    for (int k = 0; k < 5; ++k) cudaMemcpyAsync(out_words + 24 + 32 * k, srcs[k], 32 * sizeof(u32), cudaMemcpyDeviceToHost, ctx->peek_stream);
-    cudaStreamSynchronize(ctx->peek_stream);
-    for (int i = 0; i < 64; ++i) out_words[24 + 160 + i] = tmp->dbgw[i];
     return GSEG_OK;
 }
 
@@ -499,14 +476,13 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
     hp->epoch_base = ctx->epoch_next;
     hp->mask_len = len;
     hp->filter_shift = ctx->filter_shift;
-    hp->dbg_flags = getenv("GSEG_DBG_FLAGS") ? (u32)atoi(getenv("GSEG_DBG_FLAGS")) : 0u;
     hp->tail_E = ctx->run_tail_E = host_loop ? 0u : ctx->tail_E;
     hp->tail_V = ctx->run_tail_V = host_loop ? 0u : ctx->tail_V;
     hp->tail_P = ctx->tail_P;
     ctx->epoch_next += 2u * GSEG_MAXR + 8u;
     // the whole head of the control block (parameters + round-0 state + tickets) in one copy
     hh->st.V = (u32)((size_t)w * h); hh->st.E = 0; hh->st.round = 0; hh->st.phase = PH_PRED; hh->st.levels = 0; hh->st.map_off = 0; hh->st.P = 0; hh->st.pad = 0;
-    hh->Vnext = hh->st.V; hh->Enext = 0; hh->error = DERR_NONE; hh->ticketC = 0; hh->ticketE = 0; hh->doneE = 0;
+    hh->Vnext = hh->st.V; hh->error = DERR_NONE; hh->ticketC = 0; hh->ticketE = 0; hh->doneE = 0;
     memset(hh->Eacc, 0, sizeof(hh->Eacc));
     CK(cudaMemcpyAsync(ctx->d_ctl, hh, sizeof(GsegHead), cudaMemcpyHostToDevice, ctx->stream));
 

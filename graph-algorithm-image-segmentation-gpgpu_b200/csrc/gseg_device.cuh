@@ -26,7 +26,6 @@ struct GsegRunParams {
     u32 arena_cap;  // capacity of the supervertex-map arena in u32 entries
     u32 epoch_base; // first look-back tag of this run (monotonic across runs)
     int mask_len;
-    u32 dbg_flags;      // timing ablations (GSEG_DBG_FLAGS): 1 no look-back, 2 static tiles, 4 no emit, 8 no run-min
     u32 filter_shift;   // read-before-atomic filter when (E >> filter_shift) > surviving components
     u32 tail_E, tail_V, tail_P; // a round with E <= tail_E, V <= tail_V and P <= tail_P runs inside the single-cluster tail kernel
     float mask[GSEG_MAXMASK];
@@ -48,7 +47,7 @@ struct RoundState { // 8 x u32, read field by field by load_state()
 struct GsegCtl {
     GsegRunParams p;
     RoundState st;
-    u32 Vnext, Enext; // Vnext: produced by the component scan of the current round (Enext: unused, kept for layout)
+    u32 Vnext;        // produced by the component scan of the current round
     u32 error;
     u32 ticketC, ticketE; // dynamic tile tickets of the two look-back scans
     u32 doneE;            // blocks that finished the edge phase (the last one advances the round state)
@@ -59,7 +58,6 @@ struct GsegCtl {
     u32 stTail[GSEG_MAXR], stPages[GSEG_MAXR]; // 1 when the round ran in the tail kernel; pages of its edge list
     // device timeline (globaltimer, ns): start of the round-0 graph kernel; end of every round; tail rounds
     // also record the ends of their S and R phases and their start
-    u32 dbgw[64]; // debug trace
     u64 t_start, t_end[GSEG_MAXR], t_begin[GSEG_MAXR], t_S[GSEG_MAXR], t_R[GSEG_MAXR];
 };
 

@@ -58,7 +58,8 @@ def test_blur_and_weights_bit_exact(gseg, oracle, seg, w, h, conn):
         check_weights(seg.weights(), oracle.edges(pl, conn)[0])
 
 
-@pytest.mark.parametrize("w,h", [(1, 1), (1, 7), (7, 1), (2, 2), (5, 3), (17, 13), (64, 48), (257, 129), (320, 240)])
+@pytest.mark.parametrize("w,h", [(1, 1), (1, 7), (7, 1), (2, 2), (5, 3), (17, 13), (64, 48), (257, 129), (320, 240),
+                                 (1000, 37), (3, 2000), (513, 511)])
 @pytest.mark.parametrize("conn", [4, 8])
 @pytest.mark.parametrize("flags", [0, 1])
 def test_felz_partition_bit_exact(gseg, oracle, seg, w, h, conn, flags):
@@ -191,7 +192,10 @@ def test_strided_and_device_input(gseg, oracle, seg):
 
 def test_argument_errors(gseg, seg):
     img = np.zeros((8, 8, 3), np.uint8)
-    for kw in [dict(connectivity=6), dict(variant=5), dict(sigma=40.0), dict(max_rounds=-1)]:
+    for bad in (0, 9):
+        with pytest.raises(gseg.GsegError):
+            seg.set_blocks_per_sm(bad)
+    for kw in [dict(connectivity=6), dict(variant=5), dict(sigma=40.0), dict(max_rounds=-1), dict(min_size=-1), dict(k=-1.0)]:
         with pytest.raises(gseg.GsegError):
             seg.segment(img, **kw)
     big = np.zeros((2161, 3840, 3), np.uint8)
