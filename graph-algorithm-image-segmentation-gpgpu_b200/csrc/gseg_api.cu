@@ -575,6 +575,25 @@ static int level_to_round(const gseg_ctx *ctx, int level, int *round) {
     return GSEG_OK;
 }
 
+// Label image of the partition after round `round` into dst (device).  Deep hierarchies go through a
+// composed table of the late (small) rounds so that a pixel chases 3-4 maps instead of one per round.
+static void enqueue_compose(gseg_ctx *ctx, int round, int *dst) {
+    const size_t V = (size_t)ctx->w * ctx->h;
+    const GsegCtl *h = ctx->h_ctl;
+    int first = 1;
+    while (first <= round && h->stV[first] > 65536u) ++first; // first round whose input has few components
+    if (first >= 1 && first <= round && round - first >= 2 && h->stV[first] <= ctx->Vmax) {
+        const u32 n = h->stV[first];
+        u32 *F = ctx->d_wsel; // per-round scratch, free once the run is complete
+        ctx->launches += 2;
+        k_compose_table<<<grid_for(n, NT), NT, 0, ctx->stream>>>(ctx->d_ctl, ctx->d_arena, first, round, n, F);
+        k_compose_px<<<grid_for(V, NT), NT, 0, ctx->stream>>>(ctx->d_ctl, ctx->d_arena, first, F, dst);
+    } else {
+        ++ctx->launches;
+        k_compose<<<grid_for(V, NT), NT, 0, ctx->stream>>>(ctx->d_ctl, ctx->d_arena, round, dst);
+    }
+}
+
 extern "C" int gseg_labels_async(gseg_ctx *ctx, int level, int32_t *out, int mem_kind) {
     if (!ctx || !out) return GSEG_E_ARG;
     if (!ctx->valid) return GSEG_E_STATE;
@@ -584,8 +603,7 @@ extern "C" int gseg_labels_async(gseg_ctx *ctx, int level, int32_t *out, int mem
     CK(cudaSetDevice(ctx->device));
     const size_t V = (size_t)ctx->w * ctx->h;
     int *dst = mem_kind == GSEG_MEM_DEVICE ? out : ctx->d_labels[0];
-    ++ctx->launches;
-    k_compose<<<grid_for(V, NT), NT, 0, ctx->stream>>>(ctx->d_ctl, ctx->d_arena, round, dst);
+    enqueue_compose(ctx, round, dst);
     CK(cudaGetLastError());
     if (mem_kind != GSEG_MEM_DEVICE)
         CK(cudaMemcpyAsync(out, dst, V * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -639,8 +657,7 @@ extern "C" int gseg_colorize(gseg_ctx *ctx, int level, uint64_t seed, uint8_t *o
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     const size_t V = (size_t)ctx->w * ctx->h;
-    ++ctx->launches;
-    k_compose<<<grid_for(V, NT), NT, 0, ctx->stream>>>(ctx->d_ctl, ctx->d_arena, round, ctx->d_labels[0]);
+    enqueue_compose(ctx, round, ctx->d_labels[0]);
     // d_tmp is free after the run; 3V bytes fit easily
     uint8_t *dst = mem_kind == GSEG_MEM_DEVICE ? out : (uint8_t *)ctx->d_tmp;
     ++ctx->launches;

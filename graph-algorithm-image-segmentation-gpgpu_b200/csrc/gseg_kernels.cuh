@@ -907,6 +907,26 @@ __global__ void __launch_bounds__(NT) k_compose(const GsegCtl *__restrict__ ctl,
         out[p] = (int)l;
     }
 }
+// Two-step form for deep hierarchies: the maps of rounds first..last act on few components, so they are
+// composed once into a table F (n = components entering round `first`) ...
+__global__ void __launch_bounds__(NT) k_compose_table(const GsegCtl *__restrict__ ctl, const u32 *__restrict__ arena,
+                                                      int first, int last, u32 n, u32 *__restrict__ F) {
+    for (u32 c = blockIdx.x * NT + threadIdx.x; c < n; c += gridDim.x * NT) {
+        u32 l = c;
+        for (int r = first; r <= last; ++r) l = arena[ctl->map_off[r] + l];
+        F[c] = l;
+    }
+}
+// ... and every pixel chases only the early rounds 0..first-1 and then looks its label up in F.
+__global__ void __launch_bounds__(NT) k_compose_px(const GsegCtl *__restrict__ ctl, const u32 *__restrict__ arena,
+                                                   int first, const u32 *__restrict__ F, int *__restrict__ out) {
+    const u32 V0 = (u32)ctl->p.w * (u32)ctl->p.h;
+    for (u32 p = blockIdx.x * NT + threadIdx.x; p < V0; p += gridDim.x * NT) {
+        u32 l = arena[p];
+        for (int r = 1; r < first; ++r) l = arena[ctl->map_off[r] + l];
+        out[p] = (int)F[l];
+    }
+}
 // one more level from the previous one (all-levels output: V reads + V writes per level)
 __global__ void __launch_bounds__(NT) k_compose_step(const GsegCtl *__restrict__ ctl, const u32 *__restrict__ arena,
                                                      int round, const int *__restrict__ prev, int *__restrict__ out) {
