@@ -561,7 +561,7 @@ __device__ __forceinline__ void emit_row(const GsegBufs &B, int nxt, u32 pos, bo
 // the pages have become sparse (< 1/4 full) does one round re-pack the list densely with the ordered
 // scan; by then the list is small.
 template <int D, bool SP>
-__global__ void __launch_bounds__(NT) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
+__global__ void __launch_bounds__(NT, 4) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
     constexpr int ROWS = GSEG_PAGE / 32;
     const int lane = threadIdx.x & 31;
     const u32 lt = (1u << lane) - 1u;
@@ -850,7 +850,7 @@ __global__ void __launch_bounds__(NT) k_succ_scan(GsegCtl *ctl, GsegBufs B) {
     phase_S<SP>(ctl, B, st, sh);
 }
 template <bool SP>
-__global__ void __launch_bounds__(NT) k_edges(GsegCtl *ctl, GsegBufs B) {
+__global__ void __launch_bounds__(NT, 4) k_edges(GsegCtl *ctl, GsegBufs B) {
     const RoundState st = ctl->st;
     if (st.phase == PH_DONE || in_tail(ctl, st)) return;
     phase_E<SP>(ctl, B, st, ctl->Vnext);
