@@ -86,6 +86,7 @@ def load():
     L.gseg_last_error.restype = C.c_char_p
     L.gseg_last_error.argtypes = [vp]
     L.gseg_create.argtypes = [C.POINTER(vp), i32, i32, i32]
+    L.gseg_create_ex.argtypes = [C.POINTER(vp), i32, i32, i32, i32]
     L.gseg_destroy.argtypes = [vp]
     L.gseg_destroy.restype = None
     L.gseg_set_stream.argtypes = [vp, vp]
@@ -132,10 +133,10 @@ class Segmenter:
     """One gseg context (one GPU, one stream).  Mirrors the reference executables' parameter list:
     image, sigma, k, min_size, connectivity, variant / hierarchy level (BASELINE.json north_star)."""
 
-    def __init__(self, max_w, max_h, device=0):
+    def __init__(self, max_w, max_h, device=0, max_connectivity=8):
         self.L = load()
         self.h = C.c_void_p()
-        rc = self.L.gseg_create(C.byref(self.h), device, max_w, max_h)
+        rc = self.L.gseg_create_ex(C.byref(self.h), device, max_w, max_h, max_connectivity)
         if rc != 0:
             raise GsegError("gseg_create: %s" % self.L.gseg_strerror(rc).decode())
         self.device = device

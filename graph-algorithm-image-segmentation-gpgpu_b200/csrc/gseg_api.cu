@@ -28,6 +28,7 @@ static_assert(offsetof(GsegCtl, Eacc) == offsetof(GsegHead, Eacc), "GsegHead mus
 struct gseg_ctx {
     int device, max_w, max_h;
     size_t Vmax;
+    int Dmax; // directions the context was sized for (2: 4-connected only, 4: 8-connected too)
     cudaStream_t stream, own_stream;
     uint8_t *d_rgb;
     float *d_tmp, *d_planes, *d_G, *d_wgrid;
@@ -105,26 +106,30 @@ template <typename T>
 static cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T)); }
 
 extern "C" int gseg_create(gseg_ctx **out, int device, int max_w, int max_h) {
-    if (!out || max_w < 1 || max_h < 1) return GSEG_E_ARG;
+    return gseg_create_ex(out, device, max_w, max_h, 8);
+}
+
+extern "C" int gseg_create_ex(gseg_ctx **out, int device, int max_w, int max_h, int max_connectivity) {
+    if (!out || max_w < 1 || max_h < 1 || (max_connectivity != 4 && max_connectivity != 8)) return GSEG_E_ARG;
     *out = nullptr;
     const size_t V = (size_t)max_w * (size_t)max_h;
-    if (V * 4 >= 0xFFFFFFFFull) return GSEG_E_SIZE; // 32-bit edge indices
+    const size_t Dmax = max_connectivity == 8 ? 4 : 2;
+    if ((V / GSEG_PAGE + 2) * GSEG_PAGE * Dmax >= 0xFFFFFFFFull) return GSEG_E_SIZE; // 32-bit edge indices and list slots
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || device < 0 || device >= ndev) return GSEG_E_CUDA;
     gseg_ctx *ctx = (gseg_ctx *)calloc(1, sizeof(gseg_ctx));
     if (!ctx) return GSEG_E_ARG;
-    ctx->device = device; ctx->max_w = max_w; ctx->max_h = max_h; ctx->Vmax = V;
+    ctx->device = device; ctx->max_w = max_w; ctx->max_h = max_h; ctx->Vmax = V; ctx->Dmax = (int)Dmax;
     ctx->epoch_next = 1;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     ctx->stream = ctx->own_stream;
     const size_t Vp = V + 64; // slack for vector tails
-    const size_t Eslots = 4 * ((V + GSEG_PAGE - 1) / GSEG_PAGE + 1) * GSEG_PAGE;
+    const size_t Eslots = Dmax * ((V + GSEG_PAGE - 1) / GSEG_PAGE + 1) * GSEG_PAGE;
+    const size_t Pslots = Dmax * (V / GSEG_PAGE + 1) + 8;
     if (e == cudaSuccess) e = dalloc(&ctx->d_rgb, 3 * Vp);
-    if (e == cudaSuccess) e = dalloc(&ctx->d_tmp, 3 * Vp);
     if (e == cudaSuccess) e = dalloc(&ctx->d_planes, 3 * Vp);
-    if (e == cudaSuccess) e = dalloc(&ctx->d_G, Vp);
-    if (e == cudaSuccess) e = dalloc(&ctx->d_wgrid, 4 * Vp);
+    if (e == cudaSuccess) e = dalloc(&ctx->d_wgrid, Dmax * Vp);
     if (e == cudaSuccess) e = dalloc(&ctx->d_wsel, Vp);
     if (e == cudaSuccess) e = dalloc(&ctx->d_succ, Vp);
     if (e == cudaSuccess) e = dalloc(&ctx->d_rank, Vp);
@@ -134,19 +139,20 @@ extern "C" int gseg_create(gseg_ctx **out, int device, int max_w, int max_h) {
         // paged edge list: up to 4 directions x ceil(V / page) pages of GSEG_PAGE slots
         if (e == cudaSuccess) e = dalloc(&ctx->d_eab[i], Eslots);
         if (e == cudaSuccess) e = dalloc(&ctx->d_ew[i], Eslots);
-        if (e == cudaSuccess) e = dalloc(&ctx->d_pcnt[i], 4 * (V / GSEG_PAGE + 1) + 2);
-        if (e == cudaSuccess) e = dalloc(&ctx->d_poff[i], 4 * (V / GSEG_PAGE + 1) + 2);
-        if (e == cudaSuccess) e = dalloc(&ctx->d_labels[i], Vp);
+        if (e == cudaSuccess) e = dalloc(&ctx->d_pcnt[i], Pslots);
+        if (e == cudaSuccess) e = dalloc(&ctx->d_poff[i], Pslots);
     }
-    if (e == cudaSuccess) e = dalloc(&ctx->d_pscan, 4 * (V / GSEG_PAGE + 1) + 8);
-    ctx->arena_cap = 6 * V + 1024;
+    if (e == cudaSuccess) e = dalloc(&ctx->d_pscan, Pslots);
+    // one old->new map per round: V + V1 + V2 + ... ; 6V covers every input up to 2^26 pixels, above that the
+    // arena is 2.5V (a run that needs more ends with GSEG_E_ARENA) so that a 2^30-pixel context fits in HBM
+    ctx->arena_cap = V <= ((size_t)1 << 26) ? 6 * V + 1024 : V * 5 / 2 + 1024;
     if (ctx->arena_cap > 0xFFFFFFF0ull) ctx->arena_cap = 0xFFFFFFF0ull;
     if (e == cudaSuccess) e = dalloc(&ctx->d_arena, ctx->arena_cap);
     // look-back status words: one per tile of the largest tiling that uses each array
     ctx->ntilesC = V / (32 * CPT) + 2;
     const size_t img_tiles = (size_t)((max_w + TW - 1) / TW) * (size_t)((max_h + TH - 1) / TH);
     if (ctx->ntilesC < img_tiles) ctx->ntilesC = img_tiles;
-    ctx->ntilesE = 4 * (V / GSEG_PAGE + 1) + 2; // pages of the edge list
+    ctx->ntilesE = Pslots; // pages of the edge list
     if (e == cudaSuccess) e = dalloc(&ctx->d_statusC, ctx->ntilesC);
     if (e == cudaSuccess) e = dalloc(&ctx->d_statusE, ctx->ntilesE);
     if (e == cudaSuccess) e = cudaMemset(ctx->d_statusC, 0, ctx->ntilesC * sizeof(u64));
@@ -417,6 +423,15 @@ static int finish(gseg_ctx *ctx) {
     return GSEG_OK;
 }
 
+// Buffers only some paths need are allocated on first use: d_tmp (blur with more than 8 taps), d_G
+// (superpixel), d_labels (host copies of label images / colour images), d_csum (superpixel).
+template <typename T>
+static int ensure(gseg_ctx *ctx, T **p, size_t n) {
+    if (*p) return GSEG_OK;
+    CK(dalloc(p, n));
+    return GSEG_OK;
+}
+
 static int ensure_csum(gseg_ctx *ctx) {
     if (ctx->d_csum[0]) return GSEG_OK;
     for (int i = 0; i < 2; ++i) CK(dalloc(&ctx->d_csum[i], 3 * (ctx->Vmax + 64)));
@@ -452,7 +467,13 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
     ctx->valid = false;
     ctx->params = *p;
     ctx->w = w; ctx->h = h; ctx->D = p->connectivity == 8 ? 4 : 2;
-    if (p->variant == GSEG_SUPERPIX) { int rc = ensure_csum(ctx); if (rc) return rc; }
+    if (ctx->D > ctx->Dmax) return fail(ctx, GSEG_E_SIZE, "context was created for 4-connected grids only", cudaSuccess);
+    if (p->variant == GSEG_SUPERPIX) {
+        int rc = ensure_csum(ctx);
+        if (!rc) rc = ensure(ctx, &ctx->d_G, ctx->Vmax + 64);
+        if (rc) return rc;
+    }
+    if (len - 1 > 8 || len - 1 < 1) { int rc = ensure(ctx, &ctx->d_tmp, 3 * (ctx->Vmax + 64)); if (rc) return rc; }
     const uint8_t *src = rgb;
     int dstride = stride;
     if (mem_kind == GSEG_MEM_HOST) {
@@ -602,6 +623,7 @@ extern "C" int gseg_labels_async(gseg_ctx *ctx, int level, int32_t *out, int mem
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     const size_t V = (size_t)ctx->w * ctx->h;
+    if (mem_kind != GSEG_MEM_DEVICE) { rc = ensure(ctx, &ctx->d_labels[0], ctx->Vmax + 64); if (rc) return rc; }
     int *dst = mem_kind == GSEG_MEM_DEVICE ? out : ctx->d_labels[0];
     enqueue_compose(ctx, round, dst);
     CK(cudaGetLastError());
@@ -634,6 +656,8 @@ extern "C" int gseg_labels_all(gseg_ctx *ctx, int32_t *out, int max_levels, int 
         int rc = gseg_labels(ctx, -1, out, mem_kind);
         return rc ? rc : 1;
     }
+    if (mem_kind != GSEG_MEM_DEVICE)
+        for (int i = 0; i < 2; ++i) { int rc = ensure(ctx, &ctx->d_labels[i], ctx->Vmax + 64); if (rc) return rc; }
     const int *prev = nullptr;
     for (int l = 0; l < nl; ++l) {
         int *dst = mem_kind == GSEG_MEM_DEVICE ? out + (size_t)l * V : ctx->d_labels[l & 1];
@@ -657,9 +681,11 @@ extern "C" int gseg_colorize(gseg_ctx *ctx, int level, uint64_t seed, uint8_t *o
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     const size_t V = (size_t)ctx->w * ctx->h;
+    rc = ensure(ctx, &ctx->d_labels[0], ctx->Vmax + 64);
+    if (!rc && mem_kind != GSEG_MEM_DEVICE) rc = ensure(ctx, &ctx->d_labels[1], ctx->Vmax + 64); // 4V bytes >= the 3V of the colour image
+    if (rc) return rc;
     enqueue_compose(ctx, round, ctx->d_labels[0]);
-    // d_tmp is free after the run; 3V bytes fit easily
-    uint8_t *dst = mem_kind == GSEG_MEM_DEVICE ? out : (uint8_t *)ctx->d_tmp;
+    uint8_t *dst = mem_kind == GSEG_MEM_DEVICE ? out : (uint8_t *)ctx->d_labels[1];
     ++ctx->launches;
     k_colorize<<<grid_for(V, NT), NT, 0, ctx->stream>>>(ctx->d_labels[0], (u32)V, seed, dst);
     CK(cudaGetLastError());

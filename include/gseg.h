@@ -88,6 +88,9 @@ const char *gseg_last_error(const gseg_ctx *ctx);
 /* Replaces: per-branch main() device/scratch set-up.  Allocates every
  * device buffer for images up to max_w x max_h on CUDA device `device`. */
 int gseg_create(gseg_ctx **out, int device, int max_w, int max_h);
+/* Same with the largest connectivity (4 or 8) the context will be used with: a 4-connected-only context
+ * needs half the edge-list memory (a 32768 x 32768 image fits one B200 that way).  gseg_create = 8. */
+int gseg_create_ex(gseg_ctx **out, int device, int max_w, int max_h, int max_connectivity);
 void gseg_destroy(gseg_ctx *ctx);
 
 /* Run the context's work on a caller-owned CUDA stream (cudaStream_t as void*); NULL = own stream. */

@@ -9,7 +9,7 @@ gseg.build()
 import numpy as np, torch
 w, h, conn, variant, check = (int(x) for x in (sys.argv[1:6] if len(sys.argv) >= 6 else (32768, 4096, 4, 0, 1)))
 t0 = time.perf_counter()
-seg = gseg.Segmenter(w, h)
+seg = gseg.Segmenter(w, h, max_connectivity=conn)
 dimg = torch.empty((h, w, 3), dtype=torch.uint8, device="cuda")
 seg.synth(w, h, 5, out=dimg)
 torch.cuda.synchronize()
