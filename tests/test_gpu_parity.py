@@ -190,6 +190,24 @@ def test_strided_and_device_input(gseg, oracle, seg):
     assert np.array_equal(col[lab == lab[0, 0]], np.broadcast_to(col[0, 0], col[lab == lab[0, 0]].shape))
 
 
+def test_four_connected_only_context(gseg, oracle):
+    """gseg_create_ex(..., 4): half the edge-list memory, 8-connected runs are refused, results unchanged."""
+    s = gseg.Segmenter(300, 200, max_connectivity=4)
+    try:
+        img = oracle.synth(300, 200, 77)
+        for variant in (gseg.FELZ, gseg.HIER, gseg.SUPERPIX):
+            s.segment(img, sigma=0.8, k=300.0, min_size=20, connectivity=4, variant=variant)
+            ref = oracle.pipeline(img, 0.8, 300.0, 20, 4, variant)
+            assert same_partition(oracle, s.labels(), ref["labels"])
+        assert s.colorize().shape == (200, 300, 3)
+        with pytest.raises(gseg.GsegError):
+            s.segment(img, connectivity=8)
+    finally:
+        s.close()
+    with pytest.raises(gseg.GsegError):
+        gseg.Segmenter(16, 16, max_connectivity=6)
+
+
 def test_argument_errors(gseg, seg):
     img = np.zeros((8, 8, 3), np.uint8)
     for bad in (0, 9):
@@ -241,6 +259,28 @@ def test_full_size_configs(gseg, oracle, seg, w, h, conn, variant, seed):
             assert cnt.min() >= 20
     seg.segment(img, sigma=0.8, k=300.0, min_size=20, connectivity=conn, variant=variant, flags=1)
     assert np.array_equal(seg.labels(), lab)
+
+
+def test_adversarial_full_size_inputs(gseg, oracle, seg):
+    """Inputs that stress tie-breaking and long merge chains (constant, noise, 1-pixel checkerboard, stripes,
+    ramps; tools/robust.py runs the same at 1920x1080): every variant must still equal the oracle bit for bit."""
+    w, h = 960, 540
+    rng = np.random.default_rng(1)
+    yy, xx = np.mgrid[0:h, 0:w]
+    imgs = {
+        "constant": np.full((h, w, 3), 128, np.uint8),
+        "noise": rng.integers(0, 256, (h, w, 3), dtype=np.uint8),
+        "checker": np.repeat((((xx + yy) & 1) * 255).astype(np.uint8)[..., None], 3, 2),
+        "stripes": np.repeat((((xx // 7) & 1) * 200).astype(np.uint8)[..., None], 3, 2),
+        "ramp": np.stack([(xx * 255 // (w - 1)), (yy * 255 // (h - 1)), ((xx + yy) % 256)], -1).astype(np.uint8),
+    }
+    for name, img in imgs.items():
+        img = np.ascontiguousarray(img)
+        for conn, variant in [(4, 0), (8, 0), (8, 1), (4, 2)]:
+            seg.segment(img, sigma=0.8, k=300.0, min_size=20, connectivity=conn, variant=variant)
+            ref, n = oracle.segment(img, 0.8, 300.0, 20, conn, variant, max_rounds=48)
+            assert same_partition(oracle, seg.labels(), ref), (name, conn, variant)
+            assert seg.num_components() == n
 
 
 def test_sort_pairs(gseg, seg):
