@@ -221,7 +221,7 @@ __device__ __forceinline__ u64 make_key(u32 wbits, u32 idx) { return ((u64)wbits
 // of boundary between two components) and the number of atomics falls with the run length.
 // `pos` MUST increase with the lane index (it is the edge's position in the output list), so among
 // equal weights the lower lane already holds the minimum.  All 32 lanes must call.
-template <bool FILTER>
+template <bool FILTER, int WINDOW>
 __device__ __forceinline__ void warp_run_min(u64 *best, u32 id, u32 kb, u32 pos, bool act, u32 cur_hi) {
     const int lane = threadIdx.x & 31;
     const u32 pid = __shfl_up_sync(0xFFFFFFFFu, id, 1);
@@ -231,18 +231,28 @@ __device__ __forceinline__ void warp_run_min(u64 *best, u32 id, u32 kb, u32 pos,
     if (!act) kb = 0xFFFFFFFFu;
     // lanes [lane, end) belong to this lane's run, end = next head above this lane
     const u32 above = heads & ~((2u << lane) - 1u);
-    const int end = above ? __ffs(above) - 1 : 32;
+    int end = above ? __ffs(above) - 1 : 32;
+    bool lead = head;
+    if (WINDOW < 32) {
+        // early rounds: runs are short, so reduce inside windows of WINDOW lanes of a run (log2(WINDOW) steps
+        // instead of 5) and let every window issue its own atomic
+        const int start = 31 - __clz(heads & ((2u << lane) - 1u)); // first lane of this lane's run
+        const int wstart = start + ((lane - start) & ~(WINDOW - 1));
+        lead = lane == wstart;
+        end = min(end, wstart + WINDOW);
+    }
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
+    for (int o = 1; o < WINDOW; o <<= 1) {
         const u32 okb = __shfl_down_sync(0xFFFFFFFFu, kb, o);
         const u32 opos = __shfl_down_sync(0xFFFFFFFFu, pos, o);
         if (lane + o < end && okb < kb) { kb = okb; pos = opos; }
     }
-    if (head && act) {
+    if (lead && act) {
         const u64 key = make_key(kb, pos);
-        // FILTER (components with many edges each): the running minimum only ever decreases, so a key that
-        // is not below the value read now can never win; skipping it spares the L2 a same-address atomic
-        if (!FILTER || key < ld_relaxed_u64(best + id)) atomicMin(best + id, key);
+        // FILTER (components with many edges each): the running minimum only ever decreases, so a key whose
+        // weight is above the weight read earlier (cur_hi: the high word of best[id], prefetched for a whole
+        // tile at once) can never win; skipping it spares the L2 a same-address atomic
+        if (!FILTER || kb <= cur_hi) atomicMin(best + id, key);
     }
 }
 

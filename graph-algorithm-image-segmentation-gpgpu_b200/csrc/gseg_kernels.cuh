@@ -33,6 +33,9 @@ namespace cg = cooperative_groups;
 #define NT 256   // threads per block of the grid-wide kernels
 #define NTT 1024 // threads per block of the single-cluster tail kernel
 #define CPT 4    // rows of 32 components per warp tile of phase S
+#ifndef RUNWIN
+#define RUNWIN 4  // lanes per reduction window of the min-edge selection in rounds without the atomic filter
+#endif
 
 // round-0 image tiles
 #define TW 64
@@ -543,8 +546,8 @@ __device__ __forceinline__ void emit_row(const GsegBufs &B, int nxt, u32 pos, bo
         B.ew[nxt][pos] = wv;
         if (SP) kb = __float_as_uint(__fmul_rn(__uint_as_float(wv), mean_dist_g(B.csum[nxt], B.attr[nxt], a, b)));
     }
-    warp_run_min<FILTER>(B.best[nxt], a, kb, pos, act, fa);
-    warp_run_min<FILTER>(B.best[nxt], b, kb, pos, act, fb);
+    warp_run_min<FILTER, FILTER ? 32 : RUNWIN>(B.best[nxt], a, kb, pos, act, fa);
+    warp_run_min<FILTER, FILTER ? 32 : RUNWIN>(B.best[nxt], b, kb, pos, act, fb);
 }
 
 // a10 (round 0): grid edges -> paged list of inter-component edges, in edge-index order
