@@ -105,6 +105,10 @@ def load():
     L.gseg_weights.argtypes = [vp, vp, i32]
     L.gseg_blurred.argtypes = [vp, vp, i32]
     L.gseg_stats.argtypes = [vp, C.POINTER(RoundStat), i32]
+    i64 = C.c_int64
+    L.gseg_export_graph.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), vp, vp, vp, vp, vp, i64, i64]
+    L.gseg_blurred_rows.argtypes = [vp, i32, i32, vp, i32]
+    L.gseg_segment_graph.argtypes = [vp, i64, vp, vp, i64, vp, vp, vp, C.POINTER(Params), vp]
     L.gseg_synth.argtypes = [vp, vp, i32, i32, u64, i32]
     L.gseg_set_profiling.argtypes = [vp, i32]
     L.gseg_profile_read.argtypes = [vp, C.POINTER(KernelTime), i32]
@@ -237,6 +241,40 @@ class Segmenter:
         out = np.empty((3, self.hh, self.w), np.float32)
         self._ck(self.L.gseg_blurred(self.h, C.c_void_p(out.ctypes.data), MEM_HOST), "gseg_blurred")
         return out
+
+    def export_graph(self):
+        """Final component graph of the last FELZ/HIER run: dict(size, Int, ea, eb, w); ids = labels(-1)."""
+        nv, ne = C.c_int64(0), C.c_int64(0)
+        self._ck(self.L.gseg_export_graph(self.h, C.byref(nv), C.byref(ne), None, None, None, None, None, 0, 0),
+                 "gseg_export_graph")
+        size = np.empty(nv.value, np.uint32)
+        Int = np.empty(nv.value, np.float32)
+        ea = np.empty(max(ne.value, 1), np.uint32)
+        eb = np.empty(max(ne.value, 1), np.uint32)
+        w = np.empty(max(ne.value, 1), np.float32)
+        self._ck(self.L.gseg_export_graph(self.h, C.byref(nv), C.byref(ne), size.ctypes.data, Int.ctypes.data,
+                                          ea.ctypes.data, eb.ctypes.data, w.ctypes.data, len(size), len(ea)),
+                 "gseg_export_graph")
+        return dict(size=size, Int=Int, ea=ea[:ne.value], eb=eb[:ne.value], w=w[:ne.value])
+
+    def blurred_rows(self, y0, nrows=1):
+        out = np.empty((3, nrows, self.w), np.float32)
+        self._ck(self.L.gseg_blurred_rows(self.h, y0, nrows, C.c_void_p(out.ctypes.data), MEM_HOST), "gseg_blurred_rows")
+        return out
+
+    def segment_graph(self, size, Int, ea, eb, w, params=None, **kw):
+        """Boruvka rounds on an explicit graph; returns (dense final label per input component, #components)."""
+        p = params if params is not None else self.params(**kw)
+        size = np.ascontiguousarray(size, np.uint32)
+        Int = np.ascontiguousarray(Int, np.float32)
+        ea = np.ascontiguousarray(ea, np.uint32)
+        eb = np.ascontiguousarray(eb, np.uint32)
+        w = np.ascontiguousarray(w, np.float32)
+        out = np.empty(len(size), np.int32)
+        n = self._ck(self.L.gseg_segment_graph(self.h, len(size), size.ctypes.data, Int.ctypes.data, len(ea),
+                                               ea.ctypes.data, eb.ctypes.data, w.ctypes.data, C.byref(p),
+                                               out.ctypes.data), "gseg_segment_graph")
+        return out, n
 
     def stats(self):
         arr = (RoundStat * 64)()

@@ -10,6 +10,8 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <vector>
+
 #include "../../include/gseg.h"
 #include "gseg_kernels.cuh"
 #include "gseg_sort.cuh"
@@ -368,7 +370,7 @@ static void enqueue_round(gseg_ctx *c, cudaStream_t s, int r, size_t Vb, size_t 
     const GsegBufs B = bufs_of(c);
     const int cap = c->num_sms * c->occ_mult;
     mark(c, s, "k_page_scan", r);
-    k_page_scan<<<(int)((Pb + 1023) / 1024 < 64 ? (Pb + 1023) / 1024 : 64), 1024, 0, s>>>(c->d_ctl, B);
+    k_page_scan<<<grid_for(Pb, 1024, 64), 1024, 0, s>>>(c->d_ctl, B);
     mark(c, s, "k_succ_scan", r);
     if (sp) k_succ_scan<true><<<grid_for(Vb, NT * CPT, cap), NT, 0, s>>>(c->d_ctl, B);
     else k_succ_scan<false><<<grid_for(Vb, NT * CPT, cap), NT, 0, s>>>(c->d_ctl, B);
@@ -540,21 +542,27 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
     return GSEG_OK;
 }
 
-extern "C" int gseg_wait(gseg_ctx *ctx) {
-    if (!ctx) return GSEG_E_ARG;
-    if (!ctx->pending) return ctx->valid ? GSEG_OK : GSEG_E_STATE;
-    CK(cudaSetDevice(ctx->device));
+// Read the control block back; while the run is not finished (the guess of grid-wide rounds was short)
+// keep going, two rounds and a tail at a time.
+static int wait_rounds(gseg_ctx *ctx) {
     int rc = readback(ctx);
-    // the guess of grid-wide rounds was short: keep going, two rounds and a tail at a time
     while (!rc && ctx->h_ctl->st.phase != PH_DONE && ctx->h_ctl->error == DERR_NONE) {
         const int r = (int)ctx->h_ctl->st.round;
         enqueue_round(ctx, ctx->stream, r, ctx->h_ctl->st.V, ctx->h_ctl->st.P);
         enqueue_round(ctx, ctx->stream, r + 1, ctx->h_ctl->st.V, ctx->h_ctl->st.P);
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = enqueue_tail(ctx, ctx->stream);
-        if (e != cudaSuccess) { ctx->pending = false; return fail(ctx, GSEG_E_CUDA, "continuation launch", e); }
+        if (e != cudaSuccess) return fail(ctx, GSEG_E_CUDA, "continuation launch", e);
         rc = readback(ctx);
     }
+    return rc;
+}
+
+extern "C" int gseg_wait(gseg_ctx *ctx) {
+    if (!ctx) return GSEG_E_ARG;
+    if (!ctx->pending) return ctx->valid ? GSEG_OK : GSEG_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    int rc = wait_rounds(ctx);
     if (rc) { ctx->pending = false; return rc; }
     return finish(ctx);
 }
@@ -714,6 +722,145 @@ extern "C" int gseg_blurred(gseg_ctx *ctx, float *out, int mem_kind) {
                        mem_kind == GSEG_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return GSEG_OK;
+}
+
+// ---- tiled schedule: export / import of component graphs ------------------------------------------------
+extern "C" int gseg_export_graph(gseg_ctx *ctx, int64_t *n_components, int64_t *n_edges, uint32_t *size, float *Int,
+                                 uint32_t *ea, uint32_t *eb, float *w, int64_t cap_components, int64_t cap_edges) {
+    if (!ctx || !n_components || !n_edges) return GSEG_E_ARG;
+    if (!ctx->valid || ctx->params.variant == GSEG_SUPERPIX) return GSEG_E_STATE;
+    const GsegCtl *h = ctx->h_ctl;
+    const int64_t V = h->st.V, E = h->st.E;
+    *n_components = V; *n_edges = E;
+    if (!size && !Int && !ea && !eb && !w) return GSEG_OK;
+    if (!size || !Int || !ea || !eb || !w || cap_components < V || cap_edges < E) return GSEG_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const int cur = (int)(h->st.round & 1u);
+    const GsegBufs B = bufs_of(ctx);
+    const u32 P = h->st.P;
+    if (P) {
+        ctx->launches += 2;
+        k_export_scan<<<1, 1024, 0, ctx->stream>>>(B, cur, P);
+        k_export_gather<<<grid_for(P, NT / 32), NT, 0, ctx->stream>>>(B, cur, P);
+        CK(cudaGetLastError());
+    }
+    std::vector<uint2> hab, hat;
+    try { hab.resize((size_t)E); hat.resize((size_t)V); } catch (...) { return fail(ctx, GSEG_E_ARG, "host staging allocation", cudaSuccess); }
+    if (E) {
+        CK(cudaMemcpyAsync(hab.data(), ctx->d_eab[cur ^ 1], (size_t)E * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(w, ctx->d_ew[cur ^ 1], (size_t)E * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+    }
+    CK(cudaMemcpyAsync(hat.data(), ctx->d_attr[cur], (size_t)V * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    for (int64_t i = 0; i < E; ++i) { ea[i] = hab[(size_t)i].x; eb[i] = hab[(size_t)i].y; }
+    for (int64_t i = 0; i < V; ++i) { size[i] = hat[(size_t)i].x; memcpy(&Int[i], &hat[(size_t)i].y, 4); }
+    return GSEG_OK;
+}
+
+extern "C" int gseg_blurred_rows(gseg_ctx *ctx, int y0, int nrows, float *out, int mem_kind) {
+    if (!ctx || !out) return GSEG_E_ARG;
+    if (!ctx->valid) return GSEG_E_STATE;
+    if (y0 < 0 || nrows < 1 || y0 + nrows > ctx->h) return GSEG_E_ARG;
+    CK(cudaSetDevice(ctx->device));
+    const size_t V = (size_t)ctx->w * ctx->h, rowb = (size_t)ctx->w * sizeof(float);
+    CK(cudaMemcpy2DAsync(out, (size_t)nrows * rowb, ctx->d_planes + (size_t)y0 * ctx->w, V * sizeof(float), (size_t)nrows * rowb, 3,
+                         mem_kind == GSEG_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GSEG_OK;
+}
+
+static int wait_rounds(gseg_ctx *ctx);
+
+extern "C" int gseg_segment_graph(gseg_ctx *ctx, int64_t n_components, const uint32_t *size, const float *Int, int64_t n_edges,
+                                  const uint32_t *ea, const uint32_t *eb, const float *w, const gseg_params *p,
+                                  int32_t *labels_out) {
+    if (!ctx || !p || !labels_out || n_components < 1 || n_edges < 0 || !size || !Int || (n_edges && (!ea || !eb || !w)))
+        return GSEG_E_ARG;
+    if (ctx->pending) return fail(ctx, GSEG_E_STATE, "previous run not waited for", cudaSuccess);
+    if (p->variant != GSEG_FELZ && p->variant != GSEG_HIER) return fail(ctx, GSEG_E_ARG, "graph rounds: FELZ or HIER", cudaSuccess);
+    if (!(p->k >= 0.0f) || p->min_size < 0 || p->max_rounds < 0 || p->max_levels < 0) return fail(ctx, GSEG_E_ARG, "parameter range", cudaSuccess);
+    const size_t Eslots = (size_t)ctx->Dmax * ((ctx->Vmax + GSEG_PAGE - 1) / GSEG_PAGE + 1) * GSEG_PAGE;
+    if ((size_t)n_components > ctx->Vmax || (size_t)n_edges + GSEG_PAGE > Eslots)
+        return fail(ctx, GSEG_E_SIZE, "graph exceeds context capacity", cudaSuccess);
+    CK(cudaSetDevice(ctx->device));
+    ctx->valid = false;
+    ctx->params = *p;
+    ctx->w = (int)n_components; ctx->h = 1; ctx->D = 2;
+    const size_t V = (size_t)n_components, E = (size_t)n_edges;
+    std::vector<uint2> hab, hat;
+    try { hab.resize(E); hat.resize(V); } catch (...) { return fail(ctx, GSEG_E_ARG, "host staging allocation", cudaSuccess); }
+    for (size_t i = 0; i < E; ++i) {
+        if (ea[i] >= V || eb[i] >= V || ea[i] == eb[i]) return fail(ctx, GSEG_E_ARG, "edge end out of range or self-loop", cudaSuccess);
+        hab[i] = make_uint2(ea[i], eb[i]);
+    }
+    for (size_t i = 0; i < V; ++i) { hat[i].x = size[i]; memcpy(&hat[i].y, &Int[i], 4); }
+    cudaStream_t s = ctx->stream;
+    if (E) {
+        CK(cudaMemcpyAsync(ctx->d_eab[1], hab.data(), E * sizeof(uint2), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->d_ew[1], w, E * sizeof(u32), cudaMemcpyHostToDevice, s));
+    }
+    CK(cudaMemcpyAsync(ctx->d_attr[1], hat.data(), V * sizeof(uint2), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ctx->d_best[1], 0xFF, V * sizeof(u64), s));
+    CK(cudaStreamSynchronize(s)); // the staging vectors die with this scope
+    const int R = max_rounds_of(p);
+    if (ctx->epoch_next + 2u * GSEG_MAXR + 8u >= (1u << 30)) {
+        CK(cudaMemsetAsync(ctx->d_statusC, 0, ctx->ntilesC * sizeof(u64), s));
+        CK(cudaMemsetAsync(ctx->d_statusE, 0, ctx->ntilesE * sizeof(u64), s));
+        ctx->epoch_next = 1;
+    }
+    GsegHead *hh = ctx->h_head;
+    GsegRunParams *hp = &hh->p;
+    memset(hp, 0, sizeof(*hp));
+    hp->w = (int)n_components; hp->h = 1; hp->D = 2; hp->variant = p->variant;
+    hp->k = p->k; hp->min_size = p->min_size; hp->max_rounds = R + 1 > GSEG_MAXR ? GSEG_MAXR : R + 1; // rounds are numbered from 1 here
+    hp->max_levels = p->max_levels > 0 ? p->max_levels : INT_MAX;
+    hp->arena_cap = (u32)ctx->arena_cap;
+    hp->epoch_base = ctx->epoch_next;
+    hp->filter_shift = ctx->filter_shift;
+    const bool host_loop = (p->flags & GSEG_FLAG_HOST_LOOP) != 0;
+    hp->tail_E = ctx->run_tail_E = host_loop ? 0u : ctx->tail_E;
+    hp->tail_V = ctx->run_tail_V = host_loop ? 0u : ctx->tail_V;
+    hp->tail_P = ctx->tail_P;
+    ctx->epoch_next += 2u * GSEG_MAXR + 8u;
+    const u32 P = (u32)((E + GSEG_PAGE - 1) / GSEG_PAGE);
+    hh->st.V = (u32)V; hh->st.E = (u32)E; hh->st.round = 1; hh->st.phase = PH_PRED; hh->st.levels = 0; hh->st.map_off = 0;
+    hh->st.P = P; hh->st.pad = 0;
+    hh->Vnext = (u32)V; hh->error = DERR_NONE; hh->ticketC = 0; hh->ticketE = 0; hh->doneE = 0;
+    memset(hh->Eacc, 0, sizeof(hh->Eacc));
+    CK(cudaMemcpyAsync(ctx->d_ctl, hh, sizeof(GsegHead), cudaMemcpyHostToDevice, s));
+    ctx->n_marks = 0;
+    const GsegBufs B = bufs_of(ctx);
+    if (P) { ++ctx->launches; k_graph_init<<<grid_for(P, NT / 32), NT, 0, s>>>(B, (u32)E, P); }
+    CK(cudaGetLastError());
+    // the usual schedule from round 1 on; a joined graph is small, so normally everything runs in the tail
+    ctx->nbig_hint = -1;
+    int rc;
+    if (host_loop) {
+        rc = readback(ctx);
+        for (int r = 1; !rc && r <= R && ctx->h_ctl->st.phase != PH_DONE; ++r) {
+            enqueue_round(ctx, s, r, ctx->h_ctl->st.V, ctx->h_ctl->st.P);
+            CK(cudaGetLastError());
+            rc = readback(ctx);
+        }
+    } else {
+        CK(enqueue_tail(ctx, s));
+        ctx->pending = true;
+        rc = wait_rounds(ctx);
+    }
+    ctx->pending = false;
+    if (rc) return rc;
+    if (ctx->h_ctl->error == DERR_SCAN) return fail(ctx, GSEG_E_INTERNAL, "look-back watchdog", cudaSuccess);
+    if (ctx->h_ctl->error == DERR_ARENA) return fail(ctx, GSEG_E_ARENA, "map arena", cudaSuccess);
+    if (ctx->h_ctl->error == DERR_CHASE) return fail(ctx, GSEG_E_INTERNAL, "successor cycle", cudaSuccess);
+    // labels of the input components: the maps of rounds 1 .. last composed
+    const int last = (int)ctx->h_ctl->st.round - 1;
+    u32 *F = ctx->d_wsel;
+    ++ctx->launches;
+    k_compose_table<<<grid_for(V, NT), NT, 0, s>>>(ctx->d_ctl, ctx->d_arena, 1, last, (u32)V, F);
+    CK(cudaGetLastError());
+    CK(cudaMemcpyAsync(labels_out, F, V * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return (int)ctx->h_ctl->st.V;
 }
 
 extern "C" int gseg_stats(const gseg_ctx *ctx, gseg_round_stat *out, int cap) {

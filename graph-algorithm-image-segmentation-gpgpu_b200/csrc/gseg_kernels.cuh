@@ -898,6 +898,40 @@ __global__ void __launch_bounds__(NTT, 1) k_tail(GsegCtl *ctl, GsegBufs B) {
     }
 }
 
+// ---- explicit-graph entry (second phase of the tiled schedule) ---------------------------------------
+// Export: the live edge list of a finished run, pages gathered into one dense array (one warp per page,
+// destination = exclusive scan of the page counts in pscan).
+__global__ void __launch_bounds__(1024) k_export_scan(GsegBufs B, int cur, u32 P) {
+    __shared__ u32 s[34];
+    block_scan_pages(B.pcnt[cur], P, B.pscan, s);
+}
+__global__ void __launch_bounds__(NT) k_export_gather(GsegBufs B, int cur, u32 P) {
+    const int lane = threadIdx.x & 31;
+    const int nxt = cur ^ 1;
+    for (u32 g = blockIdx.x * (NT / 32) + (threadIdx.x >> 5); g < P; g += gridDim.x * (NT / 32)) {
+        const u32 cnt = B.pcnt[cur][g], src = B.poff[cur][g], dst = B.pscan[g];
+        for (u32 i = lane; i < cnt; i += 32u) { B.eab[nxt][dst + i] = B.eab[cur][src + i]; B.ew[nxt][dst + i] = B.ew[cur][src + i]; }
+    }
+}
+// Import: dense pages of GSEG_PAGE slots over a caller-supplied edge list (slot = list position = the
+// tie-break) and the per-component minimum of round 1.
+__global__ void __launch_bounds__(NT) k_graph_init(GsegBufs B, u32 E, u32 P) {
+    const int lane = threadIdx.x & 31;
+    for (u32 g = blockIdx.x * (NT / 32) + (threadIdx.x >> 5); g < P; g += gridDim.x * (NT / 32)) {
+        if (lane == 0) { B.pcnt[1][g] = min(GSEG_PAGE, E - g * GSEG_PAGE); B.poff[1][g] = g * GSEG_PAGE; }
+#pragma unroll
+        for (int j = 0; j < (int)(GSEG_PAGE / 32); ++j) {
+            const u32 e = g * GSEG_PAGE + 32u * j + lane;
+            const bool act = e < E;
+            uint2 ab = make_uint2(0u, 0u);
+            u32 wv = 0u;
+            if (act) { ab = B.eab[1][e]; wv = B.ew[1][e]; }
+            warp_run_min<false, 32>(B.best[1], ab.x, wv, e, act, 0xFFFFFFFFu);
+            warp_run_min<false, 32>(B.best[1], ab.y, wv, e, act, 0xFFFFFFFFu);
+        }
+    }
+}
+
 // ------------------------------------------------------------------------------------------------
 // a12: hierarchy materialisation.  Level l = composition of the maps of rounds 0..l.
 // ------------------------------------------------------------------------------------------------

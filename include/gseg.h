@@ -144,6 +144,25 @@ int gseg_weights(gseg_ctx *ctx, float *out, int mem_kind);
 /* Blurred image, 3 planes of w*h floats (R,G,B). */
 int gseg_blurred(gseg_ctx *ctx, float *out, int mem_kind);
 
+/* ---- tiled schedule (BASELINE.json configs[4], north_star: "cross-tile boundary edges exchanged over
+ * NVLink via NCCL before the final Boruvka rounds"; DESIGN.md "Tiled schedule") ------------------------
+ * A strip is segmented like any image; its final component graph is exported, the strips' graphs are
+ * joined by the cut edges on the host side of the exchange, and the joined graph runs the same rounds.
+ *
+ * gseg_export_graph: components (size, Int(C)) and live inter-component edges (a, b, weight; ids = the
+ * dense labels of gseg_labels(-1); list order = edge-index order) of the last FELZ/HIER run.  Call with
+ * NULL arrays to get the counts, then with host arrays of at least that capacity. */
+int gseg_export_graph(gseg_ctx *ctx, int64_t *n_components, int64_t *n_edges, uint32_t *size, float *Int,
+                      uint32_t *ea, uint32_t *eb, float *w, int64_t cap_components, int64_t cap_edges);
+/* Rows y0 .. y0+nrows-1 of the blurred planes: out[3][nrows][w] (the cut-edge weights need the boundary rows). */
+int gseg_blurred_rows(gseg_ctx *ctx, int y0, int nrows, float *out, int mem_kind);
+/* The Boruvka rounds of `params->variant` (FELZ or HIER) on an explicit graph in host memory: components
+ * with (size, Int), edges (ea, eb, w) whose list position is the tie-break.  labels_out[c] = dense final
+ * component of input component c; returns the number of final components (or a negative status). */
+int gseg_segment_graph(gseg_ctx *ctx, int64_t n_components, const uint32_t *size, const float *Int, int64_t n_edges,
+                       const uint32_t *ea, const uint32_t *eb, const float *w, const gseg_params *params,
+                       int32_t *labels_out);
+
 /* Per-round statistics of the last run; returns number of rounds (<= cap written). */
 int gseg_stats(const gseg_ctx *ctx, gseg_round_stat *out, int cap);
 

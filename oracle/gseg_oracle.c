@@ -310,6 +310,11 @@ int orc_felz_kruskal(int w, int h, int conn, const float *wts, float k, int min_
  * written for L < max_levels.  labels: final partition (FELZ) / last level reached.
  * Returns number of rounds that merged something (= number of levels for HIER/SUPERPIX).
  * ---------------------------------------------------------------------------------------------- */
+/* Optional export of the final Int(C) per representative pixel (the tiled schedule joins strips by their
+ * component attributes); thread-local so that concurrent runs do not interfere. */
+static __thread float *g_int_out = NULL;
+void orc_set_int_out(float *p) { g_int_out = p; }
+
 int orc_boruvka(int w, int h, int conn, int variant, const float *wts, float k, int min_size, int max_rounds,
                 const float *planes, int32_t *labels, int32_t *levels_out, int max_levels,
                 int32_t *ncomp_levels, int64_t *stats, int stats_cap, int *final_ncomp) {
@@ -436,10 +441,108 @@ int orc_boruvka(int w, int h, int conn, int variant, const float *wts, float k, 
         if (variant != 0 && (nrep <= 1 || levels >= max_levels)) break;
     }
     memcpy(labels, comp, V * sizeof(int32_t));
+    if (g_int_out) for (size_t i = 0; i < nrep; ++i) g_int_out[reps[i]] = Int[reps[i]];
     if (final_ncomp) *final_ncomp = (int)nrep;
     free(comp); free(size); free(nsize); free(Int); free(nInt); free(best); free(choice); free(succ);
     free(reps); free(live); free(csum); free(ncsum);
     return levels;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * The same rounds on an EXPLICIT graph: nv components with (size, Int), ne undirected edges (ea, eb, w)
+ * whose position in the list is the tie-break.  This is the second phase of the tiled schedule
+ * (BASELINE.json north_star: "cross-tile boundary edges exchanged ... before the final Boruvka
+ * rounds"; DESIGN.md "Tiled schedule"): the strips' final component graphs joined by the cut edges.
+ * variant 0 (FELZ: predicate rounds, then min-size rounds) or 1 (HIER: until one component).
+ * labels_out[c] = representative of input component c.  Returns the number of final components.
+ * ---------------------------------------------------------------------------------------------- */
+int orc_boruvka_graph(int nv, const int32_t *size0, const float *Int0, int64_t ne, const int32_t *ea, const int32_t *eb,
+                      const float *w, int variant, float k, int min_size, int max_rounds, int32_t *labels_out,
+                      int64_t *stats, int stats_cap) {
+    int32_t *comp = (int32_t *)malloc((size_t)nv * sizeof(int32_t));
+    int32_t *size = (int32_t *)malloc((size_t)nv * sizeof(int32_t));
+    int32_t *nsize = (int32_t *)malloc((size_t)nv * sizeof(int32_t));
+    float *Int = (float *)malloc((size_t)nv * sizeof(float));
+    float *nInt = (float *)malloc((size_t)nv * sizeof(float));
+    uint64_t *best = (uint64_t *)malloc((size_t)nv * sizeof(uint64_t));
+    int32_t *choice = (int32_t *)malloc((size_t)nv * sizeof(int32_t));
+    int32_t *succ = (int32_t *)malloc((size_t)nv * sizeof(int32_t));
+    int32_t *reps = (int32_t *)malloc((size_t)nv * sizeof(int32_t));
+    uint32_t *live = (uint32_t *)malloc((size_t)(ne > 0 ? ne : 1) * sizeof(uint32_t));
+    size_t nlive = 0, nrep = (size_t)nv;
+    for (int64_t i = 0; i < ne; ++i) live[nlive++] = (uint32_t)i;
+    for (int c = 0; c < nv; ++c) { comp[c] = c; size[c] = size0[c]; Int[c] = Int0[c]; reps[c] = c; }
+    int phase = 0, nstat = 0;
+    for (int round = 0; round < max_rounds; ++round) {
+        for (size_t i = 0; i < nrep; ++i) best[reps[i]] = KEY_NONE;
+        size_t nl2 = 0;
+        for (size_t i = 0; i < nlive; ++i) {
+            const uint32_t e = live[i];
+            const int32_t a = comp[ea[e]], b = comp[eb[e]];
+            if (a == b) continue;
+            live[nl2++] = e;
+            const uint64_t key = ((uint64_t)fbits(w[e]) << 32) | e;
+            if (key < best[a]) best[a] = key;
+            if (key < best[b]) best[b] = key;
+        }
+        nlive = nl2;
+        for (size_t i = 0; i < nrep; ++i) {
+            const int32_t c = reps[i];
+            choice[c] = c;
+            if (best[c] == KEY_NONE) continue;
+            const uint32_t e = (uint32_t)best[c];
+            const float wt = bitsf((uint32_t)(best[c] >> 32));
+            const int32_t a = comp[ea[e]], b = comp[eb[e]];
+            const int32_t other = a == c ? b : a;
+            int ok;
+            if (variant != 0) ok = 1;
+            else if (phase == 0) {
+                float ta = k / (float)size[a], tb = k / (float)size[b];
+                ta = Int[a] + ta; tb = Int[b] + tb;
+                ok = wt <= ta && wt <= tb;
+            } else ok = size[c] < min_size;
+            if (ok) choice[c] = other;
+        }
+        size_t merged = 0;
+        for (size_t i = 0; i < nrep; ++i) {
+            int32_t c = reps[i], s = choice[c];
+            if (s != c && choice[s] == c && c < s) s = c;
+            succ[c] = s;
+            if (s != c) ++merged;
+        }
+        if (stats && nstat < stats_cap) {
+            stats[4 * nstat] = (int64_t)nrep; stats[4 * nstat + 1] = (int64_t)nlive;
+            stats[4 * nstat + 2] = (int64_t)merged; stats[4 * nstat + 3] = phase; ++nstat;
+        }
+        if (merged == 0) {
+            if (variant == 0 && phase == 0 && min_size > 1) { phase = 1; continue; }
+            break;
+        }
+        for (size_t i = 0; i < nrep; ++i) { nsize[reps[i]] = 0; nInt[reps[i]] = 0.0f; }
+        for (size_t i = 0; i < nrep; ++i) {
+            int32_t c = reps[i], r = c;
+            while (succ[r] != r) r = succ[r];
+            choice[c] = r;
+        }
+        for (size_t i = 0; i < nrep; ++i) {
+            const int32_t c = reps[i], r = choice[c];
+            nsize[r] += size[c];
+            float m = Int[c];
+            if (succ[c] != c) { const float wt = bitsf((uint32_t)(best[c] >> 32)); if (wt > m) m = wt; }
+            if (m > nInt[r]) nInt[r] = m;
+        }
+        for (int c = 0; c < nv; ++c) comp[c] = choice[comp[c]];
+        size_t nr2 = 0;
+        for (size_t i = 0; i < nrep; ++i) {
+            const int32_t c = reps[i];
+            if (choice[c] == c) { reps[nr2++] = c; size[c] = nsize[c]; Int[c] = nInt[c]; }
+        }
+        nrep = nr2;
+        if (variant != 0 && nrep <= 1) break;
+    }
+    memcpy(labels_out, comp, (size_t)nv * sizeof(int32_t));
+    free(comp); free(size); free(nsize); free(Int); free(nInt); free(best); free(choice); free(succ); free(reps); free(live);
+    return (int)nrep;
 }
 
 /* Canonical relabelling: ids 0..n-1 in order of first appearance; two partitions are equal iff

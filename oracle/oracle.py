@@ -50,6 +50,11 @@ def lib():
         L.orc_boruvka.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, f32p, C.c_float, C.c_int, C.c_int, f32p,
                                   i32p, i32p, C.c_int, i32p, i64p, C.c_int, C.POINTER(C.c_int)]
         L.orc_boruvka.restype = C.c_int
+        L.orc_set_int_out.argtypes = [f32p]
+        L.orc_set_int_out.restype = None
+        L.orc_boruvka_graph.argtypes = [C.c_int, i32p, f32p, C.c_int64, i32p, i32p, f32p, C.c_int, C.c_float, C.c_int,
+                                        C.c_int, i32p, i64p, C.c_int]
+        L.orc_boruvka_graph.restype = C.c_int
         L.orc_canon.argtypes = [i32p, C.c_int64]
         L.orc_canon.restype = C.c_int
         L.orc_segment.argtypes = [u8p, C.c_int, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int, C.c_int, C.c_int,
@@ -158,10 +163,13 @@ def felz_kruskal(wts, w, h, conn, k, min_size):
     return lab.reshape(h, w), n
 
 
-def boruvka(wts, w, h, conn, variant, k=0.0, min_size=0, max_rounds=64, planes=None, max_levels=0):
+def boruvka(wts, w, h, conn, variant, k=0.0, min_size=0, max_rounds=64, planes=None, max_levels=0, want_int=False):
     """Returns dict(labels, levels[list of label images], ncomp[list], stats[rounds x 4], n).
-    max_levels = 0: run until one component and keep no per-level images."""
+    max_levels = 0: run until one component and keep no per-level images.
+    want_int: also "int" = final Int(C) indexed by representative pixel (the values labels take)."""
     V = h * w
+    int_out = np.zeros(V, np.float32) if want_int else None
+    lib().orc_set_int_out(_p(int_out, C.c_float) if want_int else None)
     lab = np.empty(V, np.int32)
     lev = np.empty((max(max_levels, 1), V), np.int32)
     nco = np.zeros(max(max_levels, 1), np.int32)
@@ -173,10 +181,29 @@ def boruvka(wts, w, h, conn, variant, k=0.0, min_size=0, max_rounds=64, planes=N
                            max_levels if max_levels > 0 else 1 << 30,
                            _p(nco, C.c_int32) if max_levels > 0 else None, _p(stats, C.c_int64), stats.shape[0],
                            C.byref(fin))
+    lib().orc_set_int_out(None)
     nst = int(np.count_nonzero(stats[:, 0]))
     nkeep = min(nl, max_levels)
-    return dict(labels=lab.reshape(h, w), levels=[lev[i].reshape(h, w) for i in range(nkeep)],
+    return dict(int=int_out, labels=lab.reshape(h, w), levels=[lev[i].reshape(h, w) for i in range(nkeep)],
                 ncomp=[int(x) for x in nco[:nkeep]], stats=stats[:nst].copy(), n=fin.value, nlevels=nl)
+
+
+def boruvka_graph(size, Int, ea, eb, w, variant, k=0.0, min_size=0, max_rounds=64):
+    """Rounds on an explicit graph (second phase of the tiled schedule).  Returns (labels per input
+    component = representative ids, number of final components, stats[rounds x 4])."""
+    size = np.ascontiguousarray(size, np.int32)
+    Int = np.ascontiguousarray(Int, np.float32)
+    ea = np.ascontiguousarray(ea, np.int32)
+    eb = np.ascontiguousarray(eb, np.int32)
+    w = np.ascontiguousarray(w, np.float32)
+    nv, ne = len(size), len(ea)
+    lab = np.empty(max(nv, 1), np.int32)
+    stats = np.zeros((4 * max_rounds + 8, 4), np.int64)
+    n = lib().orc_boruvka_graph(nv, _p(size, C.c_int32), _p(Int, C.c_float), ne, _p(ea, C.c_int32), _p(eb, C.c_int32),
+                                _p(w, C.c_float), variant, k, min_size, max_rounds, _p(lab, C.c_int32),
+                                _p(stats, C.c_int64), stats.shape[0])
+    nst = int(np.count_nonzero(stats[:, 0]))
+    return lab[:nv], n, stats[:nst].copy()
 
 
 def segment(img, sigma, k, min_size, conn, variant, max_rounds=64):

@@ -324,3 +324,69 @@ def test_cli_ppm_roundtrip(gseg, oracle, tmp_path):
     ref = oracle.pipeline(img, 0.8, 0.0, 0, 4, oracle.HIER, max_levels=64)
     assert same_partition(oracle, np.fromfile(labp, np.int32).reshape(h, w), ref["levels"][2])
     assert "time_ms mean" in r.stdout
+
+
+# ---- tiled schedule: graph export / import and the joined rounds ------------------------------------------------
+def _gpu_strip(seg, img, sigma, k, ms, conn):
+    seg.segment(img, sigma=sigma, k=k, min_size=ms, connectivity=conn, variant=0)
+    lab = seg.labels()
+    return lab, seg.export_graph(), seg.blurred_rows(0)[:, 0, :], seg.blurred_rows(img.shape[0] - 1)[:, 0, :]
+
+
+@pytest.mark.parametrize("flags", [0, 1])
+def test_segment_graph_matches_oracle(gseg, oracle, seg, flags):
+    """Boruvka rounds on explicit random graphs (multi-edges, ties, isolated components) vs the oracle."""
+    rng = np.random.default_rng(5)
+    for nv, ne, variant, k, ms in [(1, 0, 0, 3.0, 2), (2, 1, 0, 100.0, 0), (50, 200, 0, 4.0, 3), (300, 2000, 0, 2.0, 10),
+                                   (300, 2000, 1, 0.0, 0), (5000, 60000, 0, 3.0, 8), (40000, 300000, 0, 2.0, 4)]:
+        ea = rng.integers(0, nv, ne)
+        eb = (ea + 1 + rng.integers(0, max(nv - 1, 1), ne)) % nv if nv > 1 else ea
+        w = rng.integers(0, 16, ne).astype(np.float32) * 0.5          # many ties
+        size = rng.integers(1, 30, nv).astype(np.uint32)
+        Int = rng.integers(0, 4, nv).astype(np.float32)
+        ref, nref, st = oracle.boruvka_graph(size, Int, ea, eb, w, variant, k, ms, 48)
+        got, n = seg.segment_graph(size, Int, ea, eb, w, k=k, min_size=ms, variant=variant, flags=flags)
+        assert n == nref, (nv, ne, variant)
+        assert got.min() == 0 and got.max() == n - 1
+        # same partition of the input components
+        pairs = np.unique(np.stack([got, ref], 1), axis=0)
+        assert len(pairs) == n and len(np.unique(pairs[:, 0])) == n and len(np.unique(pairs[:, 1])) == n
+
+
+@pytest.mark.parametrize("conn", [4, 8])
+def test_export_graph_matches_oracle(gseg, oracle, seg, conn):
+    from tests.tiled_ref import oracle_strip
+    img = oracle.synth(180, 90, 41)
+    lab, g, top, bot = _gpu_strip(seg, img, 0.8, 300.0, 20, conn)
+    olab, og, otop, obot = oracle_strip(oracle, img, 0.8, 300.0, 20, conn)
+    assert same_partition(oracle, lab, olab)
+    assert np.array_equal(top.view(np.uint32), otop.view(np.uint32)) and np.array_equal(bot.view(np.uint32), obot.view(np.uint32))
+    # the graphs are equal up to the renaming of components given by the label images
+    ren = np.zeros(len(g["size"]), np.int64)
+    ren[lab.reshape(-1)] = olab.reshape(-1)
+    assert np.array_equal(g["size"], og["size"][np.argsort(ren)][np.argsort(np.argsort(ren))]) or \
+        np.array_equal(np.asarray(g["size"])[np.argsort(ren)], og["size"])
+    assert np.array_equal(np.asarray(g["Int"])[np.argsort(ren)].view(np.uint32), og["Int"].view(np.uint32))
+    assert np.array_equal(ren[g["ea"]], og["ea"]) and np.array_equal(ren[g["eb"]], og["eb"])
+    assert np.array_equal(g["w"].view(np.uint32), og["w"].view(np.uint32))
+
+
+@pytest.mark.parametrize("n_strips,conn", [(2, 4), (3, 8), (5, 4)])
+def test_tiled_schedule_matches_tiled_oracle(gseg, oracle, seg, n_strips, conn):
+    """The whole tiled schedule in one process (strips one after the other on the one GPU): phase 1 per strip,
+    join, phase 2 on the joined graph -- against the tiled oracle."""
+    import importlib
+    from tests.tiled_ref import oracle_tiled
+    tiled = importlib.import_module(gseg.__name__ + ".tiled")
+    img = oracle.synth(400, 300, 50 + n_strips)
+    recs, labs = [], []
+    for (y0, y1) in tiled.strip_rows(300, n_strips):
+        lab, g, top, bot = _gpu_strip(seg, np.ascontiguousarray(img[y0:y1]), 0.8, 300.0, 20, conn)
+        labs.append(lab)
+        recs.append(tiled.strip_record(lab, g, top, bot))
+    joined = tiled.join_strips(recs, conn)
+    comp, n = seg.segment_graph(joined["size"], joined["Int"], joined["ea"], joined["eb"], joined["w"], k=300.0, min_size=20,
+                                variant=0)
+    out = np.concatenate([comp[int(joined["offsets"][i]) + labs[i].astype(np.int64)] for i in range(n_strips)])
+    ref, nref, _, _ = oracle_tiled(oracle, img, n_strips, 0.8, 300.0, 20, conn)
+    assert n == nref and same_partition(oracle, out.reshape(300, 400), ref.reshape(300, 400))
