@@ -106,7 +106,7 @@ def load():
     L.gseg_blurred.argtypes = [vp, vp, i32]
     L.gseg_stats.argtypes = [vp, C.POINTER(RoundStat), i32]
     i64 = C.c_int64
-    L.gseg_export_graph.argtypes = [vp, C.POINTER(i64), C.POINTER(i64), vp, vp, vp, vp, vp, i64, i64]
+    L.gseg_export_graph.argtypes = [vp, i32, C.POINTER(i64), C.POINTER(i64), vp, vp, vp, vp, vp, i64, i64]
     L.gseg_blurred_rows.argtypes = [vp, i32, i32, vp, i32]
     L.gseg_segment_graph.argtypes = [vp, i64, vp, vp, i64, vp, vp, vp, C.POINTER(Params), vp]
     L.gseg_synth.argtypes = [vp, vp, i32, i32, u64, i32]
@@ -242,17 +242,18 @@ class Segmenter:
         self._ck(self.L.gseg_blurred(self.h, C.c_void_p(out.ctypes.data), MEM_HOST), "gseg_blurred")
         return out
 
-    def export_graph(self):
-        """Final component graph of the last FELZ/HIER run: dict(size, Int, ea, eb, w); ids = labels(-1)."""
+    def export_graph(self, dedup=True):
+        """Final component graph of the last FELZ/HIER run: dict(size, Int, ea, eb, w); ids = labels(-1).
+        dedup: parallel edges reduced to their minimum (weight, position) with the onesweep radix sort."""
         nv, ne = C.c_int64(0), C.c_int64(0)
-        self._ck(self.L.gseg_export_graph(self.h, C.byref(nv), C.byref(ne), None, None, None, None, None, 0, 0),
+        self._ck(self.L.gseg_export_graph(self.h, int(dedup), C.byref(nv), C.byref(ne), None, None, None, None, None, 0, 0),
                  "gseg_export_graph")
         size = np.empty(nv.value, np.uint32)
         Int = np.empty(nv.value, np.float32)
         ea = np.empty(max(ne.value, 1), np.uint32)
         eb = np.empty(max(ne.value, 1), np.uint32)
         w = np.empty(max(ne.value, 1), np.float32)
-        self._ck(self.L.gseg_export_graph(self.h, C.byref(nv), C.byref(ne), size.ctypes.data, Int.ctypes.data,
+        self._ck(self.L.gseg_export_graph(self.h, int(dedup), C.byref(nv), C.byref(ne), size.ctypes.data, Int.ctypes.data,
                                           ea.ctypes.data, eb.ctypes.data, w.ctypes.data, len(size), len(ea)),
                  "gseg_export_graph")
         return dict(size=size, Int=Int, ea=ea[:ne.value], eb=eb[:ne.value], w=w[:ne.value])

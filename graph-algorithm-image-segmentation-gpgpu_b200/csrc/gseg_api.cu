@@ -55,6 +55,12 @@ struct gseg_ctx {
     int nbig_hint;        // grid-wide rounds to enqueue before the tail (-1: estimate; adapts to the last run)
     int hint_w, hint_h, hint_variant, hint_conn;
     SortScratch sort;
+    // export of the final component graph (tiled schedule): cached dense / de-duplicated edge list
+    u64 *d_xkeys;
+    u32 *d_xvals, *d_xkeep, *d_xw, *x_w;
+    uint2 *d_xab, *x_ab;
+    size_t x_cap, x_count;
+    bool x_valid, x_dedup;
     // run state
     gseg_params params;
     int w, h, D;
@@ -217,6 +223,7 @@ extern "C" void gseg_destroy(gseg_ctx *ctx) {
     }
     cudaFree(ctx->d_pscan); cudaFree(ctx->d_arena); cudaFree(ctx->d_statusC); cudaFree(ctx->d_statusE); cudaFree(ctx->d_ctl);
     sort_scratch_free(&ctx->sort);
+    cudaFree(ctx->d_xkeys); cudaFree(ctx->d_xvals); cudaFree(ctx->d_xkeep); cudaFree(ctx->d_xab); cudaFree(ctx->d_xw);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
     if (ctx->h_head) cudaFreeHost(ctx->h_head);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -466,7 +473,7 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
     const int len = gauss_mask(p->sigma, hp->mask);
     if (len < 0) return fail(ctx, GSEG_E_ARG, "sigma too large (more than 64 taps)", cudaSuccess);
     CK(cudaSetDevice(ctx->device));
-    ctx->valid = false;
+    ctx->valid = false; ctx->x_valid = false;
     ctx->params = *p;
     ctx->w = w; ctx->h = h; ctx->D = p->connectivity == 8 ? 4 : 2;
     if (ctx->D > ctx->Dmax) return fail(ctx, GSEG_E_SIZE, "context was created for 4-connected grids only", cudaSuccess);
@@ -725,30 +732,73 @@ extern "C" int gseg_blurred(gseg_ctx *ctx, float *out, int mem_kind) {
 }
 
 // ---- tiled schedule: export / import of component graphs ------------------------------------------------
-extern "C" int gseg_export_graph(gseg_ctx *ctx, int64_t *n_components, int64_t *n_edges, uint32_t *size, float *Int,
-                                 uint32_t *ea, uint32_t *eb, float *w, int64_t cap_components, int64_t cap_edges) {
-    if (!ctx || !n_components || !n_edges) return GSEG_E_ARG;
-    if (!ctx->valid || ctx->params.variant == GSEG_SUPERPIX) return GSEG_E_STATE;
+// Device side of the export: gather the pages into a dense list and, if asked, eliminate duplicates.
+// Leaves the list in (x_ab, x_w) with x_count entries and caches it until the next run.
+static int export_prepare(gseg_ctx *ctx, int dedup) {
+    if (ctx->x_valid && ctx->x_dedup == (dedup != 0)) return GSEG_OK;
     const GsegCtl *h = ctx->h_ctl;
-    const int64_t V = h->st.V, E = h->st.E;
-    *n_components = V; *n_edges = E;
-    if (!size && !Int && !ea && !eb && !w) return GSEG_OK;
-    if (!size || !Int || !ea || !eb || !w || cap_components < V || cap_edges < E) return GSEG_E_ARG;
-    CK(cudaSetDevice(ctx->device));
+    const size_t V = h->st.V, E = h->st.E;
     const int cur = (int)(h->st.round & 1u);
     const GsegBufs B = bufs_of(ctx);
     const u32 P = h->st.P;
+    cudaStream_t s = ctx->stream;
     if (P) {
         ctx->launches += 2;
-        k_export_scan<<<1, 1024, 0, ctx->stream>>>(B, cur, P);
-        k_export_gather<<<grid_for(P, NT / 32), NT, 0, ctx->stream>>>(B, cur, P);
+        k_export_scan<<<1, 1024, 0, s>>>(B, cur, P);
+        k_export_gather<<<grid_for(P, NT / 32), NT, 0, s>>>(B, cur, P);
         CK(cudaGetLastError());
     }
+    ctx->x_ab = ctx->d_eab[cur ^ 1]; ctx->x_w = ctx->d_ew[cur ^ 1]; ctx->x_count = E;
+    if (dedup && E > 1) {
+        if (ctx->x_cap < E) {
+            cudaFree(ctx->d_xkeys); cudaFree(ctx->d_xvals); cudaFree(ctx->d_xkeep); cudaFree(ctx->d_xab); cudaFree(ctx->d_xw);
+            ctx->d_xkeys = nullptr; ctx->d_xvals = nullptr; ctx->d_xkeep = nullptr; ctx->d_xab = nullptr; ctx->d_xw = nullptr;
+            ctx->x_cap = 0;
+            CK(dalloc(&ctx->d_xkeys, E)); CK(dalloc(&ctx->d_xvals, E)); CK(dalloc(&ctx->d_xkeep, E));
+            CK(dalloc(&ctx->d_xab, E)); CK(dalloc(&ctx->d_xw, E));
+            ctx->x_cap = E;
+        }
+        int bits = 1;
+        while (bits < 64 && ((u64)V * V - 1u) >> bits) ++bits; // pair keys are < V^2
+        ctx->launches += 3;
+        k_pair_keys<<<grid_for(E, NT), NT, 0, s>>>(ctx->x_ab, (u32)E, (u32)V, ctx->d_xkeys, ctx->d_xvals, ctx->d_xkeep);
+        CK(cudaGetLastError());
+        cudaError_t e = onesweep_sort_pairs(&ctx->sort, ctx->d_xkeys, ctx->d_xvals, E, 0, bits, s);
+        if (e != cudaSuccess) return fail(ctx, GSEG_E_CUDA, "onesweep_sort_pairs", e);
+        k_pair_select<<<grid_for(E, NT), NT, 0, s>>>(ctx->d_xkeys, ctx->d_xvals, ctx->x_w, (u32)E, ctx->d_xkeep);
+        CK(cudaMemsetAsync(&ctx->d_ctl->ticketE, 0, sizeof(u32), s));
+        const u32 tag = ctx->epoch_next; // a tag no round of any run uses
+        ctx->epoch_next += 2u;
+        k_compact_keep<<<grid_for(E, 1024, 64), 1024, 0, s>>>(ctx->d_ctl, ctx->x_ab, ctx->x_w, ctx->d_xkeep, (u32)E, tag,
+                                                                ctx->d_statusE, ctx->d_xab, ctx->d_xw);
+        CK(cudaGetLastError());
+        u32 kept = 0;
+        CK(cudaMemcpyAsync(&kept, &ctx->d_ctl->Eacc[GSEG_MAXR], sizeof(u32), cudaMemcpyDeviceToHost, s));
+        CK(cudaStreamSynchronize(s));
+        ctx->x_ab = ctx->d_xab; ctx->x_w = ctx->d_xw; ctx->x_count = kept;
+    }
+    ctx->x_valid = true; ctx->x_dedup = dedup != 0;
+    return GSEG_OK;
+}
+
+extern "C" int gseg_export_graph(gseg_ctx *ctx, int dedup, int64_t *n_components, int64_t *n_edges, uint32_t *size, float *Int,
+                                 uint32_t *ea, uint32_t *eb, float *w, int64_t cap_components, int64_t cap_edges) {
+    if (!ctx || !n_components || !n_edges) return GSEG_E_ARG;
+    if (!ctx->valid || ctx->params.variant == GSEG_SUPERPIX) return GSEG_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    int rc = export_prepare(ctx, dedup);
+    if (rc) return rc;
+    const GsegCtl *h = ctx->h_ctl;
+    const int64_t V = h->st.V, E = (int64_t)ctx->x_count;
+    *n_components = V; *n_edges = E;
+    if (!size && !Int && !ea && !eb && !w) return GSEG_OK;
+    if (!size || !Int || !ea || !eb || !w || cap_components < V || cap_edges < E) return GSEG_E_ARG;
+    const int cur = (int)(h->st.round & 1u);
     std::vector<uint2> hab, hat;
     try { hab.resize((size_t)E); hat.resize((size_t)V); } catch (...) { return fail(ctx, GSEG_E_ARG, "host staging allocation", cudaSuccess); }
     if (E) {
-        CK(cudaMemcpyAsync(hab.data(), ctx->d_eab[cur ^ 1], (size_t)E * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
-        CK(cudaMemcpyAsync(w, ctx->d_ew[cur ^ 1], (size_t)E * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(hab.data(), ctx->x_ab, (size_t)E * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(w, ctx->x_w, (size_t)E * sizeof(u32), cudaMemcpyDeviceToHost, ctx->stream));
     }
     CK(cudaMemcpyAsync(hat.data(), ctx->d_attr[cur], (size_t)V * sizeof(uint2), cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
@@ -783,7 +833,7 @@ extern "C" int gseg_segment_graph(gseg_ctx *ctx, int64_t n_components, const uin
     if ((size_t)n_components > ctx->Vmax || (size_t)n_edges + GSEG_PAGE > Eslots)
         return fail(ctx, GSEG_E_SIZE, "graph exceeds context capacity", cudaSuccess);
     CK(cudaSetDevice(ctx->device));
-    ctx->valid = false;
+    ctx->valid = false; ctx->x_valid = false;
     ctx->params = *p;
     ctx->w = (int)n_components; ctx->h = 1; ctx->D = 2;
     const size_t V = (size_t)n_components, E = (size_t)n_edges;

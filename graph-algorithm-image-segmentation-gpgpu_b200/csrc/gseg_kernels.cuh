@@ -913,6 +913,54 @@ __global__ void __launch_bounds__(NT) k_export_gather(GsegBufs B, int cur, u32 P
         for (u32 i = lane; i < cnt; i += 32u) { B.eab[nxt][dst + i] = B.eab[cur][src + i]; B.ew[nxt][dst + i] = B.ew[cur][src + i]; }
     }
 }
+// Duplicate elimination of the exported list (the reference's DPP branches: sort packed keys, keep the
+// lightest of every run, Report.pdf p3 s3.2.2): key = pair of end components, payload = list position;
+// after the in-house onesweep sort (stable: positions ascend inside a run) the head of every run scans its
+// run for the minimum (weight bits, position) and marks that edge; the marked edges are compacted in list order.
+__global__ void __launch_bounds__(NT) k_pair_keys(const uint2 *__restrict__ eab, u32 E, u32 V, u64 *__restrict__ keys,
+                                                  u32 *__restrict__ vals, u32 *__restrict__ keep) {
+    for (u32 i = blockIdx.x * NT + threadIdx.x; i < E; i += gridDim.x * NT) {
+        const uint2 ab = eab[i];
+        keys[i] = (u64)min(ab.x, ab.y) * V + max(ab.x, ab.y);
+        vals[i] = i;
+        keep[i] = 0u;
+    }
+}
+__global__ void __launch_bounds__(NT) k_pair_select(const u64 *__restrict__ keys, const u32 *__restrict__ vals,
+                                                    const u32 *__restrict__ ew, u32 E, u32 *__restrict__ keep) {
+    for (u32 j = blockIdx.x * NT + threadIdx.x; j < E; j += gridDim.x * NT) {
+        const u64 k = keys[j];
+        if (j > 0 && keys[j - 1] == k) continue; // not the head of a run
+        u32 bi = vals[j], bw = ew[bi];
+        for (u32 t = j + 1; t < E && keys[t] == k; ++t) {
+            const u32 i = vals[t], w = ew[i];
+            if (w < bw) { bw = w; bi = i; } // equal weights: the earlier position (already held) wins
+        }
+        keep[bi] = 1u;
+    }
+}
+// Ordered compaction of the marked edges: chunks of blockDim edges by ticket, block-granular look-back.
+__global__ void __launch_bounds__(1024) k_compact_keep(GsegCtl *ctl, const uint2 *__restrict__ eab, const u32 *__restrict__ ew,
+                                                       const u32 *__restrict__ keep, u32 E, u32 tag, u64 *status,
+                                                       uint2 *__restrict__ oab, u32 *__restrict__ ow) {
+    __shared__ u32 s[68];
+    const int lane = threadIdx.x & 31;
+    const u32 nchunks = (E + blockDim.x - 1) / blockDim.x;
+    for (;;) {
+        if (threadIdx.x == 0) s[67] = atomicAdd(&ctl->ticketE, 1u);
+        __syncthreads();
+        const u32 chunk = s[67];
+        if (chunk >= nchunks) break;
+        const u32 i = chunk * blockDim.x + threadIdx.x;
+        const bool k = i < E && keep[i] != 0u;
+        const u32 m = __ballot_sync(0xFFFFFFFFu, k);
+        u32 bend;
+        const u32 wpre = block_ordered_offset(__popc(m), chunk, tag, status, &ctl->error, s, &bend);
+        if (k) { const u32 o = wpre + __popc(m & ((1u << lane) - 1u)); oab[o] = eab[i]; ow[o] = ew[i]; }
+        if (chunk == nchunks - 1 && threadIdx.x == 0) ctl->Eacc[GSEG_MAXR] = bend;
+        __syncthreads();
+    }
+}
 // Import: dense pages of GSEG_PAGE slots over a caller-supplied edge list (slot = list position = the
 // tie-break) and the per-component minimum of round 1.
 __global__ void __launch_bounds__(NT) k_graph_init(GsegBufs B, u32 E, u32 P) {

@@ -151,8 +151,11 @@ int gseg_blurred(gseg_ctx *ctx, float *out, int mem_kind);
  *
  * gseg_export_graph: components (size, Int(C)) and live inter-component edges (a, b, weight; ids = the
  * dense labels of gseg_labels(-1); list order = edge-index order) of the last FELZ/HIER run.  Call with
- * NULL arrays to get the counts, then with host arrays of at least that capacity. */
-int gseg_export_graph(gseg_ctx *ctx, int64_t *n_components, int64_t *n_edges, uint32_t *size, float *Int,
+ * NULL arrays to get the counts, then with host arrays of at least that capacity.
+ * dedup != 0: parallel edges between the same two components are reduced to their minimum (weight, list
+ * position) -- the reference's sort-based duplicate elimination (Report p3 s3.2.2), on the in-house
+ * onesweep radix sort; the partition the joined rounds produce is unchanged, the list is ~100x shorter. */
+int gseg_export_graph(gseg_ctx *ctx, int dedup, int64_t *n_components, int64_t *n_edges, uint32_t *size, float *Int,
                       uint32_t *ea, uint32_t *eb, float *w, int64_t cap_components, int64_t cap_edges);
 /* Rows y0 .. y0+nrows-1 of the blurred planes: out[3][nrows][w] (the cut-edge weights need the boundary rows). */
 int gseg_blurred_rows(gseg_ctx *ctx, int y0, int nrows, float *out, int mem_kind);

@@ -7,7 +7,22 @@ import numpy as np
 PKG = "graph-algorithm-image-segmentation-gpgpu_b200"
 
 
-def oracle_strip(O, img, sigma, k, min_size, conn, max_rounds=48):
+def dedup_edges(ea, eb, w):
+    """Keep, of every set of parallel edges, the one with the minimum (weight bits, list position); list order kept."""
+    ea, eb, w = np.asarray(ea, np.int64), np.asarray(eb, np.int64), np.asarray(w, np.float32)
+    if len(ea) == 0:
+        return ea.astype(np.uint32), eb.astype(np.uint32), w
+    lo, hi = np.minimum(ea, eb), np.maximum(ea, eb)
+    pair = lo * (int(hi.max()) + 1) + hi
+    idx = np.arange(len(ea))
+    order = np.lexsort((idx, w.view(np.uint32), pair))
+    first = np.ones(len(ea), bool)
+    first[1:] = pair[order][1:] != pair[order][:-1]
+    keep = np.sort(order[first])
+    return ea[keep].astype(np.uint32), eb[keep].astype(np.uint32), w[keep]
+
+
+def oracle_strip(O, img, sigma, k, min_size, conn, max_rounds=48, dedup=True):
     """(dense labels, graph, top colours, bottom colours) of one strip, from the CPU oracle."""
     h, w, _ = img.shape
     planes = O.blur(img, sigma)
@@ -32,8 +47,10 @@ def oracle_strip(O, img, sigma, k, min_size, conn, max_rounds=48):
         q = p + dy * w + dx
         keep = dense[p] != dense[q]
         ea.append(dense[p[keep]]); eb.append(dense[q[keep]]); ww.append(wts[d * V + p[keep]])
-    graph = dict(size=size, Int=Int.astype(np.float32), ea=np.concatenate(ea).astype(np.uint32),
-                 eb=np.concatenate(eb).astype(np.uint32), w=np.concatenate(ww).astype(np.float32))
+    ea, eb, ww = np.concatenate(ea), np.concatenate(eb), np.concatenate(ww).astype(np.float32)
+    if dedup:
+        ea, eb, ww = dedup_edges(ea, eb, ww)
+    graph = dict(size=size, Int=Int.astype(np.float32), ea=ea.astype(np.uint32), eb=eb.astype(np.uint32), w=ww)
     return dense.reshape(h, w), graph, planes[:, 0, :], planes[:, -1, :]
 
 
