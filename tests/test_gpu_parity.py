@@ -51,7 +51,7 @@ def test_synth_generator_matches_oracle(gseg, oracle, seg):
 @pytest.mark.parametrize("conn", [4, 8])
 def test_blur_and_weights_bit_exact(gseg, oracle, seg, w, h, conn):
     img = oracle.synth(w, h, 100 + w)
-    for sigma in (0.8, 0.0, 1.7):
+    for sigma in (0.8, 0.0, 1.7, 2.6):  # 2.6: more than 8 one-sided taps -> the general (non-tile) blur kernels
         seg.segment(img, sigma=sigma, k=300, min_size=0, connectivity=conn, variant=gseg.FELZ)
         pl = oracle.blur(img, sigma)
         assert np.array_equal(seg.blurred().view(np.uint32), pl.view(np.uint32))
