@@ -38,6 +38,7 @@ struct gseg_ctx {
     u64 *d_best[2];
     uint2 *d_attr[2];
     long long *d_csum[2];
+    float4 *d_cmean[2];
     uint2 *d_eab[2];
     u32 *d_ew[2], *d_pcnt[2], *d_poff[2], *d_pscan;
     u32 *d_arena;
@@ -218,7 +219,7 @@ extern "C" void gseg_destroy(gseg_ctx *ctx) {
     cudaFree(ctx->d_G); cudaFree(ctx->d_wgrid); cudaFree(ctx->d_wsel);
     cudaFree(ctx->d_succ); cudaFree(ctx->d_rank);
     for (int i = 0; i < 2; ++i) {
-        cudaFree(ctx->d_best[i]); cudaFree(ctx->d_attr[i]); cudaFree(ctx->d_csum[i]);
+        cudaFree(ctx->d_best[i]); cudaFree(ctx->d_attr[i]); cudaFree(ctx->d_csum[i]); cudaFree(ctx->d_cmean[i]);
         cudaFree(ctx->d_eab[i]); cudaFree(ctx->d_ew[i]); cudaFree(ctx->d_pcnt[i]); cudaFree(ctx->d_poff[i]); cudaFree(ctx->d_labels[i]);
     }
     cudaFree(ctx->d_pscan); cudaFree(ctx->d_arena); cudaFree(ctx->d_statusC); cudaFree(ctx->d_statusE); cudaFree(ctx->d_ctl);
@@ -295,7 +296,7 @@ static GsegBufs bufs_of(const gseg_ctx *c) {
     B.planes = c->d_planes; B.G = c->d_G; B.wgrid = c->d_wgrid;
     B.succ = c->d_succ; B.rank = c->d_rank; B.wsel = c->d_wsel; B.arena = c->d_arena;
     for (int i = 0; i < 2; ++i) {
-        B.best[i] = c->d_best[i]; B.attr[i] = c->d_attr[i]; B.csum[i] = c->d_csum[i];
+        B.best[i] = c->d_best[i]; B.attr[i] = c->d_attr[i]; B.csum[i] = c->d_csum[i]; B.cmean[i] = c->d_cmean[i];
         B.eab[i] = c->d_eab[i]; B.ew[i] = c->d_ew[i]; B.pcnt[i] = c->d_pcnt[i]; B.poff[i] = c->d_poff[i];
     }
     B.statusC = c->d_statusC; B.statusE = c->d_statusE; B.pscan = c->d_pscan;
@@ -364,6 +365,10 @@ static void enqueue_round0(gseg_ctx *c, cudaStream_t s) {
     mark(c, s, "k_relabel", 0);
     if (sp) k_relabel<true, true><<<grid_for(V, NT), NT, 0, s>>>(c->d_ctl, B);
     else k_relabel<true, false><<<grid_for(V, NT), NT, 0, s>>>(c->d_ctl, B);
+    if (sp) {
+        mark(c, s, "k_means", 0);
+        k_means<<<grid_for(V, NT, c->num_sms * c->occ_mult), NT, 0, s>>>(c->d_ctl, B);
+    }
     mark(c, s, "k_r0_edges", 0);
     if (D == 2) { if (sp) launch_r0_edges<2, true>(c, s, V, B); else launch_r0_edges<2, false>(c, s, V, B); }
     else { if (sp) launch_r0_edges<4, true>(c, s, V, B); else launch_r0_edges<4, false>(c, s, V, B); }
@@ -384,6 +389,10 @@ static void enqueue_round(gseg_ctx *c, cudaStream_t s, int r, size_t Vb, size_t 
     mark(c, s, "k_relabel", r);
     if (sp) k_relabel<false, true><<<grid_for(Vb, NT, cap), NT, 0, s>>>(c->d_ctl, B);
     else k_relabel<false, false><<<grid_for(Vb, NT, cap), NT, 0, s>>>(c->d_ctl, B);
+    if (sp) {
+        mark(c, s, "k_means", r);
+        k_means<<<grid_for(Vb, NT, cap), NT, 0, s>>>(c->d_ctl, B);
+    }
     mark(c, s, "k_edges", r);
     if (sp) k_edges<true><<<grid_for(Pb, NT / 32, cap), NT, 0, s>>>(c->d_ctl, B);
     else k_edges<false><<<grid_for(Pb, NT / 32, cap), NT, 0, s>>>(c->d_ctl, B);
@@ -443,7 +452,7 @@ static int ensure(gseg_ctx *ctx, T **p, size_t n) {
 
 static int ensure_csum(gseg_ctx *ctx) {
     if (ctx->d_csum[0]) return GSEG_OK;
-    for (int i = 0; i < 2; ++i) CK(dalloc(&ctx->d_csum[i], 3 * (ctx->Vmax + 64)));
+    for (int i = 0; i < 2; ++i) { CK(dalloc(&ctx->d_csum[i], 3 * (ctx->Vmax + 64))); CK(dalloc(&ctx->d_cmean[i], ctx->Vmax + 64)); }
     return GSEG_OK;
 }
 

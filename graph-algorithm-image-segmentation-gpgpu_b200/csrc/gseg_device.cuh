@@ -68,6 +68,7 @@ struct GsegBufs {
     u64 *best[2];     // per component: min outgoing edge key (weight bits << 32 | edge position)
     uint2 *attr[2];   // per component: x = size |C|, y = fp32 bits of Int(C)
     long long *csum[2]; // per component: 3 fixed-point colour sums (superpixel variant)
+    float4 *cmean[2];   // per component: mean colour = csum / (256 |C|), computed once per round from the finished sums
     uint2 *eab[2];    // per live edge: the two end components
     u32 *ew[2];       // per live edge: fp32 bits of the weight (superpixel: of the static strength)
     u32 *pcnt[2];     // per page of the edge list: live edges in the page

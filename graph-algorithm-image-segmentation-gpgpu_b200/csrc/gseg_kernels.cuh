@@ -216,6 +216,19 @@ __device__ __forceinline__ float mean_dist(const long long *ca, u32 sa, const lo
     return __fsqrt_rn(s);
 }
 
+// Superpixel round weight from the per-component means (phase M): the same fp32 operations as mean_dist,
+// with the six divisions done once per component instead of once per edge end.
+__device__ __forceinline__ float4 mean_of(const long long *csum, const uint2 *attr, u32 n) {
+    const float f = __fmul_rn(__uint2float_rn(__ldcg(&attr[n].x)), 256.0f);
+    return make_float4(__fdiv_rn(__ll2float_rn(__ldcg(csum + 3 * (size_t)n)), f), __fdiv_rn(__ll2float_rn(__ldcg(csum + 3 * (size_t)n + 1)), f),
+                       __fdiv_rn(__ll2float_rn(__ldcg(csum + 3 * (size_t)n + 2)), f), 0.f);
+}
+__device__ __forceinline__ float mean_dist_m(const float4 *cmean, u32 a, u32 b) {
+    const float4 ma = __ldcg(cmean + a), mb = __ldcg(cmean + b);
+    const float dr = __fsub_rn(ma.x, mb.x), dg = __fsub_rn(ma.y, mb.y), db = __fsub_rn(ma.z, mb.z);
+    return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dr, dr), __fmul_rn(dg, dg)), __fmul_rn(db, db)));
+}
+
 // component-mean distance from the global accumulators (written by atomics in phase R: read at L2)
 __device__ __forceinline__ float mean_dist_g(const long long *csum, const uint2 *attr, u32 a, u32 b) {
     long long ca[3] = {__ldcg(csum + 3 * (size_t)a), __ldcg(csum + 3 * (size_t)a + 1), __ldcg(csum + 3 * (size_t)a + 2)};
@@ -544,7 +557,7 @@ __device__ __forceinline__ void emit_row(const GsegBufs &B, int nxt, u32 pos, bo
     if (act) {
         B.eab[nxt][pos] = make_uint2(a, b);
         B.ew[nxt][pos] = wv;
-        if (SP) kb = __float_as_uint(__fmul_rn(__uint_as_float(wv), mean_dist_g(B.csum[nxt], B.attr[nxt], a, b)));
+        if (SP) kb = __float_as_uint(__fmul_rn(__uint_as_float(wv), mean_dist_m(B.cmean[nxt], a, b)));
     }
     warp_run_min<FILTER, FILTER ? 32 : RUNWIN>(B.best[nxt], a, kb, pos, act, fa);
     warp_run_min<FILTER, FILTER ? 32 : RUNWIN>(B.best[nxt], b, kb, pos, act, fb);
@@ -811,6 +824,12 @@ __device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const R
     if (lane == 0 && esum) atomicAdd(&ctl->Eacc[st.round], esum);
 }
 
+// a11 (superpixel), phase M: mean colour of every component of the next round, from the sums phase R finished.
+__device__ __forceinline__ void phase_M(const GsegBufs &B, int nxt, u32 Vnext) {
+    for (u32 n = blockIdx.x * blockDim.x + threadIdx.x; n < Vnext; n += gridDim.x * blockDim.x)
+        B.cmean[nxt][n] = mean_of(B.csum[nxt], B.attr[nxt], n);
+}
+
 // ---- grid-wide schedule: one kernel per phase ---------------------------------------------------
 // Every kernel sizes itself from the device-resident round state, so the host enqueues rounds without
 // reading anything back; kernels of rounds that are not needed (done / handed to the tail) exit at once.
@@ -819,6 +838,11 @@ __global__ void __launch_bounds__(NT) k_relabel(const GsegCtl *ctl, GsegBufs B) 
     const RoundState st = ctl->st;
     if (st.phase == PH_DONE || in_tail(ctl, st)) return;
     phase_R<NT, R0, SP>(ctl, B, st);
+}
+__global__ void __launch_bounds__(NT) k_means(const GsegCtl *ctl, GsegBufs B) {
+    const RoundState st = ctl->st;
+    if (st.phase == PH_DONE || in_tail(ctl, st)) return;
+    phase_M(B, (int)((st.round & 1u) ^ 1u), ctl->Vnext);
 }
 // Merging rounds only: the exclusive scan of the page counts the edge phase places its output by.
 // Blocks take chunks of 1024 counts by ticket; chunk prefixes come from a block-granular look-back.
@@ -884,6 +908,11 @@ __global__ void __launch_bounds__(NTT, 1) k_tail(GsegCtl *ctl, GsegBufs B) {
         phase_R<NTT, false, SP>(ctl, B, st);
         __threadfence();
         cl.sync();
+        if (SP) { // phase M needs the finished sums of phase R and must finish before the edge phase reads the means
+            phase_M(B, (int)((st.round & 1u) ^ 1u), Vn);
+            __threadfence();
+            cl.sync();
+        }
         if (writer) ctl->t_R[st.round] = globaltimer_ns();
         phase_E<SP>(ctl, B, st, Vn);
         __threadfence();
