@@ -390,3 +390,32 @@ def test_tiled_schedule_matches_tiled_oracle(gseg, oracle, seg, n_strips, conn):
     out = np.concatenate([comp[int(joined["offsets"][i]) + labs[i].astype(np.int64)] for i in range(n_strips)])
     ref, nref, _, _ = oracle_tiled(oracle, img, n_strips, 0.8, 300.0, 20, conn)
     assert n == nref and same_partition(oracle, out.reshape(300, 400), ref.reshape(300, 400))
+
+
+def test_randomised_sweep(gseg, oracle):
+    """A short run of tools/fuzz.py's randomised sweep (random sizes, inputs, parameters, variants, schedules,
+    tail thresholds, grid sizes); the full 4000-case run is recorded in profiles/."""
+    rng = np.random.default_rng(123)
+    s = gseg.Segmenter(700, 700)
+    try:
+        for case in range(120):
+            w, h = int(rng.integers(1, 700)), int(rng.integers(1, 700))
+            if case % 7 == 0:
+                w, h = int(rng.integers(1, 700)), int(rng.integers(1, 12))
+            kind = int(rng.integers(0, 3))
+            if kind == 0:
+                img = oracle.synth(w, h, int(rng.integers(1, 1 << 30)))
+            elif kind == 1:
+                img = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+            else:
+                img = (rng.integers(0, 4, (h, w, 3)) * 60).astype(np.uint8)
+            conn, variant = int(rng.choice([4, 8])), int(rng.choice([0, 0, 1, 2]))
+            sigma, k = float(rng.choice([0.0, 0.8, 1.3])), float(rng.choice([0.0, 30.0, 300.0, 3000.0]))
+            ms, flags = int(rng.choice([0, 2, 20, 200])), int(rng.choice([0, 0, 1]))
+            s.set_tail(*[(262144, 65536), (0, 0), (2000, 300)][int(rng.integers(0, 3))])
+            s.set_blocks_per_sm(int(rng.choice([1, 2, 4])))
+            s.segment(np.ascontiguousarray(img), sigma=sigma, k=k, min_size=ms, connectivity=conn, variant=variant, flags=flags)
+            ref, n = oracle.segment(np.ascontiguousarray(img), sigma, k, ms, conn, variant, max_rounds=48)
+            assert same_partition(oracle, s.labels(), ref), (case, w, h, kind, conn, variant, sigma, k, ms, flags)
+    finally:
+        s.close()
