@@ -126,6 +126,7 @@ __device__ __forceinline__ u32 block_excl_scan(u32 v, u32 *s) {
 
 // ---- decoupled look-back ---------------------------------------------------------------------
 // status word: [63:34] tag (30 bit, unique per scan launch), [33:32] state, [31:0] value.
+#define LB_WIN 4 /* windows of 32 predecessors fetched per look-back round trip */
 #define ST_AGG 1u
 #define ST_INC 2u
 __device__ __forceinline__ u64 pack_status(u32 tag, u32 state, u32 val) {
@@ -146,31 +147,42 @@ __device__ __forceinline__ u32 lookback_prefix(u64 *status, u32 tile, u32 tag, u
     u32 excl = 0u, spins = 0u;
     int look = (int)tile - 1;
     for (;;) {
-        const int idx = look - lane;
-        const u64 s = idx >= 0 ? ld_relaxed_u64(status + idx) : pack_status(tag, ST_INC, 0u);
-        const u32 hi = (u32)(s >> 32);
-        const bool valid = (hi >> 2) == tag && (hi & 3u) != 0u;
-        const bool inc = valid && (hi & 3u) == ST_INC;
-        const u32 incm = __ballot_sync(0xFFFFFFFFu, inc);
-        const u32 invm = __ballot_sync(0xFFFFFFFFu, !valid);
-        const int first = incm ? __ffs(incm) - 1 : 32;
-        const u32 need = first >= 31 ? 0xFFFFFFFFu : ((2u << first) - 1u);
-        if (invm & need) {
+        // four windows of 32 predecessors are loaded at once: when a whole generation of tiles starts together
+        // nobody has an inclusive prefix yet and every tile has to walk back over all of them, so the walk
+        // should cost one round trip per 128 tiles, not per 32
+        u64 sv[LB_WIN];
+#pragma unroll
+        for (int k = 0; k < LB_WIN; ++k) {
+            const int idx = look - 32 * k - lane;
+            sv[k] = idx >= 0 ? ld_relaxed_u64(status + idx) : pack_status(tag, ST_INC, 0u);
+        }
+        bool done = false, retry = false;
+#pragma unroll
+        for (int k = 0; k < LB_WIN; ++k) {
+            if (done || retry) break;
+            const u32 hi = (u32)(sv[k] >> 32);
+            const bool valid = (hi >> 2) == tag && (hi & 3u) != 0u;
+            const bool inc = valid && (hi & 3u) == ST_INC;
+            const u32 incm = __ballot_sync(0xFFFFFFFFu, inc);
+            const u32 invm = __ballot_sync(0xFFFFFFFFu, !valid);
+            const int first = incm ? __ffs(incm) - 1 : 32;
+            const u32 need = first >= 31 ? 0xFFFFFFFFu : ((2u << first) - 1u);
+            if (invm & need) { retry = true; break; } // a predecessor has not published yet: poll again from here
+            u32 v = lane <= first ? (u32)sv[k] : 0u;
+#pragma unroll
+            for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+            excl += v;
+            look -= 32;
+            if (first < 32) done = true;
+        }
+        if (done) break;
+        if (retry) {
             if (++spins > (1u << 22)) {
                 if (lane == 0) *err = DERR_SCAN;
                 return excl;
             }
-            // back off: thousands of warps polling the few cache lines at the scan frontier would queue up
-            // in one L2 slice and delay every other access behind them
-            __nanosleep(spins < 8u ? 200u : 1000u);
-            continue;
+            __nanosleep(spins < 8u ? 100u : 1000u);
         }
-        u32 v = lane <= first ? (u32)s : 0u;
-#pragma unroll
-        for (int o = 16; o; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-        excl += v;
-        if (first < 32) break;
-        look -= 32;
     }
     if (lane == 0) st_relaxed_u64(status + tile, pack_status(tag, ST_INC, excl + aggregate));
     return excl;
