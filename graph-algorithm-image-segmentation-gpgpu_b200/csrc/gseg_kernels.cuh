@@ -498,13 +498,15 @@ __device__ __forceinline__ void block_scan_pages(const u32 *pcnt, u32 P, u32 *ps
 // lanes that map to the same new component combine their contributions by warp shuffles first.
 // R0: components are pixels (size 1, Int 0, colour = the pixel's fixed-point colour).
 // ------------------------------------------------------------------------------------------------
-template <int NTH, bool R0, bool SP>
+template <int NTH, bool R0, bool SP, bool SPREAD = false>
 __device__ __forceinline__ void phase_R(const GsegCtl *ctl, const GsegBufs &B, const RoundState &st) {
     const int cur = st.round & 1, nxt = cur ^ 1;
     const u32 V = st.V, Vr = (V + 31u) & ~31u;
     u32 *map = B.arena + st.map_off;
     const u32 V0 = (u32)ctl->p.w * (u32)ctl->p.h;
-    for (u32 c = blockIdx.x * NTH + threadIdx.x; c < Vr; c += gridDim.x * NTH) {
+    // SPREAD (tail): consecutive warps' worth of components go to different blocks (see phase_S)
+    const u32 c_first = SPREAD ? ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u + (threadIdx.x & 31u) : blockIdx.x * NTH + threadIdx.x;
+    for (u32 c = c_first; c < Vr; c += gridDim.x * NTH) {
         const bool act = c < V;
         u32 m = 0u, sz = 1u, iv = 0u;
         if (act) {
@@ -636,7 +638,7 @@ __global__ void __launch_bounds__(NT, 4) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
 // a6+a7+a9 (rounds >= 1): each component's choice under the predicate / min-size rule, 2-cycle
 // removal, root flags + look-back scan = new ids; the tile clears the accumulators of its new ids.
 // ------------------------------------------------------------------------------------------------
-template <bool SP>
+template <bool SP, bool SPREAD>
 __device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, u32 *sh) {
     constexpr u32 TILE_C = 32 * CPT; // components per warp: CPT rows of 32 consecutive ids
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
@@ -653,12 +655,23 @@ __device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const R
     const bool pred = ctl->p.variant == GSEG_FELZ && phase == PH_PRED;
     const bool msz = ctl->p.variant == GSEG_FELZ && phase == PH_MINSIZE;
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ticketE = 0;
+    // SPREAD (the tail cluster: little work, all blocks resident): warp tiles, statically interleaved over
+    // the blocks so that a handful of tiles keeps every SM's issue slots busy instead of one SM's, and a
+    // warp-granular look-back.  Otherwise: block tiles by ticket and one look-back per block.
+    u32 stile = (u32)wid * gridDim.x + blockIdx.x;
     for (;;) {
-        if (threadIdx.x == 0) sh[65] = atomicAdd(&ctl->ticketC, 1u);
-        __syncthreads();
-        const u32 btile = sh[65];
-        if (btile >= ntiles) break;
-        const u32 tile = btile * nwarp + wid; // may lie beyond the last warp tile: then every row is empty
+        u32 btile = 0, tile;
+        if (SPREAD) {
+            tile = stile;
+            if (tile >= nwt) break;
+            stile += gridDim.x * (u32)nwarp;
+        } else {
+            if (threadIdx.x == 0) sh[65] = atomicAdd(&ctl->ticketC, 1u);
+            __syncthreads();
+            btile = sh[65];
+            if (btile >= ntiles) break;
+            tile = btile * nwarp + wid; // may lie beyond the last warp tile: then every row is empty
+        }
         const u32 base = tile * TILE_C + lane;
         // Three dependent gathers per component, each stage issued for all CPT rows at once:
         //   best[c] -> ends of that edge -> {attributes of both ends, best[] of the other end}.
@@ -712,9 +725,15 @@ __device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const R
             m[j] = __ballot_sync(0xFFFFFFFFu, root);
             total += __popc(m[j]);
         }
-        u32 bend;
-        const u32 pre = block_ordered_offset(total, btile, tag, B.statusC, &ctl->error, sh, &bend);
-        if (btile == ntiles - 1 && threadIdx.x == 0) ctl->Vnext = bend;
+        u32 pre;
+        if (SPREAD) {
+            pre = lookback_prefix(B.statusC, tile, tag, total, &ctl->error);
+            if (tile == nwt - 1 && lane == 0) ctl->Vnext = pre + total;
+        } else {
+            u32 bend;
+            pre = block_ordered_offset(total, btile, tag, B.statusC, &ctl->error, sh, &bend);
+            if (btile == ntiles - 1 && threadIdx.x == 0) ctl->Vnext = bend;
+        }
         u32 rowoff = pre;
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
@@ -737,7 +756,7 @@ __device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const R
 // of the G pages, a 4-step shuffle search maps a virtual slot to its page).  G = 1: page t -> page t in
 // place; G > 1: the output page g starts at pscan[G g].  No tickets, no look-back, no barriers.
 // ------------------------------------------------------------------------------------------------
-template <bool SP>
+template <bool SP, bool SPREAD = false>
 __device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, u32 Vnext) {
     constexpr int ROWS = GSEG_PAGE / 32;
     const int lane = threadIdx.x & 31;
@@ -753,7 +772,7 @@ __device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const R
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ticketC = 0;
     const u32 nwarp = blockDim.x >> 5, nw = gridDim.x * nwarp;
     u32 esum = 0;
-    for (u32 g = blockIdx.x * nwarp + (threadIdx.x >> 5); g < ngroups; g += nw) {
+    for (u32 g = SPREAD ? (threadIdx.x >> 5) * gridDim.x + blockIdx.x : blockIdx.x * nwarp + (threadIdx.x >> 5); g < ngroups; g += nw) {
         u32 mycnt = 0u, myoff = 0u;
         if ((u32)lane < G && G * g + lane < P) { mycnt = __ldcg(pc + G * g + lane); myoff = __ldcg(po + G * g + lane); }
         const u32 incl = warp_incl_scan(mycnt, lane);
@@ -826,8 +845,8 @@ __device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const R
 
 // a11 (superpixel), phase M: mean colour of every component of the next round, from the sums phase R finished.
 __device__ __forceinline__ void phase_M(const GsegBufs &B, int nxt, u32 Vnext) {
-    for (u32 n = blockIdx.x * blockDim.x + threadIdx.x; n < Vnext; n += gridDim.x * blockDim.x)
-        B.cmean[nxt][n] = mean_of(B.csum[nxt], B.attr[nxt], n);
+    for (u32 n = ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u + (threadIdx.x & 31u); n < Vnext; n += gridDim.x * blockDim.x)
+        B.cmean[nxt][n] = mean_of(B.csum[nxt], B.attr[nxt], n); // warps' worth of components interleaved over the blocks
 }
 
 // ---- grid-wide schedule: one kernel per phase ---------------------------------------------------
@@ -874,7 +893,7 @@ __global__ void __launch_bounds__(NT) k_succ_scan(GsegCtl *ctl, GsegBufs B) {
     __shared__ u32 sh[66];
     const RoundState st = ctl->st;
     if (st.phase == PH_DONE || in_tail(ctl, st)) return;
-    phase_S<SP>(ctl, B, st, sh);
+    phase_S<SP, false>(ctl, B, st, sh);
 }
 template <bool SP>
 __global__ void __launch_bounds__(NT, 4) k_edges(GsegCtl *ctl, GsegBufs B) {
@@ -900,12 +919,12 @@ __global__ void __launch_bounds__(NTT, 1) k_tail(GsegCtl *ctl, GsegBufs B) {
         if (writer) ctl->t_begin[st.round] = globaltimer_ns();
         const u32 G = group_size(st);
         if (G > 1u && blockIdx.x == gridDim.x - 1) block_scan_pages(B.pcnt[st.round & 1], st.P, B.pscan, sh);
-        phase_S<SP>(ctl, B, st, sh);
+        phase_S<SP, true>(ctl, B, st, sh);
         __threadfence();
         cl.sync();
         if (writer) ctl->t_S[st.round] = globaltimer_ns();
         const u32 Vn = ld_relaxed_u32(&ctl->Vnext);
-        phase_R<NTT, false, SP>(ctl, B, st);
+        phase_R<NTT, false, SP, true>(ctl, B, st);
         __threadfence();
         cl.sync();
         if (SP) { // phase M needs the finished sums of phase R and must finish before the edge phase reads the means
@@ -914,7 +933,7 @@ __global__ void __launch_bounds__(NTT, 1) k_tail(GsegCtl *ctl, GsegBufs B) {
             cl.sync();
         }
         if (writer) ctl->t_R[st.round] = globaltimer_ns();
-        phase_E<SP>(ctl, B, st, Vn);
+        phase_E<SP, true>(ctl, B, st, Vn);
         __threadfence();
         cl.sync();
         // One thread advances the round state and publishes it; everybody re-reads it after a fourth
