@@ -269,6 +269,40 @@ __device__ __forceinline__ void warp_run_min(u64 *best, u32 id, u32 kb, u32 pos,
     }
 }
 
+// Both ends of a row of edges at once: the two segmented minima are independent dependency chains, so
+// interleaving their shuffles halves the latency of the row (these kernels run few warps per SM in late
+// rounds and are bound by exactly this chain).
+template <bool FILTER, int WINDOW>
+__device__ __forceinline__ void warp_run_min2(u64 *best, u32 ida, u32 idb, u32 kb, u32 pos, bool act, u32 hia, u32 hib) {
+    const int lane = threadIdx.x & 31;
+    const u32 pa = __shfl_up_sync(0xFFFFFFFFu, ida, 1), pb = __shfl_up_sync(0xFFFFFFFFu, idb, 1);
+    const u32 actm = __ballot_sync(0xFFFFFFFFu, act);
+    const bool prev_act = lane != 0 && ((actm >> (lane - 1)) & 1u);
+    const bool heada = !prev_act || pa != ida, headb = !prev_act || pb != idb;
+    const u32 headsa = __ballot_sync(0xFFFFFFFFu, heada || !act), headsb = __ballot_sync(0xFFFFFFFFu, headb || !act);
+    if (!act) kb = 0xFFFFFFFFu;
+    const u32 hmask = ~((2u << lane) - 1u), lmask = (2u << lane) - 1u;
+    const u32 abva = headsa & hmask, abvb = headsb & hmask;
+    int enda = abva ? __ffs(abva) - 1 : 32, endb = abvb ? __ffs(abvb) - 1 : 32;
+    bool leada = heada, leadb = headb;
+    if (WINDOW < 32) {
+        const int sa = 31 - __clz(headsa & lmask), sb = 31 - __clz(headsb & lmask);
+        const int wa = sa + ((lane - sa) & ~(WINDOW - 1)), wb = sb + ((lane - sb) & ~(WINDOW - 1));
+        leada = lane == wa; leadb = lane == wb;
+        enda = min(enda, wa + WINDOW); endb = min(endb, wb + WINDOW);
+    }
+    u32 ka = kb, qa = pos, kbb = kb, qb = pos;
+#pragma unroll
+    for (int o = 1; o < WINDOW; o <<= 1) {
+        const u32 oka = __shfl_down_sync(0xFFFFFFFFu, ka, o), oqa = __shfl_down_sync(0xFFFFFFFFu, qa, o);
+        const u32 okb = __shfl_down_sync(0xFFFFFFFFu, kbb, o), oqb = __shfl_down_sync(0xFFFFFFFFu, qb, o);
+        if (lane + o < enda && oka < ka) { ka = oka; qa = oqa; }
+        if (lane + o < endb && okb < kbb) { kbb = okb; qb = oqb; }
+    }
+    if (leada && act && (!FILTER || ka <= hia)) atomicMin(best + ida, make_key(ka, qa));
+    if (leadb && act && (!FILTER || kbb <= hib)) atomicMin(best + idb, make_key(kbb, qb));
+}
+
 // Same run structure for the size / Int(C) accumulation of phase R: the run's first lane adds the
 // run's total size and takes the run's maximum Int.  All 32 lanes must call.
 __device__ __forceinline__ void warp_run_accumulate(uint2 *attr, u32 id, u32 sz, u32 iv, bool act) {

@@ -561,8 +561,7 @@ __device__ __forceinline__ void emit_row(const GsegBufs &B, int nxt, u32 pos, bo
         B.ew[nxt][pos] = wv;
         if (SP) kb = __float_as_uint(__fmul_rn(__uint_as_float(wv), mean_dist_m(B.cmean[nxt], a, b)));
     }
-    warp_run_min<FILTER, FILTER ? 32 : RUNWIN>(B.best[nxt], a, kb, pos, act, fa);
-    warp_run_min<FILTER, FILTER ? 32 : RUNWIN>(B.best[nxt], b, kb, pos, act, fb);
+    warp_run_min2<FILTER, FILTER ? 32 : RUNWIN>(B.best[nxt], a, b, kb, pos, act, fa, fb);
 }
 
 // a10 (round 0): grid edges -> paged list of inter-component edges, in edge-index order
