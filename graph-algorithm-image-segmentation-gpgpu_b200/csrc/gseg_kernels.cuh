@@ -272,7 +272,9 @@ __global__ void __launch_bounds__(NT) k_r0_graph(GsegCtl *ctl, GsegBufs B) {
         for (int i = threadIdx.x; i < BH * BW; i += NT) {
             const int r = i / BW, c = i - r * BW;
             const int gx = x0 - 2 + c, gy = y0 - 2 + r;
-            float v0 = 0.f, v1 = 0.f, v2 = 0.f, g = 0.f;
+            // outside the image: NaN in plane 0 (colour variants), so that every edge touching the pixel
+            // gets a NaN weight in step 2 without any bounds test there
+            float v0 = SP ? 0.f : __int_as_float(0x7FC00000), v1 = 0.f, v2 = 0.f, g = 0.f;
             if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
                 const u32 p = (u32)gy * w + gx;
                 v0 = B.planes[p]; v1 = B.planes[V + p]; v2 = B.planes[2 * V + p];
@@ -282,57 +284,64 @@ __global__ void __launch_bounds__(NT) k_r0_graph(GsegCtl *ctl, GsegBufs B) {
             if (SP) sG[i] = g;
         }
         __syncthreads();
-        // 2. own-edge weights of every halo-tile pixel (inf where an end is outside the image/halo)
+        // 2. own-edge weights of every halo-tile pixel (+inf where an end is outside the image).  Edges that
+        // leave the halo array read a neighbouring plane / row (always inside shared memory) and produce
+        // a value nobody uses: steps 3-4 only read edges with both ends inside the array.
         for (int i = threadIdx.x; i < BH * BW; i += NT) {
-            const int r = i / BW, c = i - r * BW;
-            const int gx = x0 - 2 + c, gy = y0 - 2 + r;
-            const bool in = gx >= 0 && gx < w && gy >= 0 && gy < h;
             const float p0 = sP[i], p1 = sP[BH * BW + i], p2 = sP[2 * BH * BW + i];
+            if (SP) {
+                const int r = i / BW, c = i - r * BW;
+                const int gx = x0 - 2 + c, gy = y0 - 2 + r;
+                const bool in = gx >= 0 && gx < w && gy >= 0 && gy < h;
 #pragma unroll
-            for (int d = 0; d < D; ++d) {
-                const int dx = d == 1 ? 0 : 1, dy = d == 0 ? 0 : (d == 3 ? -1 : 1);
-                const int rr = r + dy, cc = c + dx;
-                float wv = __int_as_float(GSEG_INF_BITS);
-                if (in && rr >= 0 && rr < BH && cc < BW && gx + dx < w && gy + dy < h && gy + dy >= 0) {
-                    const int j = rr * BW + cc;
-                    if (SP) {
+                for (int d = 0; d < D; ++d) {
+                    const int dx = d == 1 ? 0 : 1, dy = d == 0 ? 0 : (d == 3 ? -1 : 1);
+                    const int rr = r + dy, cc = c + dx;
+                    float wv = __int_as_float(GSEG_INF_BITS);
+                    if (in && rr >= 0 && rr < BH && cc < BW && gx + dx < w && gy + dy < h && gy + dy >= 0) {
+                        const int j = rr * BW + cc;
                         long long ca[3] = {fx8(p0), fx8(p1), fx8(p2)};
                         long long cb[3] = {fx8(sP[j]), fx8(sP[BH * BW + j]), fx8(sP[2 * BH * BW + j])};
                         wv = __fmul_rn(__fmul_rn(0.5f, __fadd_rn(sG[i], sG[j])), mean_dist(ca, 1u, cb, 1u));
-                    } else {
-                        const float dr = __fsub_rn(p0, sP[j]), dg = __fsub_rn(p1, sP[BH * BW + j]),
-                                    db = __fsub_rn(p2, sP[2 * BH * BW + j]);
-                        wv = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dr, dr), __fmul_rn(dg, dg)), __fmul_rn(db, db)));
                     }
+                    sW[d * BH * BW + i] = wv;
                 }
-                sW[d * BH * BW + i] = wv;
+            } else {
+#pragma unroll
+                for (int d = 0; d < D; ++d) {
+                    const int dx = d == 1 ? 0 : 1, dy = d == 0 ? 0 : (d == 3 ? -1 : 1);
+                    const int j = d == 3 ? max(i - BW + 1, 0) : i + dy * BW + dx; // d == 3 from row 0: unused value
+                    const float dr = __fsub_rn(p0, sP[j]), dg = __fsub_rn(p1, sP[BH * BW + j]),
+                                db = __fsub_rn(p2, sP[2 * BH * BW + j]);
+                    const float wv = __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dr, dr), __fmul_rn(dg, dg)), __fmul_rn(db, db)));
+                    sW[d * BH * BW + i] = wv == wv ? wv : __int_as_float(GSEG_INF_BITS);
+                }
             }
         }
         __syncthreads();
-        // 3. choice of every pixel of tile + 1-pixel halo
+        // 3. choice of every pixel of tile + 1-pixel halo: the minimum (weight bits, edge index) over the
+        // incident edges.  The edge indices of a pixel's candidates are in a FIXED order (direction-major,
+        // then pixel): W < E < N < S < NW < SE < NE < SW  (W, N, NW, SW = the edges owned by the opposite
+        // neighbour; for NE the owner of the reverse edge is the pixel below-left, which comes later), so
+        // a chain of strict weight comparisons in that order is the key comparison.  Absent edges carry +inf.
         for (int i = threadIdx.x; i < (BH - 2) * (BW - 2); i += NT) {
             const int r = i / (BW - 2) + 1, c = i % (BW - 2) + 1;
             const int gx = x0 - 2 + c, gy = y0 - 2 + r;
             int bdir = 255;
             if (gx >= 0 && gx < w && gy >= 0 && gy < h) {
-                const u32 p = (u32)gy * w + gx;
-                u64 best = GSEG_KEY_NONE;
-#pragma unroll
-                for (int d = 0; d < D; ++d) {
-                    const int dx = d == 1 ? 0 : 1, dy = d == 0 ? 0 : (d == 3 ? -1 : 1);
-                    const u32 wo = __float_as_uint(sW[d * BH * BW + r * BW + c]);
-                    if (wo != GSEG_INF_BITS) {
-                        const u64 key = make_key(wo, (u32)d * V + p);
-                        if (key < best) { best = key; bdir = d; }
-                    }
-                    if (gx - dx >= 0 && gy - dy >= 0 && gy - dy < h) { // the edge owned by the opposite neighbour
-                        const u32 wr = __float_as_uint(sW[d * BH * BW + (r - dy) * BW + (c - dx)]);
-                        const u32 q = (u32)((int)p - dy * w - dx);
-                        const u64 key = make_key(wr, (u32)d * V + q);
-                        if (wr != GSEG_INF_BITS && key < best) { best = key; bdir = d + 4; }
-                    }
+                const float *w0 = sW + r * BW + c;
+                u32 bw = GSEG_INF_BITS, t;
+                t = __float_as_uint(w0[-1]);                          if (t < bw) { bw = t; bdir = 4; } // W  (d0 of x-1)
+                t = __float_as_uint(w0[0]);                           if (t < bw) { bw = t; bdir = 0; } // E
+                t = __float_as_uint(w0[BH * BW - BW]);                if (t < bw) { bw = t; bdir = 5; } // N  (d1 of y-1)
+                t = __float_as_uint(w0[BH * BW]);                     if (t < bw) { bw = t; bdir = 1; } // S
+                if (D == 4) {
+                    t = __float_as_uint(w0[2 * BH * BW - BW - 1]);    if (t < bw) { bw = t; bdir = 6; } // NW (d2 of x-1,y-1)
+                    t = __float_as_uint(w0[2 * BH * BW]);             if (t < bw) { bw = t; bdir = 2; } // SE
+                    t = __float_as_uint(w0[3 * BH * BW]);             if (t < bw) { bw = t; bdir = 3; } // NE
+                    t = __float_as_uint(w0[3 * BH * BW + BW - 1]);    if (t < bw) { bw = t; bdir = 7; } // SW (d3 of x-1,y+1)
                 }
-                if (VARIANT == GSEG_FELZ && bdir != 255 && !(__uint_as_float((u32)(best >> 32)) <= kthr)) bdir = 255;
+                if (VARIANT == GSEG_FELZ && bdir != 255 && !(__uint_as_float(bw) <= kthr)) bdir = 255;
             }
             sDir[(r - 1) * (BW - 2) + (c - 1)] = (uint8_t)bdir;
         }
