@@ -44,9 +44,9 @@ def build(force=False, verbose=False):
             print(" ".join(cmd))
         subprocess.check_call(cmd)
     cli_src = os.path.join(CSRC, "gseg_cli.cpp")
-    if os.path.exists(cli_src) and (force or _newer(CLI_PATH, [cli_src, LIB_PATH, HEADER])):
+    if os.path.exists(cli_src) and (force or _newer(CLI_PATH, [cli_src, os.path.join(CSRC, "gseg_imageio.hpp"), LIB_PATH, HEADER])):
         cmd = ["g++", "-O2", "-std=c++17", "-o", CLI_PATH, cli_src, "-I", os.path.join(_ROOT, "include"),
-               "-L", _HERE, "-lgseg", "-Wl,-rpath,$ORIGIN"]
+               "-L", _HERE, "-lgseg", "-lz", "-Wl,-rpath,$ORIGIN"]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)

@@ -127,8 +127,7 @@ inline bool decode_png(const std::vector<uint8_t> &buf, std::vector<uint8_t> &rg
         uint8_t *row = &raw[(rowbytes + 1) * (size_t)y];
         const int ft = row[0];
         uint8_t *cur = row + 1;
-        const uint8_t *up = y ? row - rowbytes : zero.data(); // previous row's data starts rowbytes before this row's filter byte... + 0
-        if (y) up = &raw[(rowbytes + 1) * (size_t)(y - 1) + 1];
+        const uint8_t *up = y ? &raw[(rowbytes + 1) * (size_t)(y - 1) + 1] : zero.data(); // previous row, already unfiltered
         for (size_t i = 0; i < rowbytes; ++i) {
             const int a = i >= bpp ? cur[i - bpp] : 0, b = up[i], c = i >= bpp ? up[i - bpp] : 0;
             int pred;

@@ -317,6 +317,15 @@ def test_cli_ppm_roundtrip(gseg, oracle, tmp_path):
     assert same_partition(oracle, lab, ref["labels"])
     data = open(outp, "rb").read()
     assert data.startswith(b"P6\n%d %d\n255\n" % (w, h)) and len(data) == len(b"P6\n%d %d\n255\n" % (w, h)) + w * h * 3
+    # PNG in, PNG out (gseg_imageio.hpp): same labels, and the colour image decodes back to the PPM one
+    pin, pout, back = tmp_path / "in.png", tmp_path / "out.png", tmp_path / "back.ppm"
+    assert subprocess.run([gseg.CLI_PATH, "--convert", str(inp), str(pin)]).returncode == 0
+    r = subprocess.run([gseg.CLI_PATH, "--labels", str(labp), "0.8", "300", "20", str(pin), str(pout)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    assert same_partition(oracle, np.fromfile(labp, np.int32).reshape(h, w), ref["labels"])
+    assert subprocess.run([gseg.CLI_PATH, "--convert", str(pout), str(back)]).returncode == 0
+    assert open(back, "rb").read() == data
     # hierarchy level through the CLI, synthetic input generated on the device
     r = subprocess.run([gseg.CLI_PATH, "--variant", "hier", "--conn", "4", "--level", "2", "--synth", "%dx%d:21" % (w, h),
                         "--labels", str(labp), "--iters", "2", "0.8", "0", "0", "-", str(outp)], capture_output=True, text=True)
