@@ -159,7 +159,7 @@ extern "C" int gseg_create_ex(gseg_ctx **out, int device, int max_w, int max_h, 
     if (e == cudaSuccess) e = dalloc(&ctx->d_arena, ctx->arena_cap);
     // look-back status words: one per tile of the largest tiling that uses each array
     ctx->ntilesC = V / (32 * CPT) + 2;
-    const size_t img_tiles = (size_t)((max_w + TW - 1) / TW) * (size_t)((max_h + TH - 1) / TH);
+    const size_t img_tiles = (size_t)((max_w + TW - 1) / TW) * (size_t)((max_h + GH - 1) / GH); // round-0 graph tiles
     if (ctx->ntilesC < img_tiles) ctx->ntilesC = img_tiles;
     ctx->ntilesE = Pslots; // pages of the edge list
     if (e == cudaSuccess) e = dalloc(&ctx->d_statusC, ctx->ntilesC);
@@ -314,7 +314,7 @@ static void launch_blur(gseg_ctx *c, cudaStream_t s, int ntiles) {
 
 template <int VARIANT, int D>
 static size_t graph_smem() {
-    return (size_t)(3 + D + (VARIANT == GSEG_SUPERPIX ? 1 : 0)) * BH * BW * sizeof(float) + (size_t)(BH - 2) * (BW - 2) + 16;
+    return (size_t)(3 + D + (VARIANT == GSEG_SUPERPIX ? 1 : 0)) * BH * BW * sizeof(float) + 16; // the choice bytes reuse the colour planes
 }
 template <int VARIANT, int D>
 static void launch_r0_graph(gseg_ctx *c, cudaStream_t s, int ntiles, const GsegBufs &B) {
@@ -334,7 +334,8 @@ static void enqueue_round0(gseg_ctx *c, cudaStream_t s) {
     const int variant = c->params.variant, D = c->D;
     const bool sp = variant == GSEG_SUPERPIX;
     const GsegBufs B = bufs_of(c);
-    const int ntiles = ((c->w + TW - 1) / TW) * ((c->h + TH - 1) / TH);
+    const int ntiles = ((c->w + TW - 1) / TW) * ((c->h + TH - 1) / TH);  // blur tiles
+    const int ntilesG = ((c->w + TW - 1) / TW) * ((c->h + GH - 1) / GH); // graph tiles
     const int R = c->h_head->p.mask_len - 1;
     if (R >= 1 && R <= 8) {
         mark(c, s, "k_blur_tile", 0);
@@ -359,9 +360,9 @@ static void enqueue_round0(gseg_ctx *c, cudaStream_t s) {
         k_sobel<<<grid_for(V, NT), NT, 0, s>>>(c->d_ctl, c->d_planes, c->d_G);
     }
     mark(c, s, "k_r0_graph", 0);
-    if (variant == GSEG_FELZ) { if (D == 2) launch_r0_graph<GSEG_FELZ, 2>(c, s, ntiles, B); else launch_r0_graph<GSEG_FELZ, 4>(c, s, ntiles, B); }
-    else if (variant == GSEG_HIER) { if (D == 2) launch_r0_graph<GSEG_HIER, 2>(c, s, ntiles, B); else launch_r0_graph<GSEG_HIER, 4>(c, s, ntiles, B); }
-    else { if (D == 2) launch_r0_graph<GSEG_SUPERPIX, 2>(c, s, ntiles, B); else launch_r0_graph<GSEG_SUPERPIX, 4>(c, s, ntiles, B); }
+    if (variant == GSEG_FELZ) { if (D == 2) launch_r0_graph<GSEG_FELZ, 2>(c, s, ntilesG, B); else launch_r0_graph<GSEG_FELZ, 4>(c, s, ntilesG, B); }
+    else if (variant == GSEG_HIER) { if (D == 2) launch_r0_graph<GSEG_HIER, 2>(c, s, ntilesG, B); else launch_r0_graph<GSEG_HIER, 4>(c, s, ntilesG, B); }
+    else { if (D == 2) launch_r0_graph<GSEG_SUPERPIX, 2>(c, s, ntilesG, B); else launch_r0_graph<GSEG_SUPERPIX, 4>(c, s, ntilesG, B); }
     mark(c, s, "k_relabel", 0);
     if (sp) k_relabel<true, true><<<grid_for(V, NT), NT, 0, s>>>(c->d_ctl, B);
     else k_relabel<true, false><<<grid_for(V, NT), NT, 0, s>>>(c->d_ctl, B);
@@ -471,7 +472,7 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
     if (ctx->pending) return fail(ctx, GSEG_E_STATE, "previous run not waited for", cudaSuccess);
     if (w < 1 || h < 1 || stride < 3 * w) return fail(ctx, GSEG_E_ARG, "image geometry", cudaSuccess);
     if ((size_t)w * h > ctx->Vmax) return fail(ctx, GSEG_E_SIZE, "image exceeds context capacity", cudaSuccess);
-    if ((size_t)((w + TW - 1) / TW) * (size_t)((h + TH - 1) / TH) > ctx->ntilesC)
+    if ((size_t)((w + TW - 1) / TW) * (size_t)((h + GH - 1) / GH) > ctx->ntilesC)
         return fail(ctx, GSEG_E_SIZE, "image aspect exceeds context capacity", cudaSuccess);
     if (p->connectivity != 4 && p->connectivity != 8) return fail(ctx, GSEG_E_ARG, "connectivity must be 4 or 8", cudaSuccess);
     if (p->variant < GSEG_FELZ || p->variant > GSEG_SUPERPIX) return fail(ctx, GSEG_E_ARG, "variant", cudaSuccess);

@@ -137,13 +137,15 @@ __device__ __forceinline__ u64 pack_status(u32 tag, u32 state, u32 val) {
 // tile (sum of the aggregates of all lower tiles).  Tiles MUST be handed out through an atomic
 // ticket so that every lower tile belongs to a block that is already running.  A bounded spin
 // turns a protocol bug into an error code instead of a hung GPU.
-__device__ __forceinline__ u32 lookback_prefix(u64 *status, u32 tile, u32 tag, u32 aggregate, u32 *err) {
+// The two halves of the look-back, for callers that can do other work between publishing their aggregate and
+// needing their prefix (k_r0_graph resolves a tile after the NEXT tile's stencil work: by then the
+// predecessors have published and the walk does not wait).  One warp calls both.
+__device__ __forceinline__ void lookback_publish(u64 *status, u32 tile, u32 tag, u32 aggregate) {
+    if ((threadIdx.x & 31) == 0) st_relaxed_u64(status + tile, pack_status(tag, tile == 0 ? ST_INC : ST_AGG, aggregate));
+}
+__device__ __forceinline__ u32 lookback_resolve(u64 *status, u32 tile, u32 tag, u32 aggregate, u32 *err) {
     const int lane = threadIdx.x & 31;
-    if (tile == 0) {
-        if (lane == 0) st_relaxed_u64(status, pack_status(tag, ST_INC, aggregate));
-        return 0u;
-    }
-    if (lane == 0) st_relaxed_u64(status + tile, pack_status(tag, ST_AGG, aggregate));
+    if (tile == 0) return 0u;
     u32 excl = 0u, spins = 0u;
     int look = (int)tile - 1;
     for (;;) {
@@ -186,6 +188,10 @@ __device__ __forceinline__ u32 lookback_prefix(u64 *status, u32 tile, u32 tag, u
     }
     if (lane == 0) st_relaxed_u64(status + tile, pack_status(tag, ST_INC, excl + aggregate));
     return excl;
+}
+__device__ __forceinline__ u32 lookback_prefix(u64 *status, u32 tile, u32 tag, u32 aggregate, u32 *err) {
+    lookback_publish(status, tile, tag, aggregate);
+    return lookback_resolve(status, tile, tag, aggregate, err);
 }
 
 // Block-wide: exclusive offset of `cnt` items inside a globally ordered compaction.

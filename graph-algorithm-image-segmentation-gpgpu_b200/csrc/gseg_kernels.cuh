@@ -41,7 +41,9 @@ namespace cg = cooperative_groups;
 #define TW 64
 #define TH 32
 #define BW (TW + 4)
-#define BH (TH + 4)
+#define GH 28            // rows of a round-0 graph tile (28: five 256-thread blocks per SM fit in shared memory)
+#define GRPT (GH / 4)    // rows per thread in the successor step: 256 threads = 64 columns x 4 row groups
+#define BH (GH + 4)
 
 __constant__ int c_DX[4] = {1, 0, 1, 1};
 __constant__ int c_DY[4] = {0, 1, 1, -1};
@@ -236,6 +238,33 @@ __device__ __forceinline__ float mean_dist_g(const long long *csum, const uint2 
     return mean_dist(ca, __ldcg(&attr[a].x), cb, __ldcg(&attr[b].x));
 }
 
+// Second half of a round-0 graph tile: prefix of the tile's root count (look-back), ids of its roots
+// (thread: GRPT rows of one column starting at pixel `pix`, root flags in `flags`, `ex` roots before the
+// thread inside the tile) and the cleared accumulators of those ids.
+template <bool SP>
+__device__ __forceinline__ void r0_finish_tile(GsegCtl *ctl, const GsegBufs &B, u32 tile, u32 total, u32 ex, u32 flags, u32 pix,
+                                               u32 tag, u32 ntiles, u32 *s_scan) {
+    if (threadIdx.x < 32) {
+        const u32 pre = lookback_resolve(B.statusC, tile, tag, total, &ctl->error);
+        if (threadIdx.x == 0) s_scan[33] = pre;
+    }
+    __syncthreads();
+    const u32 pre = s_scan[33];
+    if (tile == ntiles - 1 && threadIdx.x == 0) ctl->Vnext = pre + total;
+    const u32 w = (u32)ctl->p.w;
+    u32 id = pre + ex;
+#pragma unroll
+    for (int j = 0; j < GRPT; ++j)
+        if (flags & (1u << j)) B.rank[pix + (u32)j * w] = id++;
+    // the tile owns the new ids [pre, pre + total): clear their accumulators for phase R / E
+    for (u32 i = threadIdx.x; i < total; i += NT) {
+        const u32 n = pre + i;
+        B.attr[1][n] = make_uint2(0u, 0u); B.best[1][n] = GSEG_KEY_NONE;
+        if (SP) { B.csum[1][3 * (size_t)n] = 0; B.csum[1][3 * (size_t)n + 1] = 0; B.csum[1][3 * (size_t)n + 2] = 0; }
+    }
+    __syncthreads();
+}
+
 // ------------------------------------------------------------------------------------------------
 // Round 0 on the implicit grid (every pixel is its own component): one tile pass does
 //   edge weights (a3) -> per-pixel minimum incident edge (a4; a pure stencil, no atomics) ->
@@ -252,22 +281,23 @@ __global__ void __launch_bounds__(NT) k_r0_graph(GsegCtl *ctl, GsegBufs B) {
     float *sP = reinterpret_cast<float *>(smem_raw);   // [3][BH][BW] blurred colour
     float *sW = sP + 3 * BH * BW;                      // [D][BH][BW] own-edge key weights
     float *sG = sW + D * BH * BW;                      // [BH][BW] Sobel (SP only)
-    uint8_t *sDir = reinterpret_cast<uint8_t *>(sG + (SP ? BH * BW : 0)); // [BH-2][BW-2] choices of tile + halo 1
+    uint8_t *sDir = reinterpret_cast<uint8_t *>(sP);  // [BH-2][BW-2] choices of tile + halo 1; over sP, which is dead after step 2
     __shared__ u32 s_scan[34];
     __shared__ u32 s_tile;
     const int w = ctl->p.w, h = ctl->p.h;
     const u32 V = (u32)w * (u32)h;
-    const int ntx = (w + TW - 1) / TW, nty = (h + TH - 1) / TH;
+    const int ntx = (w + TW - 1) / TW, nty = (h + GH - 1) / GH;
     const u32 ntiles = (u32)ntx * (u32)nty;
     const u32 tag = ctl->p.epoch_base + 1u;
     const float kthr = __fadd_rn(0.0f, __fdiv_rn(ctl->p.k, 1.0f)); // Int = 0, |C| = 1 on both sides
     if (blockIdx.x == 0 && threadIdx.x == 0) { ctl->ticketE = 0; ctl->t_start = globaltimer_ns(); }
+    u32 p_tile = 0xFFFFFFFFu, p_total = 0, p_ex = 0, p_flags = 0, p_pix = 0; // the tile whose ids are still to be written
     for (;;) {
         if (threadIdx.x == 0) s_tile = atomicAdd(&ctl->ticketC, 1u);
         __syncthreads();
         const u32 tile = s_tile;
         if (tile >= ntiles) break;
-        const int x0 = (int)(tile % ntx) * TW, y0 = (int)(tile / ntx) * TH;
+        const int x0 = (int)(tile % ntx) * TW, y0 = (int)(tile / ntx) * GH;
         // 1. blurred halo tile
         for (int i = threadIdx.x; i < BH * BW; i += NT) {
             const int r = i / BW, c = i - r * BW;
@@ -346,12 +376,12 @@ __global__ void __launch_bounds__(NT) k_r0_graph(GsegCtl *ctl, GsegBufs B) {
             sDir[(r - 1) * (BW - 2) + (c - 1)] = (uint8_t)bdir;
         }
         __syncthreads();
-        // 4. successor (2-cycle removal), outputs, root flags.  Thread: column t%64, rows (t/64)*8 + j.
-        const int c = (int)(threadIdx.x % TW), rg = (int)(threadIdx.x / TW) * 8;
+        // 4. successor (2-cycle removal), outputs, root flags.  Thread: column t%64, rows (t/64)*GRPT + j.
+        const int c = (int)(threadIdx.x % TW), rg = (int)(threadIdx.x / TW) * GRPT;
         const int gx = x0 + c;
         u32 flags = 0, cnt = 0;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < GRPT; ++j) {
             const int gy = y0 + rg + j;
             if (gx >= w || gy >= h) continue;
             const u32 p = (u32)gy * w + gx;
@@ -381,26 +411,19 @@ __global__ void __launch_bounds__(NT) k_r0_graph(GsegCtl *ctl, GsegBufs B) {
             }
             if (s == p) { flags |= 1u << j; ++cnt; }
         }
-        // 5. new ids of the roots, in tile order
-        const u32 ex = tile_scan_begin<NT>(cnt, tile, tag, B.statusC, &ctl->error, s_scan);
-        __syncthreads();
-        const u32 pre = s_scan[33], total = s_scan[32];
-        if (tile == ntiles - 1 && threadIdx.x == 0) ctl->Vnext = pre + total;
-        u32 id = pre + ex;
-#pragma unroll
-        for (int j = 0; j < 8; ++j)
-            if (flags & (1u << j)) B.rank[(u32)(y0 + rg + j) * w + gx] = id++;
-        // the tile owns the new ids [pre, pre + total): clear their accumulators for phase R / E
-        for (u32 i = threadIdx.x; i < total; i += NT) {
-            const u32 n = pre + i;
-            B.attr[1][n] = make_uint2(0u, 0u); B.best[1][n] = GSEG_KEY_NONE;
-            if (SP) { B.csum[1][3 * (size_t)n] = 0; B.csum[1][3 * (size_t)n + 1] = 0; B.csum[1][3 * (size_t)n + 2] = 0; }
-        }
-        __syncthreads();
+        // 5. new ids of the roots, in tile order.  The tile publishes its root count now and takes its
+        // prefix one tile later (r0_finish_tile): the look-back of a tile whose predecessors are still in
+        // their stencil steps would only wait, so the next tile's stencil runs in that time.
+        const u32 ex = block_excl_scan<NT>(cnt, s_scan);
+        const u32 total = s_scan[32];
+        if (threadIdx.x < 32) lookback_publish(B.statusC, tile, tag, total);
+        if (p_tile != 0xFFFFFFFFu) r0_finish_tile<SP>(ctl, B, p_tile, p_total, p_ex, p_flags, p_pix, tag, ntiles, s_scan);
+        else __syncthreads(); // s_scan[32] has been read by everybody before the next scan rewrites it
+        p_tile = tile; p_total = total; p_ex = ex; p_flags = flags; p_pix = (u32)(y0 + rg) * w + gx;
     }
+    if (p_tile != 0xFFFFFFFFu) r0_finish_tile<SP>(ctl, B, p_tile, p_total, p_ex, p_flags, p_pix, tag, ntiles, s_scan);
 }
 
-// ------------------------------------------------------------------------------------------------
 // Round state helpers.
 // ------------------------------------------------------------------------------------------------
 __device__ __forceinline__ bool in_tail(const GsegCtl *ctl, const RoundState &st) {
