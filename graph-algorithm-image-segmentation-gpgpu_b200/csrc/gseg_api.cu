@@ -382,11 +382,13 @@ static void enqueue_round(gseg_ctx *c, cudaStream_t s, int r, size_t Vb, size_t 
     const bool sp = c->params.variant == GSEG_SUPERPIX;
     const GsegBufs B = bufs_of(c);
     const int cap = c->num_sms * c->occ_mult;
-    mark(c, s, "k_page_scan", r);
-    k_page_scan<<<grid_for(Pb, 1024, 64), 1024, 0, s>>>(c->d_ctl, B);
+    if (Pb > GSEG_PSCAN_INLINE) { // Pb bounds the round's page count: below, the successor kernel's extra block scans
+        mark(c, s, "k_page_scan", r);
+        k_page_scan<<<grid_for(Pb, 1024, 64), 1024, 0, s>>>(c->d_ctl, B);
+    }
     mark(c, s, "k_succ_scan", r);
-    if (sp) k_succ_scan<true><<<grid_for(Vb, NT * CPT, cap), NT, 0, s>>>(c->d_ctl, B);
-    else k_succ_scan<false><<<grid_for(Vb, NT * CPT, cap), NT, 0, s>>>(c->d_ctl, B);
+    if (sp) k_succ_scan<true><<<grid_for(Vb, NT * CPT, cap) + 1, NT, 0, s>>>(c->d_ctl, B);
+    else k_succ_scan<false><<<grid_for(Vb, NT * CPT, cap) + 1, NT, 0, s>>>(c->d_ctl, B);
     mark(c, s, "k_relabel", r);
     if (sp) k_relabel<false, true><<<grid_for(Vb, NT, cap), NT, 0, s>>>(c->d_ctl, B);
     else k_relabel<false, false><<<grid_for(Vb, NT, cap), NT, 0, s>>>(c->d_ctl, B);

@@ -499,14 +499,24 @@ __device__ __forceinline__ u32 group_size(const RoundState &st) {
     return G;
 }
 
-// Exclusive scan of the page counts by ONE block (any block size that is a multiple of 32, <= 1024).
-// s: >= 34 u32 of shared memory.
+// Exclusive scan of the page counts by ONE block (any block size that is a multiple of 32, <= 1024), four
+// counts per thread and step.  s: >= 34 u32 of shared memory.  Up to GSEG_PSCAN_INLINE pages this runs as
+// one extra block of the successor kernel (and of the tail), beside the work it is independent of; above,
+// k_page_scan does it grid-wide.
+#define GSEG_PSCAN_INLINE 65536u
 __device__ __forceinline__ void block_scan_pages(const u32 *pcnt, u32 P, u32 *pscan, u32 *s) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     u32 carry = 0;
-    for (u32 base = 0; base < P; base += blockDim.x) {
-        const u32 i = base + threadIdx.x;
-        const u32 v = i < P ? __ldcg(pcnt + i) : 0u;
+    for (u32 base = 0; base < P; base += 4u * blockDim.x) {
+        const u32 i = base + 4u * threadIdx.x;
+        uint4 q = make_uint4(0u, 0u, 0u, 0u);
+        if (i + 3u < P) q = __ldcg(reinterpret_cast<const uint4 *>(pcnt + i));
+        else {
+            if (i < P) q.x = __ldcg(pcnt + i);
+            if (i + 1u < P) q.y = __ldcg(pcnt + i + 1u);
+            if (i + 2u < P) q.z = __ldcg(pcnt + i + 2u);
+        }
+        const u32 v = q.x + q.y + q.z + q.w;
         const u32 inc = warp_incl_scan(v, lane);
         if (lane == 31) s[wid] = inc;
         __syncthreads();
@@ -517,7 +527,14 @@ __device__ __forceinline__ void block_scan_pages(const u32 *pcnt, u32 P, u32 *ps
             if (lane == 31) s[32] = xi;
         }
         __syncthreads();
-        if (i < P) pscan[i] = carry + s[wid] + inc - v;
+        const u32 e = carry + s[wid] + inc - v;
+        const uint4 o = make_uint4(e, e + q.x, e + q.x + q.y, e + q.x + q.y + q.z);
+        if (i + 3u < P) *reinterpret_cast<uint4 *>(pscan + i) = o;
+        else {
+            if (i < P) pscan[i] = o.x;
+            if (i + 1u < P) pscan[i + 1u] = o.y;
+            if (i + 2u < P) pscan[i + 2u] = o.z;
+        }
         carry += s[32];
         __syncthreads();
     }
@@ -894,12 +911,13 @@ __global__ void __launch_bounds__(NT) k_means(const GsegCtl *ctl, GsegBufs B) {
     if (st.phase == PH_DONE || in_tail(ctl, st)) return;
     phase_M(B, (int)((st.round & 1u) ^ 1u), ctl->Vnext);
 }
-// Merging rounds only: the exclusive scan of the page counts the edge phase places its output by.
+// Merging rounds with more than GSEG_PSCAN_INLINE pages only: the exclusive scan of the page counts the edge
+// phase places its output by (smaller ones: block_scan_pages inside k_succ_scan).
 // Blocks take chunks of 1024 counts by ticket; chunk prefixes come from a block-granular look-back.
 __global__ void __launch_bounds__(1024) k_page_scan(GsegCtl *ctl, GsegBufs B) {
     __shared__ u32 s[68];
     const RoundState st = ctl->st;
-    if (st.phase == PH_DONE || in_tail(ctl, st) || group_size(st) == 1u) return;
+    if (st.phase == PH_DONE || in_tail(ctl, st) || group_size(st) == 1u || st.P <= GSEG_PSCAN_INLINE) return;
     const u32 P = st.P, nchunks = (P + 1023u) / 1024u;
     const u32 tag = ctl->p.epoch_base + st.round * 2u + 2u;
     const u32 *pc = B.pcnt[st.round & 1];
@@ -924,6 +942,10 @@ __global__ void __launch_bounds__(NT) k_succ_scan(GsegCtl *ctl, GsegBufs B) {
     __shared__ u32 sh[66];
     const RoundState st = ctl->st;
     if (st.phase == PH_DONE || in_tail(ctl, st)) return;
+    if (blockIdx.x == gridDim.x - 1) { // the extra block: page scan of a merging round (block tiles go by ticket, nobody misses it)
+        if (group_size(st) > 1u && st.P <= GSEG_PSCAN_INLINE) block_scan_pages(B.pcnt[st.round & 1], st.P, B.pscan, sh);
+        return;
+    }
     phase_S<SP, false>(ctl, B, st, sh);
 }
 template <bool SP>
