@@ -27,6 +27,8 @@ struct GsegHead {
 };
 static_assert(offsetof(GsegCtl, Eacc) == offsetof(GsegHead, Eacc), "GsegHead must mirror the head of GsegCtl");
 
+static const size_t TAIL_SMEM = 2 * (size_t)GSEG_TAIL_STAGE * sizeof(u32); // k_tail's staging area (phase_E)
+
 struct gseg_ctx {
     int device, max_w, max_h;
     size_t Vmax;
@@ -176,13 +178,15 @@ extern "C" int gseg_create_ex(gseg_ctx **out, int device, int max_w, int max_h, 
         cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         cudaFuncSetAttribute(k_tail<true>, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
         int want = 16;
+        cudaFuncSetAttribute(k_tail<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM);
+        cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM);
         if (const char *ev = getenv("GSEG_TAIL_CLUSTER")) want = atoi(ev);
         if (want < 1) want = 1;
         if (want > 16) want = 16;
         for (; want > 1; want >>= 1) {
             cudaLaunchConfig_t cfg = {};
             cudaLaunchAttribute at[1];
-            cfg.gridDim = dim3(want); cfg.blockDim = dim3(NTT); cfg.dynamicSmemBytes = 0;
+            cfg.gridDim = dim3(want); cfg.blockDim = dim3(NTT); cfg.dynamicSmemBytes = TAIL_SMEM;
             at[0].id = cudaLaunchAttributeClusterDimension;
             at[0].val.clusterDim.x = want; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
             cfg.attrs = at; cfg.numAttrs = 1;
@@ -406,7 +410,7 @@ static cudaError_t enqueue_tail(gseg_ctx *c, cudaStream_t s) {
     cudaLaunchConfig_t cfg = {};
     cudaLaunchAttribute at[1];
     cfg.gridDim = dim3(c->tail_cluster); cfg.blockDim = dim3(NTT);
-    cfg.dynamicSmemBytes = 0; cfg.stream = s;
+    cfg.dynamicSmemBytes = TAIL_SMEM; cfg.stream = s;
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = c->tail_cluster; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
     cfg.attrs = at; cfg.numAttrs = 1;

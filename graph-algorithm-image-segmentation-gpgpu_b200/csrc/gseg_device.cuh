@@ -279,7 +279,8 @@ __device__ __forceinline__ void warp_run_min(u64 *best, u32 id, u32 kb, u32 pos,
 // interleaving their shuffles halves the latency of the row (these kernels run few warps per SM in late
 // rounds and are bound by exactly this chain).
 template <bool FILTER, int WINDOW>
-__device__ __forceinline__ void warp_run_min2(u64 *best, u32 ida, u32 idb, u32 kb, u32 pos, bool act, u32 hia, u32 hib) {
+__device__ __forceinline__ void warp_run_min2(u64 *best, u32 ida, u32 idb, u32 kb, u32 pos, bool act, u32 hia, u32 hib,
+                                              u32 *sfilter = nullptr) {
     const int lane = threadIdx.x & 31;
     const u32 pa = __shfl_up_sync(0xFFFFFFFFu, ida, 1), pb = __shfl_up_sync(0xFFFFFFFFu, idb, 1);
     const u32 actm = __ballot_sync(0xFFFFFFFFu, act);
@@ -304,6 +305,14 @@ __device__ __forceinline__ void warp_run_min2(u64 *best, u32 ida, u32 idb, u32 k
         const u32 okb = __shfl_down_sync(0xFFFFFFFFu, kbb, o), oqb = __shfl_down_sync(0xFFFFFFFFu, qb, o);
         if (lane + o < enda && oka < ka) { ka = oka; qa = oqa; }
         if (lane + o < endb && okb < kbb) { kbb = okb; qb = oqb; }
+    }
+    if (FILTER && sfilter) {
+        // block-local filter in shared memory (tail, few components): the lightest weight this block has seen
+        // per component, seeded from the global minima.  Whoever lowers (or ties) an entry also sends its key
+        // to the global minimum, so an entry never promises more than what reaches best[].
+        if (leada && act && ka <= atomicMin(sfilter + ida, ka)) atomicMin(best + ida, make_key(ka, qa));
+        if (leadb && act && kbb <= atomicMin(sfilter + idb, kbb)) atomicMin(best + idb, make_key(kbb, qb));
+        return;
     }
     if (leada && act && (!FILTER || ka <= hia)) atomicMin(best + ida, make_key(ka, qa));
     if (leadb && act && (!FILTER || kbb <= hib)) atomicMin(best + idb, make_key(kbb, qb));

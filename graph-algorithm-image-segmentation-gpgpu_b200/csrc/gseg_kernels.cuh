@@ -504,6 +504,7 @@ __device__ __forceinline__ u32 group_size(const RoundState &st) {
 // one extra block of the successor kernel (and of the tail), beside the work it is independent of; above,
 // k_page_scan does it grid-wide.
 #define GSEG_PSCAN_INLINE 65536u
+#define GSEG_TAIL_STAGE 16384u // components whose map / minima the tail stages in shared memory (2 x 64 KB)
 __device__ __forceinline__ void block_scan_pages(const u32 *pcnt, u32 P, u32 *pscan, u32 *s) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     u32 carry = 0;
@@ -603,14 +604,14 @@ __device__ __forceinline__ void phase_R(const GsegCtl *ctl, const GsegBufs &B, c
 // ------------------------------------------------------------------------------------------------
 template <bool SP, bool FILTER>
 __device__ __forceinline__ void emit_row(const GsegBufs &B, int nxt, u32 pos, bool act, u32 a, u32 b, u32 wv,
-                                         u32 fa = 0xFFFFFFFFu, u32 fb = 0xFFFFFFFFu) {
+                                         u32 fa = 0xFFFFFFFFu, u32 fb = 0xFFFFFFFFu, u32 *sfilter = nullptr) {
     u32 kb = wv;
     if (act) {
         B.eab[nxt][pos] = make_uint2(a, b);
         B.ew[nxt][pos] = wv;
         if (SP) kb = __float_as_uint(__fmul_rn(__uint_as_float(wv), mean_dist_m(B.cmean[nxt], a, b)));
     }
-    warp_run_min2<FILTER, FILTER ? 32 : RUNWIN>(B.best[nxt], a, b, kb, pos, act, fa, fb);
+    warp_run_min2<FILTER, FILTER ? 32 : RUNWIN>(B.best[nxt], a, b, kb, pos, act, fa, fb, sfilter);
 }
 
 // a10 (round 0): grid edges -> paged list of inter-component edges, in edge-index order
@@ -805,7 +806,7 @@ __device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const R
 // place; G > 1: the output page g starts at pscan[G g].  No tickets, no look-back, no barriers.
 // ------------------------------------------------------------------------------------------------
 template <bool SP, bool SPREAD = false>
-__device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, u32 Vnext) {
+__device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, u32 Vnext, u32 *stage = nullptr) {
     constexpr int ROWS = GSEG_PAGE / 32;
     const int lane = threadIdx.x & 31;
     const u32 lt = (1u << lane) - 1u;
@@ -819,6 +820,19 @@ __device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const R
     const u32 G = group_size(st), ngroups = (P + G - 1u) / G;
     if (blockIdx.x == 0 && threadIdx.x == 0) ctl->ticketC = 0;
     const u32 nwarp = blockDim.x >> 5, nw = gridDim.x * nwarp;
+    // Tail with few components: every warp gathers from the same few lines of map[] and best[], and an L2
+    // slice serves one request per line at a time (measured: 11 of 16 us of a small round went there).  Each
+    // block stages the map and the minima's weights in shared memory once and gathers from there.
+    const bool staged = SPREAD && stage != nullptr && st.V <= GSEG_TAIL_STAGE;
+    u32 *s_map = stage, *s_bhi = stage + GSEG_TAIL_STAGE;
+    if (staged) {
+        for (u32 i = threadIdx.x; i < st.V; i += blockDim.x) s_map[i] = __ldcg(map + i);
+        if (filter) {
+            const u32 *bhi = reinterpret_cast<const u32 *>(B.best[nxt]) + 1;
+            for (u32 i = threadIdx.x; i < Vnext; i += blockDim.x) s_bhi[i] = ld_relaxed_u32(bhi + 2 * (size_t)i);
+        }
+        __syncthreads();
+    }
     u32 esum = 0;
     for (u32 g = SPREAD ? (threadIdx.x >> 5) * gridDim.x + blockIdx.x : blockIdx.x * nwarp + (threadIdx.x >> 5); g < ngroups; g += nw) {
         u32 mycnt = 0u, myoff = 0u;
@@ -851,14 +865,23 @@ __device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const R
             for (int j = 0; j < ROWS; ++j) {
                 bool keep = false;
                 if (c0 + 32u * j + lane < cnt) {
-                    a[j] = __ldcg(map + a[j]); b[j] = __ldcg(map + b[j]);
+                    if (staged) { a[j] = s_map[a[j]]; b[j] = s_map[b[j]]; }
+                    else { a[j] = __ldcg(map + a[j]); b[j] = __ldcg(map + b[j]); }
                     keep = a[j] != b[j];
                 }
                 m[j] = __ballot_sync(0xFFFFFFFFu, keep);
                 total += __popc(m[j]);
             }
             u32 rowoff = out_base + written;
-            if (filter) {
+            if (filter && staged) {
+#pragma unroll
+                for (int j = 0; j < ROWS; ++j) {
+                    if (m[j] == 0u) continue; // warp-uniform
+                    const bool act = (m[j] >> lane) & 1u;
+                    emit_row<SP, true>(B, nxt, rowoff + __popc(m[j] & lt), act, a[j], b[j], wv[j], 0u, 0u, s_bhi);
+                    rowoff += __popc(m[j]);
+                }
+            } else if (filter) {
                 // weights of the current minima of both ends, for all rows at once (one round trip)
                 u32 fa[ROWS], fb[ROWS];
                 const u32 *bhi = reinterpret_cast<const u32 *>(B.best[nxt]) + 1; // high word = weight bits
@@ -963,6 +986,7 @@ __global__ void __launch_bounds__(NT, 4) k_edges(GsegCtl *ctl, GsegBufs B) {
 // co-scheduled by hardware, so tails of different images run side by side on disjoint SMs.
 template <bool SP>
 __global__ void __launch_bounds__(NTT, 1) k_tail(GsegCtl *ctl, GsegBufs B) {
+    extern __shared__ __align__(16) u32 tail_stage[]; // 2 x GSEG_TAIL_STAGE u32 (phase_E)
     __shared__ u32 sh[66];
     cg::cluster_group cl = cg::this_cluster();
     const bool writer = blockIdx.x == 0 && threadIdx.x == 0;
@@ -986,7 +1010,7 @@ __global__ void __launch_bounds__(NTT, 1) k_tail(GsegCtl *ctl, GsegBufs B) {
             cl.sync();
         }
         if (writer) ctl->t_R[st.round] = globaltimer_ns();
-        phase_E<SP, true>(ctl, B, st, Vn);
+        phase_E<SP, true>(ctl, B, st, Vn, tail_stage);
         __threadfence();
         cl.sync();
         // One thread advances the round state and publishes it; everybody re-reads it after a fourth
