@@ -645,16 +645,18 @@ __global__ void __launch_bounds__(NT, 4) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
         const int dx = d == 1 ? 0 : 1, dy = d == 0 ? 0 : (d == 3 ? -1 : 1);
         const int off = dy * w + dx;
         const u32 p0 = (tile - (u32)d * tpd) * GSEG_PAGE + lane;
-        u32 a[ROWS], b[ROWS], m[ROWS];
+        u32 a[ROWS], b[ROWS], m[ROWS], wv[ROWS];
+        const float *wg = B.wgrid + (size_t)d * V + p0;
         int y = (int)(p0 / (u32)w), x = (int)(p0 - (u32)y * (u32)w);
 #pragma unroll
         for (int j = 0; j < ROWS; ++j) {
             const u32 p = p0 + 32u * j;
             bool keep = false;
-            a[j] = b[j] = 0u;
+            a[j] = b[j] = wv[j] = 0u;
             if (p < V && x + dx < w && y + dy < h && y + dy >= 0) {
                 a[j] = map[p];
                 b[j] = map[(u32)((int)p + off)];
+                wv[j] = __float_as_uint(wg[32 * j]); // with the ids, not row by row between the emits: one round trip per page
                 keep = a[j] != b[j];
             }
             m[j] = __ballot_sync(0xFFFFFFFFu, keep);
@@ -666,14 +668,12 @@ __global__ void __launch_bounds__(NT, 4) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
         for (int j = 0; j < ROWS; ++j) total += __popc(m[j]);
         if (lane == 0) { B.pcnt[1][tile] = total; B.poff[1][tile] = tile * GSEG_PAGE; }
         esum += total;
-        const float *wg = B.wgrid + (size_t)d * V + p0;
         u32 rowoff = tile * GSEG_PAGE;
 #pragma unroll
         for (int j = 0; j < ROWS; ++j) {
             if (m[j] == 0u) continue; // warp-uniform
             const bool act = (m[j] >> lane) & 1u;
-            const u32 wv = act ? __float_as_uint(wg[32 * j]) : 0u;
-            emit_row<SP, false>(B, 1, rowoff + __popc(m[j] & lt), act, a[j], b[j], wv);
+            emit_row<SP, false>(B, 1, rowoff + __popc(m[j] & lt), act, a[j], b[j], wv[j]);
             rowoff += __popc(m[j]);
         }
     }
