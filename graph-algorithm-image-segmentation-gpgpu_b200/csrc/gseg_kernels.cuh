@@ -499,25 +499,32 @@ __device__ __forceinline__ u32 group_size(const RoundState &st) {
     return G;
 }
 
-// Exclusive scan of the page counts by ONE block (any block size that is a multiple of 32, <= 1024), four
-// counts per thread and step.  s: >= 34 u32 of shared memory.  Up to GSEG_PSCAN_INLINE pages this runs as
-// one extra block of the successor kernel (and of the tail), beside the work it is independent of; above,
-// k_page_scan does it grid-wide.
-#define GSEG_PSCAN_INLINE 65536u
+// Exclusive scan of the page counts by ONE block (any block size that is a multiple of 32, <= 1024), 16
+// counts per thread and step (four 16-byte loads in flight: a step costs one memory round trip whatever its
+// width).  s: >= 34 u32 of shared memory.  Up to GSEG_PSCAN_INLINE pages this runs as one extra block of the
+// successor kernel (and of the tail), beside the work it is independent of; above, k_page_scan does it
+// grid-wide.
+#define GSEG_PSCAN_INLINE 32768u
 #define GSEG_TAIL_STAGE 16384u // components whose map / minima the tail stages in shared memory (2 x 64 KB)
 __device__ __forceinline__ void block_scan_pages(const u32 *pcnt, u32 P, u32 *pscan, u32 *s) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
     u32 carry = 0;
-    for (u32 base = 0; base < P; base += 4u * blockDim.x) {
-        const u32 i = base + 4u * threadIdx.x;
-        uint4 q = make_uint4(0u, 0u, 0u, 0u);
-        if (i + 3u < P) q = __ldcg(reinterpret_cast<const uint4 *>(pcnt + i));
-        else {
-            if (i < P) q.x = __ldcg(pcnt + i);
-            if (i + 1u < P) q.y = __ldcg(pcnt + i + 1u);
-            if (i + 2u < P) q.z = __ldcg(pcnt + i + 2u);
+    for (u32 base = 0; base < P; base += 16u * blockDim.x) {
+        const u32 i = base + 16u * threadIdx.x;
+        u32 q[16];
+        if (i + 15u < P) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+                const uint4 t = __ldcg(reinterpret_cast<const uint4 *>(pcnt + i) + k);
+                q[4 * k] = t.x; q[4 * k + 1] = t.y; q[4 * k + 2] = t.z; q[4 * k + 3] = t.w;
+            }
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k) q[k] = i + k < P ? __ldcg(pcnt + i + k) : 0u;
         }
-        const u32 v = q.x + q.y + q.z + q.w;
+        u32 v = 0;
+#pragma unroll
+        for (int k = 0; k < 16; ++k) { const u32 t = q[k]; q[k] = v; v += t; } // q: exclusive inside the thread
         const u32 inc = warp_incl_scan(v, lane);
         if (lane == 31) s[wid] = inc;
         __syncthreads();
@@ -529,12 +536,14 @@ __device__ __forceinline__ void block_scan_pages(const u32 *pcnt, u32 P, u32 *ps
         }
         __syncthreads();
         const u32 e = carry + s[wid] + inc - v;
-        const uint4 o = make_uint4(e, e + q.x, e + q.x + q.y, e + q.x + q.y + q.z);
-        if (i + 3u < P) *reinterpret_cast<uint4 *>(pscan + i) = o;
-        else {
-            if (i < P) pscan[i] = o.x;
-            if (i + 1u < P) pscan[i + 1u] = o.y;
-            if (i + 2u < P) pscan[i + 2u] = o.z;
+        if (i + 15u < P) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                reinterpret_cast<uint4 *>(pscan + i)[k] = make_uint4(e + q[4 * k], e + q[4 * k + 1], e + q[4 * k + 2], e + q[4 * k + 3]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < 16; ++k)
+                if (i + k < P) pscan[i + k] = e + q[k];
         }
         carry += s[32];
         __syncthreads();
@@ -708,6 +717,35 @@ __device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const R
     // the blocks so that a handful of tiles keeps every SM's issue slots busy instead of one SM's, and a
     // warp-granular look-back.  Otherwise: block tiles by ticket and one look-back per block.
     u32 stile = (u32)wid * gridDim.x + blockIdx.x;
+    // ids of a warp tile's roots (row masks m, first id pre) and the cleared accumulators of those ids
+    auto write_ids = [&](u32 pre, u32 base, const u32 *m, u32 total) {
+        u32 rowoff = pre;
+#pragma unroll
+        for (int j = 0; j < CPT; ++j) {
+            if ((m[j] >> lane) & 1u) B.rank[base + 32u * j] = rowoff + __popc(m[j] & lt);
+            rowoff += __popc(m[j]);
+        }
+        // the tile owns the new ids [pre, pre + total): clear their accumulators for phase R / E
+        for (u32 i = lane; i < total; i += 32u) {
+            const u32 n = pre + i;
+            B.attr[nxt][n] = make_uint2(0u, 0u); B.best[nxt][n] = GSEG_KEY_NONE;
+            if (SP) { B.csum[nxt][3 * (size_t)n] = 0; B.csum[nxt][3 * (size_t)n + 1] = 0; B.csum[nxt][3 * (size_t)n + 2] = 0; }
+        }
+    };
+    // second half of a block tile: prefix of the block's root count, then every warp writes its ids
+    auto finish_block = [&](u32 btile, u32 base, u32 below, u32 all, const u32 *m, u32 total) {
+        if (wid == 0) {
+            const u32 pre = lookback_resolve(B.statusC, btile, tag, all, &ctl->error);
+            if (lane == 0) sh[64] = pre;
+        }
+        __syncthreads();
+        const u32 bpre = sh[64];
+        if (btile == ntiles - 1 && threadIdx.x == 0) ctl->Vnext = bpre + all;
+        write_ids(bpre + below, base, m, total);
+        __syncthreads(); // sh[64] is read before the next tile's ticket / prefix overwrite it
+    };
+    bool p_have = false;
+    u32 p_btile = 0, p_base = 0, p_below = 0, p_all = 0, p_total = 0, p_m[CPT] = {};
     for (;;) {
         u32 btile = 0, tile;
         if (SPREAD) {
@@ -774,28 +812,28 @@ __device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const R
             m[j] = __ballot_sync(0xFFFFFFFFu, root);
             total += __popc(m[j]);
         }
-        u32 pre;
         if (SPREAD) {
-            pre = lookback_prefix(B.statusC, tile, tag, total, &ctl->error);
+            const u32 pre = lookback_prefix(B.statusC, tile, tag, total, &ctl->error);
             if (tile == nwt - 1 && lane == 0) ctl->Vnext = pre + total;
+            write_ids(pre, base, m, total);
         } else {
-            u32 bend;
-            pre = block_ordered_offset(total, btile, tag, B.statusC, &ctl->error, sh, &bend);
-            if (btile == ntiles - 1 && threadIdx.x == 0) ctl->Vnext = bend;
-        }
-        u32 rowoff = pre;
+            // The block publishes its root count now and takes its prefix after the NEXT tile's gathers (see
+            // k_r0_graph): a look-back right here mostly waits for predecessors that are still gathering.
+            if (lane == 0) sh[wid] = total;
+            __syncthreads();
+            const u32 v = lane < nwarp ? sh[lane] : 0u;
+            u32 below = lane < wid ? v : 0u, all = v;
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) {
-            if ((m[j] >> lane) & 1u) B.rank[base + 32u * j] = rowoff + __popc(m[j] & lt);
-            rowoff += __popc(m[j]);
-        }
-        // the tile owns the new ids [pre, pre + total): clear their accumulators for phase R / E
-        for (u32 i = lane; i < total; i += 32u) {
-            const u32 n = pre + i;
-            B.attr[nxt][n] = make_uint2(0u, 0u); B.best[nxt][n] = GSEG_KEY_NONE;
-            if (SP) { B.csum[nxt][3 * (size_t)n] = 0; B.csum[nxt][3 * (size_t)n + 1] = 0; B.csum[nxt][3 * (size_t)n + 2] = 0; }
+            for (int o = 16; o; o >>= 1) { below += __shfl_xor_sync(0xFFFFFFFFu, below, o); all += __shfl_xor_sync(0xFFFFFFFFu, all, o); }
+            if (wid == 0) lookback_publish(B.statusC, btile, tag, all);
+            __syncthreads(); // sh[] is free again
+            if (p_have) finish_block(p_btile, p_base, p_below, p_all, p_m, p_total);
+            p_have = true; p_btile = btile; p_base = base; p_below = below; p_all = all; p_total = total;
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) p_m[j] = m[j];
         }
     }
+    if (!SPREAD && p_have) finish_block(p_btile, p_base, p_below, p_all, p_m, p_total);
 }
 
 // ------------------------------------------------------------------------------------------------
