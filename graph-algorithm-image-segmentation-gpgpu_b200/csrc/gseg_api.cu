@@ -27,7 +27,7 @@ struct GsegHead {
 };
 static_assert(offsetof(GsegCtl, Eacc) == offsetof(GsegHead, Eacc), "GsegHead must mirror the head of GsegCtl");
 
-static const size_t TAIL_SMEM = 2 * (size_t)GSEG_TAIL_STAGE * sizeof(u32); // k_tail's staging area (phase_E)
+static const size_t TAIL_SMEM = (2 * (size_t)GSEG_TAIL_STAGE + 2 * (NTT / 32)) * sizeof(u32); // k_tail: staged map + minima, survivor-count exchange (phase_E)
 
 struct gseg_ctx {
     int device, max_w, max_h;

@@ -843,8 +843,8 @@ __device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const R
 // of the G pages, a 4-step shuffle search maps a virtual slot to its page).  G = 1: page t -> page t in
 // place; G > 1: the output page g starts at pscan[G g].  No tickets, no look-back, no barriers.
 // ------------------------------------------------------------------------------------------------
-template <bool SP, bool SPREAD = false>
-__device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, u32 Vnext, u32 *stage = nullptr) {
+template <bool SP, bool SPREAD, int RW>
+__device__ __forceinline__ void phase_E_rows(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, u32 Vnext, u32 *stage) {
     constexpr int ROWS = GSEG_PAGE / 32;
     const int lane = threadIdx.x & 31;
     const u32 lt = (1u << lane) - 1u;
@@ -871,8 +871,15 @@ __device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const R
         }
         __syncthreads();
     }
-    u32 esum = 0;
-    for (u32 g = SPREAD ? (threadIdx.x >> 5) * gridDim.x + blockIdx.x : blockIdx.x * nwarp + (threadIdx.x >> 5); g < ngroups; g += nw) {
+    // RW < 8 (tail rounds with fewer pages than warps): a page is shared by NQ = 8 / RW consecutive warps,
+    // RW rows of every 8-row tile each, because a page's latency chain (gathers, then row after row of emits)
+    // is what a small round costs.  The warps of a page exchange their survivor counts through shared memory
+    // and a named barrier; the slots alternate between tiles, so one barrier per tile is enough.
+    constexpr int NQ = ROWS / RW;
+    const u32 wid = threadIdx.x >> 5, q = SPREAD ? (wid & (NQ - 1)) : 0u, grp = wid / NQ;
+    u32 *s_ex = stage + 2 * GSEG_TAIL_STAGE; // [2][nwarp / NQ][NQ] (SPREAD only)
+    u32 esum = 0, parity = 0;
+    for (u32 g = SPREAD ? grp * gridDim.x + blockIdx.x : blockIdx.x * nwarp + wid; g < ngroups; g += SPREAD ? gridDim.x * (nwarp / NQ) : nw) {
         u32 mycnt = 0u, myoff = 0u;
         if ((u32)lane < G && G * g + lane < P) { mycnt = __ldcg(pc + G * g + lane); myoff = __ldcg(po + G * g + lane); }
         const u32 incl = warp_incl_scan(mycnt, lane);
@@ -880,10 +887,10 @@ __device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const R
         const u32 out_base = G > 1u ? __ldcg(B.pscan + G * g) : __shfl_sync(0xFFFFFFFFu, myoff, 0);
         u32 written = 0;
         for (u32 c0 = 0; c0 < cnt; c0 += GSEG_PAGE) { // a virtual page can exceed one 8-row tile
-            u32 a[ROWS], b[ROWS], wv[ROWS], m[ROWS];
+            u32 a[RW], b[RW], wv[RW], m[RW];
 #pragma unroll
-            for (int j = 0; j < ROWS; ++j) {
-                const u32 i = c0 + 32u * j + lane;
+            for (int j = 0; j < RW; ++j) {
+                const u32 i = c0 + 32u * (q * RW + j) + lane;
                 u32 k = 0u; // input page of virtual slot i: the last page whose first slot is <= i
                 if (G > 1u) {
 #pragma unroll
@@ -898,22 +905,32 @@ __device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const R
                 if (i < cnt) { ab = __ldcg(eab + src); wv[j] = __ldcg(ew + src); }
                 a[j] = ab.x; b[j] = ab.y;
             }
-            u32 total = 0;
+            u32 sub = 0;
 #pragma unroll
-            for (int j = 0; j < ROWS; ++j) {
+            for (int j = 0; j < RW; ++j) {
                 bool keep = false;
-                if (c0 + 32u * j + lane < cnt) {
+                if (c0 + 32u * (q * RW + j) + lane < cnt) {
                     if (staged) { a[j] = s_map[a[j]]; b[j] = s_map[b[j]]; }
                     else { a[j] = __ldcg(map + a[j]); b[j] = __ldcg(map + b[j]); }
                     keep = a[j] != b[j];
                 }
                 m[j] = __ballot_sync(0xFFFFFFFFu, keep);
-                total += __popc(m[j]);
+                sub += __popc(m[j]);
             }
-            u32 rowoff = out_base + written;
+            u32 before = 0, total = sub; // survivors in the rows of the lower warps of the page / in the whole tile
+            if (NQ > 1) {
+                u32 *ex = s_ex + (parity * (nwarp / NQ) + grp) * NQ;
+                if (lane == 0) ex[q] = sub;
+                asm volatile("bar.sync %0, %1;" ::"r"(1u + grp), "r"(32u * NQ) : "memory");
+                total = 0;
+#pragma unroll
+                for (u32 t = 0; t < (u32)NQ; ++t) { const u32 v = ex[t]; total += v; if (t < q) before += v; }
+                parity ^= 1u;
+            }
+            u32 rowoff = out_base + written + before;
             if (filter && staged) {
 #pragma unroll
-                for (int j = 0; j < ROWS; ++j) {
+                for (int j = 0; j < RW; ++j) {
                     if (m[j] == 0u) continue; // warp-uniform
                     const bool act = (m[j] >> lane) & 1u;
                     emit_row<SP, true>(B, nxt, rowoff + __popc(m[j] & lt), act, a[j], b[j], wv[j], 0u, 0u, s_bhi);
@@ -921,15 +938,15 @@ __device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const R
                 }
             } else if (filter) {
                 // weights of the current minima of both ends, for all rows at once (one round trip)
-                u32 fa[ROWS], fb[ROWS];
+                u32 fa[RW], fb[RW];
                 const u32 *bhi = reinterpret_cast<const u32 *>(B.best[nxt]) + 1; // high word = weight bits
 #pragma unroll
-                for (int j = 0; j < ROWS; ++j) {
+                for (int j = 0; j < RW; ++j) {
                     fa[j] = fb[j] = 0xFFFFFFFFu;
                     if ((m[j] >> lane) & 1u) { fa[j] = ld_relaxed_u32(bhi + 2 * (size_t)a[j]); fb[j] = ld_relaxed_u32(bhi + 2 * (size_t)b[j]); }
                 }
 #pragma unroll
-                for (int j = 0; j < ROWS; ++j) {
+                for (int j = 0; j < RW; ++j) {
                     if (m[j] == 0u) continue; // warp-uniform
                     const bool act = (m[j] >> lane) & 1u;
                     emit_row<SP, true>(B, nxt, rowoff + __popc(m[j] & lt), act, a[j], b[j], wv[j], fa[j], fb[j]);
@@ -937,7 +954,7 @@ __device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const R
                 }
             } else {
 #pragma unroll
-                for (int j = 0; j < ROWS; ++j) {
+                for (int j = 0; j < RW; ++j) {
                     if (m[j] == 0u) continue; // warp-uniform
                     const bool act = (m[j] >> lane) & 1u;
                     emit_row<SP, false>(B, nxt, rowoff + __popc(m[j] & lt), act, a[j], b[j], wv[j]);
@@ -946,10 +963,24 @@ __device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const R
             }
             written += total;
         }
-        if (lane == 0) { B.pcnt[nxt][g] = written; B.poff[nxt][g] = out_base; }
-        esum += written;
+        if (q == 0u) {
+            if (lane == 0) { B.pcnt[nxt][g] = written; B.poff[nxt][g] = out_base; }
+            esum += written;
+        }
     }
     if (lane == 0 && esum) atomicAdd(&ctl->Eacc[st.round], esum);
+}
+template <bool SP, bool SPREAD = false>
+__device__ __forceinline__ void phase_E(GsegCtl *ctl, const GsegBufs &B, const RoundState &st, u32 Vnext, u32 *stage = nullptr) {
+    if (SPREAD) {
+        const u32 G = group_size(st), ngroups = (st.P + G - 1u) / G;
+        // measured on the 16 x 32-warp tail: four warps per page win up to ~2 pages per warp (507 pages: 19.8 ->
+        // 13.0 us, 127: 14.4 -> 7.5 us), one warp per page wins beyond (2025 pages: 29.7 vs 35.1 us)
+        if (ngroups <= 2u * gridDim.x * (blockDim.x >> 5)) phase_E_rows<SP, true, 2>(ctl, B, st, Vnext, stage);
+        else phase_E_rows<SP, true, GSEG_PAGE / 32>(ctl, B, st, Vnext, stage);
+    } else {
+        phase_E_rows<SP, false, GSEG_PAGE / 32>(ctl, B, st, Vnext, stage);
+    }
 }
 
 // a11 (superpixel), phase M: mean colour of every component of the next round, from the sums phase R finished.
