@@ -48,6 +48,12 @@ namespace cg = cooperative_groups;
 __constant__ int c_DX[4] = {1, 0, 1, 1};
 __constant__ int c_DY[4] = {0, 1, 1, -1};
 
+// Gathers of arrays a PREVIOUS kernel wrote: the grid-wide kernels (one launch per phase) may serve them from
+// L1, where neighbouring lanes' lines are already resident; the tail kernel runs every round inside one
+// launch, its L1 would hold last round's lines, so it reads through to L2.
+template <bool L1, typename T>
+__device__ __forceinline__ T ld_prev(const T *p) { return L1 ? *p : __ldcg(p); }
+
 // ------------------------------------------------------------------------------------------------
 // a1: separable Gaussian, clamped borders.  u8 interleaved RGB -> 3 fp32 planes.
 // Tile kernel: (TW+2R) x (TH+2R) input pixels -> fp32 planes in shared memory (32-bit loads of the
@@ -569,20 +575,20 @@ __device__ __forceinline__ void phase_R(const GsegCtl *ctl, const GsegBufs &B, c
         const bool act = c < V;
         u32 m = 0u, sz = 1u, iv = 0u;
         if (act) {
-            u32 r = ld_relaxed_u32(B.succ + c);
+            u32 r = SPREAD ? ld_relaxed_u32(B.succ + c) : B.succ[c];
             if (r != c) {
                 u32 steps = 0;
                 for (;;) {
-                    const u32 rr = ld_relaxed_u32(B.succ + r);
+                    const u32 rr = SPREAD ? ld_relaxed_u32(B.succ + r) : B.succ[r]; // stale = an older ancestor: still valid
                     if (rr == r) break;
                     r = rr;
                     if (++steps > V) { ((GsegCtl *)ctl)->error = DERR_CHASE; break; } // a cycle can only come from a bug: fail, do not hang
                 }
                 B.succ[c] = r;
             }
-            m = __ldcg(B.rank + r);
+            m = ld_prev<!SPREAD>(B.rank + r);
             map[c] = m;
-            if (!R0) { const uint2 at = __ldcg(B.attr[cur] + c); sz = at.x; iv = at.y; }
+            if (!R0) { const uint2 at = ld_prev<!SPREAD>(B.attr[cur] + c); sz = at.x; iv = at.y; }
             if (r != c) iv = max(iv, __ldcg(B.wsel + c));
         }
         warp_run_accumulate(B.attr[nxt], m, sz, iv, act);
@@ -767,16 +773,16 @@ __device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const R
         u64 key[CPT], key2[CPT];
         uint2 ab[CPT], ta[CPT], tb[CPT];
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) key[j] = base + 32u * j < V ? __ldcg(best + base + 32u * j) : GSEG_KEY_NONE;
+        for (int j = 0; j < CPT; ++j) key[j] = base + 32u * j < V ? ld_prev<!SPREAD>(best + base + 32u * j) : GSEG_KEY_NONE;
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) ab[j] = key[j] != GSEG_KEY_NONE ? __ldcg(eab + (u32)key[j]) : make_uint2(0u, 0u);
+        for (int j = 0; j < CPT; ++j) ab[j] = key[j] != GSEG_KEY_NONE ? ld_prev<!SPREAD>(eab + (u32)key[j]) : make_uint2(0u, 0u);
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
             key2[j] = GSEG_KEY_NONE; ta[j] = tb[j] = make_uint2(1u, 0u);
             if (key[j] != GSEG_KEY_NONE) {
                 const u32 c = base + 32u * j, other = ab[j].x == c ? ab[j].y : ab[j].x;
-                key2[j] = __ldcg(best + other);
-                if (pred || msz) { ta[j] = __ldcg(attr + ab[j].x); tb[j] = __ldcg(attr + ab[j].y); }
+                key2[j] = ld_prev<!SPREAD>(best + other);
+                if (pred || msz) { ta[j] = ld_prev<!SPREAD>(attr + ab[j].x); tb[j] = ld_prev<!SPREAD>(attr + ab[j].y); }
             }
         }
         u32 m[CPT], total = 0;
@@ -911,14 +917,14 @@ __device__ __forceinline__ void phase_E_rows(GsegCtl *ctl, const GsegBufs &B, co
                 bool keep = false;
                 if (c0 + 32u * (q * RW + j) + lane < cnt) {
                     if (staged) { a[j] = s_map[a[j]]; b[j] = s_map[b[j]]; }
-                    else { a[j] = __ldcg(map + a[j]); b[j] = __ldcg(map + b[j]); }
+                    else { a[j] = ld_prev<!SPREAD>(map + a[j]); b[j] = ld_prev<!SPREAD>(map + b[j]); }
                     keep = a[j] != b[j];
                 }
                 m[j] = __ballot_sync(0xFFFFFFFFu, keep);
                 sub += __popc(m[j]);
             }
             u32 before = 0, total = sub; // survivors in the rows of the lower warps of the page / in the whole tile
-            if (NQ > 1) {
+            if constexpr (NQ > 1) {
                 u32 *ex = s_ex + (parity * (nwarp / NQ) + grp) * NQ;
                 if (lane == 0) ex[q] = sub;
                 asm volatile("bar.sync %0, %1;" ::"r"(1u + grp), "r"(32u * NQ) : "memory");
