@@ -308,7 +308,7 @@ static GsegBufs bufs_of(const gseg_ctx *c) {
 }
 
 template <int R>
-static size_t blur_smem() { return (size_t)3 * (TH + 2 * R) * (BLUR_PF(R) + BLUR_PH) * sizeof(float); }
+static size_t blur_smem() { return (size_t)3 * (TH + 2 * R) * (BLUR_PF(R) + BLUR_PH * sizeof(float)); } // 8-bit staged input + fp32 horizontal pass
 template <int R>
 static void launch_blur(gseg_ctx *c, cudaStream_t s, int ntiles) {
     static bool attr[64] = {false}; // the opt-in is per function and per device

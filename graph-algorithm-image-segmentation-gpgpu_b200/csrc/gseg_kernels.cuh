@@ -56,21 +56,23 @@ __device__ __forceinline__ T ld_prev(const T *p) { return L1 ? *p : __ldcg(p); }
 
 // ------------------------------------------------------------------------------------------------
 // a1: separable Gaussian, clamped borders.  u8 interleaved RGB -> 3 fp32 planes.
-// Tile kernel: (TW+2R) x (TH+2R) input pixels -> fp32 planes in shared memory (32-bit loads of the
-// interleaved bytes where the tile is interior and 4-byte aligned); horizontal pass, shared -> shared;
+// Tile kernel: (TW+2R) x (TH+2R) input pixels -> three 8-bit planes in shared memory (32-bit loads of the
+// interleaved bytes where the tile is interior and 4-byte aligned, de-interleaved with byte permutes;
+// converted to fp32 when the horizontal pass reads them); horizontal pass, shared -> shared (fp32);
 // vertical pass -> global.  Each thread produces 8 outputs along the filter direction from 8+2R
 // register-held taps (2 shared loads per output instead of 2R+1).  Lanes run ACROSS the filter
 // direction (over rows in the horizontal pass, over columns in the vertical pass) and the shared row
 // pitches are odd, so every shared access of a warp is bank-conflict free.
 // ------------------------------------------------------------------------------------------------
-#define BLUR_PF(R) ((TW + 2 * (R)) | 1)  // pitch of the staged input planes
+#define BLUR_PF(R) (4 * ((((TW + 2 * (R)) + 3) / 4) | 1)) // byte pitch of the staged input planes: an odd number of words
 #define BLUR_PH (TW + 1)                 // pitch of the horizontally filtered planes
 template <int R>
 __global__ void __launch_bounds__(NT) k_blur_tile(const GsegCtl *__restrict__ ctl, float *__restrict__ planes) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     constexpr int IW = TW + 2 * R, IH = TH + 2 * R, PF = BLUR_PF(R), PH = BLUR_PH;
-    float *sF = reinterpret_cast<float *>(smem_raw); // [3][IH][PF] input as fp32
-    float *sH = sF + 3 * IH * PF;                    // [3][IH][PH] after the horizontal pass
+    uint8_t *sF = smem_raw;                                      // [3][IH][PF] input planes, still 8-bit (a quarter of
+                                                                 // the fp32 staging: five blocks per SM instead of three)
+    float *sH = reinterpret_cast<float *>(smem_raw + 3 * IH * PF); // [3][IH][PH] after the horizontal pass
     const int w = ctl->p.w, h = ctl->p.h, stride = ctl->p.stride;
     const uint8_t *__restrict__ rgb = ctl->p.rgb;
     float m[R + 1];
@@ -78,7 +80,7 @@ __global__ void __launch_bounds__(NT) k_blur_tile(const GsegCtl *__restrict__ ct
     for (int i = 0; i <= R; ++i) m[i] = ctl->p.mask[i];
     const int ntx = (w + TW - 1) / TW;
     const int x0 = (blockIdx.x % ntx) * TW, y0 = (blockIdx.x / ntx) * TH;
-    // 1. stage: 4 pixels (12 bytes) per item
+    // 1. stage: 4 pixels (12 interleaved bytes -> one word per colour plane) per item
     const bool fast = x0 - R >= 0 && x0 - R + IW <= w && (stride & 3) == 0 && ((3 * (x0 - R)) & 3) == 0 &&
                       (reinterpret_cast<size_t>(rgb) & 3) == 0 && (IW & 3) == 0;
     constexpr int G4 = (IW + 3) / 4;
@@ -86,17 +88,13 @@ __global__ void __launch_bounds__(NT) k_blur_tile(const GsegCtl *__restrict__ ct
         const int r = item / G4, g = item - r * G4;
         const int gy = min(max(y0 - R + r, 0), h - 1);
         const uint8_t *row = rgb + (size_t)gy * stride;
-        float *d0 = sF + r * PF + 4 * g;
+        uint8_t *d0 = sF + r * PF + 4 * g;
         if (fast) {
             const uint32_t *wp = reinterpret_cast<const uint32_t *>(row + 3 * (x0 - R) + 12 * g);
-            const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2];
-            const uint32_t b[12] = {w0 & 255u, (w0 >> 8) & 255u, (w0 >> 16) & 255u, w0 >> 24,
-                                    w1 & 255u, (w1 >> 8) & 255u, (w1 >> 16) & 255u, w1 >> 24,
-                                    w2 & 255u, (w2 >> 8) & 255u, (w2 >> 16) & 255u, w2 >> 24};
-#pragma unroll
-            for (int q = 0; q < 4; ++q)
-#pragma unroll
-                for (int ch = 0; ch < 3; ++ch) d0[ch * IH * PF + q] = (float)b[3 * q + ch];
+            const uint32_t w0 = wp[0], w1 = wp[1], w2 = wp[2]; // r0 g0 b0 r1 | g1 b1 r2 g2 | b2 r3 g3 b3
+            *reinterpret_cast<uint32_t *>(d0) = __byte_perm(__byte_perm(w0, w1, 0x0630), w2, 0x5210);
+            *reinterpret_cast<uint32_t *>(d0 + IH * PF) = __byte_perm(__byte_perm(w0, w1, 0x0741), w2, 0x6210);
+            *reinterpret_cast<uint32_t *>(d0 + 2 * IH * PF) = __byte_perm(__byte_perm(w0, w1, 0x0052), w2, 0x7410);
         } else {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -104,7 +102,7 @@ __global__ void __launch_bounds__(NT) k_blur_tile(const GsegCtl *__restrict__ ct
                 if (px >= IW) break;
                 const int gx = min(max(x0 - R + px, 0), w - 1);
 #pragma unroll
-                for (int ch = 0; ch < 3; ++ch) d0[ch * IH * PF + q] = (float)row[3 * gx + ch];
+                for (int ch = 0; ch < 3; ++ch) d0[ch * IH * PF + q] = row[3 * gx + ch];
             }
         }
     }
@@ -113,9 +111,14 @@ __global__ void __launch_bounds__(NT) k_blur_tile(const GsegCtl *__restrict__ ct
     for (int item = threadIdx.x; item < 3 * (TW / 8) * IH; item += NT) {
         const int r = item % IH, g = (item / IH) % (TW / 8), ch = item / (IH * (TW / 8));
         float v[8 + 2 * R];
-        const float *src = sF + (ch * IH + r) * PF + g * 8;
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(sF + (ch * IH + r) * PF + g * 8);
 #pragma unroll
-        for (int j = 0; j < 8 + 2 * R; ++j) v[j] = src[j];
+        for (int q = 0; q < (8 + 2 * R + 3) / 4; ++q) {
+            const uint32_t t = src[q];
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (4 * q + k < 8 + 2 * R) v[4 * q + k] = (float)((t >> (8 * k)) & 255u);
+        }
         float *dst = sH + (ch * IH + r) * PH + g * 8;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
