@@ -9,6 +9,8 @@
   counts are all-gathered so every rank (and the caller) sees the whole batch's summary.  The label
   images stay on the rank that produced them.
 """
+import os
+
 import numpy as np
 
 
@@ -25,7 +27,7 @@ class ContextPool:
         self.segs = [gseg.Segmenter(max_w, max_h, device=device) for _ in range(max(1, contexts))]
         if len(self.segs) >= 4:  # many contexts in flight: size each grid for 2 blocks per SM so kernels overlap
             for s in self.segs:
-                s.set_blocks_per_sm(2)
+                s.set_blocks_per_sm(int(os.environ.get("GSEG_POOL_BLOCKS_PER_SM", "2")))
 
     def close(self):
         for s in self.segs:
