@@ -194,20 +194,6 @@ __device__ __forceinline__ u32 lookback_prefix(u64 *status, u32 tile, u32 tag, u
     return lookback_resolve(status, tile, tag, aggregate, err);
 }
 
-// Block-wide: exclusive offset of `cnt` items inside a globally ordered compaction.
-// Returns this thread's offset INSIDE the tile; afterwards s[32] = tile total, s[33] = tile prefix.
-// Warp 0 runs the look-back; callers may overlap independent work between this call's return and the
-// next __syncthreads(), after which s[33] is valid for everyone.
-template <int NTHR>
-__device__ __forceinline__ u32 tile_scan_begin(u32 cnt, u32 tile, u32 tag, u64 *status, u32 *err, u32 *s) {
-    const u32 ex = block_excl_scan<NTHR>(cnt, s);
-    if (threadIdx.x < 32) {
-        const u32 pre = lookback_prefix(status, tile, tag, s[32], err);
-        if (threadIdx.x == 0) s[33] = pre;
-    }
-    return ex;
-}
-
 // Block-granular ordered offsets for warps that each hold one count: the warps of a block exchange
 // their counts through shared memory, warp 0 scans them and runs ONE decoupled look-back for the block
 // (so the scan has gridDim participants, not gridDim x warps: short look-back walks), and every warp
