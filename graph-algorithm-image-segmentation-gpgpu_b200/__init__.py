@@ -95,6 +95,10 @@ def load():
     L.gseg_segment.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(Params)]
     L.gseg_segment_async.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(Params)]
     L.gseg_wait.argtypes = [vp]
+    L.gseg_jpeg_info.argtypes = [vp, C.c_size_t, C.POINTER(i32), C.POINTER(i32)]
+    L.gseg_segment_jpeg.argtypes = [vp, vp, C.c_size_t, C.POINTER(Params), C.POINTER(i32), C.POINTER(i32)]
+    L.gseg_segment_jpeg_async.argtypes = [vp, vp, C.c_size_t, C.POINTER(Params), C.POINTER(i32), C.POINTER(i32)]
+    L.gseg_input_rgb.argtypes = [vp, vp, i32]
     L.gseg_num_levels.argtypes = [vp]
     L.gseg_num_components.argtypes = [vp, i32]
     L.gseg_labels.argtypes = [vp, i32, vp, i32]
@@ -121,6 +125,16 @@ def load():
 
 class GsegError(RuntimeError):
     pass
+
+
+def jpeg_info(data):
+    """(w, h) of a JPEG (gseg_jpeg_info; needs a CUDA device and libnvjpeg like the decode itself)."""
+    L = load()
+    w, h = C.c_int32(0), C.c_int32(0)
+    rc = L.gseg_jpeg_info(data, len(data), C.byref(w), C.byref(h))
+    if rc:
+        raise GsegError("gseg_jpeg_info: %s" % L.gseg_strerror(rc).decode())
+    return int(w.value), int(h.value)
 
 
 def _is_torch(x):
@@ -197,6 +211,24 @@ class Segmenter:
     def wait(self):
         self._ck(self.L.gseg_wait(self.h), "gseg_wait")
         return self
+
+    def segment_jpeg(self, data, params=None, wait=True, **kw):
+        """data: the bytes of a JPEG file.  nvJPEG decodes them on the GPU into the context's staged RGB
+        buffer and the usual path runs on it (gseg_segment_jpeg); returns (w, h)."""
+        p = params if params is not None else self.params(**kw)
+        buf = (C.c_char * len(data)).from_buffer_copy(data)
+        w, h = C.c_int32(0), C.c_int32(0)
+        fn = self.L.gseg_segment_jpeg if wait else self.L.gseg_segment_jpeg_async
+        self._keep = buf
+        self._ck(fn(self.h, C.cast(buf, C.c_void_p), len(data), C.byref(p), C.byref(w), C.byref(h)), "gseg_segment_jpeg")
+        self.w, self.hh, self.D = int(w.value), int(h.value), (4 if p.connectivity == 8 else 2)
+        return self.w, self.hh
+
+    def input_rgb(self):
+        """(h, w, 3) uint8: the image the last run read, when the context staged it (host input or JPEG)."""
+        out = np.empty((self.hh, self.w, 3), np.uint8)
+        self._ck(self.L.gseg_input_rgb(self.h, out.ctypes.data, 0), "gseg_input_rgb")
+        return out
 
     def num_levels(self):
         return self._ck(self.L.gseg_num_levels(self.h), "gseg_num_levels")

@@ -3,6 +3,8 @@
 // There is no CPU path in this file: every compute entry point launches the CUDA kernels of
 // gseg_kernels.cuh and fails with GSEG_E_CUDA when no device is usable.
 #include <cuda_runtime.h>
+#include <dlfcn.h>
+#include <nvjpeg.h> // types and prototypes only: the library is loaded with dlopen on first use
 #include <limits.h>
 #include <stddef.h>
 #include <math.h>
@@ -68,6 +70,8 @@ struct gseg_ctx {
     gseg_params params;
     int w, h, D;
     bool valid, pending;
+    bool rgb_staged;              // the last run read its input from d_rgb (host input or JPEG)
+    nvjpegHandle_t jpg_handle; nvjpegJpegState_t jpg_state; // nvJPEG objects, created on first gseg_segment_jpeg
     u32 epoch_next;
     char err[256];
     // per-kernel profiling (host-driven schedule only) and launch accounting
@@ -101,6 +105,7 @@ extern "C" const char *gseg_strerror(int s) {
     case GSEG_E_INTERNAL: return "device-side watchdog tripped";
     case GSEG_E_STATE: return "no completed segmentation in this context";
     case GSEG_E_LEVEL: return "hierarchy level out of range";
+    case GSEG_E_UNSUPPORTED: return "optional dependency missing at run time";
     default: return "unknown status";
     }
 }
@@ -215,6 +220,102 @@ extern "C" int gseg_create_ex(gseg_ctx **out, int device, int max_w, int max_h, 
     return GSEG_OK;
 }
 
+
+// ---- nvJPEG (optional, dlopen) ------------------------------------------------------------------------
+// JPEG input decoded on the GPU into the staged RGB buffer.  Library code, outside
+// the hot path; libgseg.so has no link-time dependency on it.
+struct NvJpegApi {
+    void *lib;
+    decltype(&nvjpegCreateSimple) create;
+    decltype(&nvjpegDestroy) destroy;
+    decltype(&nvjpegJpegStateCreate) state_create;
+    decltype(&nvjpegJpegStateDestroy) state_destroy;
+    decltype(&nvjpegGetImageInfo) info;
+    decltype(&nvjpegDecode) decode;
+    bool ok;
+};
+static NvJpegApi *nvjpeg_api() {
+    static NvJpegApi api = [] {
+        NvJpegApi a = {};
+        const char *names[] = {"libnvjpeg.so.12", "libnvjpeg.so"};
+        for (const char *n : names)
+            if ((a.lib = dlopen(n, RTLD_NOW | RTLD_LOCAL))) break;
+        if (!a.lib) return a;
+        a.create = (decltype(a.create))dlsym(a.lib, "nvjpegCreateSimple");
+        a.destroy = (decltype(a.destroy))dlsym(a.lib, "nvjpegDestroy");
+        a.state_create = (decltype(a.state_create))dlsym(a.lib, "nvjpegJpegStateCreate");
+        a.state_destroy = (decltype(a.state_destroy))dlsym(a.lib, "nvjpegJpegStateDestroy");
+        a.info = (decltype(a.info))dlsym(a.lib, "nvjpegGetImageInfo");
+        a.decode = (decltype(a.decode))dlsym(a.lib, "nvjpegDecode");
+        a.ok = a.create && a.destroy && a.state_create && a.state_destroy && a.info && a.decode;
+        return a;
+    }();
+    return api.ok ? &api : nullptr;
+}
+static void jpeg_release(gseg_ctx *ctx) {
+    NvJpegApi *a = nvjpeg_api();
+    if (!a) return;
+    if (ctx->jpg_state) a->state_destroy(ctx->jpg_state);
+    if (ctx->jpg_handle) a->destroy(ctx->jpg_handle);
+    ctx->jpg_state = nullptr; ctx->jpg_handle = nullptr;
+}
+static int jpeg_size(NvJpegApi *a, nvjpegHandle_t hnd, const void *jpeg, size_t nbytes, int *w, int *h) {
+    int ncomp = 0, ws[NVJPEG_MAX_COMPONENT] = {0}, hs[NVJPEG_MAX_COMPONENT] = {0};
+    nvjpegChromaSubsampling_t sub;
+    if (a->info(hnd, (const unsigned char *)jpeg, nbytes, &ncomp, &sub, ws, hs) != NVJPEG_STATUS_SUCCESS || ws[0] < 1 || hs[0] < 1)
+        return GSEG_E_ARG;
+    *w = ws[0]; *h = hs[0];
+    return GSEG_OK;
+}
+
+extern "C" int gseg_jpeg_info(const void *jpeg, size_t nbytes, int *w, int *h) {
+    if (!jpeg || !nbytes || !w || !h) return GSEG_E_ARG;
+    NvJpegApi *a = nvjpeg_api();
+    if (!a) return GSEG_E_UNSUPPORTED;
+    nvjpegHandle_t hnd = nullptr;
+    if (a->create(&hnd) != NVJPEG_STATUS_SUCCESS) return GSEG_E_CUDA; // needs a CUDA device, like everything else here
+    const int rc = jpeg_size(a, hnd, jpeg, nbytes, w, h);
+    a->destroy(hnd);
+    return rc;
+}
+
+extern "C" int gseg_segment_jpeg_async(gseg_ctx *ctx, const void *jpeg, size_t nbytes, const gseg_params *p, int *w, int *h) {
+    if (!ctx || !jpeg || !nbytes || !p) return GSEG_E_ARG;
+    if (ctx->pending) return fail(ctx, GSEG_E_STATE, "previous run not waited for", cudaSuccess);
+    NvJpegApi *a = nvjpeg_api();
+    if (!a) return fail(ctx, GSEG_E_UNSUPPORTED, "libnvjpeg.so.12 could not be loaded", cudaSuccess);
+    CK(cudaSetDevice(ctx->device));
+    if (!ctx->jpg_handle) {
+        if (a->create(&ctx->jpg_handle) != NVJPEG_STATUS_SUCCESS) { ctx->jpg_handle = nullptr; return fail(ctx, GSEG_E_CUDA, "nvjpegCreateSimple", cudaSuccess); }
+        if (a->state_create(ctx->jpg_handle, &ctx->jpg_state) != NVJPEG_STATUS_SUCCESS) { ctx->jpg_state = nullptr; return fail(ctx, GSEG_E_CUDA, "nvjpegJpegStateCreate", cudaSuccess); }
+    }
+    int iw = 0, ih = 0;
+    if (jpeg_size(a, ctx->jpg_handle, jpeg, nbytes, &iw, &ih)) return fail(ctx, GSEG_E_ARG, "not a JPEG nvJPEG can parse", cudaSuccess);
+    if (w) *w = iw;
+    if (h) *h = ih;
+    if ((size_t)iw * ih > ctx->Vmax) return fail(ctx, GSEG_E_SIZE, "image exceeds context capacity", cudaSuccess);
+    nvjpegImage_t out = {};
+    out.channel[0] = ctx->d_rgb; out.pitch[0] = (size_t)3 * iw; // interleaved RGB, tightly packed
+    ctx->valid = false;
+    if (a->decode(ctx->jpg_handle, ctx->jpg_state, (const unsigned char *)jpeg, nbytes, NVJPEG_OUTPUT_RGBI, &out, ctx->stream) != NVJPEG_STATUS_SUCCESS)
+        return fail(ctx, GSEG_E_ARG, "nvjpegDecode failed (unsupported or corrupt JPEG)", cudaSuccess);
+    return gseg_segment_async(ctx, ctx->d_rgb, iw, ih, 3 * iw, GSEG_MEM_DEVICE, p); // same stream: ordered after the decode
+}
+extern "C" int gseg_segment_jpeg(gseg_ctx *ctx, const void *jpeg, size_t nbytes, const gseg_params *p, int *w, int *h) {
+    const int rc = gseg_segment_jpeg_async(ctx, jpeg, nbytes, p, w, h);
+    return rc ? rc : gseg_wait(ctx);
+}
+extern "C" int gseg_input_rgb(gseg_ctx *ctx, uint8_t *out, int mem_kind) {
+    if (!ctx || !out) return GSEG_E_ARG;
+    if (ctx->pending) { const int rc = gseg_wait(ctx); if (rc) return rc; }
+    if (!ctx->valid || !ctx->rgb_staged) return fail(ctx, GSEG_E_STATE, "the last run's input was not staged by the context", cudaSuccess);
+    if (mem_kind != GSEG_MEM_HOST && mem_kind != GSEG_MEM_DEVICE) return fail(ctx, GSEG_E_ARG, "mem_kind", cudaSuccess);
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(out, ctx->d_rgb, (size_t)3 * ctx->w * ctx->h, mem_kind == GSEG_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaStreamSynchronize(ctx->stream));
+    return GSEG_OK;
+}
+
 extern "C" void gseg_destroy(gseg_ctx *ctx) {
     if (!ctx) return;
     cudaSetDevice(ctx->device);
@@ -227,6 +328,7 @@ extern "C" void gseg_destroy(gseg_ctx *ctx) {
         cudaFree(ctx->d_eab[i]); cudaFree(ctx->d_ew[i]); cudaFree(ctx->d_pcnt[i]); cudaFree(ctx->d_poff[i]); cudaFree(ctx->d_labels[i]);
     }
     cudaFree(ctx->d_pscan); cudaFree(ctx->d_arena); cudaFree(ctx->d_statusC); cudaFree(ctx->d_statusE); cudaFree(ctx->d_ctl);
+    jpeg_release(ctx);
     sort_scratch_free(&ctx->sort);
     cudaFree(ctx->d_xkeys); cudaFree(ctx->d_xvals); cudaFree(ctx->d_xkeep); cudaFree(ctx->d_xab); cudaFree(ctx->d_xw);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
@@ -507,6 +609,7 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
         src = ctx->d_rgb;
         dstride = 3 * w;
     }
+    ctx->rgb_staged = src == ctx->d_rgb;
     const int R = max_rounds_of(p);
     const bool host_loop = (p->flags & GSEG_FLAG_HOST_LOOP) != 0;
     // look-back tags: 2 per round, 30 bits; recycle the tag space long before it wraps

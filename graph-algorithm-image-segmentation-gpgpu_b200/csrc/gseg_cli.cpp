@@ -7,7 +7,8 @@
 // this file: it parses arguments, reads/writes PPM and calls libgseg.so.
 //
 //   gseg [options] sigma k min_size input output
-//     input: binary PPM/PGM or PNG (by content); output: PNG if the name ends in .png, else PPM
+//     input: binary PPM/PGM, PNG or JPEG (by content; JPEG is decoded on the GPU through
+//     gseg_segment_jpeg / nvJPEG); output: PNG if the name ends in .png, else PPM
 //     (gseg_imageio.hpp; the GPU branches read through cv::imread)
 //     --variant felz|hier|superpix   reference branch semantics (default felz)
 //     --conn 4|8                     grid connectivity (default 8, as in `segment`)
@@ -32,7 +33,7 @@
 static int usage() {
     fprintf(stderr,
             "usage: gseg [--variant felz|hier|superpix] [--conn 4|8] [--level L] [--labels FILE]\n"
-            "            [--synth WxH:SEED] [--iters N] [--device D] sigma k min_size input.{ppm,pgm,png} output.{ppm,png}\n"
+            "            [--synth WxH:SEED] [--iters N] [--device D] sigma k min_size input.{ppm,pgm,png,jpg} output.{ppm,png}\n"
             "       gseg --convert input output\n");
     return 2;
 }
@@ -86,13 +87,28 @@ int main(int argc, char **argv) {
     std::vector<uint8_t> img;
     int w = sw, h = sh;
     std::string ioerr;
-    if (!sw && !gsegio::read_image(in_path, img, w, h, ioerr)) {
-        fprintf(stderr, "gseg: cannot read %s: %s\n", in_path, ioerr.c_str());
-        return 1;
+    std::vector<uint8_t> jpeg; // JPEG input: decoded on the GPU by gseg_segment_jpeg (nvJPEG), not by this program
+    if (!sw) {
+        std::vector<uint8_t> raw;
+        if (gsegio::read_file(in_path, raw) && raw.size() > 2 && raw[0] == 0xFF && raw[1] == 0xD8) {
+            const int jrc = gseg_jpeg_info(raw.data(), raw.size(), &w, &h);
+            if (jrc) { fprintf(stderr, "gseg: cannot read JPEG %s: %s\n", in_path, gseg_strerror(jrc)); return 1; }
+            jpeg.swap(raw);
+        } else if (!gsegio::read_image(in_path, img, w, h, ioerr)) {
+            fprintf(stderr, "gseg: cannot read %s: %s\n", in_path, ioerr.c_str());
+            return 1;
+        }
     }
     gseg_ctx *ctx = nullptr;
     int rc = gseg_create(&ctx, device, w, h);
     if (rc) { fprintf(stderr, "gseg: gseg_create: %s\n", gseg_strerror(rc)); return 1; }
+    if (!jpeg.empty()) { // first run straight from the compressed bytes; the decoded pixels come back for the timing loop
+        rc = gseg_segment_jpeg(ctx, jpeg.data(), jpeg.size(), &p, &w, &h);
+        if (rc) { fprintf(stderr, "gseg: gseg_segment_jpeg: %s (%s)\n", gseg_strerror(rc), gseg_last_error(ctx)); return 1; }
+        img.resize((size_t)w * h * 3);
+        rc = gseg_input_rgb(ctx, img.data(), GSEG_MEM_HOST);
+        if (rc) { fprintf(stderr, "gseg: gseg_input_rgb: %s\n", gseg_strerror(rc)); return 1; }
+    }
     if (sw) {
         img.resize((size_t)w * h * 3);
         rc = gseg_synth(ctx, img.data(), w, h, sseed, GSEG_MEM_HOST);

@@ -20,6 +20,7 @@
 #ifndef GSEG_H
 #define GSEG_H
 
+#include <stddef.h>
 #include <stdint.h>
 
 #ifdef __cplusplus
@@ -51,7 +52,8 @@ typedef enum gseg_status {
     GSEG_E_ARENA = -4,   /* supervertex-map arena exhausted (pathological round count) */
     GSEG_E_INTERNAL = -5, /* device-side watchdog tripped */
     GSEG_E_STATE = -6,   /* result requested before a successful gseg_segment */
-    GSEG_E_LEVEL = -7    /* hierarchy level out of range */
+    GSEG_E_LEVEL = -7,   /* hierarchy level out of range */
+    GSEG_E_UNSUPPORTED = -8 /* optional dependency missing at run time (nvJPEG for gseg_segment_jpeg) */
 } gseg_status;
 
 /* Parameters of one segmentation (BASELINE.json north_star: sigma, k, min_size, hierarchy level). */
@@ -165,6 +167,22 @@ int gseg_blurred_rows(gseg_ctx *ctx, int y0, int nrows, float *out, int mem_kind
 int gseg_segment_graph(gseg_ctx *ctx, int64_t n_components, const uint32_t *size, const float *Int, int64_t n_edges,
                        const uint32_t *ea, const uint32_t *eb, const float *w, const gseg_params *params,
                        int32_t *labels_out);
+
+/* ---- JPEG input decoded on the GPU --------------------------------------
+ * The reference's batch benchmark reads a JPEG data set through cv::imread on the host (README.md:26).
+ * Here the compressed bytes go to the GPU: nvJPEG (CUDA toolkit library, loaded with dlopen on first
+ * use -- libgseg.so itself does not depend on it) decodes into the context's staged RGB buffer on the
+ * context's stream and the usual path runs on it; the decoded image never visits the host.
+ *   gseg_jpeg_info          width / height of a JPEG (host only: parses the header).
+ *   gseg_segment_jpeg_async decode + enqueue the segmentation (complete it with gseg_wait, or use
+ *   gseg_segment_jpeg       the blocking form); *w, *h receive the image size.
+ *   gseg_input_rgb          the interleaved RGB image the last run read, when it was staged by the
+ *                           context (host input or JPEG); GSEG_E_STATE for caller-owned device input.
+ * GSEG_E_UNSUPPORTED when libnvjpeg cannot be loaded, GSEG_E_ARG for data nvJPEG rejects. */
+int gseg_jpeg_info(const void *jpeg, size_t nbytes, int *w, int *h);
+int gseg_segment_jpeg_async(gseg_ctx *ctx, const void *jpeg, size_t nbytes, const gseg_params *params, int *w, int *h);
+int gseg_segment_jpeg(gseg_ctx *ctx, const void *jpeg, size_t nbytes, const gseg_params *params, int *w, int *h);
+int gseg_input_rgb(gseg_ctx *ctx, uint8_t *out_rgb, int mem_kind);
 
 /* Per-round statistics of the last run; returns number of rounds (<= cap written). */
 int gseg_stats(const gseg_ctx *ctx, gseg_round_stat *out, int cap);

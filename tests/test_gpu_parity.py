@@ -335,6 +335,70 @@ def test_cli_ppm_roundtrip(gseg, oracle, tmp_path):
     assert "time_ms mean" in r.stdout
 
 
+def test_jpeg_input_decoded_on_gpu(gseg, oracle, tmp_path):
+    """JPEG bytes -> nvJPEG on the context's stream -> the usual path.  The partition is
+    checked against the oracle run on the very pixels the GPU decoded (gseg_input_rgb); the decode itself
+    is checked for sanity against libjpeg (cv2)."""
+    import subprocess
+    import torch
+    cv2 = pytest.importorskip("cv2")
+    cases = [(320, 240, [cv2.IMWRITE_JPEG_QUALITY, 92]), (321, 243, [cv2.IMWRITE_JPEG_QUALITY, 75])]
+    if hasattr(cv2, "IMWRITE_JPEG_SAMPLING_FACTOR"):
+        cases.append((200, 150, [cv2.IMWRITE_JPEG_QUALITY, 85, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444]))
+    seg = gseg.Segmenter(400, 300)
+    for i, (w, h, enc_params) in enumerate(cases):
+        img = oracle.synth(w, h, 33 + i)
+        ok, enc = cv2.imencode(".jpg", np.ascontiguousarray(img[..., ::-1]), enc_params)
+        assert ok
+        data = enc.tobytes()
+        try:
+            wh = seg.segment_jpeg(data, sigma=0.8, k=300.0, min_size=20, connectivity=8, variant=0)
+        except gseg.GsegError as e:
+            if "optional dependency" in str(e):
+                pytest.skip("libnvjpeg not loadable on this box")
+            raise
+        assert wh == (w, h) and gseg.jpeg_info(data) == (w, h)
+        rgb = seg.input_rgb()
+        dec = cv2.imdecode(enc, cv2.IMREAD_COLOR)[..., ::-1]
+        # the same picture as libjpeg's decode (chroma upsampling and IDCT rounding differ between the decoders:
+        # a few grey levels on noisy 4:2:0 content; a wrong decode would be off by tens)
+        assert np.abs(rgb.astype(np.int32) - dec.astype(np.int32)).mean() < 8.0
+        ref = oracle.pipeline(rgb, 0.8, 300.0, 20, 8, oracle.FELZ)
+        assert seg.num_components() == ref["n"]
+        assert same_partition(oracle, seg.labels(), ref["labels"])
+    # grey-scale JPEG: decoded to three equal channels
+    g = oracle.synth(160, 120, 40)[..., 0]
+    ok, enc = cv2.imencode(".jpg", np.ascontiguousarray(g), [cv2.IMWRITE_JPEG_QUALITY, 90])
+    seg.segment_jpeg(enc.tobytes(), sigma=0.5, k=200.0, min_size=10, connectivity=4, variant=1)
+    rgb = seg.input_rgb()
+    assert np.array_equal(rgb[..., 0], rgb[..., 1]) and np.array_equal(rgb[..., 0], rgb[..., 2])
+    ref = oracle.pipeline(rgb, 0.5, 200.0, 10, 4, oracle.HIER, max_levels=64)
+    assert seg.num_levels() == len(ref["levels"])
+    assert same_partition(oracle, seg.labels(1), ref["levels"][1])
+    # not a JPEG / too large for the context: errors, and the context stays usable
+    with pytest.raises(gseg.GsegError):
+        seg.segment_jpeg(b"\xff\xd8\xff\xe0 this is not a jpeg" + bytes(64), sigma=0.8, k=300.0, min_size=20)
+    big = np.zeros((400, 600, 3), np.uint8)
+    with pytest.raises(gseg.GsegError):
+        seg.segment_jpeg(cv2.imencode(".jpg", big)[1].tobytes(), sigma=0.8, k=300.0, min_size=20)
+    img = oracle.synth(64, 48, 7)
+    seg.segment(img, sigma=0.8, k=300.0, min_size=20, connectivity=8, variant=0)
+    assert same_partition(oracle, seg.labels(), oracle.pipeline(img, 0.8, 300.0, 20, 8, oracle.FELZ)["labels"])
+    dimg = torch.from_numpy(img).cuda()
+    seg.segment(dimg, sigma=0.8, k=300.0, min_size=20, connectivity=8, variant=0)
+    with pytest.raises(gseg.GsegError):      # caller-owned device input is not kept by the context
+        seg.input_rgb()
+    # the CLI takes the same file
+    w, h, _ = cases[0]
+    ok, enc = cv2.imencode(".jpg", np.ascontiguousarray(oracle.synth(w, h, 33)[..., ::-1]), cases[0][2])
+    jp, outp, labp = tmp_path / "in.jpg", tmp_path / "out.png", tmp_path / "lab.bin"
+    jp.write_bytes(enc.tobytes())
+    r = subprocess.run([gseg.CLI_PATH, "--labels", str(labp), "0.8", "300", "20", str(jp), str(outp)], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    seg.segment_jpeg(enc.tobytes(), sigma=0.8, k=300.0, min_size=20, connectivity=8, variant=0)
+    assert same_partition(oracle, np.fromfile(labp, np.int32).reshape(h, w), seg.labels())
+
+
 # ---- tiled schedule: graph export / import and the joined rounds ------------------------------------------------
 def _gpu_strip(seg, img, sigma, k, ms, conn):
     seg.segment(img, sigma=sigma, k=k, min_size=ms, connectivity=conn, variant=0)
