@@ -42,6 +42,25 @@ def test_no_gpu_fails_loudly(gseg):
     assert "no CPU fallback" in str(e.value)
 
 
+def test_jpeg_entry_points_without_gpu(gseg):
+    """nvJPEG is loaded with dlopen (libgseg.so must not link it); without a device the JPEG helpers fail
+    like everything else (no host decoder behind them); argument errors do not need a device."""
+    import subprocess
+    import torch
+    L = gseg.load()
+    w, h = C.c_int32(0), C.c_int32(0)
+    assert L.gseg_jpeg_info(None, 0, C.byref(w), C.byref(h)) == -1
+    assert L.gseg_segment_jpeg(None, b"x", 1, None, None, None) == -1
+    assert L.gseg_input_rgb(None, None, 0) == -1
+    assert L.gseg_strerror(-8).decode().startswith("optional dependency")
+    deps = subprocess.run(["ldd", gseg.LIB_PATH], capture_output=True, text=True).stdout
+    assert "nvjpeg" not in deps
+    if not torch.cuda.is_available():
+        with pytest.raises(gseg.GsegError) as e:
+            gseg.jpeg_info(b"\xff\xd8\xff\xe0" + bytes(32))
+        assert "no CPU fallback" in str(e.value) or "optional dependency" in str(e.value)
+
+
 def test_bad_create_args(gseg):
     L = gseg.load()
     h = C.c_void_p()
