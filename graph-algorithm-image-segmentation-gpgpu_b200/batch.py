@@ -35,7 +35,8 @@ class ContextPool:
         self.segs = []
 
     def run(self, images, on_result, **params):
-        """Segment every image of `images`; `on_result(i, segmenter)` is called once image i is complete
+        """Segment every image of `images` (arrays / tensors, or `bytes` holding a JPEG file, which nvJPEG
+        decodes on the context's stream: SURVEY.md s8f N2); `on_result(i, segmenter)` is called once image i is complete
         (read its labels there; `segmenter.labels(out=..., wait=False)` keeps the copy-out asynchronous: it
         is ordered before the context's next image and completed before run() returns)."""
         S = len(self.segs)
@@ -50,7 +51,10 @@ class ContextPool:
                 on_result(pending[j], self.segs[j])
                 pending[j] = -1
             if i < n:
-                self.segs[j].segment(images[i], wait=False, **params)
+                if isinstance(images[i], (bytes, bytearray, memoryview)):  # a JPEG file's bytes: decoded on the GPU
+                    self.segs[j].segment_jpeg(bytes(images[i]), wait=False, **params)
+                else:
+                    self.segs[j].segment(images[i], wait=False, **params)
                 pending[j] = i
         for s in self.segs:
             s.sync()

@@ -399,6 +399,41 @@ def test_jpeg_input_decoded_on_gpu(gseg, oracle, tmp_path):
     assert same_partition(oracle, np.fromfile(labp, np.int32).reshape(h, w), seg.labels())
 
 
+def test_context_pool_takes_jpeg_bytes(gseg, oracle):
+    """Batched mode fed with compressed images (a mix of JPEG bytes and arrays through the rolling pipeline)."""
+    cv2 = pytest.importorskip("cv2")
+    from importlib import import_module
+    batch = import_module(gseg.__name__ + ".batch")
+    w, h = 240, 160
+    items, kinds = [], []
+    for i in range(9):
+        img = oracle.synth(w, h, 700 + i)
+        if i % 3 == 2:
+            items.append(img); kinds.append("array")
+        else:
+            items.append(cv2.imencode(".jpg", np.ascontiguousarray(img[..., ::-1]), [cv2.IMWRITE_JPEG_QUALITY, 90])[1].tobytes())
+            kinds.append("jpeg")
+    pool = batch.ContextPool(gseg, w, h, contexts=4)
+    got = {}
+    try:
+        try:
+            pool.run(items, lambda i, s: got.__setitem__(i, (s.input_rgb(), s.labels().copy(), s.num_components())),
+                     sigma=0.8, k=300.0, min_size=20, connectivity=4, variant=0)
+        except gseg.GsegError as e:
+            if "optional dependency" in str(e):
+                pytest.skip("libnvjpeg not loadable on this box")
+            raise
+    finally:
+        pool.close()
+    assert sorted(got) == list(range(9))
+    for i in range(9):
+        rgb, lab, n = got[i]
+        if kinds[i] == "array":
+            assert np.array_equal(rgb, items[i])
+        ref = oracle.pipeline(rgb, 0.8, 300.0, 20, 4, oracle.FELZ)
+        assert n == ref["n"] and same_partition(oracle, lab, ref["labels"])
+
+
 # ---- tiled schedule: graph export / import and the joined rounds ------------------------------------------------
 def _gpu_strip(seg, img, sigma, k, ms, conn):
     seg.segment(img, sigma=sigma, k=k, min_size=ms, connectivity=conn, variant=0)
