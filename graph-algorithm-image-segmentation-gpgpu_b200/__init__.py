@@ -18,11 +18,15 @@ _ROOT = os.path.dirname(_HERE)
 CSRC = os.path.join(_HERE, "csrc")
 LIB_PATH = os.environ.get("GSEG_LIB") or os.path.join(_HERE, "libgseg.so")
 CLI_PATH = os.path.join(_HERE, "gseg")
+BATCH_PATH = os.path.join(_HERE, "gseg_batch")
 HEADER = os.path.join(_ROOT, "include", "gseg.h")
 
 FELZ, HIER, SUPERPIX = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 FLAG_HOST_LOOP = 1
+CAP_SUPERPIX, CAP_WIDE_SIGMA, CAP_LEVELS = 1, 2, 4
+OUT_NONE, OUT_LABELS, OUT_HIERARCHY = 0, 1, 2
+POOL_MAXLEVELS = 64
 
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
               "-Xcompiler", "-fPIC,-ffp-contract=off"]
@@ -37,19 +41,22 @@ def _newer(target, sources):
 
 def build(force=False, verbose=False):
     """Compile libgseg.so (and the gseg CLI) in-tree for sm_100a with nvcc.  Works without a GPU."""
-    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC))] + [HEADER]
+    srcs = [os.path.join(CSRC, f) for f in sorted(os.listdir(CSRC)) if f.endswith((".cu", ".cuh"))] + [HEADER]
     if force or _newer(LIB_PATH, srcs):
-        cmd = ["nvcc"] + NVCC_FLAGS + ["-shared", "-o", LIB_PATH, os.path.join(CSRC, "gseg_api.cu")]
+        cmd = ["nvcc"] + NVCC_FLAGS + ["-shared", "-o", LIB_PATH, os.path.join(CSRC, "gseg_api.cu"),
+                                       os.path.join(CSRC, "gseg_pool.cu")]
         if verbose:
             print(" ".join(cmd))
         subprocess.check_call(cmd)
-    cli_src = os.path.join(CSRC, "gseg_cli.cpp")
-    if os.path.exists(cli_src) and (force or _newer(CLI_PATH, [cli_src, os.path.join(CSRC, "gseg_imageio.hpp"), LIB_PATH, HEADER])):
-        cmd = ["g++", "-O2", "-std=c++17", "-o", CLI_PATH, cli_src, "-I", os.path.join(_ROOT, "include"),
-               "-L", _HERE, "-lgseg", "-lz", "-Wl,-rpath,$ORIGIN"]
-        if verbose:
-            print(" ".join(cmd))
-        subprocess.check_call(cmd)
+    # C++ host programs over the C-ABI (no CUDA headers): the `segment`-style CLI and the batch benchmark loop
+    for exe, src, deps in ((CLI_PATH, "gseg_cli.cpp", ["gseg_imageio.hpp"]), (BATCH_PATH, "gseg_batch.cpp", [])):
+        path = os.path.join(CSRC, src)
+        if os.path.exists(path) and (force or _newer(exe, [path, LIB_PATH, HEADER] + [os.path.join(CSRC, d) for d in deps])):
+            cmd = ["g++", "-O2", "-std=c++17", "-o", exe, path, "-I", os.path.join(_ROOT, "include"),
+                   "-L", _HERE, "-lgseg", "-lz", "-Wl,-rpath,$ORIGIN"]
+            if verbose:
+                print(" ".join(cmd))
+            subprocess.check_call(cmd)
     return LIB_PATH
 
 
@@ -59,7 +66,21 @@ class Params(C.Structure):
 
 
 class KernelTime(C.Structure):
-    _fields_ = [("name", C.c_char * 24), ("round", C.c_int32), ("ms", C.c_float), ("algo_bytes", C.c_double)]
+    _fields_ = [("name", C.c_char * 24), ("round", C.c_int32), ("ms", C.c_float), ("algo_bytes", C.c_double),
+                ("strict_bytes", C.c_double)]
+
+
+class PoolJob(C.Structure):
+    _fields_ = [("input", C.c_void_p), ("jpeg_bytes", C.c_size_t), ("w", C.c_int32), ("h", C.c_int32),
+                ("stride_bytes", C.c_int32), ("mem_kind", C.c_int32), ("params", Params), ("out_mode", C.c_int32),
+                ("level", C.c_int32), ("elem_bytes", C.c_int32), ("out_mem_kind", C.c_int32), ("out", C.c_void_p),
+                ("out_capacity", C.c_size_t), ("user", C.c_void_p)]
+
+
+class PoolResult(C.Structure):
+    _fields_ = [("ticket", C.c_int64), ("status", C.c_int32), ("w", C.c_int32), ("h", C.c_int32), ("n_levels", C.c_int32),
+                ("n_components", C.c_int32), ("elem_bytes", C.c_int32), ("out_bytes", C.c_int64),
+                ("offsets", C.c_int64 * (POOL_MAXLEVELS + 1)), ("out", C.c_void_p), ("user", C.c_void_p)]
 
 
 class RoundStat(C.Structure):
@@ -114,11 +135,42 @@ def load():
     L.gseg_blurred_rows.argtypes = [vp, i32, i32, vp, i32]
     L.gseg_segment_graph.argtypes = [vp, i64, vp, vp, i64, vp, vp, vp, C.POINTER(Params), vp]
     L.gseg_synth.argtypes = [vp, vp, i32, i32, u64, i32]
+    L.gseg_synth_rows.argtypes = [vp, vp, i32, i32, i32, u64, i32]
     L.gseg_set_profiling.argtypes = [vp, i32]
     L.gseg_profile_read.argtypes = [vp, C.POINTER(KernelTime), i32]
     L.gseg_launch_count.argtypes = [vp]
     L.gseg_launch_count.restype = C.c_longlong
     L.gseg_sort_pairs_u64.argtypes = [vp, vp, vp, C.c_int64, i32, i32]
+    L.gseg_reserve.argtypes = [vp, C.c_uint32]
+    L.gseg_host_alloc.argtypes = [C.c_size_t]
+    L.gseg_host_alloc.restype = vp
+    L.gseg_host_free.argtypes = [vp]
+    L.gseg_host_free.restype = None
+    L.gseg_get_stream.argtypes = [vp]
+    L.gseg_get_stream.restype = vp
+    L.gseg_label_bytes.argtypes = [vp, i32]
+    L.gseg_labels_ex.argtypes = [vp, i32, vp, i32, i32]
+    L.gseg_labels_ex_async.argtypes = [vp, i32, vp, i32, i32]
+    L.gseg_hierarchy.argtypes = [vp, vp, i64, C.POINTER(i64), i32, i32]
+    L.gseg_hierarchy_async.argtypes = [vp, vp, i64, C.POINTER(i64), i32, i32]
+    L.gseg_segment_strip_async.argtypes = [vp, vp, i32, i32, i32, i32, i32, i32, C.POINTER(Params)]
+    L.gseg_strip_record.argtypes = [vp, i32, vp, i64, C.POINTER(i64)]
+    L.gseg_join_segment.argtypes = [vp, vp, i32, i64, i32, C.POINTER(Params), vp, i32, i32, C.POINTER(i64), C.POINTER(i64)]
+    L.gseg_compaction_count.argtypes = [vp]
+    L.gseg_compaction_count.restype = C.c_longlong
+    L.gseg_pool_create.argtypes = [C.POINTER(vp), i32, i32, i32, i32, i32, C.c_uint32]
+    L.gseg_pool_destroy.argtypes = [vp]
+    L.gseg_pool_destroy.restype = None
+    L.gseg_pool_contexts.argtypes = [vp]
+    L.gseg_pool_context.argtypes = [vp, i32]
+    L.gseg_pool_context.restype = vp
+    L.gseg_pool_pending.argtypes = [vp]
+    L.gseg_pool_last_error.argtypes = [vp]
+    L.gseg_pool_last_error.restype = C.c_char_p
+    L.gseg_pool_submit.argtypes = [vp, C.POINTER(PoolJob), C.POINTER(i64)]
+    L.gseg_pool_next.argtypes = [vp, C.POINTER(PoolResult)]
+    L.gseg_pool_run.argtypes = [vp, C.POINTER(PoolJob), i32, C.POINTER(PoolResult)]
+    L.gseg_pool_copy_ceiling.argtypes = [vp, C.POINTER(PoolJob), C.POINTER(PoolResult), i32, i32, C.POINTER(C.c_double)]
     _lib = L
     return L
 
@@ -151,20 +203,27 @@ class Segmenter:
     """One gseg context (one GPU, one stream).  Mirrors the reference executables' parameter list:
     image, sigma, k, min_size, connectivity, variant / hierarchy level (BASELINE.json north_star)."""
 
-    def __init__(self, max_w, max_h, device=0, max_connectivity=8):
+    def __init__(self, max_w, max_h, device=0, max_connectivity=8, _borrowed=None):
         self.L = load()
         self.h = C.c_void_p()
-        rc = self.L.gseg_create_ex(C.byref(self.h), device, max_w, max_h, max_connectivity)
-        if rc != 0:
-            raise GsegError("gseg_create: %s" % self.L.gseg_strerror(rc).decode())
+        self.owned = _borrowed is None
+        if _borrowed is not None:  # a context owned by a Pool
+            self.h = C.c_void_p(_borrowed)
+        else:
+            rc = self.L.gseg_create_ex(C.byref(self.h), device, max_w, max_h, max_connectivity)
+            if rc != 0:
+                raise GsegError("gseg_create: %s" % self.L.gseg_strerror(rc).decode())
         self.device = device
         self.w = self.hh = 0
         self.D = 2
 
     def close(self):
-        if self.h:
+        if self.h and self.owned:
             self.L.gseg_destroy(self.h)
-            self.h = C.c_void_p()
+        self.h = C.c_void_p()
+
+    def reserve(self, caps):
+        self._ck(self.L.gseg_reserve(self.h, caps), "gseg_reserve")
 
     def __del__(self):
         try:
@@ -236,15 +295,75 @@ class Segmenter:
     def num_components(self, level=-1):
         return self._ck(self.L.gseg_num_components(self.h, level), "gseg_num_components")
 
-    def labels(self, level=-1, out=None, wait=True):
+    def labels(self, level=-1, out=None, wait=True, dtype=None):
         """Label image of a level.  wait=False only enqueues it (out must be a CUDA tensor or pinned
-        host memory); sync() or any later synchronous call completes it."""
+        host memory); sync() or any later synchronous call completes it.  dtype: np.int32 (default), np.uint16 or
+        np.uint8 (lossless: raises when the level has more components than the type holds), or "auto" = the
+        narrowest that fits; with `out` given its element size decides."""
         if out is None:
-            out = np.empty((self.hh, self.w), np.int32)
+            if dtype == "auto":
+                dtype = {1: np.uint8, 2: np.uint16, 4: np.int32}[self.label_bytes(level)]
+            out = np.empty((self.hh, self.w), dtype or np.int32)
+        eb = int(out.element_size()) if _is_torch(out) else int(out.itemsize)
         ptr, kind = _ptr(out)
-        fn = self.L.gseg_labels if wait else self.L.gseg_labels_async
-        self._ck(fn(self.h, level, C.c_void_p(ptr), kind), "gseg_labels")
+        fn = self.L.gseg_labels_ex if wait else self.L.gseg_labels_ex_async
+        self._ck(fn(self.h, level, C.c_void_p(ptr), eb, kind), "gseg_labels_ex")
         return out
+
+    def label_bytes(self, level=-1):
+        return self._ck(self.L.gseg_label_bytes(self.h, level), "gseg_label_bytes")
+
+    def hierarchy(self):
+        """The stored hierarchy (gseg_hierarchy): (entries uint32, offsets int64[n_levels + 1]); level l of pixel p =
+        entries[offsets[l] + level l-1 of p], level -1 = p itself."""
+        offs = (C.c_int64 * (POOL_MAXLEVELS + 1))()
+        n = self._ck(self.L.gseg_hierarchy(self.h, None, 0, offs, POOL_MAXLEVELS + 1, MEM_HOST), "gseg_hierarchy")
+        out = np.empty(int(offs[n]), np.uint32)
+        self._ck(self.L.gseg_hierarchy(self.h, out.ctypes.data, len(out), offs, POOL_MAXLEVELS + 1, MEM_HOST), "gseg_hierarchy")
+        return out, np.array(offs[:n + 1], np.int64)
+
+    def compaction_count(self):
+        return int(self.L.gseg_compaction_count(self.h))
+
+    def segment_strip(self, buf, halo_top, halo_bottom, params=None, wait=True, **kw):
+        """buf: (halo_top + h + halo_bottom, w, 3) uint8 -- a strip of a larger image with its halo rows."""
+        p = params if params is not None else self.params(**kw)
+        hin, w = int(buf.shape[0]), int(buf.shape[1])
+        hh = hin - halo_top - halo_bottom
+        stride = buf.stride(0) if _is_torch(buf) else buf.strides[0]
+        ptr, kind = _ptr(buf)
+        self.w, self.hh, self.D = w, hh, (4 if p.connectivity == 8 else 2)
+        self._keep = buf
+        self._ck(self.L.gseg_segment_strip_async(self.h, C.c_void_p(ptr), w, hh, stride, kind, halo_top, halo_bottom, C.byref(p)),
+                 "gseg_segment_strip_async")
+        if wait:
+            self.wait()
+        return self
+
+    def strip_record_bytes(self, dedup=True):
+        n = C.c_int64(0)
+        self._ck(self.L.gseg_strip_record(self.h, int(dedup), None, 0, C.byref(n)), "gseg_strip_record")
+        return int(n.value)
+
+    def strip_record(self, dev_ptr, cap_bytes, dedup=True):
+        n = C.c_int64(0)
+        self._ck(self.L.gseg_strip_record(self.h, int(dedup), C.c_void_p(dev_ptr), cap_bytes, C.byref(n)), "gseg_strip_record")
+        return int(n.value)
+
+    def join_segment(self, records_dev_ptr, n_strips, stride_bytes, my_strip, out=None, params=None, **kw):
+        """Join the gathered strip records on the device, run the rounds on the joined graph and write this strip's
+        final label image into `out` (CUDA tensor or pinned/host array; its element size picks the label type).
+        Returns (n_final, n_joined_components, n_joined_edges)."""
+        p = params if params is not None else self.params(**kw)
+        nv, ne = C.c_int64(0), C.c_int64(0)
+        ptr, kind, eb = None, MEM_DEVICE, 4
+        if out is not None:
+            ptr, kind = _ptr(out)
+            eb = int(out.element_size()) if _is_torch(out) else int(out.itemsize)
+        n = self._ck(self.L.gseg_join_segment(self.h, C.c_void_p(records_dev_ptr), n_strips, stride_bytes, my_strip, C.byref(p),
+                                              C.c_void_p(ptr) if ptr else None, eb, kind, C.byref(nv), C.byref(ne)),
+                     "gseg_join_segment")
+        return n, int(nv.value), int(ne.value)
 
     def sync(self):
         self._ck(self.L.gseg_sync(self.h), "gseg_sync")
@@ -329,6 +448,12 @@ class Segmenter:
         n = self._ck(self.L.gseg_profile_read(self.h, arr, 1024), "gseg_profile_read")
         return [(arr[i].name.decode(), arr[i].round, arr[i].ms, arr[i].algo_bytes) for i in range(n)]
 
+    def profile_ex(self):
+        """[(kernel name, round, ms, algorithmic bytes, strict bytes)] -- see gseg_kernel_time in gseg.h."""
+        arr = (KernelTime * 1024)()
+        n = self._ck(self.L.gseg_profile_read(self.h, arr, 1024), "gseg_profile_read")
+        return [(arr[i].name.decode(), arr[i].round, arr[i].ms, arr[i].algo_bytes, arr[i].strict_bytes) for i in range(n)]
+
     def launch_count(self):
         return int(self.L.gseg_launch_count(self.h))
 
@@ -337,6 +462,14 @@ class Segmenter:
             out = np.empty((h, w, 3), np.uint8)
         ptr, kind = _ptr(out)
         self._ck(self.L.gseg_synth(self.h, C.c_void_p(ptr), w, h, seed, kind), "gseg_synth")
+        return out
+
+    def synth_rows(self, w, y_first, nrows, seed, out=None):
+        """Rows [y_first, y_first + nrows) of the synthetic image of width w."""
+        if out is None:
+            out = np.empty((nrows, w, 3), np.uint8)
+        ptr, kind = _ptr(out)
+        self._ck(self.L.gseg_synth_rows(self.h, C.c_void_p(ptr), w, y_first, nrows, seed, kind), "gseg_synth_rows")
         return out
 
     def sort_pairs(self, keys_dev_ptr, vals_dev_ptr, n, begin_bit=0, end_bit=64):

@@ -2,9 +2,13 @@
 
 * `shard(n_items, rank, world)`: which images of a global batch a rank owns (image i -> rank i mod N;
   SURVEY.md section 8e "batched: replicas only, no collective").
-* `ContextPool`: S gseg contexts (one CUDA stream each) on one GPU; images are issued round-robin
-  with `gseg_segment_async`, so the latency-bound late rounds of one image (a single thread-block
-  cluster) overlap the bandwidth-bound early rounds of the next.
+* `Pool`: ctypes mirror of the C++ batch pipeline `gseg_pool_*` (csrc/gseg_pool.cu): S contexts (one CUDA
+  stream each) on one GPU in a rolling schedule, outputs in the narrowest lossless label type, results in
+  submission order.  This is what `bench.py` measures; a C++ caller reaches the same throughput through
+  the same entry points (`csrc/gseg_batch.cpp`).
+* `ContextPool`: the same rolling schedule written in Python over `Segmenter`s, for callers that want a
+  callback with the live context of every finished image (read anything from it: labels of several
+  levels, statistics, the exported graph).
 * `segment_sharded`: the N-GPU driver: every rank segments its shard and the per-image component
   counts are all-gathered so every rank (and the caller) sees the whole batch's summary.  The label
   images stay on the rank that produced them.
@@ -59,6 +63,96 @@ class ContextPool:
         for s in self.segs:
             s.sync()
         return n
+
+
+class Pool:
+    """ctypes mirror of gseg_pool_* (include/gseg.h "batch pipeline").  No compute, no fallback."""
+
+    def __init__(self, gseg, max_w, max_h, device=0, contexts=8, max_connectivity=8, caps=0):
+        import ctypes as C
+        self.gseg, self.L, self.C = gseg, gseg.load(), C
+        self.h = C.c_void_p()
+        rc = self.L.gseg_pool_create(C.byref(self.h), device, max_w, max_h, max_connectivity, contexts, caps)
+        if rc != 0:
+            raise gseg.GsegError("gseg_pool_create: %s" % self.L.gseg_strerror(rc).decode())
+        self.contexts = contexts
+        self.segs = [gseg.Segmenter(max_w, max_h, device=device, _borrowed=self.L.gseg_pool_context(self.h, i))
+                     for i in range(contexts)]
+
+    def close(self):
+        if self.h:
+            self.L.gseg_pool_destroy(self.h)
+            self.h = self.C.c_void_p()
+            self.segs = []
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc, what):
+        if rc < 0:
+            raise self.gseg.GsegError("%s: %s (%s)" % (what, self.L.gseg_strerror(rc).decode(),
+                                                       self.L.gseg_pool_last_error(self.h).decode()))
+        return rc
+
+    def jobs(self, images, outs, out_mode=1, level=-1, elem_bytes=0, **params):
+        """A ctypes array of gseg_pool_job: images[i] (arrays / tensors of (h, w, 3) uint8, or bytes of a JPEG file)
+        -> outs[i] (array / tensor receiving the label image or the hierarchy; None with out_mode 0)."""
+        g = self.gseg
+        arr = (g.PoolJob * len(images))()
+        keep = []
+        p = g.Params(params.get("sigma", 0.8), params.get("k", 300.0), params.get("min_size", 20), params.get("connectivity", 4),
+                     params.get("variant", g.FELZ), params.get("max_levels", 0), params.get("max_rounds", 0), params.get("flags", 0))
+        for i, img in enumerate(images):
+            j = arr[i]
+            if isinstance(img, (bytes, bytearray, memoryview)):
+                buf = (self.C.c_char * len(img)).from_buffer_copy(bytes(img))
+                keep.append(buf)
+                j.input, j.jpeg_bytes, j.mem_kind = self.C.cast(buf, self.C.c_void_p), len(img), g.MEM_HOST
+            else:
+                ptr, kind = g._ptr(img)
+                j.input, j.jpeg_bytes, j.mem_kind = ptr, 0, kind
+                j.h, j.w = int(img.shape[0]), int(img.shape[1])
+                j.stride_bytes = int(img.stride(0)) if g._is_torch(img) else int(img.strides[0])
+            j.params, j.out_mode, j.level, j.elem_bytes = p, out_mode, level, elem_bytes
+            out = outs[i] if outs is not None else None
+            if out is not None:
+                optr, okind = g._ptr(out)
+                j.out, j.out_mem_kind = optr, okind
+                j.out_capacity = int(out.numel() * out.element_size()) if g._is_torch(out) else int(out.nbytes)
+            j.user = i
+        arr._keep = (keep, images, outs)
+        return arr
+
+    def run(self, jobs):
+        """gseg_pool_run: the whole batch through the rolling pipeline; returns the ctypes array of results."""
+        res = (self.gseg.PoolResult * len(jobs))()
+        self._ck(self.L.gseg_pool_run(self.h, jobs, len(jobs), res), "gseg_pool_run")
+        return res
+
+    def submit(self, job):
+        t = self.C.c_int64(0)
+        self._ck(self.L.gseg_pool_submit(self.h, self.C.byref(job), self.C.byref(t)), "gseg_pool_submit")
+        return int(t.value)
+
+    def next(self):
+        r = self.gseg.PoolResult()
+        self._ck(self.L.gseg_pool_next(self.h, self.C.byref(r)), "gseg_pool_next")
+        return r
+
+    def pending(self):
+        return self.L.gseg_pool_pending(self.h)
+
+    def copy_ceiling(self, jobs, results, reps=3):
+        """ms per batch of the batch's host<->device copies alone (gseg_pool_copy_ceiling)."""
+        ms = self.C.c_double(0)
+        self._ck(self.L.gseg_pool_copy_ceiling(self.h, jobs, results, len(jobs), reps, self.C.byref(ms)), "gseg_pool_copy_ceiling")
+        return float(ms.value)
+
+    def launch_count(self):
+        return sum(s.launch_count() for s in self.segs)
 
 
 def segment_sharded(n_items, load_image, segment_one, dist=None):

@@ -26,8 +26,10 @@ struct GsegHead {
     GsegRunParams p;
     RoundState st;
     u32 Vnext, error, ticketC, ticketE, doneE, Eacc[GSEG_MAXR + 1];
+    u32 map_skip[GSEG_MAXR + 1], resume_phase;
 };
 static_assert(offsetof(GsegCtl, Eacc) == offsetof(GsegHead, Eacc), "GsegHead must mirror the head of GsegCtl");
+static_assert(offsetof(GsegCtl, resume_phase) == offsetof(GsegHead, resume_phase), "GsegHead must mirror the head of GsegCtl");
 
 static const size_t TAIL_SMEM = (2 * (size_t)GSEG_TAIL_STAGE + 2 * (NTT / 32)) * sizeof(u32); // k_tail: staged map + minima, survivor-count exchange (phase_E)
 
@@ -70,6 +72,11 @@ struct gseg_ctx {
     gseg_params params;
     int w, h, D;
     bool valid, pending;
+    bool graph_mode;              // the last run was gseg_segment_graph (rounds numbered from 1, no pixel map)
+    bool strip_labels;            // d_labels[0] holds the dense labels of the strip gseg_strip_record described
+    int strip_w, strip_h, halo_top;
+    u32 strip_nV;
+    long long compactions;        // arena compactions since creation (FELZ)
     bool rgb_staged;              // the last run read its input from d_rgb (host input or JPEG)
     nvjpegHandle_t jpg_handle; nvjpegJpegState_t jpg_state; // nvJPEG objects, created on first gseg_segment_jpeg
     u32 epoch_next;
@@ -106,6 +113,7 @@ extern "C" const char *gseg_strerror(int s) {
     case GSEG_E_STATE: return "no completed segmentation in this context";
     case GSEG_E_LEVEL: return "hierarchy level out of range";
     case GSEG_E_UNSUPPORTED: return "optional dependency missing at run time";
+    case GSEG_E_RANGE: return "label type too narrow for the component count, or output buffer too small";
     default: return "unknown status";
     }
 }
@@ -162,8 +170,13 @@ extern "C" int gseg_create_ex(gseg_ctx **out, int device, int max_w, int max_h, 
     // one old->new map per round: V + V1 + V2 + ... ; 6V covers every input up to 2^26 pixels, above that the
     // arena is 2.5V (a run that needs more ends with GSEG_E_ARENA) so that a 2^30-pixel context fits in HBM
     ctx->arena_cap = V <= ((size_t)1 << 26) ? 6 * V + 1024 : V * 5 / 2 + 1024;
+    if (const char *ev = getenv("GSEG_ARENA_FACTOR")) { // test knob: arena entries per pixel (exercises the compaction)
+        const double f = atof(ev);
+        if (f >= 1.0 && f <= 16.0) ctx->arena_cap = (size_t)(f * (double)V) + 64;
+    }
     if (ctx->arena_cap > 0xFFFFFFF0ull) ctx->arena_cap = 0xFFFFFFF0ull;
     if (e == cudaSuccess) e = dalloc(&ctx->d_arena, ctx->arena_cap);
+    if (e == cudaSuccess) e = dalloc(&ctx->d_labels[0], Vp); // staging of label images that go to host memory
     // look-back status words: one per tile of the largest tiling that uses each array
     ctx->ntilesC = V / (32 * CPT) + 2;
     const size_t img_tiles = (size_t)((max_w + TW - 1) / TW) * (size_t)((max_h + GH - 1) / GH); // round-0 graph tiles
@@ -253,6 +266,7 @@ static NvJpegApi *nvjpeg_api() {
     return api.ok ? &api : nullptr;
 }
 static void jpeg_release(gseg_ctx *ctx) {
+    if (!ctx->jpg_state && !ctx->jpg_handle) return; // JPEG never used: do not even load the library
     NvJpegApi *a = nvjpeg_api();
     if (!a) return;
     if (ctx->jpg_state) a->state_destroy(ctx->jpg_state);
@@ -287,7 +301,11 @@ extern "C" int gseg_segment_jpeg_async(gseg_ctx *ctx, const void *jpeg, size_t n
     CK(cudaSetDevice(ctx->device));
     if (!ctx->jpg_handle) {
         if (a->create(&ctx->jpg_handle) != NVJPEG_STATUS_SUCCESS) { ctx->jpg_handle = nullptr; return fail(ctx, GSEG_E_CUDA, "nvjpegCreateSimple", cudaSuccess); }
-        if (a->state_create(ctx->jpg_handle, &ctx->jpg_state) != NVJPEG_STATUS_SUCCESS) { ctx->jpg_state = nullptr; return fail(ctx, GSEG_E_CUDA, "nvjpegJpegStateCreate", cudaSuccess); }
+        if (a->state_create(ctx->jpg_handle, &ctx->jpg_state) != NVJPEG_STATUS_SUCCESS) {
+            a->destroy(ctx->jpg_handle); // no half-built pair: the next call starts over
+            ctx->jpg_handle = nullptr; ctx->jpg_state = nullptr;
+            return fail(ctx, GSEG_E_CUDA, "nvjpegJpegStateCreate", cudaSuccess);
+        }
     }
     int iw = 0, ih = 0;
     if (jpeg_size(a, ctx->jpg_handle, jpeg, nbytes, &iw, &ih)) return fail(ctx, GSEG_E_ARG, "not a JPEG nvJPEG can parse", cudaSuccess);
@@ -311,7 +329,8 @@ extern "C" int gseg_input_rgb(gseg_ctx *ctx, uint8_t *out, int mem_kind) {
     if (!ctx->valid || !ctx->rgb_staged) return fail(ctx, GSEG_E_STATE, "the last run's input was not staged by the context", cudaSuccess);
     if (mem_kind != GSEG_MEM_HOST && mem_kind != GSEG_MEM_DEVICE) return fail(ctx, GSEG_E_ARG, "mem_kind", cudaSuccess);
     CK(cudaSetDevice(ctx->device));
-    CK(cudaMemcpyAsync(out, ctx->d_rgb, (size_t)3 * ctx->w * ctx->h, mem_kind == GSEG_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
+    CK(cudaMemcpyAsync(out, ctx->d_rgb + (size_t)3 * ctx->w * ctx->halo_top, (size_t)3 * ctx->w * ctx->h,
+                       mem_kind == GSEG_MEM_HOST ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return GSEG_OK;
 }
@@ -331,6 +350,8 @@ extern "C" void gseg_destroy(gseg_ctx *ctx) {
     jpeg_release(ctx);
     sort_scratch_free(&ctx->sort);
     cudaFree(ctx->d_xkeys); cudaFree(ctx->d_xvals); cudaFree(ctx->d_xkeep); cudaFree(ctx->d_xab); cudaFree(ctx->d_xw);
+    for (int i = 0; i <= GSEG_MAXMARK; ++i)
+        if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
     if (ctx->h_head) cudaFreeHost(ctx->h_head);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
@@ -343,6 +364,8 @@ extern "C" int gseg_set_stream(gseg_ctx *ctx, void *s) {
     ctx->stream = s ? (cudaStream_t)s : ctx->own_stream;
     return GSEG_OK;
 }
+
+extern "C" void *gseg_get_stream(const gseg_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 extern "C" int gseg_set_tail(gseg_ctx *ctx, uint32_t max_edges, uint32_t max_components) {
     if (!ctx) return GSEG_E_ARG;
@@ -457,7 +480,7 @@ static void enqueue_round0(gseg_ctx *c, cudaStream_t s) {
         }
     } else {
         mark(c, s, "k_blur_h", 0);
-        k_blur_h<<<grid_for(V, NT), NT, 0, s>>>(c->d_ctl, c->d_tmp);
+        k_blur_h<<<grid_for((size_t)c->w * c->h_head->p.h_in, NT), NT, 0, s>>>(c->d_ctl, c->d_tmp);
         mark(c, s, "k_blur_v", 0);
         k_blur_v<<<grid_for(3 * V, NT), NT, 0, s>>>(c->d_ctl, c->d_tmp, c->d_planes);
     }
@@ -550,8 +573,59 @@ static int finish(gseg_ctx *ctx) {
     return GSEG_OK;
 }
 
-// Buffers only some paths need are allocated on first use: d_tmp (blur with more than 8 taps), d_G
-// (superpixel), d_labels (host copies of label images / colour images), d_csum (superpixel).
+// Arena compaction (FELZ and explicit-graph FELZ runs only: they need the final partition, not the levels).
+// The device stopped because the next round's map does not fit (error = DERR_ARENA, resume_phase = the phase
+// to go on with).  Fold the stored maps into one and resume:
+//   A: the maps of all live rounds f..r (f = first live round >= 1) into round f's slot;
+//   B: if that does not free enough, everything into round 0's pixel map, in place.
+// Returns 1 when the run can go on, 0 when nothing could be freed (a genuine GSEG_E_ARENA), < 0 on CUDA errors.
+static int compact_arena(gseg_ctx *ctx) {
+    GsegCtl *h = ctx->h_ctl;
+    if (ctx->params.variant != GSEG_FELZ || h->resume_phase == PH_DONE) return 0;
+    const int rn = (int)h->st.round;          // the round that could not start
+    const int r0 = ctx->graph_mode ? 1 : 0;   // first round that stored a map
+    const u64 cap = ctx->arena_cap, Vn = h->st.V;
+    int f = -1, live = 0;
+    for (int r = r0 + 1; r < rn; ++r)
+        if (!h->map_skip[r]) { if (f < 0) f = r; ++live; }
+    cudaStream_t s = ctx->stream;
+    bool done = false;
+    if (live >= 2 && (u64)h->map_off[f] + h->stV[f] + Vn <= cap) { // A
+        const u32 n = h->stV[f];
+        ctx->launches += 1;
+        k_compose_table<<<grid_for(n, NT), NT, 0, s>>>(ctx->d_ctl, ctx->d_arena, f, rn - 1, n, ctx->d_wsel); // wsel is dead between rounds
+        CK(cudaGetLastError());
+        CK(cudaMemcpyAsync(ctx->d_arena + h->map_off[f], ctx->d_wsel, (size_t)n * sizeof(u32), cudaMemcpyDeviceToDevice, s));
+        for (int r = f + 1; r < rn; ++r) h->map_skip[r] = 1;
+        h->st.map_off = h->map_off[f] + n;
+        done = true;
+    } else if (!ctx->graph_mode && live >= 1 && (u64)h->stV[0] + Vn <= cap) { // B
+        ctx->launches += 1;
+        k_compose_inplace<<<grid_for(h->stV[0], NT), NT, 0, s>>>(ctx->d_ctl, ctx->d_arena, rn - 1);
+        CK(cudaGetLastError());
+        for (int r = 1; r < rn; ++r) h->map_skip[r] = 1;
+        h->st.map_off = h->stV[0];
+        done = true;
+    }
+    if (!done) return 0;
+    h->map_off[rn] = h->st.map_off;
+    h->st.phase = h->resume_phase; h->resume_phase = PH_DONE; h->error = DERR_NONE;
+    // the device is idle (the read-back synchronised) and h is its exact image: write the patched block back
+    CK(cudaMemcpyAsync(ctx->d_ctl, h, sizeof(GsegCtl), cudaMemcpyHostToDevice, s));
+    CK(cudaStreamSynchronize(s)); // h is about to be overwritten by the next read-back
+    ++ctx->compactions;
+    return 1;
+}
+
+// After a read-back: does the run have to go on?  (Handles the arena compaction.)  < 0 on errors.
+static int run_continues(gseg_ctx *ctx) {
+    if (ctx->h_ctl->error == DERR_ARENA) return compact_arena(ctx);
+    return ctx->h_ctl->st.phase != PH_DONE && ctx->h_ctl->error == DERR_NONE ? 1 : 0;
+}
+
+// Buffers only some paths need: d_tmp (blur with more than 8 taps), d_G + d_csum + d_cmean (superpixel),
+// d_labels[1] (all-levels / colour images to host memory).  gseg_reserve allocates them up front; without
+// it they are allocated by the first call that needs them (an allocation synchronises the device).
 template <typename T>
 static int ensure(gseg_ctx *ctx, T **p, size_t n) {
     if (*p) return GSEG_OK;
@@ -560,9 +634,33 @@ static int ensure(gseg_ctx *ctx, T **p, size_t n) {
 }
 
 static int ensure_csum(gseg_ctx *ctx) {
-    if (ctx->d_csum[0]) return GSEG_OK;
-    for (int i = 0; i < 2; ++i) { CK(dalloc(&ctx->d_csum[i], 3 * (ctx->Vmax + 64))); CK(dalloc(&ctx->d_cmean[i], ctx->Vmax + 64)); }
+    if (ctx->d_csum[0] && ctx->d_csum[1] && ctx->d_cmean[0] && ctx->d_cmean[1]) return GSEG_OK;
+    for (int i = 0; i < 2; ++i) {
+        int rc = ensure(ctx, &ctx->d_csum[i], 3 * (ctx->Vmax + 64));
+        if (!rc) rc = ensure(ctx, &ctx->d_cmean[i], ctx->Vmax + 64);
+        if (rc) return rc;
+    }
     return GSEG_OK;
+}
+
+extern "C" int gseg_reserve(gseg_ctx *ctx, uint32_t caps) {
+    if (!ctx || (caps & ~(GSEG_CAP_SUPERPIX | GSEG_CAP_WIDE_SIGMA | GSEG_CAP_LEVELS))) return GSEG_E_ARG;
+    if (ctx->pending) return GSEG_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    int rc = GSEG_OK;
+    if (caps & GSEG_CAP_SUPERPIX) { rc = ensure_csum(ctx); if (!rc) rc = ensure(ctx, &ctx->d_G, ctx->Vmax + 64); }
+    if (!rc && (caps & GSEG_CAP_WIDE_SIGMA)) rc = ensure(ctx, &ctx->d_tmp, 3 * (ctx->Vmax + 64));
+    if (!rc && (caps & GSEG_CAP_LEVELS)) rc = ensure(ctx, &ctx->d_labels[1], ctx->Vmax + 64);
+    return rc;
+}
+
+extern "C" void *gseg_host_alloc(size_t bytes) {
+    void *p = nullptr;
+    if (!bytes || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
+extern "C" void gseg_host_free(void *p) {
+    if (p) cudaFreeHost(p);
 }
 
 // Grid-wide rounds to enqueue ahead of the tail when nothing is known about the image: live edges
@@ -574,12 +672,16 @@ static int estimate_nbig(const gseg_ctx *c) {
     return n;
 }
 
-extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int h, int stride, int mem_kind,
-                                  const gseg_params *p) {
+// rgb points at the first row of the buffer: halo_top rows of halo, the h rows to segment, halo_bottom rows of halo.
+static int segment_async_impl(gseg_ctx *ctx, const uint8_t *rgb, int w, int h, int stride, int mem_kind, int halo_top,
+                              int halo_bottom, const gseg_params *p) {
     if (!ctx || !rgb || !p) return GSEG_E_ARG;
     if (ctx->pending) return fail(ctx, GSEG_E_STATE, "previous run not waited for", cudaSuccess);
-    if (w < 1 || h < 1 || stride < 3 * w) return fail(ctx, GSEG_E_ARG, "image geometry", cudaSuccess);
+    if (w < 1 || h < 1 || stride < 3 * w || halo_top < 0 || halo_bottom < 0) return fail(ctx, GSEG_E_ARG, "image geometry", cudaSuccess);
     if ((size_t)w * h > ctx->Vmax) return fail(ctx, GSEG_E_SIZE, "image exceeds context capacity", cudaSuccess);
+    const int h_in = h + halo_top + halo_bottom;
+    if (mem_kind == GSEG_MEM_HOST && (size_t)w * h_in > ctx->Vmax) // host input is staged whole, halo rows included
+        return fail(ctx, GSEG_E_SIZE, "strip + halo rows exceed the context's staging capacity", cudaSuccess);
     if ((size_t)((w + TW - 1) / TW) * (size_t)((h + GH - 1) / GH) > ctx->ntilesC)
         return fail(ctx, GSEG_E_SIZE, "image aspect exceeds context capacity", cudaSuccess);
     if (p->connectivity != 4 && p->connectivity != 8) return fail(ctx, GSEG_E_ARG, "connectivity must be 4 or 8", cudaSuccess);
@@ -591,7 +693,7 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
     const int len = gauss_mask(p->sigma, hp->mask);
     if (len < 0) return fail(ctx, GSEG_E_ARG, "sigma too large (more than 64 taps)", cudaSuccess);
     CK(cudaSetDevice(ctx->device));
-    ctx->valid = false; ctx->x_valid = false;
+    ctx->valid = false; ctx->x_valid = false; ctx->graph_mode = false; ctx->strip_labels = false; ctx->halo_top = halo_top;
     ctx->params = *p;
     ctx->w = w; ctx->h = h; ctx->D = p->connectivity == 8 ? 4 : 2;
     if (ctx->D > ctx->Dmax) return fail(ctx, GSEG_E_SIZE, "context was created for 4-connected grids only", cudaSuccess);
@@ -600,12 +702,19 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
         if (!rc) rc = ensure(ctx, &ctx->d_G, ctx->Vmax + 64);
         if (rc) return rc;
     }
-    if (len - 1 > 8 || len - 1 < 1) { int rc = ensure(ctx, &ctx->d_tmp, 3 * (ctx->Vmax + 64)); if (rc) return rc; }
+    if (len - 1 > 8 || len - 1 < 1) {
+        if ((size_t)w * h_in > ctx->Vmax) return fail(ctx, GSEG_E_SIZE, "wide-sigma strip + halo rows exceed the context capacity", cudaSuccess);
+        int rc = ensure(ctx, &ctx->d_tmp, 3 * (ctx->Vmax + 64));
+        if (rc) return rc;
+    }
     const uint8_t *src = rgb;
     int dstride = stride;
     if (mem_kind == GSEG_MEM_HOST) {
-        CK(cudaMemcpy2DAsync(ctx->d_rgb, (size_t)3 * w, rgb, (size_t)stride, (size_t)3 * w, (size_t)h,
-                             cudaMemcpyHostToDevice, ctx->stream));
+        if (stride == 3 * w) // tightly packed rows: one linear copy (a pitched copy is issued row by row)
+            CK(cudaMemcpyAsync(ctx->d_rgb, rgb, (size_t)3 * w * h_in, cudaMemcpyHostToDevice, ctx->stream));
+        else
+            CK(cudaMemcpy2DAsync(ctx->d_rgb, (size_t)3 * w, rgb, (size_t)stride, (size_t)3 * w, (size_t)h_in,
+                                 cudaMemcpyHostToDevice, ctx->stream));
         src = ctx->d_rgb;
         dstride = 3 * w;
     }
@@ -619,6 +728,7 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
         ctx->epoch_next = 1;
     }
     hp->rgb = src; hp->w = w; hp->h = h; hp->stride = dstride; hp->D = ctx->D; hp->variant = p->variant;
+    hp->h_in = h_in; hp->y_off = halo_top;
     hp->k = p->k; hp->min_size = p->min_size; hp->max_rounds = R;
     hp->max_levels = p->max_levels > 0 ? p->max_levels : INT_MAX;
     hp->arena_cap = (u32)ctx->arena_cap;
@@ -633,6 +743,7 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
     hh->st.V = (u32)((size_t)w * h); hh->st.E = 0; hh->st.round = 0; hh->st.phase = PH_PRED; hh->st.levels = 0; hh->st.map_off = 0; hh->st.P = 0; hh->st.pad = 0;
     hh->Vnext = hh->st.V; hh->error = DERR_NONE; hh->ticketC = 0; hh->ticketE = 0; hh->doneE = 0;
     memset(hh->Eacc, 0, sizeof(hh->Eacc));
+    memset(hh->map_skip, 0, sizeof(hh->map_skip)); hh->resume_phase = PH_DONE;
     CK(cudaMemcpyAsync(ctx->d_ctl, hh, sizeof(GsegHead), cudaMemcpyHostToDevice, ctx->stream));
 
     ctx->n_marks = 0;
@@ -657,8 +768,9 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
     mark_end(ctx, ctx->stream);
     int rc = readback(ctx);
     if (rc) return rc;
-    for (int r = 1; r < R && ctx->h_ctl->st.phase != PH_DONE; ++r) {
-        enqueue_round(ctx, ctx->stream, r, ctx->h_ctl->st.V, ctx->h_ctl->st.P);
+    for (int go; (go = run_continues(ctx)) != 0;) {
+        if (go < 0) return go;
+        enqueue_round(ctx, ctx->stream, (int)ctx->h_ctl->st.round, ctx->h_ctl->st.V, ctx->h_ctl->st.P);
         mark_end(ctx, ctx->stream);
         CK(cudaGetLastError());
         rc = readback(ctx);
@@ -672,7 +784,9 @@ extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int 
 // keep going, two rounds and a tail at a time.
 static int wait_rounds(gseg_ctx *ctx) {
     int rc = readback(ctx);
-    while (!rc && ctx->h_ctl->st.phase != PH_DONE && ctx->h_ctl->error == DERR_NONE) {
+    if (ctx->params.flags & GSEG_FLAG_HOST_LOOP) return rc; // the host loop already ran the rounds to the end
+    for (int go; !rc && (go = run_continues(ctx)) != 0;) {
+        if (go < 0) return go;
         const int r = (int)ctx->h_ctl->st.round;
         enqueue_round(ctx, ctx->stream, r, ctx->h_ctl->st.V, ctx->h_ctl->st.P);
         enqueue_round(ctx, ctx->stream, r + 1, ctx->h_ctl->st.V, ctx->h_ctl->st.P);
@@ -682,6 +796,18 @@ static int wait_rounds(gseg_ctx *ctx) {
         rc = readback(ctx);
     }
     return rc;
+}
+
+extern "C" int gseg_segment_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int h, int stride, int mem_kind,
+                                  const gseg_params *p) {
+    return segment_async_impl(ctx, rgb, w, h, stride, mem_kind, 0, 0, p);
+}
+
+extern "C" int gseg_segment_strip_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int h, int stride, int mem_kind, int halo_top,
+                                        int halo_bottom, const gseg_params *p) {
+    if (p && p->variant == GSEG_SUPERPIX) // the Sobel plane would need a halo of blurred rows
+        return fail(ctx, GSEG_E_ARG, "strips: FELZ or HIER", cudaSuccess);
+    return segment_async_impl(ctx, rgb, w, h, stride, mem_kind, halo_top, halo_bottom, p);
 }
 
 extern "C" int gseg_wait(gseg_ctx *ctx) {
@@ -732,38 +858,96 @@ static int level_to_round(const gseg_ctx *ctx, int level, int *round) {
 
 // Label image of the partition after round `round` into dst (device).  Deep hierarchies go through a
 // composed table of the late (small) rounds so that a pixel chases 3-4 maps instead of one per round.
-static void enqueue_compose(gseg_ctx *ctx, int round, int *dst) {
+template <typename OutT>
+static void enqueue_compose(gseg_ctx *ctx, int round, OutT *dst) {
     const size_t V = (size_t)ctx->w * ctx->h;
     const GsegCtl *h = ctx->h_ctl;
     int first = 1;
-    while (first <= round && h->stV[first] > 65536u) ++first; // first round whose input has few components
+    while (first <= round && (h->stV[first] > 65536u || h->map_skip[first])) ++first; // first live round whose input has few components
     if (first >= 1 && first <= round && round - first >= 2 && h->stV[first] <= ctx->Vmax) {
         const u32 n = h->stV[first];
         u32 *F = ctx->d_wsel; // per-round scratch, free once the run is complete
         ctx->launches += 2;
         k_compose_table<<<grid_for(n, NT), NT, 0, ctx->stream>>>(ctx->d_ctl, ctx->d_arena, first, round, n, F);
-        k_compose_px<<<grid_for(V, NT), NT, 0, ctx->stream>>>(ctx->d_ctl, ctx->d_arena, first, F, dst);
+        k_compose_px<OutT><<<grid_for(V, NT), NT, 0, ctx->stream>>>(ctx->d_ctl, ctx->d_arena, first, F, dst);
     } else {
         ++ctx->launches;
-        k_compose<<<grid_for(V, NT), NT, 0, ctx->stream>>>(ctx->d_ctl, ctx->d_arena, round, dst);
+        k_compose<OutT><<<grid_for(V, NT), NT, 0, ctx->stream>>>(ctx->d_ctl, ctx->d_arena, round, dst);
     }
 }
 
-extern "C" int gseg_labels_async(gseg_ctx *ctx, int level, int32_t *out, int mem_kind) {
-    if (!ctx || !out) return GSEG_E_ARG;
+extern "C" int gseg_label_bytes(const gseg_ctx *ctx, int level) {
+    const int n = gseg_num_components(ctx, level);
+    if (n < 0) return n;
+    return n <= 256 ? 1 : (n <= 65536 ? 2 : 4);
+}
+
+extern "C" int gseg_labels_ex_async(gseg_ctx *ctx, int level, void *out, int elem_bytes, int mem_kind) {
+    if (!ctx || !out || (elem_bytes != 1 && elem_bytes != 2 && elem_bytes != 4)) return GSEG_E_ARG;
+    if (mem_kind != GSEG_MEM_HOST && mem_kind != GSEG_MEM_DEVICE) return GSEG_E_ARG;
     if (!ctx->valid) return GSEG_E_STATE;
+    if (ctx->graph_mode) return fail(ctx, GSEG_E_STATE, "the last run was an explicit-graph run (no label image)", cudaSuccess);
     int round;
     int rc = level_to_round(ctx, level, &round);
     if (rc) return rc;
+    const int need = gseg_label_bytes(ctx, level);
+    if (need < 0) return need;
+    if (need > elem_bytes) return fail(ctx, GSEG_E_RANGE, "label element type too narrow for this level", cudaSuccess);
     CK(cudaSetDevice(ctx->device));
     const size_t V = (size_t)ctx->w * ctx->h;
-    if (mem_kind != GSEG_MEM_DEVICE) { rc = ensure(ctx, &ctx->d_labels[0], ctx->Vmax + 64); if (rc) return rc; }
-    int *dst = mem_kind == GSEG_MEM_DEVICE ? out : ctx->d_labels[0];
-    enqueue_compose(ctx, round, dst);
+    void *dst = mem_kind == GSEG_MEM_DEVICE ? out : (void *)ctx->d_labels[0];
+    if (elem_bytes == 4) enqueue_compose<int>(ctx, round, (int *)dst);
+    else if (elem_bytes == 2) enqueue_compose<uint16_t>(ctx, round, (uint16_t *)dst);
+    else enqueue_compose<uint8_t>(ctx, round, (uint8_t *)dst);
     CK(cudaGetLastError());
     if (mem_kind != GSEG_MEM_DEVICE)
-        CK(cudaMemcpyAsync(out, dst, V * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+        CK(cudaMemcpyAsync(out, dst, V * (size_t)elem_bytes, cudaMemcpyDeviceToHost, ctx->stream));
     return GSEG_OK;
+}
+
+extern "C" int gseg_labels_async(gseg_ctx *ctx, int level, int32_t *out, int mem_kind) {
+    return gseg_labels_ex_async(ctx, level, out, 4, mem_kind);
+}
+
+extern "C" int gseg_labels_ex(gseg_ctx *ctx, int level, void *out, int elem_bytes, int mem_kind) {
+    int rc = gseg_labels_ex_async(ctx, level, out, elem_bytes, mem_kind);
+    if (rc) return rc;
+    return gseg_sync(ctx);
+}
+
+// The stored hierarchy: the arena holds one old-id -> new-id map per round back to back, which IS the
+// representation the header describes; one linear copy.
+extern "C" int gseg_hierarchy_async(gseg_ctx *ctx, uint32_t *out, int64_t cap_entries, int64_t *offsets, int cap_offsets,
+                                    int mem_kind) {
+    if (!ctx || !offsets) return GSEG_E_ARG;
+    if (mem_kind != GSEG_MEM_HOST && mem_kind != GSEG_MEM_DEVICE) return GSEG_E_ARG;
+    if (!ctx->valid) return GSEG_E_STATE;
+    if (ctx->graph_mode) return fail(ctx, GSEG_E_STATE, "the last run was an explicit-graph run", cudaSuccess);
+    const GsegCtl *h = ctx->h_ctl;
+    const size_t V = (size_t)ctx->w * ctx->h;
+    if (ctx->params.variant == GSEG_FELZ) { // one level: the final partition
+        if (cap_offsets < 2) return GSEG_E_RANGE;
+        offsets[0] = 0; offsets[1] = (int64_t)V;
+        if (!out) return 1;
+        if (cap_entries < (int64_t)V) return GSEG_E_RANGE;
+        const int rc = gseg_labels_ex_async(ctx, -1, out, 4, mem_kind);
+        return rc ? rc : 1;
+    }
+    const int nl = (int)h->st.levels > 0 ? (int)h->st.levels : 1; // a run without any merge still has round 0's identity map
+    if (cap_offsets < nl + 1) return GSEG_E_RANGE;
+    for (int l = 0; l <= nl; ++l) offsets[l] = (int64_t)h->map_off[l];
+    if (!out) return nl;
+    if (cap_entries < offsets[nl]) return GSEG_E_RANGE;
+    CK(cudaSetDevice(ctx->device));
+    CK(cudaMemcpyAsync(out, ctx->d_arena, (size_t)offsets[nl] * sizeof(u32),
+                       mem_kind == GSEG_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    return nl;
+}
+extern "C" int gseg_hierarchy(gseg_ctx *ctx, uint32_t *out, int64_t cap_entries, int64_t *offsets, int cap_offsets, int mem_kind) {
+    const int n = gseg_hierarchy_async(ctx, out, cap_entries, offsets, cap_offsets, mem_kind);
+    if (n < 0 || !out) return n;
+    const int rc = gseg_sync(ctx);
+    return rc ? rc : n;
 }
 
 extern "C" int gseg_sync(gseg_ctx *ctx) {
@@ -790,13 +974,12 @@ extern "C" int gseg_labels_all(gseg_ctx *ctx, int32_t *out, int max_levels, int 
         int rc = gseg_labels(ctx, -1, out, mem_kind);
         return rc ? rc : 1;
     }
-    if (mem_kind != GSEG_MEM_DEVICE)
-        for (int i = 0; i < 2; ++i) { int rc = ensure(ctx, &ctx->d_labels[i], ctx->Vmax + 64); if (rc) return rc; }
+    if (mem_kind != GSEG_MEM_DEVICE) { int rc = ensure(ctx, &ctx->d_labels[1], ctx->Vmax + 64); if (rc) return rc; }
     const int *prev = nullptr;
     for (int l = 0; l < nl; ++l) {
         int *dst = mem_kind == GSEG_MEM_DEVICE ? out + (size_t)l * V : ctx->d_labels[l & 1];
         ++ctx->launches;
-        if (l == 0) k_compose<<<grid_for(V, NT), NT, 0, ctx->stream>>>(ctx->d_ctl, ctx->d_arena, 0, dst);
+        if (l == 0) k_compose<int><<<grid_for(V, NT), NT, 0, ctx->stream>>>(ctx->d_ctl, ctx->d_arena, 0, dst);
         else k_compose_step<<<grid_for(V, NT), NT, 0, ctx->stream>>>(ctx->d_ctl, ctx->d_arena, l, prev, dst);
         if (mem_kind != GSEG_MEM_DEVICE)
             CK(cudaMemcpyAsync(out + (size_t)l * V, dst, V * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
@@ -815,10 +998,9 @@ extern "C" int gseg_colorize(gseg_ctx *ctx, int level, uint64_t seed, uint8_t *o
     if (rc) return rc;
     CK(cudaSetDevice(ctx->device));
     const size_t V = (size_t)ctx->w * ctx->h;
-    rc = ensure(ctx, &ctx->d_labels[0], ctx->Vmax + 64);
-    if (!rc && mem_kind != GSEG_MEM_DEVICE) rc = ensure(ctx, &ctx->d_labels[1], ctx->Vmax + 64); // 4V bytes >= the 3V of the colour image
+    if (mem_kind != GSEG_MEM_DEVICE) rc = ensure(ctx, &ctx->d_labels[1], ctx->Vmax + 64); // 4V bytes >= the 3V of the colour image
     if (rc) return rc;
-    enqueue_compose(ctx, round, ctx->d_labels[0]);
+    enqueue_compose<int>(ctx, round, ctx->d_labels[0]);
     uint8_t *dst = mem_kind == GSEG_MEM_DEVICE ? out : (uint8_t *)ctx->d_labels[1];
     ++ctx->launches;
     k_colorize<<<grid_for(V, NT), NT, 0, ctx->stream>>>(ctx->d_labels[0], (u32)V, seed, dst);
@@ -931,46 +1113,24 @@ extern "C" int gseg_blurred_rows(gseg_ctx *ctx, int y0, int nrows, float *out, i
     if (!ctx->valid) return GSEG_E_STATE;
     if (y0 < 0 || nrows < 1 || y0 + nrows > ctx->h) return GSEG_E_ARG;
     CK(cudaSetDevice(ctx->device));
-    const size_t V = (size_t)ctx->w * ctx->h, rowb = (size_t)ctx->w * sizeof(float);
-    CK(cudaMemcpy2DAsync(out, (size_t)nrows * rowb, ctx->d_planes + (size_t)y0 * ctx->w, V * sizeof(float), (size_t)nrows * rowb, 3,
-                         mem_kind == GSEG_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
+    const size_t V = (size_t)ctx->w * ctx->h, n = (size_t)nrows * ctx->w;
+    for (int c = 0; c < 3; ++c) // one linear copy per plane (a pitched copy's pitch would be V * 4 bytes: beyond CUDA's limit for large strips)
+        CK(cudaMemcpyAsync(out + (size_t)c * n, ctx->d_planes + (size_t)c * V + (size_t)y0 * ctx->w, n * sizeof(float),
+                           mem_kind == GSEG_MEM_DEVICE ? cudaMemcpyDeviceToDevice : cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return GSEG_OK;
 }
 
 static int wait_rounds(gseg_ctx *ctx);
 
-extern "C" int gseg_segment_graph(gseg_ctx *ctx, int64_t n_components, const uint32_t *size, const float *Int, int64_t n_edges,
-                                  const uint32_t *ea, const uint32_t *eb, const float *w, const gseg_params *p,
-                                  int32_t *labels_out) {
-    if (!ctx || !p || !labels_out || n_components < 1 || n_edges < 0 || !size || !Int || (n_edges && (!ea || !eb || !w)))
-        return GSEG_E_ARG;
-    if (ctx->pending) return fail(ctx, GSEG_E_STATE, "previous run not waited for", cudaSuccess);
-    if (p->variant != GSEG_FELZ && p->variant != GSEG_HIER) return fail(ctx, GSEG_E_ARG, "graph rounds: FELZ or HIER", cudaSuccess);
-    if (!(p->k >= 0.0f) || p->min_size < 0 || p->max_rounds < 0 || p->max_levels < 0) return fail(ctx, GSEG_E_ARG, "parameter range", cudaSuccess);
-    const size_t Eslots = (size_t)ctx->Dmax * ((ctx->Vmax + GSEG_PAGE - 1) / GSEG_PAGE + 1) * GSEG_PAGE;
-    if ((size_t)n_components > ctx->Vmax || (size_t)n_edges + GSEG_PAGE > Eslots)
-        return fail(ctx, GSEG_E_SIZE, "graph exceeds context capacity", cudaSuccess);
-    CK(cudaSetDevice(ctx->device));
-    ctx->valid = false; ctx->x_valid = false;
-    ctx->params = *p;
-    ctx->w = (int)n_components; ctx->h = 1; ctx->D = 2;
-    const size_t V = (size_t)n_components, E = (size_t)n_edges;
-    std::vector<uint2> hab, hat;
-    try { hab.resize(E); hat.resize(V); } catch (...) { return fail(ctx, GSEG_E_ARG, "host staging allocation", cudaSuccess); }
-    for (size_t i = 0; i < E; ++i) {
-        if (ea[i] >= V || eb[i] >= V || ea[i] == eb[i]) return fail(ctx, GSEG_E_ARG, "edge end out of range or self-loop", cudaSuccess);
-        hab[i] = make_uint2(ea[i], eb[i]);
-    }
-    for (size_t i = 0; i < V; ++i) { hat[i].x = size[i]; memcpy(&hat[i].y, &Int[i], 4); }
+// The Boruvka rounds on an explicit graph that already sits in the context's buffers: attr[1][0..V), eab[1] /
+// ew[1][0..E) in list order, best[1][0..V) = none.  Leaves the composed label of every input component in
+// d_wsel and returns the number of final components (or a negative status).
+static int graph_run(gseg_ctx *ctx, size_t V, size_t E, const gseg_params *p) {
     cudaStream_t s = ctx->stream;
-    if (E) {
-        CK(cudaMemcpyAsync(ctx->d_eab[1], hab.data(), E * sizeof(uint2), cudaMemcpyHostToDevice, s));
-        CK(cudaMemcpyAsync(ctx->d_ew[1], w, E * sizeof(u32), cudaMemcpyHostToDevice, s));
-    }
-    CK(cudaMemcpyAsync(ctx->d_attr[1], hat.data(), V * sizeof(uint2), cudaMemcpyHostToDevice, s));
-    CK(cudaMemsetAsync(ctx->d_best[1], 0xFF, V * sizeof(u64), s));
-    CK(cudaStreamSynchronize(s)); // the staging vectors die with this scope
+    ctx->valid = false; ctx->x_valid = false; ctx->graph_mode = true;
+    ctx->params = *p;
+    ctx->w = (int)V; ctx->h = 1; ctx->D = 2;
     const int R = max_rounds_of(p);
     if (ctx->epoch_next + 2u * GSEG_MAXR + 8u >= (1u << 30)) {
         CK(cudaMemsetAsync(ctx->d_statusC, 0, ctx->ntilesC * sizeof(u64), s));
@@ -980,7 +1140,7 @@ extern "C" int gseg_segment_graph(gseg_ctx *ctx, int64_t n_components, const uin
     GsegHead *hh = ctx->h_head;
     GsegRunParams *hp = &hh->p;
     memset(hp, 0, sizeof(*hp));
-    hp->w = (int)n_components; hp->h = 1; hp->D = 2; hp->variant = p->variant;
+    hp->w = (int)V; hp->h = 1; hp->h_in = 1; hp->D = 2; hp->variant = p->variant;
     hp->k = p->k; hp->min_size = p->min_size; hp->max_rounds = R + 1 > GSEG_MAXR ? GSEG_MAXR : R + 1; // rounds are numbered from 1 here
     hp->max_levels = p->max_levels > 0 ? p->max_levels : INT_MAX;
     hp->arena_cap = (u32)ctx->arena_cap;
@@ -996,6 +1156,7 @@ extern "C" int gseg_segment_graph(gseg_ctx *ctx, int64_t n_components, const uin
     hh->st.P = P; hh->st.pad = 0;
     hh->Vnext = (u32)V; hh->error = DERR_NONE; hh->ticketC = 0; hh->ticketE = 0; hh->doneE = 0;
     memset(hh->Eacc, 0, sizeof(hh->Eacc));
+    memset(hh->map_skip, 0, sizeof(hh->map_skip)); hh->resume_phase = PH_DONE;
     CK(cudaMemcpyAsync(ctx->d_ctl, hh, sizeof(GsegHead), cudaMemcpyHostToDevice, s));
     ctx->n_marks = 0;
     const GsegBufs B = bufs_of(ctx);
@@ -1006,8 +1167,9 @@ extern "C" int gseg_segment_graph(gseg_ctx *ctx, int64_t n_components, const uin
     int rc;
     if (host_loop) {
         rc = readback(ctx);
-        for (int r = 1; !rc && r <= R && ctx->h_ctl->st.phase != PH_DONE; ++r) {
-            enqueue_round(ctx, s, r, ctx->h_ctl->st.V, ctx->h_ctl->st.P);
+        for (int go; !rc && (go = run_continues(ctx)) != 0;) {
+            if (go < 0) { rc = go; break; }
+            enqueue_round(ctx, s, (int)ctx->h_ctl->st.round, ctx->h_ctl->st.V, ctx->h_ctl->st.P);
             CK(cudaGetLastError());
             rc = readback(ctx);
         }
@@ -1023,13 +1185,148 @@ extern "C" int gseg_segment_graph(gseg_ctx *ctx, int64_t n_components, const uin
     if (ctx->h_ctl->error == DERR_CHASE) return fail(ctx, GSEG_E_INTERNAL, "successor cycle", cudaSuccess);
     // labels of the input components: the maps of rounds 1 .. last composed
     const int last = (int)ctx->h_ctl->st.round - 1;
-    u32 *F = ctx->d_wsel;
     ++ctx->launches;
-    k_compose_table<<<grid_for(V, NT), NT, 0, s>>>(ctx->d_ctl, ctx->d_arena, 1, last, (u32)V, F);
+    k_compose_table<<<grid_for(V, NT), NT, 0, s>>>(ctx->d_ctl, ctx->d_arena, 1, last, (u32)V, ctx->d_wsel);
     CK(cudaGetLastError());
-    CK(cudaMemcpyAsync(labels_out, F, V * sizeof(u32), cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
     return (int)ctx->h_ctl->st.V;
+}
+
+static size_t edge_slots(const gseg_ctx *ctx) {
+    return (size_t)ctx->Dmax * ((ctx->Vmax + GSEG_PAGE - 1) / GSEG_PAGE + 1) * GSEG_PAGE;
+}
+
+extern "C" int gseg_segment_graph(gseg_ctx *ctx, int64_t n_components, const uint32_t *size, const float *Int, int64_t n_edges,
+                                  const uint32_t *ea, const uint32_t *eb, const float *w, const gseg_params *p,
+                                  int32_t *labels_out) {
+    if (!ctx || !p || !labels_out || n_components < 1 || n_edges < 0 || !size || !Int || (n_edges && (!ea || !eb || !w)))
+        return GSEG_E_ARG;
+    if (ctx->pending) return fail(ctx, GSEG_E_STATE, "previous run not waited for", cudaSuccess);
+    if (p->variant != GSEG_FELZ && p->variant != GSEG_HIER) return fail(ctx, GSEG_E_ARG, "graph rounds: FELZ or HIER", cudaSuccess);
+    if (!(p->k >= 0.0f) || p->min_size < 0 || p->max_rounds < 0 || p->max_levels < 0) return fail(ctx, GSEG_E_ARG, "parameter range", cudaSuccess);
+    if ((size_t)n_components > ctx->Vmax || (size_t)n_edges + GSEG_PAGE > edge_slots(ctx))
+        return fail(ctx, GSEG_E_SIZE, "graph exceeds context capacity", cudaSuccess);
+    CK(cudaSetDevice(ctx->device));
+    const size_t V = (size_t)n_components, E = (size_t)n_edges;
+    std::vector<uint2> hab, hat;
+    try { hab.resize(E); hat.resize(V); } catch (...) { return fail(ctx, GSEG_E_ARG, "host staging allocation", cudaSuccess); }
+    // every comparison of the engine orders fp32 values by their bit patterns: only non-negative, non-NaN
+    // weights and Int(C) order like their values (-0.0 would sort above every finite weight)
+    auto bad_float = [](float f) { u32 b; memcpy(&b, &f, 4); return (b >> 31) != 0u || b > GSEG_INF_BITS; };
+    for (size_t i = 0; i < E; ++i) {
+        if (ea[i] >= V || eb[i] >= V || ea[i] == eb[i]) return fail(ctx, GSEG_E_ARG, "edge end out of range or self-loop", cudaSuccess);
+        if (bad_float(w[i])) return fail(ctx, GSEG_E_ARG, "edge weight negative (sign bit set) or NaN", cudaSuccess);
+        hab[i] = make_uint2(ea[i], eb[i]);
+    }
+    for (size_t i = 0; i < V; ++i) {
+        if (bad_float(Int[i])) return fail(ctx, GSEG_E_ARG, "Int(C) negative (sign bit set) or NaN", cudaSuccess);
+        hat[i].x = size[i]; memcpy(&hat[i].y, &Int[i], 4);
+    }
+    cudaStream_t s = ctx->stream;
+    if (E) {
+        CK(cudaMemcpyAsync(ctx->d_eab[1], hab.data(), E * sizeof(uint2), cudaMemcpyHostToDevice, s));
+        CK(cudaMemcpyAsync(ctx->d_ew[1], w, E * sizeof(u32), cudaMemcpyHostToDevice, s));
+    }
+    CK(cudaMemcpyAsync(ctx->d_attr[1], hat.data(), V * sizeof(uint2), cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ctx->d_best[1], 0xFF, V * sizeof(u64), s));
+    CK(cudaStreamSynchronize(s)); // the staging vectors die with this scope
+    const int n = graph_run(ctx, V, E, p);
+    if (n < 0) return n;
+    CK(cudaMemcpyAsync(labels_out, ctx->d_wsel, V * sizeof(u32), cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    return n;
+}
+
+// ---- tiled schedule on the device: strip record, join, joined rounds ----------------------------------------
+extern "C" int gseg_strip_record(gseg_ctx *ctx, int dedup, void *dev_out, int64_t cap_bytes, int64_t *bytes) {
+    if (!ctx || !bytes) return GSEG_E_ARG;
+    if (!ctx->valid || ctx->graph_mode || ctx->params.variant == GSEG_SUPERPIX) return GSEG_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    int rc = export_prepare(ctx, dedup);
+    if (rc) return rc;
+    const GsegCtl *h = ctx->h_ctl;
+    const size_t nV = h->st.V, nE = ctx->x_count, w = (size_t)ctx->w;
+    *bytes = (int64_t)(rec_words(nV, nE, w) * sizeof(u32));
+    if (!dev_out) return GSEG_OK;
+    if (cap_bytes < *bytes) return GSEG_E_RANGE;
+    cudaStream_t s = ctx->stream;
+    u32 *rec = (u32 *)dev_out;
+    const int cur = (int)(h->st.round & 1u);
+    // the strip's dense label image stays in d_labels[0]: gseg_join_segment maps it through the joined result
+    int round;
+    rc = level_to_round(ctx, -1, &round);
+    if (rc) return rc;
+    enqueue_compose<int>(ctx, round, ctx->d_labels[0]);
+    CK(cudaMemcpyAsync(rec + GSEG_REC_HEAD, ctx->d_attr[cur], nV * sizeof(uint2), cudaMemcpyDeviceToDevice, s));
+    if (nE) {
+        CK(cudaMemcpyAsync(rec + GSEG_REC_HEAD + 2 * nV, ctx->x_ab, nE * sizeof(uint2), cudaMemcpyDeviceToDevice, s));
+        CK(cudaMemcpyAsync(rec + GSEG_REC_HEAD + 2 * nV + 2 * nE, ctx->x_w, nE * sizeof(u32), cudaMemcpyDeviceToDevice, s));
+    }
+    ++ctx->launches;
+    k_record_rows<<<grid_for(w, NT), NT, 0, s>>>(ctx->d_labels[0], ctx->d_planes, (u32)ctx->w, (u32)ctx->h, (u32)nV, (u32)nE, rec);
+    CK(cudaGetLastError());
+    ctx->strip_w = ctx->w; ctx->strip_h = ctx->h; ctx->strip_nV = (u32)nV; ctx->strip_labels = true;
+    CK(cudaStreamSynchronize(s));
+    return GSEG_OK;
+}
+
+extern "C" int gseg_join_segment(gseg_ctx *ctx, const void *dev_records, int n_strips, int64_t record_stride_bytes, int my_strip,
+                                 const gseg_params *p, void *labels_out, int elem_bytes, int mem_kind, int64_t *n_joined_components,
+                                 int64_t *n_joined_edges) {
+    if (!ctx || !dev_records || !p || n_strips < 1 || n_strips > GSEG_MAX_STRIPS || my_strip < 0 || my_strip >= n_strips ||
+        record_stride_bytes < (int64_t)(GSEG_REC_HEAD * sizeof(u32)) || (record_stride_bytes & 3))
+        return GSEG_E_ARG;
+    if (labels_out && elem_bytes != 1 && elem_bytes != 2 && elem_bytes != 4) return GSEG_E_ARG;
+    if (mem_kind != GSEG_MEM_HOST && mem_kind != GSEG_MEM_DEVICE) return GSEG_E_ARG;
+    if (ctx->pending) return fail(ctx, GSEG_E_STATE, "previous run not waited for", cudaSuccess);
+    if (!ctx->strip_labels) return fail(ctx, GSEG_E_STATE, "gseg_strip_record has not been called for this strip", cudaSuccess);
+    if (p->variant != GSEG_FELZ && p->variant != GSEG_HIER) return fail(ctx, GSEG_E_ARG, "graph rounds: FELZ or HIER", cudaSuccess);
+    if (p->connectivity != 4 && p->connectivity != 8) return fail(ctx, GSEG_E_ARG, "connectivity must be 4 or 8", cudaSuccess);
+    CK(cudaSetDevice(ctx->device));
+    cudaStream_t s = ctx->stream;
+    // the record headers (32 bytes each) are the only thing the host reads
+    u32 heads[GSEG_MAX_STRIPS][GSEG_REC_HEAD];
+    CK(cudaMemcpy2DAsync(heads, sizeof(heads[0]), dev_records, (size_t)record_stride_bytes, sizeof(heads[0]), (size_t)n_strips,
+                         cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    JoinDesc jd;
+    memset(&jd, 0, sizeof(jd));
+    jd.n_strips = (u32)n_strips; jd.w = heads[0][3]; jd.conn = (u32)p->connectivity;
+    jd.ncut = p->connectivity == 8 ? jd.w + 2u * (jd.w - 1u) : jd.w;
+    jd.stride_words = (unsigned long long)record_stride_bytes / 4u;
+    u64 vo = 0, eo = 0;
+    for (int i = 0; i < n_strips; ++i) {
+        if (heads[i][0] != GSEG_REC_MAGIC || heads[i][3] != jd.w) return fail(ctx, GSEG_E_ARG, "not a strip record (or strips of different widths)", cudaSuccess);
+        if ((u64)rec_words(heads[i][1], heads[i][2], jd.w) * 4u > (u64)record_stride_bytes) return fail(ctx, GSEG_E_ARG, "record stride shorter than a record", cudaSuccess);
+        jd.voff[i] = (u32)vo; jd.eoff[i] = (u32)eo; jd.ne[i] = heads[i][2];
+        vo += heads[i][1];
+        eo += heads[i][2] + (i + 1 < n_strips ? jd.ncut : 0u);
+    }
+    jd.voff[n_strips] = (u32)vo; jd.eoff[n_strips] = (u32)eo;
+    if (vo > ctx->Vmax || eo + GSEG_PAGE > edge_slots(ctx) || vo >= 0xFFFFFFFFull || eo >= 0xFFFFFFFFull)
+        return fail(ctx, GSEG_E_SIZE, "joined graph exceeds context capacity", cudaSuccess);
+    if ((u32)ctx->strip_w != jd.w || heads[my_strip][1] != ctx->strip_nV) return fail(ctx, GSEG_E_ARG, "my_strip is not this context's record", cudaSuccess);
+    if (n_joined_components) *n_joined_components = (int64_t)vo;
+    if (n_joined_edges) *n_joined_edges = (int64_t)eo;
+    ++ctx->launches;
+    k_join<<<grid_for(vo + eo, NT), NT, 0, s>>>(jd, (const u32 *)dev_records, bufs_of(ctx));
+    CK(cudaGetLastError());
+    const int n = graph_run(ctx, (size_t)vo, (size_t)eo, p);
+    if (n < 0) return n;
+    if (labels_out) {
+        const size_t Vs = (size_t)ctx->strip_w * ctx->strip_h;
+        void *dst = labels_out;
+        if (mem_kind != GSEG_MEM_DEVICE) { int rc = ensure(ctx, &ctx->d_labels[1], ctx->Vmax + 64); if (rc) return rc; dst = ctx->d_labels[1]; }
+        if (elem_bytes == 1 ? n > 256 : (elem_bytes == 2 ? n > 65536 : false)) return fail(ctx, GSEG_E_RANGE, "label element type too narrow", cudaSuccess);
+        ++ctx->launches;
+        const int g = grid_for(Vs, NT);
+        if (elem_bytes == 4) k_map_labels<int><<<g, NT, 0, s>>>(ctx->d_labels[0], ctx->d_wsel, jd.voff[my_strip], Vs, (int *)dst);
+        else if (elem_bytes == 2) k_map_labels<uint16_t><<<g, NT, 0, s>>>(ctx->d_labels[0], ctx->d_wsel, jd.voff[my_strip], Vs, (uint16_t *)dst);
+        else k_map_labels<uint8_t><<<g, NT, 0, s>>>(ctx->d_labels[0], ctx->d_wsel, jd.voff[my_strip], Vs, (uint8_t *)dst);
+        CK(cudaGetLastError());
+        if (mem_kind != GSEG_MEM_DEVICE) CK(cudaMemcpyAsync(labels_out, dst, Vs * (size_t)elem_bytes, cudaMemcpyDeviceToHost, s));
+    }
+    CK(cudaStreamSynchronize(s));
+    return n;
 }
 
 extern "C" int gseg_stats(const gseg_ctx *ctx, gseg_round_stat *out, int cap) {
@@ -1052,19 +1349,24 @@ extern "C" int gseg_stats(const gseg_ctx *ctx, gseg_round_stat *out, int cap) {
     return n;
 }
 
-extern "C" int gseg_synth(gseg_ctx *ctx, uint8_t *out, int w, int h, uint64_t seed, int mem_kind) {
-    if (!ctx || !out || w < 1 || h < 1) return GSEG_E_ARG;
-    if ((size_t)w * h > ctx->Vmax) return GSEG_E_SIZE;
+extern "C" int gseg_synth_rows(gseg_ctx *ctx, uint8_t *out, int w, int y_first, int nrows, uint64_t seed, int mem_kind) {
+    if (!ctx || !out || w < 1 || nrows < 1 || y_first < 0) return GSEG_E_ARG;
+    if (mem_kind != GSEG_MEM_HOST && mem_kind != GSEG_MEM_DEVICE) return GSEG_E_ARG;
+    if (mem_kind == GSEG_MEM_HOST && (size_t)w * nrows > ctx->Vmax) return GSEG_E_SIZE; // staged through the context
     if (ctx->pending) return GSEG_E_STATE;
     CK(cudaSetDevice(ctx->device));
-    const size_t V = (size_t)w * h;
+    const size_t V = (size_t)w * nrows;
     uint8_t *dst = mem_kind == GSEG_MEM_DEVICE ? out : ctx->d_rgb;
     ++ctx->launches;
-    k_synth<<<grid_for(V, NT), NT, 0, ctx->stream>>>(dst, w, h, seed);
+    k_synth<<<grid_for(V, NT), NT, 0, ctx->stream>>>(dst, w, nrows, seed, y_first);
     CK(cudaGetLastError());
     if (mem_kind != GSEG_MEM_DEVICE) CK(cudaMemcpyAsync(out, dst, 3 * V, cudaMemcpyDeviceToHost, ctx->stream));
     CK(cudaStreamSynchronize(ctx->stream));
     return GSEG_OK;
+}
+
+extern "C" int gseg_synth(gseg_ctx *ctx, uint8_t *out, int w, int h, uint64_t seed, int mem_kind) {
+    return gseg_synth_rows(ctx, out, w, 0, h, seed, mem_kind);
 }
 
 extern "C" int gseg_sort_pairs_u64(gseg_ctx *ctx, uint64_t *keys, uint32_t *vals, int64_t n, int begin_bit, int end_bit) {
@@ -1085,34 +1387,46 @@ extern "C" int gseg_set_profiling(gseg_ctx *ctx, int on) {
 }
 
 extern "C" long long gseg_launch_count(const gseg_ctx *ctx) { return ctx ? ctx->launches : 0; }
+extern "C" long long gseg_compaction_count(const gseg_ctx *ctx) { return ctx ? ctx->compactions : 0; }
 
-// Algorithmic bytes of one kernel launch (DESIGN.md "Kernels"): every input array
-// read once, every output written once, gathers and atomics at element size.
-static double algo_bytes(const gseg_ctx *c, const char *name, int r) {
+// Algorithmic bytes of one kernel launch, SURVEY.md section 8(d) accounting: every input array read once, every
+// output written once, gathers at element size, and the per-component minimum as ONE 8-byte word per component
+// of the next round (section 8(d) "min-edge select: 8 V write"), not 8 bytes per atomic.  strict = the same with
+// every gathered array counted once however many elements gather from it.  E0 = grid edges that exist.
+static void algo_bytes(const gseg_ctx *c, const char *name, int r, double *algo, double *strict) {
     const GsegCtl *h = c->h_ctl;
-    if (r < 0) return 0;
-    const double V0 = (double)c->w * c->h, D = c->D;
+    *algo = *strict = 0;
+    if (r < 0) return;
+    const double W = c->w, H = c->h, V0 = W * H;
+    const double E0 = c->D == 2 ? 2 * V0 - W - H : 4 * V0 - 3 * W - 3 * H + 2;
     const double V = r == 0 ? V0 : h->stV[r], E = r == 0 ? 0 : h->stE[r], Vn = h->stVafter[r];
     const double En = (r + 1 < (int)h->st.round) ? h->stE[r + 1] : h->st.E;
     const bool sp = c->params.variant == GSEG_SUPERPIX;
-    const double acc = sp ? 40 : 16; // accumulators per new component: (size, Int) 8 + best 8 [+ 3 colour sums 24]
-    if (!strcmp(name, "k_blur_tile")) return 3 * V0 + 12 * V0;            // u8 image in, 3 fp32 planes out
-    if (!strcmp(name, "k_blur_h")) return 3 * V0 + 12 * V0;
-    if (!strcmp(name, "k_blur_v")) return 12 * V0 + 12 * V0;
-    if (!strcmp(name, "k_sobel")) return 12 * V0 + 4 * V0;
-    // planes (+G) in; D weight planes, successor, chosen weight out; rank + cleared accumulators per root
-    if (!strcmp(name, "k_r0_graph")) return (sp ? 16 : 12) * V0 + 4 * D * V0 + 8 * V0 + (4 + acc) * Vn;
-    // succ in, rank gather, map out, old (size, Int) [+ colour sums] in, wsel of merged in, accumulators updated
-    if (!strcmp(name, "k_relabel"))
-        return 4 * V + 4 * V + 4 * V + (r == 0 ? (sp ? 12 * V : 0) : (sp ? 32 : 8) * V) + 4 * (V - Vn) + (sp ? 32 : 8) * Vn;
-    // per direction plane: map of the pixel and of its neighbour (4 + 4 B per grid edge), weights of survivors,
-    // 12 B per surviving edge out, both ends' min-edge words (8 B each)
-    if (!strcmp(name, "k_r0_edges")) return 8 * D * V0 + 4 * En + 12 * En + 16 * En;
-    // best + chosen edge ends + both sides' (size, Int) + partner's best; succ, wsel out; rank + cleared accumulators
-    if (!strcmp(name, "k_succ_scan")) return 8 * V + 8 * V + 16 * V + 8 * V + 8 * V + (4 + acc) * Vn;
-    // 12 B per edge in, two 4 B map gathers, 12 B per surviving edge out, both ends' min-edge words
-    if (!strcmp(name, "k_edges")) return 12 * E + 8 * E + 12 * En + 16 * En + (sp ? 56 * En : 0);
-    return 0;
+    const double acc = sp ? 40 : 16; // cleared accumulators per new component: (size, Int) 8 + minimum 8 [+ 3 colour sums 24]
+    double a = 0, s = 0;
+    if (!strcmp(name, "k_blur_tile") || !strcmp(name, "k_blur_h")) a = s = 3 * V0 + 12 * V0;   // u8 image in, 3 fp32 planes out
+    else if (!strcmp(name, "k_blur_v")) a = s = 12 * V0 + 12 * V0;
+    else if (!strcmp(name, "k_sobel")) a = s = 12 * V0 + 4 * V0;
+    // planes (+G) in; weights out (4 E0), successor + chosen weight out (8 V), new id of every root + its cleared accumulators
+    else if (!strcmp(name, "k_r0_graph")) a = s = (sp ? 16 : 12) * V0 + 4 * E0 + 8 * V0 + (4 + acc) * Vn;
+    // pointer jump (one pass): succ in, one 4-byte gather up the chain; new id of the root: a 4-byte gather; map out;
+    // contraction: old (size, Int) [+ colour sums] in, chosen weight of the merged in, (size, Int) [+ sums] per new component out
+    else if (!strcmp(name, "k_relabel")) {
+        const double attr_in = r == 0 ? (sp ? 12 * V : 0) : (sp ? 32 : 8) * V, out = (sp ? 32 : 8) * Vn;
+        a = 4 * V + 4 * V + 4 * V + 4 * V + attr_in + 4 * (V - Vn) + out;
+        s = 4 * V + 4 * Vn + 4 * V + attr_in + 4 * (V - Vn) + out; // the chain is inside succ[], the ids gathered are Vn distinct words
+    }
+    // grid edges: weight in (the ends are implicit), both ends' new ids gathered (4 + 4), survivors out (12), one minimum per component
+    else if (!strcmp(name, "k_r0_edges")) { a = 4 * E0 + 8 * E0 + 12 * En + 8 * Vn; s = 4 * E0 + 4 * V0 + 12 * En + 8 * Vn; }
+    // per component: its minimum in (8), that edge's ends gathered (8), (size, Int) of both ends (16) and the partner's
+    // minimum (8) gathered; successor + chosen weight out (8); new id of every root + its cleared accumulators
+    else if (!strcmp(name, "k_succ_scan")) { a = 8 * V + 8 * V + 16 * V + 8 * V + 8 * V + (4 + acc) * Vn; s = 8 * V + 8 * V + 8 * V + 8 * V + (4 + acc) * Vn; }
+    // 12 B per edge in, both ends' new ids gathered, 12 B per survivor out, one minimum per component
+    // (superpixel: + both ends' 16-byte means gathered per survivor)
+    else if (!strcmp(name, "k_edges")) { a = 12 * E + 8 * E + 12 * En + 8 * Vn + (sp ? 32 * En : 0); s = 12 * E + 4 * V + 12 * En + 8 * Vn + (sp ? 16 * Vn : 0); }
+    else if (!strcmp(name, "k_means")) a = s = 32 * Vn + 16 * Vn;
+    else if (!strcmp(name, "k_page_scan")) a = s = 8.0 * h->stPages[r];
+    *algo = a; *strict = s;
 }
 
 extern "C" int gseg_profile_read(gseg_ctx *ctx, gseg_kernel_time *out, int cap) {
@@ -1129,7 +1443,7 @@ extern "C" int gseg_profile_read(gseg_ctx *ctx, gseg_kernel_time *out, int cap) 
             snprintf(out[n].name, sizeof(out[n].name), "%s", ctx->mark_name[i]);
             out[n].round = ctx->mark_round[i];
             out[n].ms = ms;
-            out[n].algo_bytes = algo_bytes(ctx, ctx->mark_name[i], ctx->mark_round[i]);
+            algo_bytes(ctx, ctx->mark_name[i], ctx->mark_round[i], &out[n].algo_bytes, &out[n].strict_bytes);
         }
         ++n;
     }

@@ -17,6 +17,8 @@
 //     --synth WxH:SEED               ignore input.ppm, segment the deterministic synthetic image
 //     --iters N                      timing loop: N runs after 2 warm-ups, mean +- std (excludes I/O)
 //     --device D                     CUDA device ordinal
+//     --host-loop                    host-driven schedule (one read-back per round, the reference's "conventional" driver)
+//     --tail E,V                     largest round (edges, components) the single-cluster tail kernel takes; 0,0 = never
 //   gseg --convert input output      file conversion only (no GPU): exercises the readers/writers
 #include <chrono>
 #include <cmath>
@@ -33,7 +35,7 @@
 static int usage() {
     fprintf(stderr,
             "usage: gseg [--variant felz|hier|superpix] [--conn 4|8] [--level L] [--labels FILE]\n"
-            "            [--synth WxH:SEED] [--iters N] [--device D] sigma k min_size input.{ppm,pgm,png,jpg} output.{ppm,png}\n"
+            "            [--synth WxH:SEED] [--iters N] [--device D] [--host-loop] [--tail E,V] sigma k min_size input.{ppm,pgm,png,jpg} output.{ppm,png}\n"
             "       gseg --convert input output\n");
     return 2;
 }
@@ -53,6 +55,7 @@ int main(int argc, char **argv) {
     p.connectivity = 8;
     p.variant = GSEG_FELZ;
     int level = -1, iters = 0, device = 0, sw = 0, sh = 0;
+    long long tail_e = -1, tail_v = -1;
     unsigned long long sseed = 0;
     const char *labels_path = nullptr;
     std::vector<const char *> pos;
@@ -73,6 +76,8 @@ int main(int argc, char **argv) {
         else if (a == "--labels") labels_path = need("--labels");
         else if (a == "--iters") iters = atoi(need("--iters"));
         else if (a == "--device") device = atoi(need("--device"));
+        else if (a == "--host-loop") p.flags |= GSEG_FLAG_HOST_LOOP;
+        else if (a == "--tail") { if (sscanf(need("--tail"), "%lld,%lld", &tail_e, &tail_v) != 2 || tail_e < 0 || tail_v < 0) return usage(); }
         else if (a == "--synth") {
             if (sscanf(need("--synth"), "%dx%d:%llu", &sw, &sh, &sseed) != 3 || sw < 1 || sh < 1) return usage();
         } else if (a.size() > 2 && a[0] == '-' && a[1] == '-') return usage();
@@ -102,6 +107,7 @@ int main(int argc, char **argv) {
     gseg_ctx *ctx = nullptr;
     int rc = gseg_create(&ctx, device, w, h);
     if (rc) { fprintf(stderr, "gseg: gseg_create: %s\n", gseg_strerror(rc)); return 1; }
+    if (tail_e >= 0) gseg_set_tail(ctx, (uint32_t)tail_e, (uint32_t)tail_v);
     if (!jpeg.empty()) { // first run straight from the compressed bytes; the decoded pixels come back for the timing loop
         rc = gseg_segment_jpeg(ctx, jpeg.data(), jpeg.size(), &p, &w, &h);
         if (rc) { fprintf(stderr, "gseg: gseg_segment_jpeg: %s (%s)\n", gseg_strerror(rc), gseg_last_error(ctx)); return 1; }

@@ -19,8 +19,10 @@ enum { DERR_NONE = 0, DERR_SCAN = 1, DERR_ARENA = 2, DERR_CHASE = 3 };
 
 // Parameters of one run; filled by the host in pinned memory and copied into GsegCtl::p.
 struct GsegRunParams {
-    const uint8_t *rgb; // device pointer of the input image
+    const uint8_t *rgb; // device pointer of the input image (strips: of its first halo row)
     int w, h, stride, D, variant;
+    int h_in, y_off;    // strips of a larger image: rows in the input buffer (halo included) and rows of halo above the strip;
+                        // the blur reads them instead of clamping at the strip's own edge (whole images: h_in = h, y_off = 0)
     float k;
     int min_size, max_rounds, max_levels;
     u32 arena_cap;  // capacity of the supervertex-map arena in u32 entries
@@ -52,6 +54,8 @@ struct GsegCtl {
     u32 ticketC, ticketE; // dynamic tile tickets of the two look-back scans
     u32 doneE;            // blocks that finished the edge phase (the last one advances the round state)
     u32 Eacc[GSEG_MAXR + 1]; // Eacc[r]: edges emitted by round r's edge phase (zeroed by the host; never reset on the device)
+    u32 map_skip[GSEG_MAXR + 1]; // 1: round r's map has been folded into an earlier one (arena compaction, FELZ only)
+    u32 resume_phase;            // phase the run continues with after the host compacted the arena (error == DERR_ARENA)
     // ---- end of host-initialised head ----
     u32 map_off[GSEG_MAXR + 1];
     u32 stV[GSEG_MAXR], stE[GSEG_MAXR], stM[GSEG_MAXR], stP[GSEG_MAXR], stVafter[GSEG_MAXR];

@@ -73,7 +73,7 @@ __global__ void __launch_bounds__(NT) k_blur_tile(const GsegCtl *__restrict__ ct
     uint8_t *sF = smem_raw;                                      // [3][IH][PF] input planes, still 8-bit (a quarter of
                                                                  // the fp32 staging: five blocks per SM instead of three)
     float *sH = reinterpret_cast<float *>(smem_raw + 3 * IH * PF); // [3][IH][PH] after the horizontal pass
-    const int w = ctl->p.w, h = ctl->p.h, stride = ctl->p.stride;
+    const int w = ctl->p.w, h = ctl->p.h, stride = ctl->p.stride, h_in = ctl->p.h_in, y_off = ctl->p.y_off;
     const uint8_t *__restrict__ rgb = ctl->p.rgb;
     float m[R + 1];
 #pragma unroll
@@ -86,7 +86,7 @@ __global__ void __launch_bounds__(NT) k_blur_tile(const GsegCtl *__restrict__ ct
     constexpr int G4 = (IW + 3) / 4;
     for (int item = threadIdx.x; item < IH * G4; item += NT) {
         const int r = item / G4, g = item - r * G4;
-        const int gy = min(max(y0 - R + r, 0), h - 1);
+        const int gy = min(max(y0 - R + r + y_off, 0), h_in - 1); // row of the input buffer (halo rows count)
         const uint8_t *row = rgb + (size_t)gy * stride;
         uint8_t *d0 = sF + r * PF + 4 * g;
         if (fast) {
@@ -153,7 +153,7 @@ __global__ void __launch_bounds__(NT) k_blur_tile(const GsegCtl *__restrict__ ct
 
 // general-sigma fallback (more than 8 one-sided taps)
 __global__ void __launch_bounds__(NT) k_blur_h(const GsegCtl *__restrict__ ctl, float *__restrict__ tmp) {
-    const int w = ctl->p.w, h = ctl->p.h, stride = ctl->p.stride, len = ctl->p.mask_len;
+    const int w = ctl->p.w, h = ctl->p.h_in, stride = ctl->p.stride, len = ctl->p.mask_len; // every row of the buffer, halo included
     const uint8_t *__restrict__ rgb = ctl->p.rgb;
     const float *m = ctl->p.mask;
     const u32 V = (u32)w * (u32)h;
@@ -174,16 +174,16 @@ __global__ void __launch_bounds__(NT) k_blur_h(const GsegCtl *__restrict__ ctl, 
 }
 __global__ void __launch_bounds__(NT) k_blur_v(const GsegCtl *__restrict__ ctl, const float *__restrict__ tmp,
                                                float *__restrict__ planes) {
-    const int w = ctl->p.w, h = ctl->p.h, len = ctl->p.mask_len;
+    const int w = ctl->p.w, h = ctl->p.h, len = ctl->p.mask_len, h_in = ctl->p.h_in, y_off = ctl->p.y_off;
     const float *m = ctl->p.mask;
-    const u32 V = (u32)w * (u32)h;
+    const u32 V = (u32)w * (u32)h, Vin = (u32)w * (u32)h_in;
     for (u32 t = blockIdx.x * NT + threadIdx.x; t < 3u * V; t += gridDim.x * NT) {
         const u32 c = t / V, p = t - c * V;
-        const int y = p / w, x = p - y * w;
-        const float *pl = tmp + (size_t)c * V;
-        float s = __fmul_rn(m[0], pl[p]);
+        const int y = p / w + y_off, x = p % w; // y: row in the input buffer
+        const float *pl = tmp + (size_t)c * Vin;
+        float s = __fmul_rn(m[0], pl[(size_t)y * w + x]);
         for (int i = 1; i < len; ++i) {
-            const int yu = max(y - i, 0), yd = min(y + i, h - 1);
+            const int yu = max(y - i, 0), yd = min(y + i, h_in - 1);
             const float pair = __fadd_rn(pl[(size_t)yu * w + x], pl[(size_t)yd * w + x]);
             s = __fadd_rn(s, __fmul_rn(m[i], pair));
         }
@@ -455,8 +455,15 @@ __device__ __forceinline__ void advance_state(GsegCtl *ctl, RoundState &st, u32 
     }
     const u32 next_off = st.map_off + V;
     if ((int)(r + 1) >= ctl->p.max_rounds) phase = PH_DONE;
+    // The next round's map does not fit the arena: stop here and leave the phase to continue with in the control
+    // block.  The host folds the stored maps of a FELZ run into one (only the final partition is needed) and
+    // resumes; hierarchy variants at least halve V every round, so their maps always fit.
     bool arena_err = false;
-    if (phase != PH_DONE && (u64)next_off + (u64)Vn > (u64)ctl->p.arena_cap) { arena_err = true; phase = PH_DONE; }
+    if (phase != PH_DONE && (u64)next_off + (u64)Vn > (u64)ctl->p.arena_cap) {
+        arena_err = true;
+        if (writer) ctl->resume_phase = phase;
+        phase = PH_DONE;
+    }
     if (writer) {
         ctl->stTail[r] = tail_flag; ctl->stPages[r] = st.P;
         ctl->stV[r] = V; ctl->stE[r] = st.E; ctl->stM[r] = merged; ctl->stP[r] = st.phase; ctl->stVafter[r] = Vn;
@@ -1183,16 +1190,128 @@ __global__ void __launch_bounds__(NT) k_graph_init(GsegBufs B, u32 E, u32 P) {
     }
 }
 
+// ---- tiled schedule on the device (BASELINE.json configs[4]; DESIGN.md "Tiled schedule") ---------------
+// Strip record (32-bit words, device memory): header[8] = {magic, nV, nE, w, 0...} | attr uint2[nV] (size, Int bits)
+// | eab uint2[nE] | ew u32[nE] | top_lab[w] | bot_lab[w] | top_col f32[3][w] | bot_col f32[3][w].
+#define GSEG_REC_MAGIC 0x47534731u
+#define GSEG_REC_HEAD 8u
+#define GSEG_MAX_STRIPS 64
+__host__ __device__ __forceinline__ size_t rec_words(size_t nV, size_t nE, size_t w) { return GSEG_REC_HEAD + 2 * nV + 3 * nE + 8 * w; }
+
+// header + first / last row of the strip's dense label image and of its blurred planes
+__global__ void __launch_bounds__(NT) k_record_rows(const int *__restrict__ labels, const float *__restrict__ planes, u32 w, u32 h,
+                                                    u32 nV, u32 nE, u32 *__restrict__ rec) {
+    const size_t V = (size_t)w * h;
+    u32 *top_lab = rec + GSEG_REC_HEAD + 2 * (size_t)nV + 3 * (size_t)nE, *bot_lab = top_lab + w;
+    float *top_col = reinterpret_cast<float *>(bot_lab + w), *bot_col = top_col + 3 * (size_t)w;
+    if (blockIdx.x == 0 && threadIdx.x < GSEG_REC_HEAD)
+        rec[threadIdx.x] = threadIdx.x == 0 ? GSEG_REC_MAGIC : threadIdx.x == 1 ? nV : threadIdx.x == 2 ? nE : threadIdx.x == 3 ? w : 0u;
+    for (u32 x = blockIdx.x * NT + threadIdx.x; x < w; x += gridDim.x * NT) {
+        top_lab[x] = (u32)labels[x];
+        bot_lab[x] = (u32)labels[(size_t)(h - 1) * w + x];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+            top_col[(size_t)c * w + x] = planes[c * V + x];
+            bot_col[(size_t)c * w + x] = planes[c * V + (size_t)(h - 1) * w + x];
+        }
+    }
+}
+
+struct JoinDesc {
+    u32 n_strips, w, conn, ncut; // ncut: cut edges per strip boundary (w, or w + 2 (w - 1) when 8-connected)
+    unsigned long long stride_words;   // distance between the gathered records
+    u32 voff[GSEG_MAX_STRIPS + 1];     // first joined component id of strip s
+    u32 ne[GSEG_MAX_STRIPS];           // edges of strip s
+    u32 eoff[GSEG_MAX_STRIPS + 1];     // list position of strip s's first own edge; its cut edges to s + 1 follow them
+};
+__device__ __forceinline__ float l2_rn(float a0, float a1, float a2, float b0, float b1, float b2) {
+    const float dr = __fsub_rn(a0, b0), dg = __fsub_rn(a1, b1), db = __fsub_rn(a2, b2);
+    return __fsqrt_rn(__fadd_rn(__fadd_rn(__fmul_rn(dr, dr), __fmul_rn(dg, dg)), __fmul_rn(db, db)));
+}
+// The join on the device: components renumbered strip by strip (id + voff[s]); list = strip 0's edges, the cut
+// edges 0|1 (S for x = 0..w-1, then SE, then NE; weight = L2 distance of the two blurred end pixels, same
+// operation order as k_r0_graph), strip 1's edges, ...  Writes the graph where k_graph_init expects it.
+__global__ void __launch_bounds__(NT) k_join(const __grid_constant__ JoinDesc jd, const u32 *__restrict__ recs, GsegBufs B) {
+    const u32 S = jd.n_strips, w = jd.w;
+    const u32 Vtot = jd.voff[S], Etot = jd.eoff[S];
+    for (size_t i = (size_t)blockIdx.x * NT + threadIdx.x; i < (size_t)Vtot + Etot; i += (size_t)gridDim.x * NT) {
+        if (i < Vtot) {
+            u32 s = 0;
+            while (s + 1 < S && jd.voff[s + 1] <= (u32)i) ++s;
+            const u32 *rec = recs + (size_t)s * jd.stride_words;
+            B.attr[1][i] = reinterpret_cast<const uint2 *>(rec + GSEG_REC_HEAD)[(u32)i - jd.voff[s]];
+            B.best[1][i] = GSEG_KEY_NONE;
+            continue;
+        }
+        const u32 j = (u32)(i - Vtot);
+        u32 s = 0;
+        while (s + 1 < S && jd.eoff[s + 1] <= j) ++s;
+        const u32 *rec = recs + (size_t)s * jd.stride_words;
+        const u32 nV = jd.voff[s + 1] - jd.voff[s], nE = jd.ne[s], k = j - jd.eoff[s];
+        if (k < nE) { // one of the strip's own edges
+            uint2 ab = reinterpret_cast<const uint2 *>(rec + GSEG_REC_HEAD + 2 * (size_t)nV)[k];
+            ab.x += jd.voff[s]; ab.y += jd.voff[s];
+            B.eab[1][j] = ab;
+            B.ew[1][j] = rec[GSEG_REC_HEAD + 2 * (size_t)nV + 2 * (size_t)nE + k];
+            continue;
+        }
+        // cut edge between strip s (its bottom row) and strip s + 1 (its top row)
+        const u32 *rec2 = recs + (size_t)(s + 1) * jd.stride_words;
+        const u32 nV2 = jd.voff[s + 2] - jd.voff[s + 1], nE2 = jd.ne[s + 1];
+        const u32 *bot_lab = rec + GSEG_REC_HEAD + 2 * (size_t)nV + 3 * (size_t)nE + w;
+        const float *bot_col = reinterpret_cast<const float *>(bot_lab + w) + 3 * (size_t)w;
+        const u32 *top_lab = rec2 + GSEG_REC_HEAD + 2 * (size_t)nV2 + 3 * (size_t)nE2;
+        const float *top_col = reinterpret_cast<const float *>(top_lab + 2 * (size_t)w);
+        const u32 c = k - nE;
+        u32 a, b, xa, xb;
+        bool a_is_bot = true;
+        if (c < w) { xa = c; xb = c; }                              // S
+        else if (c < 2 * w - 1) { xa = c - w; xb = xa + 1; }        // SE: (x, last row) -> (x + 1, first row)
+        else { xa = c - (2 * w - 1); xb = xa + 1; a_is_bot = false; } // NE: (x, first row of s + 1) -> (x + 1, last row of s)
+        float wv;
+        if (a_is_bot) {
+            a = bot_lab[xa] + jd.voff[s]; b = top_lab[xb] + jd.voff[s + 1];
+            wv = l2_rn(bot_col[xa], bot_col[w + xa], bot_col[2 * (size_t)w + xa], top_col[xb], top_col[w + xb], top_col[2 * (size_t)w + xb]);
+        } else {
+            a = top_lab[xa] + jd.voff[s + 1]; b = bot_lab[xb] + jd.voff[s];
+            wv = l2_rn(top_col[xa], top_col[w + xa], top_col[2 * (size_t)w + xa], bot_col[xb], bot_col[w + xb], bot_col[2 * (size_t)w + xb]);
+        }
+        B.eab[1][j] = make_uint2(a, b);
+        B.ew[1][j] = __float_as_uint(wv);
+    }
+}
+// final labels of a strip: joined-graph label of (strip-local dense id + the strip's id offset)
+template <typename OutT>
+__global__ void __launch_bounds__(NT) k_map_labels(const int *__restrict__ labels, const u32 *__restrict__ F, u32 off, size_t V,
+                                                   OutT *__restrict__ out) {
+    for (size_t p = (size_t)blockIdx.x * NT + threadIdx.x; p < V; p += (size_t)gridDim.x * NT) out[p] = (OutT)F[off + (u32)labels[p]];
+}
+
 // ------------------------------------------------------------------------------------------------
-// a12: hierarchy materialisation.  Level l = composition of the maps of rounds 0..l.
+// a12: hierarchy materialisation.  Level l = composition of the maps of rounds 0..l.  OutT: int32, or
+// uint16 / uint8 when the level has few enough components (the label image is most of what an end-to-end
+// run sends back over PCIe).  Rounds whose map the host folded into an earlier one (map_skip) are passed over.
 // ------------------------------------------------------------------------------------------------
+template <typename OutT>
 __global__ void __launch_bounds__(NT) k_compose(const GsegCtl *__restrict__ ctl, const u32 *__restrict__ arena,
-                                                int last_round, int *__restrict__ out) {
+                                                int last_round, OutT *__restrict__ out) {
     const u32 V0 = (u32)ctl->p.w * (u32)ctl->p.h;
     for (u32 p = blockIdx.x * NT + threadIdx.x; p < V0; p += gridDim.x * NT) {
         u32 l = arena[p];
-        for (int r = 1; r <= last_round; ++r) l = arena[ctl->map_off[r] + l];
-        out[p] = (int)l;
+        for (int r = 1; r <= last_round; ++r)
+            if (!ctl->map_skip[r]) l = arena[ctl->map_off[r] + l];
+        out[p] = (OutT)l;
+    }
+}
+// Arena compaction (FELZ): rounds 0..last folded into round 0's map in place.  A pixel's chase reads its own
+// round-0 entry and entries of later maps only, so overwriting the round-0 entries as we go is safe.
+__global__ void __launch_bounds__(NT) k_compose_inplace(const GsegCtl *ctl, u32 *arena, int last_round) {
+    const u32 V0 = (u32)ctl->p.w * (u32)ctl->p.h;
+    for (u32 p = blockIdx.x * NT + threadIdx.x; p < V0; p += gridDim.x * NT) {
+        u32 l = arena[p];
+        for (int r = 1; r <= last_round; ++r)
+            if (!ctl->map_skip[r]) l = arena[ctl->map_off[r] + l];
+        arena[p] = l;
     }
 }
 // Two-step form for deep hierarchies: the maps of rounds first..last act on few components, so they are
@@ -1201,18 +1320,21 @@ __global__ void __launch_bounds__(NT) k_compose_table(const GsegCtl *__restrict_
                                                       int first, int last, u32 n, u32 *__restrict__ F) {
     for (u32 c = blockIdx.x * NT + threadIdx.x; c < n; c += gridDim.x * NT) {
         u32 l = c;
-        for (int r = first; r <= last; ++r) l = arena[ctl->map_off[r] + l];
+        for (int r = first; r <= last; ++r)
+            if (!ctl->map_skip[r]) l = arena[ctl->map_off[r] + l];
         F[c] = l;
     }
 }
 // ... and every pixel chases only the early rounds 0..first-1 and then looks its label up in F.
+template <typename OutT>
 __global__ void __launch_bounds__(NT) k_compose_px(const GsegCtl *__restrict__ ctl, const u32 *__restrict__ arena,
-                                                   int first, const u32 *__restrict__ F, int *__restrict__ out) {
+                                                   int first, const u32 *__restrict__ F, OutT *__restrict__ out) {
     const u32 V0 = (u32)ctl->p.w * (u32)ctl->p.h;
     for (u32 p = blockIdx.x * NT + threadIdx.x; p < V0; p += gridDim.x * NT) {
         u32 l = arena[p];
-        for (int r = 1; r < first; ++r) l = arena[ctl->map_off[r] + l];
-        out[p] = (int)F[l];
+        for (int r = 1; r < first; ++r)
+            if (!ctl->map_skip[r]) l = arena[ctl->map_off[r] + l];
+        out[p] = (OutT)F[l];
     }
 }
 // one more level from the previous one (all-levels output: V reads + V writes per level)
@@ -1245,10 +1367,12 @@ __global__ void __launch_bounds__(NT) k_colorize(const int *__restrict__ labels,
 }
 
 // Synthetic input generator; integer arithmetic only.
-__global__ void __launch_bounds__(NT) k_synth(uint8_t *__restrict__ rgb, int w, int h, u64 seed) {
-    const u32 V = (u32)w * (u32)h;
-    for (u32 p = blockIdx.x * NT + threadIdx.x; p < V; p += gridDim.x * NT) {
-        const int y = p / w, x = p - y * w;
+// Rows [y_first, y_first + h) of the image of width w (a pixel depends on its coordinates and the seed only, so a
+// strip of a larger image can be generated on its own).
+__global__ void __launch_bounds__(NT) k_synth(uint8_t *__restrict__ rgb, int w, int h, u64 seed, int y_first) {
+    const size_t V = (size_t)w * (size_t)h;
+    for (size_t p = (size_t)blockIdx.x * NT + threadIdx.x; p < V; p += (size_t)gridDim.x * NT) {
+        const int y = (int)(p / (size_t)w) + y_first, x = (int)(p % (size_t)w);
         const int cx = x >> 6, cy = y >> 6;
         long long bestd = 0x7FFFFFFFFFFFFFFFll;
         u64 besth = 0;
@@ -1266,7 +1390,7 @@ __global__ void __launch_bounds__(NT) k_synth(uint8_t *__restrict__ rgb, int w, 
         for (int c = 0; c < 3; ++c) {
             const int base = (int)((besth >> (16 + 8 * c)) & 255);
             const int n = (int)(((hn >> (16 * c)) & 0xFFFF) % 17) - 8;
-            rgb[3 * (size_t)p + c] = (uint8_t)min(max(base + n, 0), 255);
+            rgb[3 * p + c] = (uint8_t)min(max(base + n, 0), 255);
         }
     }
 }

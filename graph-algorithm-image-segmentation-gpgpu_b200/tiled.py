@@ -2,9 +2,18 @@
 north_star: "only the gigapixel single-image case is tiled, with cross-tile boundary edges exchanged
 over NVLink via NCCL before the final Boruvka rounds").  Host-side logic only: no compute, no fallback.
 
+Two drivers of the same schedule:
+  segment_tiled_device  the product path: strip + halo rows on the GPU, strip record written by the engine into
+                        device memory, all-gather of device buffers (NCCL over NVLink, no host bounce), join +
+                        joined rounds + final relabel on the device (gseg_strip_record / gseg_join_segment);
+  segment_tiled         the same steps with the join done in numpy on host arrays: the executable specification the
+                        CPU tests run over gloo with the oracle standing in for the engine.
+
 Semantics (restated by the oracle in tests/tiled_ref.py; DESIGN.md "Tiled schedule"):
-  phase 1  every strip is segmented as an image of its own (blur with clamped borders at the strip's
-           edges, Boruvka-Felzenszwalb to completion) -- no communication;
+  phase 1  every strip is segmented on its own (Boruvka-Felzenszwalb to completion) -- no communication.  The
+           strip is blurred with ceil(4 sigma) halo rows of the neighbouring strips (device driver; the host
+           driver's stand-in takes the strip's rows of the whole image's blur), so its blurred pixels and all edge
+           weights, cut edges included, are those of the untiled image;
   exchange every rank contributes its final component graph (sizes, Int(C), live inter-component edges in
            list order) and the blurred colours + labels of its first and last row; all-gather over NCCL;
   phase 2  the strips' graphs are joined: components renumbered strip by strip; edge list = strip 0's
@@ -12,8 +21,8 @@ Semantics (restated by the oracle in tests/tiled_ref.py; DESIGN.md "Tiled schedu
            the L2 colour distance of its two blurred end pixels; cut edges of one boundary are ordered
            S (x = 0..w-1), then SE, then NE (8-connected only).  The same rounds (predicate, then min-size)
            run on the joined graph; list position is the tie-break.
-The result differs from an untiled run of the same image (the strips' blurs and early rounds do not
-see each other); it is exact with respect to the tiled oracle.
+The graph is the untiled image's graph; the partition still differs from an untiled run (a strip's rounds run
+to completion before they see the neighbour strips' components) and is exact with respect to the tiled oracle.
 """
 import numpy as np
 
@@ -117,6 +126,79 @@ def exchange(rec, dist, device="cpu"):
     dist.all_gather(gi, ti)      # the boundary-edge exchange: NCCL over NVLink on the GPU box, gloo in CPU tests
     dist.all_gather(gf, tf)
     return [_unpack(gi[r].cpu().numpy()[:int(all_lens[r][0])], gf[r].cpu().numpy()[:int(all_lens[r][1])]) for r in range(world)]
+
+
+def halo_rows(sigma):
+    """Rows of halo a strip needs on every side that has a neighbour: the blur's half width ceil(4 sigma)."""
+    import math
+    return int(math.ceil(max(float(np.float32(sigma)), 0.01) * 4.0))
+
+
+def strip_with_halo(h, n_strips, i, sigma):
+    """(y0, y1, halo_top, halo_bottom) of strip i: its rows [y0, y1) and the halo rows that exist around them."""
+    y0, y1 = strip_rows(h, n_strips)[i]
+    r = halo_rows(sigma)
+    return y0, y1, min(r, y0), min(r, h - y1)
+
+
+class DeviceTiler:
+    """The tiled schedule on the device for one rank's strip (see module docstring).  Buffers are kept across calls."""
+
+    def __init__(self, seg, dist=None):
+        import torch
+        self.seg, self.torch = seg, torch
+        self.dist = dist if dist is not None and dist.is_initialized() and dist.get_world_size() > 1 else None
+        self.rank = self.dist.get_rank() if self.dist else 0
+        self.world = self.dist.get_world_size() if self.dist else 1
+        self.send = self.recv = None
+        self.sizes = torch.zeros(1, dtype=torch.int64, device="cuda")
+        self.times = {}
+        # one stream for the engine's kernels and the collective, so that they are ordered without host round trips
+        # (torch's default stream has handle 0, which gseg_set_stream reads as "the context's own stream")
+        self.stream = torch.cuda.Stream()
+        seg.set_stream(self.stream.cuda_stream)
+
+    def run(self, buf, halo_top, halo_bottom, out=None, **params):
+        """buf: (halo_top + hs + halo_bottom, w, 3) uint8 CUDA tensor; out: (hs, w) CUDA tensor (int32 / int16-as-
+        uint16 / uint8) or pinned host array for the strip's final labels.  Returns (n_final, n_joined, e_joined)."""
+        with self.torch.cuda.stream(self.stream):
+            return self._run(buf, halo_top, halo_bottom, out, params)
+
+    def _run(self, buf, halo_top, halo_bottom, out, params):
+        import time
+        torch, seg, T = self.torch, self.seg, self.times
+        t0 = time.perf_counter()
+        seg.segment_strip(buf, halo_top, halo_bottom, **params)
+        T["phase1"] = time.perf_counter() - t0
+        t1 = time.perf_counter()
+        nbytes = seg.strip_record_bytes()               # export + duplicate elimination happen here
+        T["export"] = time.perf_counter() - t1
+        t1 = time.perf_counter()
+        stride = nbytes
+        if self.dist:
+            self.sizes[0] = nbytes
+            self.dist.all_reduce(self.sizes, op=self.dist.ReduceOp.MAX)
+            stride = int(self.sizes.item())
+        stride = (stride + 255) & ~255
+        if self.send is None or self.send.numel() < stride:
+            self.send = torch.empty(stride * 2, dtype=torch.uint8, device="cuda")
+            self.recv = torch.empty(stride * 2 * self.world, dtype=torch.uint8, device="cuda")
+        send = self.send[:stride]
+        seg.strip_record(send.data_ptr(), stride)
+        if self.dist:
+            recv = self.recv[:stride * self.world]
+            self.dist.all_gather_into_tensor(recv, send)   # the boundary exchange: device buffers over NVLink
+            torch.cuda.current_stream().synchronize()
+        else:
+            recv = send
+        T["exchange"] = time.perf_counter() - t1
+        T["exchange_bytes"] = stride * self.world
+        t1 = time.perf_counter()
+        p = {k: v for k, v in params.items() if k in ("k", "min_size", "connectivity", "variant", "max_rounds", "max_levels", "flags")}
+        res = seg.join_segment(recv.data_ptr(), self.world, stride, self.rank, out=out, sigma=params.get("sigma", 0.8), **p)
+        T["join_phase2"] = time.perf_counter() - t1
+        T["total"] = time.perf_counter() - t0
+        return res
 
 
 def segment_tiled(strip_img, segment_strip, segment_graph, conn, dist=None, device="cpu"):

@@ -13,7 +13,10 @@
  *
  * Conventions: plain pointers and sizes only; 0 = success, negative = gseg_status; nothing throws
  * across the boundary; the caller owns every input/output buffer, the context owns all device
- * scratch (allocated once in gseg_create, never inside gseg_segment); one context per GPU per host
+ * scratch.  gseg_create allocates everything the FELZ / HIER paths with sigma <= 2 need; the buffers
+ * only some paths use (superpixel colour sums, the wide-sigma blur plane, the second label staging
+ * buffer) are allocated by gseg_reserve, or on the first call that needs them when gseg_reserve was
+ * not called -- after that nothing allocates inside gseg_segment.  One context per GPU per host
  * thread, contexts are independent and not thread-safe.  There is no CPU fallback: every entry
  * point that computes requires a CUDA device and fails with GSEG_E_CUDA otherwise.
  */
@@ -27,7 +30,7 @@
 extern "C" {
 #endif
 
-#define GSEG_VERSION 100
+#define GSEG_VERSION 200
 
 /* variant -- which reference branch's semantics to run */
 #define GSEG_FELZ 0     /* cuda-mst-naive: Boruvka + Felzenszwalb predicate + min-size (Report p2-3 s3.1) */
@@ -53,7 +56,8 @@ typedef enum gseg_status {
     GSEG_E_INTERNAL = -5, /* device-side watchdog tripped */
     GSEG_E_STATE = -6,   /* result requested before a successful gseg_segment */
     GSEG_E_LEVEL = -7,   /* hierarchy level out of range */
-    GSEG_E_UNSUPPORTED = -8 /* optional dependency missing at run time (nvJPEG for gseg_segment_jpeg) */
+    GSEG_E_UNSUPPORTED = -8, /* optional dependency missing at run time (nvJPEG for gseg_segment_jpeg) */
+    GSEG_E_RANGE = -9    /* label element type too narrow for the number of components / output buffer too small */
 } gseg_status;
 
 /* Parameters of one segmentation (BASELINE.json north_star: sigma, k, min_size, hierarchy level). */
@@ -95,8 +99,21 @@ int gseg_create(gseg_ctx **out, int device, int max_w, int max_h);
 int gseg_create_ex(gseg_ctx **out, int device, int max_w, int max_h, int max_connectivity);
 void gseg_destroy(gseg_ctx *ctx);
 
+/* Optional buffers, allocated up front instead of on first use (an allocation synchronises the whole
+ * device and stalls the other contexts of a pool): caps = OR of GSEG_CAP_*. */
+#define GSEG_CAP_SUPERPIX 1u   /* colour sums + means + Sobel plane of the superpixel variant */
+#define GSEG_CAP_WIDE_SIGMA 2u /* intermediate plane of the general blur (more than 8 one-sided taps) */
+#define GSEG_CAP_LEVELS 4u     /* second staging buffer of gseg_labels_all / gseg_colorize to host memory */
+int gseg_reserve(gseg_ctx *ctx, uint32_t caps);
+
+/* Pinned host memory for inputs/outputs of the asynchronous calls (cudaHostAlloc behind a plain pointer, so a
+ * C/C++ caller needs no CUDA headers). */
+void *gseg_host_alloc(size_t bytes);
+void gseg_host_free(void *p);
+
 /* Run the context's work on a caller-owned CUDA stream (cudaStream_t as void*); NULL = own stream. */
 int gseg_set_stream(gseg_ctx *ctx, void *cuda_stream);
+void *gseg_get_stream(const gseg_ctx *ctx); /* the cudaStream_t the context's work is enqueued on */
 
 /* Scheduling knob (no effect on results): a Boruvka round whose graph has at most max_edges live edges
  * and max_components components runs inside the single-cluster tail kernel instead of grid-wide
@@ -134,6 +151,22 @@ int gseg_labels(gseg_ctx *ctx, int level, int32_t *out, int mem_kind);
 int gseg_labels_async(gseg_ctx *ctx, int level, int32_t *out, int mem_kind);
 int gseg_sync(gseg_ctx *ctx);
 
+/* The same label image in a narrower element type: elem_bytes = 4 (int32), 2 (uint16) or 1 (uint8).  Lossless:
+ * GSEG_E_RANGE when gseg_num_components(level) does not fit the type.  gseg_label_bytes returns the narrowest
+ * of 1, 2, 4 that holds `level`.  A 1080p FELZ partition has ~10^2 components: its label image leaves the GPU
+ * in 2 MB instead of 8 (the device->host copy is the larger half of an end-to-end run's PCIe bytes). */
+int gseg_label_bytes(const gseg_ctx *ctx, int level);
+int gseg_labels_ex(gseg_ctx *ctx, int level, void *out, int elem_bytes, int mem_kind);
+int gseg_labels_ex_async(gseg_ctx *ctx, int level, void *out, int elem_bytes, int mem_kind);
+
+/* The hierarchy in its stored form -- the per-round supervertex ids the reference keeps and materialises on
+ * demand (Report p4 s3.2.3 par.1): out[offsets[l] + i] = id at level l of component i of level l-1 (level -1 =
+ * pixels, so the first w*h entries are the level-0 label image); offsets[n_levels] = entries written.  Returns
+ * n_levels (HIER / SUPERPIX; FELZ: 1 level = the final label image).  GSEG_E_RANGE when cap_entries or
+ * cap_offsets (needs n_levels + 1) is too small; call with out = NULL to get the sizes. */
+int gseg_hierarchy(gseg_ctx *ctx, uint32_t *out, int64_t cap_entries, int64_t *offsets, int cap_offsets, int mem_kind);
+int gseg_hierarchy_async(gseg_ctx *ctx, uint32_t *out, int64_t cap_entries, int64_t *offsets, int cap_offsets, int mem_kind);
+
 /* All levels 0..n-1 in one pass (level l at out + l*w*h); n = min(max_levels, gseg_num_levels). */
 int gseg_labels_all(gseg_ctx *ctx, int32_t *out, int max_levels, int mem_kind);
 
@@ -168,6 +201,29 @@ int gseg_segment_graph(gseg_ctx *ctx, int64_t n_components, const uint32_t *size
                        const uint32_t *ea, const uint32_t *eb, const float *w, const gseg_params *params,
                        int32_t *labels_out);
 
+/* ---- tiled schedule, device side (no host bounce: the exchange is an all-gather of device buffers) ----------
+ * gseg_segment_strip_async: one horizontal strip of a larger image.  `rgb` points at the first row of a buffer
+ *   holding halo_top rows above the strip, the strip's h rows, and halo_bottom rows below it; with halo >=
+ *   ceil(4 sigma) rows on every side that has a neighbour strip, the strip's blurred pixels and hence all of
+ *   its edge weights (and the cut edges') are bit-identical to the untiled image's (SURVEY.md section 8e
+ *   "4-row input halo").  The graph covers the strip's h rows only.  FELZ / HIER.
+ * gseg_strip_record: what a strip contributes to the exchange, written to DEVICE memory as 32-bit words:
+ *   header[8] = {magic, nV, nE, w, 0, 0, 0, 0} | (size, Int bits)[nV] | (a, b)[nE] | weight bits[nE] |
+ *   labels of the first row [w] | of the last row [w] | blurred colours of the first row [3][w] | last row [3][w].
+ *   dev_out = NULL: only *bytes is set.  Keeps the strip's dense label image in the context.
+ * gseg_join_segment: `dev_records` = n_strips records (strip order = top to bottom) at a distance of
+ *   record_stride_bytes (the output of an all-gather of equal-size buffers).  Joins them on the device --
+ *   components renumbered strip by strip; list = strip 0's edges, cut edges 0|1 (S, then SE, NE; weights from the
+ *   two blurred boundary rows), strip 1's edges, ... -- runs the rounds of params->variant on the joined graph and
+ *   writes the final label image of strip `my_strip` (image-global dense ids; elem_bytes 1/2/4 as in
+ *   gseg_labels_ex; labels_out may be NULL).  Returns the number of final components. */
+int gseg_segment_strip_async(gseg_ctx *ctx, const uint8_t *rgb, int w, int h, int stride_bytes, int mem_kind, int halo_top,
+                             int halo_bottom, const gseg_params *params);
+int gseg_strip_record(gseg_ctx *ctx, int dedup, void *dev_out, int64_t cap_bytes, int64_t *bytes);
+int gseg_join_segment(gseg_ctx *ctx, const void *dev_records, int n_strips, int64_t record_stride_bytes, int my_strip,
+                      const gseg_params *params, void *labels_out, int elem_bytes, int mem_kind, int64_t *n_joined_components,
+                      int64_t *n_joined_edges);
+
 /* ---- JPEG input decoded on the GPU --------------------------------------
  * The reference's batch benchmark reads a JPEG data set through cv::imread on the host (README.md:26).
  * Here the compressed bytes go to the GPU: nvJPEG (CUDA toolkit library, loaded with dlopen on first
@@ -189,6 +245,9 @@ int gseg_stats(const gseg_ctx *ctx, gseg_round_stat *out, int cap);
 
 /* Deterministic synthetic input: w*h*3 bytes into host or device memory. */
 int gseg_synth(gseg_ctx *ctx, uint8_t *out_rgb, int w, int h, uint64_t seed, int mem_kind);
+/* Rows [y_first, y_first + nrows) of the synthetic image of width w and the same seed (a pixel depends on its
+ * coordinates and the seed only): strips of the gigapixel image are generated where they are segmented. */
+int gseg_synth_rows(gseg_ctx *ctx, uint8_t *out_rgb, int w, int y_first, int nrows, uint64_t seed, int mem_kind);
 
 /* Measurement support (SURVEY.md section 5 "tracing"; section 8d): with profiling on, the host-driven
  * schedule brackets every kernel with CUDA events on the context's stream. */
@@ -196,12 +255,64 @@ typedef struct gseg_kernel_time {
     char name[24];
     int32_t round;
     float ms;
-    double algo_bytes; /* algorithmic bytes of this launch (DESIGN.md "Kernels") */
+    double algo_bytes;   /* algorithmic bytes of this launch: SURVEY.md section 8(d) accounting -- every input array read
+                            once, every output written once, gathers at element size, one 8-byte minimum per component
+                            (not per atomic) -- see DESIGN.md "Kernels" */
+    double strict_bytes; /* the same with every gathered array counted once however often it is gathered */
 } gseg_kernel_time;
 int gseg_set_profiling(gseg_ctx *ctx, int on);
 int gseg_profile_read(gseg_ctx *ctx, gseg_kernel_time *out, int cap);
 /* Kernels launched by this context since creation (graph replays count their kernel nodes). */
 long long gseg_launch_count(const gseg_ctx *ctx);
+/* Arena compactions since creation (FELZ runs whose per-round maps outgrew the arena were folded and resumed). */
+long long gseg_compaction_count(const gseg_ctx *ctx);
+
+/* ---- batch pipeline (the reference's loop over the images of its performance data set, Report.pdf p4 s4.1;
+ * README.md:26-28) ---------------------------------------------------------------------------------------
+ * A pool owns n_contexts contexts (one CUDA stream each) on one GPU and keeps them in flight: job t runs on
+ * context t mod n_contexts, a context gets its next job as soon as its previous one is complete, the output
+ * copy of a job is ordered before the next job of its context, and results come back in submission order.
+ * Inputs and outputs of asynchronous copies should be pinned (gseg_host_alloc); an input must stay valid until
+ * the job's result has been returned.  Not thread-safe: call a pool from one host thread.
+ *   gseg_pool_submit  enqueue one job (may first wait for the previous job of the same context)
+ *   gseg_pool_next    the oldest job's result, its output complete in job.out (GSEG_E_STATE: nothing in flight)
+ *   gseg_pool_run     a whole batch: n submits, n results (results[i] belongs to jobs[i])
+ *   gseg_pool_copy_ceiling  the batch's host<->device copies alone (same buffers, bytes and streams, no
+ *                     kernels), ms per batch: what the box's PCIe / host memory allows for this batch */
+#define GSEG_OUT_NONE 0      /* nothing leaves the context (results stay there until its next job) */
+#define GSEG_OUT_LABELS 1    /* label image of `level`; elem_bytes 0 = the narrowest lossless type, else 1 / 2 / 4 */
+#define GSEG_OUT_HIERARCHY 2 /* the stored hierarchy (gseg_hierarchy): level-0 labels + one map per further level */
+#define GSEG_POOL_MAXLEVELS 64
+typedef struct gseg_pool gseg_pool;
+typedef struct gseg_pool_job {
+    const void *input;    /* interleaved 8-bit RGB, or a JPEG file's bytes when jpeg_bytes != 0 */
+    size_t jpeg_bytes;
+    int32_t w, h, stride_bytes /* 0 = 3*w */, mem_kind;
+    gseg_params params;
+    int32_t out_mode, level, elem_bytes, out_mem_kind;
+    void *out;
+    size_t out_capacity;  /* bytes */
+    void *user;           /* returned with the result */
+} gseg_pool_job;
+typedef struct gseg_pool_result {
+    int64_t ticket;       /* submission index */
+    int32_t status;       /* gseg_status of the job */
+    int32_t w, h, n_levels, n_components /* at job.level */, elem_bytes;
+    int64_t out_bytes;    /* bytes written to job.out */
+    int64_t offsets[GSEG_POOL_MAXLEVELS + 1]; /* GSEG_OUT_HIERARCHY: gseg_hierarchy's offsets */
+    void *out, *user;
+} gseg_pool_result;
+int gseg_pool_create(gseg_pool **out, int device, int max_w, int max_h, int max_connectivity, int n_contexts, uint32_t caps);
+void gseg_pool_destroy(gseg_pool *pool);
+int gseg_pool_contexts(const gseg_pool *pool);
+gseg_ctx *gseg_pool_context(gseg_pool *pool, int i);
+int gseg_pool_pending(const gseg_pool *pool);
+const char *gseg_pool_last_error(const gseg_pool *pool);
+int gseg_pool_submit(gseg_pool *pool, const gseg_pool_job *job, int64_t *ticket);
+int gseg_pool_next(gseg_pool *pool, gseg_pool_result *out);
+int gseg_pool_run(gseg_pool *pool, const gseg_pool_job *jobs, int n, gseg_pool_result *results);
+int gseg_pool_copy_ceiling(gseg_pool *pool, const gseg_pool_job *jobs, const gseg_pool_result *results, int n, int reps,
+                           double *ms_per_batch);
 
 /* Stand-alone primitives of the edge-dedup path (Report p3 s3.2.2
  * "sort"): in-house onesweep radix sort of 64-bit keys with 32-bit payload, on device memory. */

@@ -23,7 +23,7 @@ def test_header_symbols_exported(gseg):
 
 def test_version_and_strerror(gseg):
     L = gseg.load()
-    assert L.gseg_version() == 100
+    assert L.gseg_version() == 200
     assert L.gseg_strerror(0) == b"ok"
     assert b"no CPU fallback" in L.gseg_strerror(-2)
 

@@ -435,10 +435,10 @@ def test_context_pool_takes_jpeg_bytes(gseg, oracle):
 
 
 # ---- tiled schedule: graph export / import and the joined rounds ------------------------------------------------
-def _gpu_strip(seg, img, sigma, k, ms, conn):
-    seg.segment(img, sigma=sigma, k=k, min_size=ms, connectivity=conn, variant=0)
+def _gpu_strip(seg, img, sigma, k, ms, conn, halo_top=0, halo_bottom=0):
+    seg.segment_strip(img, halo_top, halo_bottom, sigma=sigma, k=k, min_size=ms, connectivity=conn, variant=0)
     lab = seg.labels()
-    return lab, seg.export_graph(), seg.blurred_rows(0)[:, 0, :], seg.blurred_rows(img.shape[0] - 1)[:, 0, :]
+    return lab, seg.export_graph(), seg.blurred_rows(0)[:, 0, :], seg.blurred_rows(lab.shape[0] - 1)[:, 0, :]
 
 
 @pytest.mark.parametrize("flags", [0, 1])
@@ -488,8 +488,9 @@ def test_tiled_schedule_matches_tiled_oracle(gseg, oracle, seg, n_strips, conn):
     tiled = importlib.import_module(gseg.__name__ + ".tiled")
     img = oracle.synth(400, 300, 50 + n_strips)
     recs, labs = [], []
-    for (y0, y1) in tiled.strip_rows(300, n_strips):
-        lab, g, top, bot = _gpu_strip(seg, np.ascontiguousarray(img[y0:y1]), 0.8, 300.0, 20, conn)
+    for i in range(n_strips):
+        y0, y1, ht, hb = tiled.strip_with_halo(300, n_strips, i, 0.8)
+        lab, g, top, bot = _gpu_strip(seg, np.ascontiguousarray(img[y0 - ht:y1 + hb]), 0.8, 300.0, 20, conn, ht, hb)
         labs.append(lab)
         recs.append(tiled.strip_record(lab, g, top, bot))
     joined = tiled.join_strips(recs, conn)

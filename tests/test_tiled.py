@@ -56,6 +56,21 @@ def test_record_pack_roundtrip(oracle):
         assert np.array_equal(a.astype(np.float64), b.astype(np.float64)), key
 
 
+def test_halo_geometry_and_blur_equivalence(oracle):
+    """A strip blurred with ceil(4 sigma) halo rows has exactly the untiled image's blurred pixels."""
+    t = importlib.import_module(PKG + ".tiled")
+    assert t.halo_rows(0.8) == 4 and t.halo_rows(0.5) == 2 and t.halo_rows(2.0) == 8
+    assert t.strip_with_halo(100, 4, 0, 0.8) == (0, 25, 0, 4)
+    assert t.strip_with_halo(100, 4, 3, 0.8) == (75, 100, 4, 0)
+    assert t.strip_with_halo(6, 3, 1, 0.8) == (2, 4, 2, 2)   # halo clipped to the rows that exist
+    img = oracle.synth(64, 90, 3)
+    whole = oracle.blur(img, 0.8)
+    for i in range(3):
+        y0, y1, ht, hb = t.strip_with_halo(90, 3, i, 0.8)
+        part = oracle.blur(np.ascontiguousarray(img[y0 - ht:y1 + hb]), 0.8)[:, ht:ht + (y1 - y0), :]
+        assert np.array_equal(part.view(np.uint32), whole[:, y0:y1, :].view(np.uint32))
+
+
 def test_tiled_oracle_sanity(oracle):
     from tests.tiled_ref import oracle_tiled
     img = oracle.synth(200, 160, 9)
@@ -76,16 +91,16 @@ def _worker(rank, world, port, q):
     from oracle import oracle as O
     from tests.tiled_ref import oracle_strip
     img = O.synth(150, 120, 31)
-    y0, y1 = t.strip_rows(120, world)[rank]
+    y0, y1, ht, hb = t.strip_with_halo(120, world, rank, 0.8)
 
-    def seg_strip(strip):
-        return oracle_strip(O, strip, 0.8, 300.0, 20, 8)
+    def seg_strip(buf):
+        return oracle_strip(O, buf, 0.8, 300.0, 20, 8, halo_top=ht, halo_bottom=hb)
 
     def seg_graph(size, Int, ea, eb, w):
         lab, n, _ = O.boruvka_graph(size, Int, ea, eb, w, O.FELZ, 300.0, 20, 48)
         return lab, n
 
-    lab, n = t.segment_tiled(np.ascontiguousarray(img[y0:y1]), seg_strip, seg_graph, 8, dist)
+    lab, n = t.segment_tiled(np.ascontiguousarray(img[y0 - ht:y1 + hb]), seg_strip, seg_graph, 8, dist)
     q.put((rank, lab, n))
     dist.barrier()
     dist.destroy_process_group()

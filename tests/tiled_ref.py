@@ -22,10 +22,12 @@ def dedup_edges(ea, eb, w):
     return ea[keep].astype(np.uint32), eb[keep].astype(np.uint32), w[keep]
 
 
-def oracle_strip(O, img, sigma, k, min_size, conn, max_rounds=48, dedup=True):
-    """(dense labels, graph, top colours, bottom colours) of one strip, from the CPU oracle."""
-    h, w, _ = img.shape
-    planes = O.blur(img, sigma)
+def oracle_strip(O, img, sigma, k, min_size, conn, max_rounds=48, dedup=True, halo_top=0, halo_bottom=0):
+    """(dense labels, graph, top colours, bottom colours) of one strip, from the CPU oracle.  img holds halo_top rows
+    above and halo_bottom rows below the strip: they take part in the blur only."""
+    hin, w, _ = img.shape
+    h = hin - halo_top - halo_bottom
+    planes = np.ascontiguousarray(O.blur(img, sigma)[:, halo_top:halo_top + h, :])
     wts, _ = O.edges(planes, conn)
     r = O.boruvka(wts, w, h, conn, O.FELZ, k, min_size, max_rounds, planes, 0, want_int=True)
     rep = r["labels"].reshape(-1)
@@ -59,8 +61,10 @@ def oracle_tiled(O, img, n_strips, sigma, k, min_size, conn, max_rounds=48):
     tiled = importlib.import_module(PKG + ".tiled")
     h = img.shape[0]
     recs, labs = [], []
-    for (y0, y1) in tiled.strip_rows(h, n_strips):
-        lab, graph, top, bot = oracle_strip(O, np.ascontiguousarray(img[y0:y1]), sigma, k, min_size, conn, max_rounds)
+    for i in range(n_strips):
+        y0, y1, ht, hb = tiled.strip_with_halo(h, n_strips, i, sigma)
+        lab, graph, top, bot = oracle_strip(O, np.ascontiguousarray(img[y0 - ht:y1 + hb]), sigma, k, min_size, conn, max_rounds,
+                                            halo_top=ht, halo_bottom=hb)
         labs.append(lab)
         recs.append(tiled.strip_record(lab, graph, top, bot))
     joined = tiled.join_strips(recs, conn)
