@@ -114,7 +114,7 @@ def test_pool_c_abi_pipeline(gseg, oracle):
                           sigma=0.8, k=0.0, min_size=0, connectivity=4, variant=gseg.SUPERPIX)
         res3 = pool.run(jobs3)
         for i in (0, n - 1):
-            ref = oracle.pipeline(imgs[i].numpy(), 0.8, 0.0, 0, 4, oracle.SUPERPIX)
+            ref = oracle.pipeline(imgs[i].numpy(), 0.8, 0.0, 0, 4, oracle.SUPERPIX, max_levels=64)
             r = res3[i]
             assert r.status == 0 and r.n_levels == ref["nlevels"] and r.n_components == ref["ncomp"][3]
             ent = hout[i].numpy().view(np.uint32)
@@ -160,7 +160,7 @@ def test_arena_compaction_and_exhaustion(gseg, oracle, monkeypatch):
                 assert len(g["size"]) == s.num_components() and int(g["size"].sum()) == w * h
             # hierarchy variants at least halve V per round: they never need the compaction
             s.segment(noise, sigma=0.0, k=0.0, min_size=0, connectivity=8, variant=1)
-            ref = oracle.pipeline(noise, 0.0, 0.0, 0, 8, 1)
+            ref = oracle.pipeline(noise, 0.0, 0.0, 0, 8, 1, max_levels=64)
             assert s.num_levels() == ref["nlevels"] and same_partition(oracle, s.labels(), ref["labels"])
         finally:
             s.close()
