@@ -170,8 +170,10 @@ def test_arena_compaction_and_exhaustion(gseg, oracle, monkeypatch):
         with pytest.raises(gseg.GsegError) as e:
             s.segment(noise, sigma=0.0, k=0.0, min_size=20, connectivity=4, variant=0)
         assert "arena" in str(e.value)
-        s.segment(smooth, sigma=0.8, k=5000.0, min_size=0, connectivity=4, variant=0)   # the context stays usable
-        assert s.num_components() >= 1
+        small = oracle.synth(40, 30, 8)                            # the context stays usable (a small image fits any arena)
+        s.segment(small, sigma=0.8, k=300.0, min_size=20, connectivity=4, variant=0)
+        ref, n = oracle.segment(small, 0.8, 300.0, 20, 4, 0, max_rounds=48)
+        assert s.num_components() == n and same_partition(oracle, s.labels(), ref)
     finally:
         s.close()
 
