@@ -24,6 +24,7 @@ HEADER = os.path.join(_ROOT, "include", "gseg.h")
 FELZ, HIER, SUPERPIX = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 FLAG_HOST_LOOP = 1
+FLAG_NO_DEDUP = 2
 CAP_SUPERPIX, CAP_WIDE_SIGMA, CAP_LEVELS = 1, 2, 4
 OUT_NONE, OUT_LABELS, OUT_HIERARCHY = 0, 1, 2
 POOL_MAXLEVELS = 64
@@ -86,7 +87,7 @@ class PoolResult(C.Structure):
 class RoundStat(C.Structure):
     _fields_ = [("n_components", C.c_int64), ("n_edges", C.c_int64), ("n_merged", C.c_int64),
                 ("phase", C.c_int32), ("in_tail", C.c_int32), ("us_end", C.c_float), ("us_S", C.c_float),
-                ("us_R", C.c_float), ("us_E", C.c_float), ("n_pages", C.c_int32), ("reserved", C.c_int32)]
+                ("us_R", C.c_float), ("us_E", C.c_float), ("n_pages", C.c_int32), ("n_edges_dedup", C.c_int32)]
 
 
 _lib = None
@@ -432,6 +433,12 @@ class Segmenter:
         arr = (RoundStat * 64)()
         n = self._ck(self.L.gseg_stats(self.h, arr, 64), "gseg_stats")
         return [(arr[i].n_components, arr[i].n_edges, arr[i].n_merged, arr[i].phase) for i in range(n)]
+
+    def dedup_rounds(self):
+        """[(round, edges before, edges after)] of the duplicate eliminations of the last run."""
+        arr = (RoundStat * 64)()
+        n = self._ck(self.L.gseg_stats(self.h, arr, 64), "gseg_stats")
+        return [(i, arr[i].n_edges, arr[i].n_edges_dedup) for i in range(n) if arr[i].n_edges_dedup]
 
     def timeline(self):
         """Device timeline of the last run: [(round, in_tail, us_end, us_S, us_R, us_E)]."""

@@ -17,6 +17,7 @@
 #include "../../include/gseg.h"
 #include "gseg_kernels.cuh"
 #include "gseg_sort.cuh"
+#include "gseg_dedup.cuh"
 
 #define GSEG_MAXMARK 1024
 #define GRID_CAP (148 * 8)
@@ -27,9 +28,12 @@ struct GsegHead {
     RoundState st;
     u32 Vnext, error, ticketC, ticketE, doneE, Eacc[GSEG_MAXR + 1];
     u32 map_skip[GSEG_MAXR + 1], resume_phase;
+    u32 stDedupIn[GSEG_MAXR + 1], stDedupOut[GSEG_MAXR + 1];
 };
 static_assert(offsetof(GsegCtl, Eacc) == offsetof(GsegHead, Eacc), "GsegHead must mirror the head of GsegCtl");
 static_assert(offsetof(GsegCtl, resume_phase) == offsetof(GsegHead, resume_phase), "GsegHead must mirror the head of GsegCtl");
+static_assert(offsetof(GsegCtl, stDedupOut) == offsetof(GsegHead, stDedupOut), "GsegHead must mirror the head of GsegCtl");
+#define GSEG_EPOCHS_PER_RUN (2u * GSEG_MAXR + 8u + 32u) /* look-back tags a run may use: 2 per round, 8 spare, 32 de-duplications */
 
 static const size_t TAIL_SMEM = (2 * (size_t)GSEG_TAIL_STAGE + 2 * (NTT / 32)) * sizeof(u32); // k_tail: staged map + minima, survivor-count exchange (phase_E)
 
@@ -62,7 +66,14 @@ struct gseg_ctx {
     int nbig_hint;        // grid-wide rounds to enqueue before the tail (-1: estimate; adapts to the last run)
     int hint_w, hint_h, hint_variant, hint_conn;
     SortScratch sort;
-    // export of the final component graph (tiled schedule): cached dense / de-duplicated edge list
+    // duplicate elimination between rounds (gseg_dedup.cuh): descriptor in device memory, arrays of dd_cap edges
+    DedupDev *d_dd;
+    u64 *d_winner;
+    size_t dd_cap;
+    u32 dd_min_edges, dd_min_ratio;
+    bool dd_on;
+    // export of the final component graph (tiled schedule): cached dense / de-duplicated edge list; shares the
+    // arrays below with the duplicate elimination
     u64 *d_xkeys;
     u32 *d_xvals, *d_xkeep, *d_xw, *x_w;
     uint2 *d_xab, *x_ab;
@@ -129,6 +140,19 @@ static inline int grid_for(size_t n, int per_block, int cap = GRID_CAP) {
 template <typename T>
 static cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T)); }
 
+// The de-duplication's descriptor: pointers into the context's arrays (re-sent when a sort grew the scratch).
+static cudaError_t upload_dd(gseg_ctx *ctx) {
+    DedupDev dd;
+    memset(&dd, 0, sizeof(dd));
+    dd.sort.keys[0] = ctx->d_xkeys; dd.sort.keys[1] = ctx->sort.keys_alt;
+    dd.sort.vals[0] = ctx->d_xvals; dd.sort.vals[1] = ctx->sort.vals_alt;
+    dd.sort.hist = ctx->sort.hist; dd.sort.status = ctx->sort.status; dd.sort.tickets = ctx->sort.tickets;
+    dd.xab = ctx->d_xab; dd.xw = ctx->d_xw; dd.winner = ctx->d_winner; dd.keep = ctx->d_xkeep;
+    const size_t cap = ctx->dd_cap < ctx->sort.cap_n ? ctx->dd_cap : ctx->sort.cap_n;
+    dd.cap = (u32)cap; dd.min_edges = ctx->dd_min_edges; dd.min_ratio = ctx->dd_min_ratio; dd.disabled = ctx->dd_on ? 0u : 1u;
+    return cudaMemcpy(ctx->d_dd, &dd, sizeof(dd), cudaMemcpyHostToDevice);
+}
+
 extern "C" int gseg_create(gseg_ctx **out, int device, int max_w, int max_h) {
     return gseg_create_ex(out, device, max_w, max_h, 8);
 }
@@ -188,6 +212,23 @@ extern "C" int gseg_create_ex(gseg_ctx **out, int device, int max_w, int max_h, 
     if (e == cudaSuccess) e = cudaMemset(ctx->d_statusE, 0, ctx->ntilesE * sizeof(u64));
     if (e == cudaSuccess) e = dalloc(&ctx->d_ctl, 1);
     if (e == cudaSuccess) e = cudaMemset(ctx->d_ctl, 0, sizeof(GsegCtl));
+    // duplicate elimination / graph export: arrays for up to dd_cap edges (it runs once V <= 65536, when the list has
+    // shrunk far below the grid's edge count), sort scratch included -- nothing of this allocates later
+    ctx->dd_cap = V < ((size_t)1 << 24) ? V : ((size_t)1 << 24);
+    if (ctx->dd_cap < 4096) ctx->dd_cap = 4096;
+    ctx->dd_on = true; ctx->dd_min_edges = 8192u; ctx->dd_min_ratio = 8u;
+    if (const char *ev = getenv("GSEG_DEDUP")) ctx->dd_on = atoi(ev) != 0;
+    if (const char *ev = getenv("GSEG_DEDUP_MIN")) ctx->dd_min_edges = (u32)strtoul(ev, nullptr, 10);
+    if (const char *ev = getenv("GSEG_DEDUP_RATIO")) ctx->dd_min_ratio = (u32)strtoul(ev, nullptr, 10);
+    if (e == cudaSuccess) e = dalloc(&ctx->d_xkeys, ctx->dd_cap);
+    if (e == cudaSuccess) e = dalloc(&ctx->d_xvals, ctx->dd_cap);
+    if (e == cudaSuccess) e = dalloc(&ctx->d_xkeep, ctx->dd_cap);
+    if (e == cudaSuccess) e = dalloc(&ctx->d_xab, ctx->dd_cap);
+    if (e == cudaSuccess) e = dalloc(&ctx->d_xw, ctx->dd_cap);
+    if (e == cudaSuccess) e = dalloc(&ctx->d_winner, ctx->dd_cap);
+    if (e == cudaSuccess) { ctx->x_cap = ctx->dd_cap; e = sort_scratch_reserve(&ctx->sort, ctx->dd_cap); }
+    if (e == cudaSuccess) e = dalloc(&ctx->d_dd, 1);
+    if (e == cudaSuccess) e = upload_dd(ctx);
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_ctl, sizeof(GsegCtl));
     if (e == cudaSuccess) e = cudaMallocHost((void **)&ctx->h_head, sizeof(GsegHead));
     if (e == cudaSuccess) e = cudaDeviceGetAttribute(&ctx->num_sms, cudaDevAttrMultiProcessorCount, device);
@@ -350,6 +391,7 @@ extern "C" void gseg_destroy(gseg_ctx *ctx) {
     jpeg_release(ctx);
     sort_scratch_free(&ctx->sort);
     cudaFree(ctx->d_xkeys); cudaFree(ctx->d_xvals); cudaFree(ctx->d_xkeep); cudaFree(ctx->d_xab); cudaFree(ctx->d_xw);
+    cudaFree(ctx->d_winner); cudaFree(ctx->d_dd);
     for (int i = 0; i <= GSEG_MAXMARK; ++i)
         if (ctx->ev[i]) cudaEventDestroy(ctx->ev[i]);
     if (ctx->h_ctl) cudaFreeHost(ctx->h_ctl);
@@ -530,6 +572,47 @@ static void enqueue_round(gseg_ctx *c, cudaStream_t s, int r, size_t Vb, size_t 
     else k_edges<false><<<grid_for(Pb, NT / 32, cap), NT, 0, s>>>(c->d_ctl, B);
 }
 
+// Duplicate elimination between rounds (gseg_dedup.cuh): 11 launches that size themselves from the device-resident
+// state and exit at once unless the plan kernel decides to run.  Enqueued in front of every tail launch.
+static u32 dedup_V(const gseg_ctx *c) { // components from which on the list is de-duplicated: where the tail takes over
+    const u32 v = c->tail_V > 1024u ? c->tail_V : 1024u;
+    return v < 65536u ? v : 65536u;
+}
+static bool dedup_enabled(const gseg_ctx *c) {
+    return c->dd_on && c->params.variant != GSEG_SUPERPIX && !(c->params.flags & GSEG_FLAG_NO_DEDUP);
+}
+static void enqueue_dedup(gseg_ctx *c, cudaStream_t s, int round) {
+    const GsegBufs B = bufs_of(c);
+    const int cap = c->num_sms * c->occ_mult;
+    const size_t ntiles = (c->dd_cap + SORT_TILE - 1) / SORT_TILE;
+    const int gs = (int)(ntiles < (size_t)c->num_sms * 2 ? ntiles : (size_t)c->num_sms * 2);
+    mark(c, s, "k_dd_plan", round);
+    k_dd_plan<<<1, 1024, 0, s>>>(c->d_ctl, B, c->d_dd);
+    mark(c, s, "k_dd_keys", round);
+    k_dd_keys<<<cap, NT, 0, s>>>(c->d_ctl, B, c->d_dd);
+    mark(c, s, "k_sort_scan", round);
+    k_sort_scan_dev<<<4, SORT_RADIX, 0, s>>>(&c->d_dd->sort);
+    for (int p = 0; p < 4; ++p) { // two ids of <= 16 bits each: at most four 8-bit passes
+        mark(c, s, "k_sort_onesweep", round);
+        k_sort_onesweep_dev<<<gs, SORT_NT, sort_smem_bytes(), s>>>(&c->d_dd->sort, p);
+    }
+    mark(c, s, "k_dd_select", round);
+    k_dd_select<<<cap, NT, 0, s>>>(c->d_dd);
+    mark(c, s, "k_dd_mark", round);
+    k_dd_mark<<<cap, NT, 0, s>>>(c->d_ctl, B, c->d_dd);
+    mark(c, s, "k_dd_compact", round);
+    k_dd_compact<<<grid_for(c->dd_cap, 1024, 64), 1024, 0, s>>>(c->d_ctl, B, c->d_dd);
+    mark(c, s, "k_dd_finish", round);
+    k_dd_finish<<<cap, NT, 0, s>>>(c->d_ctl, B, c->d_dd);
+}
+// Host-driven schedule: the same decision as k_dd_plan, from the state just read back (so that the profiled schedule
+// only launches the sequence when it runs).
+static bool dedup_wanted_host(const gseg_ctx *c) {
+    const RoundState &st = c->h_ctl->st;
+    return dedup_enabled(c) && st.phase != PH_DONE && st.round >= 1u && st.V >= 2u && st.V <= dedup_V(c) && st.E <= c->dd_cap &&
+           st.E >= c->dd_min_edges && st.E / st.V >= c->dd_min_ratio;
+}
+
 // The tail: one cluster runs every remaining (small) round.
 static cudaError_t enqueue_tail(gseg_ctx *c, cudaStream_t s) {
     cudaLaunchConfig_t cfg = {};
@@ -668,7 +751,10 @@ extern "C" void gseg_host_free(void *p) {
 static int estimate_nbig(const gseg_ctx *c) {
     double E = 0.62 * (double)c->w * c->h * c->D, V = 0.3 * (double)c->w * c->h;
     int n = 0;
-    while ((E > c->tail_E || V > c->tail_V) && n < GSEG_MAXR) { E *= 0.6; V *= 0.27; ++n; }
+    // with the duplicate elimination in front of the tail, the tail takes over as soon as V <= tail_V (the list then
+    // shrinks to ~3 V edges); without it, when the list itself has shrunk to tail_E
+    const bool dd = dedup_enabled(c);
+    while ((V > c->tail_V || (dd ? V > dedup_V(c) : E > c->tail_E)) && n < GSEG_MAXR) { E *= 0.6; V *= 0.27; ++n; }
     return n;
 }
 
@@ -722,7 +808,7 @@ static int segment_async_impl(gseg_ctx *ctx, const uint8_t *rgb, int w, int h, i
     const int R = max_rounds_of(p);
     const bool host_loop = (p->flags & GSEG_FLAG_HOST_LOOP) != 0;
     // look-back tags: 2 per round, 30 bits; recycle the tag space long before it wraps
-    if (ctx->epoch_next + 2u * GSEG_MAXR + 8u >= (1u << 30)) {
+    if (ctx->epoch_next + GSEG_EPOCHS_PER_RUN >= (1u << 30)) {
         CK(cudaMemsetAsync(ctx->d_statusC, 0, ctx->ntilesC * sizeof(u64), ctx->stream));
         CK(cudaMemsetAsync(ctx->d_statusE, 0, ctx->ntilesE * sizeof(u64), ctx->stream));
         ctx->epoch_next = 1;
@@ -738,12 +824,14 @@ static int segment_async_impl(gseg_ctx *ctx, const uint8_t *rgb, int w, int h, i
     hp->tail_E = ctx->run_tail_E = host_loop ? 0u : ctx->tail_E;
     hp->tail_V = ctx->run_tail_V = host_loop ? 0u : ctx->tail_V;
     hp->tail_P = ctx->tail_P;
-    ctx->epoch_next += 2u * GSEG_MAXR + 8u;
+    hp->no_dedup = dedup_enabled(ctx) ? 0u : 1u; hp->dd_V = dedup_V(ctx);
+    ctx->epoch_next += GSEG_EPOCHS_PER_RUN;
     // the whole head of the control block (parameters + round-0 state + tickets) in one copy
     hh->st.V = (u32)((size_t)w * h); hh->st.E = 0; hh->st.round = 0; hh->st.phase = PH_PRED; hh->st.levels = 0; hh->st.map_off = 0; hh->st.P = 0; hh->st.pad = 0;
     hh->Vnext = hh->st.V; hh->error = DERR_NONE; hh->ticketC = 0; hh->ticketE = 0; hh->doneE = 0;
     memset(hh->Eacc, 0, sizeof(hh->Eacc));
     memset(hh->map_skip, 0, sizeof(hh->map_skip)); hh->resume_phase = PH_DONE;
+    memset(hh->stDedupIn, 0, sizeof(hh->stDedupIn)); memset(hh->stDedupOut, 0, sizeof(hh->stDedupOut));
     CK(cudaMemcpyAsync(ctx->d_ctl, hh, sizeof(GsegHead), cudaMemcpyHostToDevice, ctx->stream));
 
     ctx->n_marks = 0;
@@ -759,6 +847,7 @@ static int segment_async_impl(gseg_ctx *ctx, const uint8_t *rgb, int w, int h, i
         if (nbig > R - 1) nbig = R - 1;
         const size_t V = (size_t)w * h;
         for (int r = 1; r <= nbig; ++r) enqueue_round(ctx, ctx->stream, r, V, (size_t)ctx->D * (V / GSEG_PAGE + 1));
+        if (dedup_enabled(ctx)) enqueue_dedup(ctx, ctx->stream, -1);
         CK(cudaGetLastError());
         CK(enqueue_tail(ctx, ctx->stream));
         ctx->pending = true;
@@ -770,6 +859,13 @@ static int segment_async_impl(gseg_ctx *ctx, const uint8_t *rgb, int w, int h, i
     if (rc) return rc;
     for (int go; (go = run_continues(ctx)) != 0;) {
         if (go < 0) return go;
+        if (dedup_wanted_host(ctx)) {
+            enqueue_dedup(ctx, ctx->stream, (int)ctx->h_ctl->st.round);
+            mark_end(ctx, ctx->stream);
+            CK(cudaGetLastError());
+            rc = readback(ctx);
+            if (rc) return rc;
+        }
         enqueue_round(ctx, ctx->stream, (int)ctx->h_ctl->st.round, ctx->h_ctl->st.V, ctx->h_ctl->st.P);
         mark_end(ctx, ctx->stream);
         CK(cudaGetLastError());
@@ -790,6 +886,7 @@ static int wait_rounds(gseg_ctx *ctx) {
         const int r = (int)ctx->h_ctl->st.round;
         enqueue_round(ctx, ctx->stream, r, ctx->h_ctl->st.V, ctx->h_ctl->st.P);
         enqueue_round(ctx, ctx->stream, r + 1, ctx->h_ctl->st.V, ctx->h_ctl->st.P);
+        if (dedup_enabled(ctx)) enqueue_dedup(ctx, ctx->stream, -1);
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = enqueue_tail(ctx, ctx->stream);
         if (e != cudaSuccess) return fail(ctx, GSEG_E_CUDA, "continuation launch", e);
@@ -1051,14 +1148,7 @@ static int export_prepare(gseg_ctx *ctx, int dedup) {
     }
     ctx->x_ab = ctx->d_eab[cur ^ 1]; ctx->x_w = ctx->d_ew[cur ^ 1]; ctx->x_count = E;
     if (dedup && E > 1) {
-        if (ctx->x_cap < E) {
-            cudaFree(ctx->d_xkeys); cudaFree(ctx->d_xvals); cudaFree(ctx->d_xkeep); cudaFree(ctx->d_xab); cudaFree(ctx->d_xw);
-            ctx->d_xkeys = nullptr; ctx->d_xvals = nullptr; ctx->d_xkeep = nullptr; ctx->d_xab = nullptr; ctx->d_xw = nullptr;
-            ctx->x_cap = 0;
-            CK(dalloc(&ctx->d_xkeys, E)); CK(dalloc(&ctx->d_xvals, E)); CK(dalloc(&ctx->d_xkeep, E));
-            CK(dalloc(&ctx->d_xab, E)); CK(dalloc(&ctx->d_xw, E));
-            ctx->x_cap = E;
-        }
+        if (ctx->x_cap < E) return fail(ctx, GSEG_E_SIZE, "graph export with duplicate elimination: more live edges than the context's de-duplication arrays hold", cudaSuccess);
         int bits = 1;
         while (bits < 64 && ((u64)V * V - 1u) >> bits) ++bits; // pair keys are < V^2
         ctx->launches += 3;
@@ -1066,7 +1156,12 @@ static int export_prepare(gseg_ctx *ctx, int dedup) {
         CK(cudaGetLastError());
         cudaError_t e = onesweep_sort_pairs(&ctx->sort, ctx->d_xkeys, ctx->d_xvals, E, 0, bits, s);
         if (e != cudaSuccess) return fail(ctx, GSEG_E_CUDA, "onesweep_sort_pairs", e);
-        k_pair_select<<<grid_for(E, NT), NT, 0, s>>>(ctx->d_xkeys, ctx->d_xvals, ctx->x_w, (u32)E, ctx->d_xkeep);
+        // minimum (weight, list position) of every run of equal pairs, in parallel (segmented warp minima + one atomic per
+        // run part), then the winners' flags
+        CK(cudaMemsetAsync(ctx->d_winner, 0xFF, E * sizeof(u64), s));
+        k_pair_select_runs<<<grid_for(E, NT), NT, 0, s>>>(ctx->d_xkeys, ctx->d_xvals, ctx->x_w, (u32)E, ctx->d_winner);
+        k_pair_mark_runs<<<grid_for(E, NT), NT, 0, s>>>(ctx->d_xkeys, ctx->d_winner, (u32)E, ctx->d_xkeep);
+        ++ctx->launches;
         CK(cudaMemsetAsync(&ctx->d_ctl->ticketE, 0, sizeof(u32), s));
         const u32 tag = ctx->epoch_next; // a tag no round of any run uses
         ctx->epoch_next += 2u;
@@ -1132,7 +1227,7 @@ static int graph_run(gseg_ctx *ctx, size_t V, size_t E, const gseg_params *p) {
     ctx->params = *p;
     ctx->w = (int)V; ctx->h = 1; ctx->D = 2;
     const int R = max_rounds_of(p);
-    if (ctx->epoch_next + 2u * GSEG_MAXR + 8u >= (1u << 30)) {
+    if (ctx->epoch_next + GSEG_EPOCHS_PER_RUN >= (1u << 30)) {
         CK(cudaMemsetAsync(ctx->d_statusC, 0, ctx->ntilesC * sizeof(u64), s));
         CK(cudaMemsetAsync(ctx->d_statusE, 0, ctx->ntilesE * sizeof(u64), s));
         ctx->epoch_next = 1;
@@ -1150,13 +1245,15 @@ static int graph_run(gseg_ctx *ctx, size_t V, size_t E, const gseg_params *p) {
     hp->tail_E = ctx->run_tail_E = host_loop ? 0u : ctx->tail_E;
     hp->tail_V = ctx->run_tail_V = host_loop ? 0u : ctx->tail_V;
     hp->tail_P = ctx->tail_P;
-    ctx->epoch_next += 2u * GSEG_MAXR + 8u;
+    hp->no_dedup = dedup_enabled(ctx) ? 0u : 1u; hp->dd_V = dedup_V(ctx);
+    ctx->epoch_next += GSEG_EPOCHS_PER_RUN;
     const u32 P = (u32)((E + GSEG_PAGE - 1) / GSEG_PAGE);
     hh->st.V = (u32)V; hh->st.E = (u32)E; hh->st.round = 1; hh->st.phase = PH_PRED; hh->st.levels = 0; hh->st.map_off = 0;
     hh->st.P = P; hh->st.pad = 0;
     hh->Vnext = (u32)V; hh->error = DERR_NONE; hh->ticketC = 0; hh->ticketE = 0; hh->doneE = 0;
     memset(hh->Eacc, 0, sizeof(hh->Eacc));
     memset(hh->map_skip, 0, sizeof(hh->map_skip)); hh->resume_phase = PH_DONE;
+    memset(hh->stDedupIn, 0, sizeof(hh->stDedupIn)); memset(hh->stDedupOut, 0, sizeof(hh->stDedupOut));
     CK(cudaMemcpyAsync(ctx->d_ctl, hh, sizeof(GsegHead), cudaMemcpyHostToDevice, s));
     ctx->n_marks = 0;
     const GsegBufs B = bufs_of(ctx);
@@ -1169,11 +1266,18 @@ static int graph_run(gseg_ctx *ctx, size_t V, size_t E, const gseg_params *p) {
         rc = readback(ctx);
         for (int go; !rc && (go = run_continues(ctx)) != 0;) {
             if (go < 0) { rc = go; break; }
+            if (dedup_wanted_host(ctx)) {
+                enqueue_dedup(ctx, s, (int)ctx->h_ctl->st.round);
+                CK(cudaGetLastError());
+                if ((rc = readback(ctx)) != 0) break;
+            }
             enqueue_round(ctx, s, (int)ctx->h_ctl->st.round, ctx->h_ctl->st.V, ctx->h_ctl->st.P);
             CK(cudaGetLastError());
             rc = readback(ctx);
         }
     } else {
+        if (dedup_enabled(ctx)) enqueue_dedup(ctx, s, -1);
+        CK(cudaGetLastError());
         CK(enqueue_tail(ctx, s));
         ctx->pending = true;
         rc = wait_rounds(ctx);
@@ -1334,13 +1438,13 @@ extern "C" int gseg_stats(const gseg_ctx *ctx, gseg_round_stat *out, int cap) {
     const int n = (int)ctx->h_ctl->st.round;
     for (int i = 0; i < n && i < cap && out; ++i) {
         out[i].n_components = ctx->h_ctl->stV[i];
-        out[i].n_edges = i == 0 ? 0 : ctx->h_ctl->stE[i];
+        out[i].n_edges = i == 0 ? 0 : (ctx->h_ctl->stDedupIn[i] ? ctx->h_ctl->stDedupIn[i] : ctx->h_ctl->stE[i]);
         out[i].n_merged = ctx->h_ctl->stM[i];
         out[i].phase = (int32_t)ctx->h_ctl->stP[i];
         const GsegCtl *hc = ctx->h_ctl;
         const bool tail = hc->stTail[i] != 0;
         out[i].in_tail = tail ? 1 : 0;
-        out[i].n_pages = (int32_t)hc->stPages[i]; out[i].reserved = 0;
+        out[i].n_pages = (int32_t)hc->stPages[i]; out[i].n_edges_dedup = (int32_t)hc->stDedupOut[i];
         out[i].us_end = (float)((double)(hc->t_end[i] - hc->t_start) * 1e-3);
         out[i].us_S = tail ? (float)((double)(hc->t_S[i] - hc->t_begin[i]) * 1e-3) : 0.f;
         out[i].us_R = tail ? (float)((double)(hc->t_R[i] - hc->t_S[i]) * 1e-3) : 0.f;
@@ -1372,9 +1476,12 @@ extern "C" int gseg_synth(gseg_ctx *ctx, uint8_t *out, int w, int h, uint64_t se
 extern "C" int gseg_sort_pairs_u64(gseg_ctx *ctx, uint64_t *keys, uint32_t *vals, int64_t n, int begin_bit, int end_bit) {
     if (!ctx || !keys || n < 0 || begin_bit < 0 || end_bit > 64 || begin_bit >= end_bit) return GSEG_E_ARG;
     CK(cudaSetDevice(ctx->device));
+    const u64 *before = ctx->sort.keys_alt;
+    const u32 *before_s = ctx->sort.status;
     cudaError_t e = onesweep_sort_pairs(&ctx->sort, (u64 *)keys, (u32 *)vals, (size_t)n, begin_bit, end_bit, ctx->stream);
     if (e != cudaSuccess) return fail(ctx, GSEG_E_CUDA, "onesweep_sort_pairs", e);
     CK(cudaStreamSynchronize(ctx->stream));
+    if (before != ctx->sort.keys_alt || before_s != ctx->sort.status) CK(upload_dd(ctx)); // a larger sort than any before: the scratch moved
     return GSEG_OK;
 }
 

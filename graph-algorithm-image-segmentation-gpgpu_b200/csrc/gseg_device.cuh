@@ -29,6 +29,8 @@ struct GsegRunParams {
     u32 epoch_base; // first look-back tag of this run (monotonic across runs)
     int mask_len;
     u32 filter_shift;   // read-before-atomic filter when (E >> filter_shift) > surviving components
+    u32 no_dedup;       // GSEG_FLAG_NO_DEDUP: never run the duplicate elimination between rounds
+    u32 dd_V;           // ... which runs once the graph has at most this many components (<= 65536: two ids in a 32-bit key)
     u32 tail_E, tail_V, tail_P; // a round with E <= tail_E, V <= tail_V and P <= tail_P runs inside the single-cluster tail kernel
     float mask[GSEG_MAXMASK];
 };
@@ -56,6 +58,7 @@ struct GsegCtl {
     u32 Eacc[GSEG_MAXR + 1]; // Eacc[r]: edges emitted by round r's edge phase (zeroed by the host; never reset on the device)
     u32 map_skip[GSEG_MAXR + 1]; // 1: round r's map has been folded into an earlier one (arena compaction, FELZ only)
     u32 resume_phase;            // phase the run continues with after the host compacted the arena (error == DERR_ARENA)
+    u32 stDedupIn[GSEG_MAXR + 1], stDedupOut[GSEG_MAXR + 1]; // round r ran on a list de-duplicated from In to Out edges (0: no)
     // ---- end of host-initialised head ----
     u32 map_off[GSEG_MAXR + 1];
     u32 stV[GSEG_MAXR], stE[GSEG_MAXR], stM[GSEG_MAXR], stP[GSEG_MAXR], stVafter[GSEG_MAXR];

@@ -1125,8 +1125,9 @@ __global__ void __launch_bounds__(NT) k_export_gather(GsegBufs B, int cur, u32 P
 }
 // Duplicate elimination of the exported list (the reference's DPP branches: sort packed keys, keep the
 // lightest of every run, Report.pdf p3 s3.2.2): key = pair of end components, payload = list position;
-// after the in-house onesweep sort (stable: positions ascend inside a run) the head of every run scans its
-// run for the minimum (weight bits, position) and marks that edge; the marked edges are compacted in list order.
+// after the in-house onesweep sort the minimum (weight bits, position) of every run is found in parallel
+// (k_pair_select_runs / k_pair_mark_runs, gseg_dedup.cuh) and that edge is marked; the marked edges are compacted in
+// list order.
 __global__ void __launch_bounds__(NT) k_pair_keys(const uint2 *__restrict__ eab, u32 E, u32 V, u64 *__restrict__ keys,
                                                   u32 *__restrict__ vals, u32 *__restrict__ keep) {
     for (u32 i = blockIdx.x * NT + threadIdx.x; i < E; i += gridDim.x * NT) {
@@ -1134,19 +1135,6 @@ __global__ void __launch_bounds__(NT) k_pair_keys(const uint2 *__restrict__ eab,
         keys[i] = (u64)min(ab.x, ab.y) * V + max(ab.x, ab.y);
         vals[i] = i;
         keep[i] = 0u;
-    }
-}
-__global__ void __launch_bounds__(NT) k_pair_select(const u64 *__restrict__ keys, const u32 *__restrict__ vals,
-                                                    const u32 *__restrict__ ew, u32 E, u32 *__restrict__ keep) {
-    for (u32 j = blockIdx.x * NT + threadIdx.x; j < E; j += gridDim.x * NT) {
-        const u64 k = keys[j];
-        if (j > 0 && keys[j - 1] == k) continue; // not the head of a run
-        u32 bi = vals[j], bw = ew[bi];
-        for (u32 t = j + 1; t < E && keys[t] == k; ++t) {
-            const u32 i = vals[t], w = ew[i];
-            if (w < bw) { bw = w; bi = i; } // equal weights: the earlier position (already held) wins
-        }
-        keep[bi] = 1u;
     }
 }
 // Ordered compaction of the marked edges: chunks of blockDim edges by ticket, block-granular look-back.

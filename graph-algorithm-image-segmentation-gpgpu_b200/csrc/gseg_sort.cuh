@@ -62,11 +62,11 @@ __global__ void __launch_bounds__(SORT_RADIX) k_sort_scan(u32 *hist) {
 #define SORT_FLAG_INC (2u << 30)
 #define SORT_VAL_MASK ((1u << 30) - 1u)
 
+// One LSD pass over all tiles (tiles by ticket: every lower tile belongs to a block that is already running).
 template <bool HAS_VALS>
-__global__ void __launch_bounds__(SORT_NT) k_sort_onesweep(const u64 *__restrict__ kin, const u32 *__restrict__ vin,
-                                                           u64 *__restrict__ kout, u32 *__restrict__ vout, size_t n,
-                                                           int lo, int bits, const u32 *__restrict__ goff,
-                                                           u32 *status, u32 *ticket, u32 *err) {
+__device__ __forceinline__ void sort_pass(const u64 *__restrict__ kin, const u32 *__restrict__ vin, u64 *__restrict__ kout,
+                                          u32 *__restrict__ vout, size_t n, int lo, int bits, const u32 *__restrict__ goff,
+                                          u32 *status, u32 *ticket, u32 *err) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     u64 *s_keys = reinterpret_cast<u64 *>(smem_raw);                           // SORT_TILE
     u32 *s_vals = reinterpret_cast<u32 *>(s_keys + SORT_TILE);                 // SORT_TILE
@@ -167,6 +167,79 @@ __global__ void __launch_bounds__(SORT_NT) k_sort_onesweep(const u64 *__restrict
     }
 }
 
+template <bool HAS_VALS>
+__global__ void __launch_bounds__(SORT_NT) k_sort_onesweep(const u64 *__restrict__ kin, const u32 *__restrict__ vin,
+                                                           u64 *__restrict__ kout, u32 *__restrict__ vout, size_t n,
+                                                           int lo, int bits, const u32 *__restrict__ goff,
+                                                           u32 *status, u32 *ticket, u32 *err) {
+    sort_pass<HAS_VALS>(kin, vin, kout, vout, n, lo, bits, goff, status, ticket, err);
+}
+
+// Device-driven form (duplicate elimination between rounds, gseg_dedup.cuh): size, bit range and the buffers of pass
+// `pass` come from a descriptor in device memory that an earlier kernel of the same stream filled; a pass that is
+// not needed exits at once, so the host can enqueue the worst case without knowing the graph.
+struct SortDev {
+    u32 active, n, npass, key_bits; // key_bits: total bits of the sort key
+    u64 *keys[2];
+    u32 *vals[2];
+    u32 *hist, *status, *tickets;   // hist [SORT_MAXPASS][256]; status [npass][ntiles(n)][256]; tickets [SORT_MAXPASS + 1]
+};
+__global__ void __launch_bounds__(SORT_NT) k_sort_onesweep_dev(const SortDev *__restrict__ sd, int pass) {
+    if (!sd->active || (u32)pass >= sd->npass) return;
+    const size_t n = sd->n;
+    const size_t ntiles = (n + SORT_TILE - 1) / SORT_TILE;
+    const int lo = 8 * pass, bits = min(8, (int)sd->key_bits - lo);
+    sort_pass<true>(sd->keys[pass & 1], sd->vals[pass & 1], sd->keys[(pass & 1) ^ 1], sd->vals[(pass & 1) ^ 1], n, lo, bits,
+                    sd->hist + pass * SORT_RADIX, sd->status + (size_t)pass * ntiles * SORT_RADIX, sd->tickets + pass,
+                    sd->tickets + SORT_MAXPASS);
+}
+__global__ void __launch_bounds__(SORT_RADIX) k_sort_scan_dev(const SortDev *__restrict__ sd) {
+    __shared__ u32 s[34];
+    if (!sd->active || blockIdx.x >= sd->npass) return;
+    u32 *h = sd->hist + blockIdx.x * SORT_RADIX;
+    const u32 v = h[threadIdx.x];
+    const u32 ex = block_excl_scan<SORT_RADIX>(v, s);
+    h[threadIdx.x] = ex;
+}
+
+static size_t sort_smem_bytes() {
+    return SORT_TILE * (sizeof(u64) + sizeof(u32)) + ((SORT_NT / 32) * SORT_RADIX + 2 * SORT_RADIX) * sizeof(u32);
+}
+static cudaError_t sort_set_attrs(SortScratch *s) {
+    if (s->attr_set) return cudaSuccess;
+    cudaError_t e;
+    const int smem = (int)sort_smem_bytes();
+    if ((e = cudaFuncSetAttribute(k_sort_onesweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_sort_onesweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    if ((e = cudaFuncSetAttribute(k_sort_onesweep_dev, cudaFuncAttributeMaxDynamicSharedMemorySize, smem)) != cudaSuccess) return e;
+    s->attr_set = true;
+    return cudaSuccess;
+}
+// Scratch for sorts of up to n keys in up to SORT_MAXPASS passes, allocated up front (gseg_create) so that neither the
+// de-duplication between rounds nor the export of a strip's graph allocates.
+static cudaError_t sort_scratch_reserve(SortScratch *s, size_t n) {
+    cudaError_t e;
+    const size_t need_status = (size_t)SORT_MAXPASS * ((n + SORT_TILE - 1) / SORT_TILE) * SORT_RADIX;
+    if (s->cap_n < n) {
+        cudaFree(s->keys_alt); cudaFree(s->vals_alt);
+        s->keys_alt = nullptr; s->vals_alt = nullptr; s->cap_n = 0;
+        if ((e = cudaMalloc((void **)&s->keys_alt, n * sizeof(u64))) != cudaSuccess) return e;
+        if ((e = cudaMalloc((void **)&s->vals_alt, n * sizeof(u32))) != cudaSuccess) return e;
+        s->cap_n = n;
+    }
+    if (s->cap_status < need_status) {
+        cudaFree(s->status);
+        s->status = nullptr; s->cap_status = 0;
+        if ((e = cudaMalloc((void **)&s->status, need_status * sizeof(u32))) != cudaSuccess) return e;
+        s->cap_status = need_status;
+    }
+    if (!s->hist) {
+        if ((e = cudaMalloc((void **)&s->hist, SORT_MAXPASS * SORT_RADIX * sizeof(u32))) != cudaSuccess) return e;
+        if ((e = cudaMalloc((void **)&s->tickets, (SORT_MAXPASS + 1) * sizeof(u32))) != cudaSuccess) return e;
+    }
+    return sort_set_attrs(s);
+}
+
 static cudaError_t onesweep_sort_pairs(SortScratch *s, u64 *keys, u32 *vals, size_t n, int begin_bit, int end_bit,
                                        cudaStream_t st) {
     if (n == 0) return cudaSuccess;
@@ -192,12 +265,8 @@ static cudaError_t onesweep_sort_pairs(SortScratch *s, u64 *keys, u32 *vals, siz
         if ((e = cudaMalloc((void **)&s->hist, SORT_MAXPASS * SORT_RADIX * sizeof(u32))) != cudaSuccess) return e;
         if ((e = cudaMalloc((void **)&s->tickets, (SORT_MAXPASS + 1) * sizeof(u32))) != cudaSuccess) return e;
     }
-    const size_t smem = SORT_TILE * (sizeof(u64) + sizeof(u32)) + ((SORT_NT / 32) * SORT_RADIX + 2 * SORT_RADIX) * sizeof(u32);
-    if (!s->attr_set) {
-        if ((e = cudaFuncSetAttribute(k_sort_onesweep<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        if ((e = cudaFuncSetAttribute(k_sort_onesweep<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)) != cudaSuccess) return e;
-        s->attr_set = true;
-    }
+    const size_t smem = sort_smem_bytes();
+    if ((e = sort_set_attrs(s)) != cudaSuccess) return e;
     cudaMemsetAsync(s->hist, 0, SORT_MAXPASS * SORT_RADIX * sizeof(u32), st);
     cudaMemsetAsync(s->tickets, 0, (SORT_MAXPASS + 1) * sizeof(u32), st);
     cudaMemsetAsync(s->status, 0, need_status * sizeof(u32), st);

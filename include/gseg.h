@@ -47,6 +47,9 @@ extern "C" {
                                   enqueues the whole run without reading anything back, and all small rounds
                                   run inside one persistent thread-block-cluster kernel. */
 
+#define GSEG_FLAG_NO_DEDUP 2u  /* do not eliminate duplicate edges between rounds (measurement / A-B only: results are
+                                  identical either way, see csrc/gseg_dedup.cuh) */
+
 typedef enum gseg_status {
     GSEG_OK = 0,
     GSEG_E_ARG = -1,     /* bad argument (null pointer, size, connectivity, variant, sigma range) */
@@ -75,14 +78,16 @@ typedef struct gseg_params {
 /* One row per executed Boruvka round (SURVEY.md section 5 "metrics": V_r, E_r per round). */
 typedef struct gseg_round_stat {
     int64_t n_components; /* components entering the round */
-    int64_t n_edges;      /* live (inter-component) edges entering the round */
+    int64_t n_edges;      /* live (inter-component) edges entering the round, parallel edges included, as the list
+                             carried them -- until the duplicate elimination has run (n_edges_dedup != 0); from the
+                             round after it on, the edges of the de-duplicated list */
     int64_t n_merged;     /* components merged away by the round */
     int32_t phase;        /* 0 = predicate / hierarchy round, 1 = min-size round */
     int32_t in_tail;      /* 1 when the round ran inside the single-cluster tail kernel */
     float us_end;         /* device clock at the end of the round, microseconds since round 0's graph kernel started */
     float us_S, us_R, us_E; /* tail rounds: duration of the choose/scan, flatten and edge phases (else 0) */
     int32_t n_pages;      /* pages of the edge list entering the round */
-    int32_t reserved;
+    int32_t n_edges_dedup; /* != 0: the list was de-duplicated right before this round, to this many edges */
 } gseg_round_stat;
 
 typedef struct gseg_ctx gseg_ctx;

@@ -72,7 +72,11 @@ def test_felz_partition_bit_exact(gseg, oracle, seg, w, h, conn, flags):
         assert lab.min() == 0 and lab.max() == ref["n"] - 1   # dense ids
         st = seg.stats()
         assert [tuple(int(x) for x in r[[0, 2, 3]]) for r in ref["stats"]] == [(a, c, d) for a, b, c, d in st]
-        assert [int(r[1]) for r in ref["stats"]][1:] == [b for a, b, c, d in st][1:]
+        # live edges per round equal the oracle's (which carries every parallel edge) up to and including the round in
+        # front of which the engine eliminated duplicates; V, merged and phase of every round are unaffected by that
+        dd = seg.dedup_rounds()
+        upto = dd[0][0] + 1 if dd else len(st)
+        assert [int(r[1]) for r in ref["stats"]][1:upto] == [b for a, b, c, d in st][1:upto]
 
 
 @pytest.mark.parametrize("w,h", [(1, 1), (1, 7), (2, 2), (17, 13), (64, 48), (257, 129), (320, 240)])

@@ -267,3 +267,68 @@ def test_cpp_batch_program(gseg, oracle):
     ref = [oracle.pipeline(oracle.synth(320, 240, 500 + i), 0.8, 300.0, 20, 8, oracle.FELZ)["n"] for i in range(12)]
     assert counts == ref
     assert "Mpixel/s" in r.stdout
+
+
+@pytest.mark.parametrize("variant,conn,w,h,seed", [(0, 4, 1920, 1080, 2), (0, 8, 640, 480, 5), (1, 8, 1280, 720, 6), (1, 4, 700, 500, 7)])
+def test_duplicate_elimination_between_rounds(gseg, oracle, variant, conn, w, h, seed):
+    """a10 on the round path: once the graph has few components but many parallel edges, the list is sorted by
+    component pair (in-house onesweep), the lightest edge of every run is kept and the list is re-compacted.  Same
+    partition (every hierarchy level) with and without it, in both schedules; the step actually ran; it shrinks E."""
+    s = gseg.Segmenter(w, h)
+    try:
+        img = oracle.synth(w, h, seed)
+        kw = dict(sigma=0.8, k=300.0, min_size=20, connectivity=conn, variant=variant)
+        ref = oracle.pipeline(img, 0.8, 300.0, 20, conn, variant, max_levels=64 if variant else 0)
+        for flags in (0, gseg.FLAG_HOST_LOOP):
+            for rep in range(2):                                   # the second run uses the adapted round guess
+                s.segment(img, flags=flags, **kw)
+                dd = s.dedup_rounds()
+                assert len(dd) >= 1, (flags, rep, s.stats())
+                r, before, after = dd[0]
+                assert after < before and after * 4 <= before, dd
+                assert same_partition(oracle, s.labels(), ref["labels"]) and s.num_components() == ref["n"]
+                st = s.stats()
+                assert [tuple(int(x) for x in q[[0, 2, 3]]) for q in ref["stats"]] == [(a, c, d) for a, b, c, d in st]
+                assert [int(q[1]) for q in ref["stats"]][1:r + 1] == [b for a, b, c, d in st][1:r + 1]
+                if variant:
+                    for l in range(ref["nlevels"]):
+                        assert same_partition(oracle, s.labels(l), ref["levels"][l]), l
+            s.segment(img, flags=flags | gseg.FLAG_NO_DEDUP, **kw)
+            assert s.dedup_rounds() == [] and same_partition(oracle, s.labels(), ref["labels"])
+            assert [int(q[1]) for q in ref["stats"]][1:] == [b for a, b, c, d in s.stats()][1:]
+        # the exported graph of a run that de-duplicated mid-way equals the one of a run that did not
+        if variant == 0:
+            s.segment(img, **kw)
+            g1 = s.export_graph()
+            s.segment(img, flags=gseg.FLAG_NO_DEDUP, **kw)
+            g2 = s.export_graph()
+            for key in g1:
+                assert np.array_equal(np.asarray(g1[key]).view(np.uint32), np.asarray(g2[key]).view(np.uint32)), key
+    finally:
+        s.close()
+
+
+def test_duplicate_elimination_forced_everywhere(gseg, oracle, monkeypatch):
+    """With the thresholds at their minimum the step runs on tiny and degenerate graphs too (ties everywhere, a handful
+    of components): partitions still equal the oracle's."""
+    monkeypatch.setenv("GSEG_DEDUP_MIN", "1")
+    monkeypatch.setenv("GSEG_DEDUP_RATIO", "1")
+    rng = np.random.default_rng(17)
+    s = gseg.Segmenter(300, 300)
+    try:
+        ran = 0
+        for case in range(60):
+            w, h = int(rng.integers(2, 300)), int(rng.integers(2, 300))
+            kind = case % 3
+            img = oracle.synth(w, h, 900 + case) if kind == 0 else (rng.integers(0, 256, (h, w, 3), dtype=np.uint8) if kind == 1
+                                                                      else (rng.integers(0, 3, (h, w, 3)) * 90).astype(np.uint8))
+            conn, variant = int(rng.choice([4, 8])), int(rng.choice([0, 0, 1]))
+            k, ms, flags = float(rng.choice([0.0, 30.0, 300.0])), int(rng.choice([0, 5, 50])), int(rng.choice([0, 1]))
+            s.set_tail(*[(262144, 65536), (0, 0), (3000, 500)][case % 3])
+            s.segment(np.ascontiguousarray(img), sigma=0.8, k=k, min_size=ms, connectivity=conn, variant=variant, flags=flags)
+            ref, n = oracle.segment(np.ascontiguousarray(img), 0.8, k, ms, conn, variant, max_rounds=48)
+            assert s.num_components() == n and same_partition(oracle, s.labels(), ref), (case, w, h, kind, conn, variant, k, ms, flags)
+            ran += len(s.dedup_rounds())
+        assert ran >= 30
+    finally:
+        s.close()
