@@ -143,6 +143,7 @@ def load():
     L.gseg_launch_count.restype = C.c_longlong
     L.gseg_sort_pairs_u64.argtypes = [vp, vp, vp, C.c_int64, i32, i32]
     L.gseg_reserve.argtypes = [vp, C.c_uint32]
+    L.gseg_set_dedup.argtypes = [vp, i32, C.c_uint32, C.c_uint32]
     L.gseg_host_alloc.argtypes = [C.c_size_t]
     L.gseg_host_alloc.restype = vp
     L.gseg_host_free.argtypes = [vp]
@@ -243,6 +244,10 @@ class Segmenter:
 
     def set_tail(self, max_edges, max_components):
         self._ck(self.L.gseg_set_tail(self.h, max_edges, max_components), "gseg_set_tail")
+
+    def set_dedup(self, on, min_edges=0, min_ratio=0):
+        """Duplicate-edge elimination between rounds (sort by component pair, keep the lightest of every run)."""
+        self._ck(self.L.gseg_set_dedup(self.h, int(on), min_edges, min_ratio), "gseg_set_dedup")
 
     def set_blocks_per_sm(self, blocks):
         self._ck(self.L.gseg_set_blocks_per_sm(self.h, blocks), "gseg_set_blocks_per_sm")
@@ -435,7 +440,8 @@ class Segmenter:
         return [(arr[i].n_components, arr[i].n_edges, arr[i].n_merged, arr[i].phase) for i in range(n)]
 
     def dedup_rounds(self):
-        """[(round, edges before, edges after)] of the duplicate eliminations of the last run."""
+        """[(round, n_edges, n_edges_dedup)] of the rounds of the last run whose list had duplicates dropped (the
+        first entry is the first such round; see gseg_round_stat)."""
         arr = (RoundStat * 64)()
         n = self._ck(self.L.gseg_stats(self.h, arr, 64), "gseg_stats")
         return [(i, arr[i].n_edges, arr[i].n_edges_dedup) for i in range(n) if arr[i].n_edges_dedup]

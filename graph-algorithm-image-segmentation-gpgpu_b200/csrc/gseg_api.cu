@@ -216,7 +216,9 @@ extern "C" int gseg_create_ex(gseg_ctx **out, int device, int max_w, int max_h, 
     // shrunk far below the grid's edge count), sort scratch included -- nothing of this allocates later
     ctx->dd_cap = V < ((size_t)1 << 24) ? V : ((size_t)1 << 24);
     if (ctx->dd_cap < 4096) ctx->dd_cap = 4096;
-    ctx->dd_on = true; ctx->dd_min_edges = 8192u; ctx->dd_min_ratio = 8u;
+    // Off by default: measured on B200 (DESIGN.md "Duplicate elimination"), at 1080p and 4K the rounds that remain once
+    // V <= 65536 cost less than the sort; gseg_set_dedup / GSEG_DEDUP=1 switch it on.
+    ctx->dd_on = false; ctx->dd_min_edges = 8192u; ctx->dd_min_ratio = 8u;
     if (const char *ev = getenv("GSEG_DEDUP")) ctx->dd_on = atoi(ev) != 0;
     if (const char *ev = getenv("GSEG_DEDUP_MIN")) ctx->dd_min_edges = (u32)strtoul(ev, nullptr, 10);
     if (const char *ev = getenv("GSEG_DEDUP_RATIO")) ctx->dd_min_ratio = (u32)strtoul(ev, nullptr, 10);
@@ -417,6 +419,18 @@ extern "C" int gseg_set_tail(gseg_ctx *ctx, uint32_t max_edges, uint32_t max_com
     return GSEG_OK;
 }
 
+extern "C" int gseg_set_dedup(gseg_ctx *ctx, int on, uint32_t min_edges, uint32_t min_ratio) {
+    if (!ctx) return GSEG_E_ARG;
+    if (ctx->pending) return GSEG_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    ctx->dd_on = on != 0;
+    if (min_edges) ctx->dd_min_edges = min_edges;
+    if (min_ratio) ctx->dd_min_ratio = min_ratio;
+    ctx->nbig_hint = -1;
+    CK(upload_dd(ctx));
+    return GSEG_OK;
+}
+
 extern "C" int gseg_set_blocks_per_sm(gseg_ctx *ctx, int blocks) {
     if (!ctx || blocks < 1 || blocks > 8) return GSEG_E_ARG;
     if (ctx->pending) return GSEG_E_STATE;
@@ -601,7 +615,7 @@ static void enqueue_dedup(gseg_ctx *c, cudaStream_t s, int round) {
     mark(c, s, "k_dd_mark", round);
     k_dd_mark<<<cap, NT, 0, s>>>(c->d_ctl, B, c->d_dd);
     mark(c, s, "k_dd_compact", round);
-    k_dd_compact<<<grid_for(c->dd_cap, 1024, 64), 1024, 0, s>>>(c->d_ctl, B, c->d_dd);
+    k_dd_compact<<<grid_for(c->dd_cap, 4096, c->num_sms * 2), 1024, 0, s>>>(c->d_ctl, B, c->d_dd);
     mark(c, s, "k_dd_finish", round);
     k_dd_finish<<<cap, NT, 0, s>>>(c->d_ctl, B, c->d_dd);
 }
@@ -1435,16 +1449,20 @@ extern "C" int gseg_join_segment(gseg_ctx *ctx, const void *dev_records, int n_s
 
 extern "C" int gseg_stats(const gseg_ctx *ctx, gseg_round_stat *out, int cap) {
     if (!ctx || !ctx->valid) return GSEG_E_STATE;
-    const int n = (int)ctx->h_ctl->st.round;
+    const GsegCtl *hc = ctx->h_ctl;
+    const int n = (int)hc->st.round;
+    bool deduped = false; // the list entering round i has had duplicates removed (by the sort step in front of it or of an earlier round)
     for (int i = 0; i < n && i < cap && out; ++i) {
-        out[i].n_components = ctx->h_ctl->stV[i];
-        out[i].n_edges = i == 0 ? 0 : (ctx->h_ctl->stDedupIn[i] ? ctx->h_ctl->stDedupIn[i] : ctx->h_ctl->stE[i]);
-        out[i].n_merged = ctx->h_ctl->stM[i];
-        out[i].phase = (int32_t)ctx->h_ctl->stP[i];
-        const GsegCtl *hc = ctx->h_ctl;
+        if (hc->stDedupOut[i]) deduped = true;
+        out[i].n_components = hc->stV[i];
+        // the sort step knows both counts of the round it ran in front of; n_edges stays the list as it was carried
+        out[i].n_edges = i == 0 ? 0 : (hc->stDedupIn[i] ? hc->stDedupIn[i] : hc->stE[i]);
+        out[i].n_merged = hc->stM[i];
+        out[i].phase = (int32_t)hc->stP[i];
         const bool tail = hc->stTail[i] != 0;
         out[i].in_tail = tail ? 1 : 0;
-        out[i].n_pages = (int32_t)hc->stPages[i]; out[i].n_edges_dedup = (int32_t)hc->stDedupOut[i];
+        out[i].n_pages = (int32_t)hc->stPages[i];
+        out[i].n_edges_dedup = deduped ? (int32_t)(hc->stDedupOut[i] ? hc->stDedupOut[i] : hc->stE[i]) : 0;
         out[i].us_end = (float)((double)(hc->t_end[i] - hc->t_start) * 1e-3);
         out[i].us_S = tail ? (float)((double)(hc->t_S[i] - hc->t_begin[i]) * 1e-3) : 0.f;
         out[i].us_R = tail ? (float)((double)(hc->t_R[i] - hc->t_S[i]) * 1e-3) : 0.f;

@@ -178,24 +178,36 @@ __global__ void __launch_bounds__(NT) k_dd_mark(const GsegCtl *ctl, GsegBufs B, 
     for (u32 c = blockIdx.x * NT + threadIdx.x; c < st.V; c += gridDim.x * NT) best[c] = GSEG_KEY_NONE;
 }
 
-// Ordered compaction of the flagged edges: chunks of blockDim list positions by ticket, block-granular look-back.
+// Ordered compaction of the flagged edges: chunks of 4 x blockDim list positions by ticket (4 consecutive positions per
+// thread), block-granular look-back.
 __global__ void __launch_bounds__(1024) k_dd_compact(GsegCtl *ctl, GsegBufs B, DedupDev *dd) {
     __shared__ u32 s[68];
     if (!dd->sort.active) return;
     const RoundState st = load_state(ctl);
     const int cur = st.round & 1, lane = threadIdx.x & 31;
-    const u32 n = dd->sort.n, nchunks = (n + blockDim.x - 1) / blockDim.x, tag = dd->tag;
+    const u32 CH = 4u * blockDim.x;
+    const u32 n = dd->sort.n, nchunks = (n + CH - 1u) / CH, tag = dd->tag;
     for (;;) {
         if (threadIdx.x == 0) s[67] = atomicAdd(&ctl->ticketE, 1u);
         __syncthreads();
         const u32 chunk = s[67];
         if (chunk >= nchunks) break;
-        const u32 i = chunk * blockDim.x + threadIdx.x;
-        const bool k = i < n && dd->keep[i] != 0u;
-        const u32 m = __ballot_sync(0xFFFFFFFFu, k);
+        const u32 i0 = chunk * CH + 4u * threadIdx.x;
+        u32 kb = 0u;
+        if (i0 + 3u < n) {
+            const uint4 k4 = *reinterpret_cast<const uint4 *>(dd->keep + i0);
+            kb = (k4.x ? 1u : 0u) | (k4.y ? 2u : 0u) | (k4.z ? 4u : 0u) | (k4.w ? 8u : 0u);
+        } else {
+            for (u32 q = 0; q < 4u; ++q)
+                if (i0 + q < n && dd->keep[i0 + q]) kb |= 1u << q;
+        }
+        const u32 cnt = (u32)__popc(kb);
+        const u32 inc = warp_incl_scan(cnt, lane);
         u32 bend;
-        const u32 wpre = block_ordered_offset(__popc(m), chunk, tag, B.statusE, &ctl->error, s, &bend);
-        if (k) { const u32 o = wpre + __popc(m & ((1u << lane) - 1u)); B.eab[cur][o] = dd->xab[i]; B.ew[cur][o] = dd->xw[i]; }
+        const u32 wpre = block_ordered_offset(__shfl_sync(0xFFFFFFFFu, inc, 31), chunk, tag, B.statusE, &ctl->error, s, &bend);
+        u32 o = wpre + inc - cnt;
+        for (u32 q = 0; q < 4u; ++q)
+            if ((kb >> q) & 1u) { B.eab[cur][o] = dd->xab[i0 + q]; B.ew[cur][o] = dd->xw[i0 + q]; ++o; }
         if (chunk == nchunks - 1 && threadIdx.x == 0) dd->kept = bend;
         __syncthreads();
     }

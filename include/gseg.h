@@ -78,16 +78,17 @@ typedef struct gseg_params {
 /* One row per executed Boruvka round (SURVEY.md section 5 "metrics": V_r, E_r per round). */
 typedef struct gseg_round_stat {
     int64_t n_components; /* components entering the round */
-    int64_t n_edges;      /* live (inter-component) edges entering the round, parallel edges included, as the list
-                             carried them -- until the duplicate elimination has run (n_edges_dedup != 0); from the
-                             round after it on, the edges of the de-duplicated list */
+    int64_t n_edges;      /* live (inter-component) edges of the list entering the round.  Until duplicates have been
+                             dropped (n_edges_dedup == 0) this is every parallel edge, i.e. the count a plain
+                             Boruvka contraction carries */
     int64_t n_merged;     /* components merged away by the round */
     int32_t phase;        /* 0 = predicate / hierarchy round, 1 = min-size round */
     int32_t in_tail;      /* 1 when the round ran inside the single-cluster tail kernel */
     float us_end;         /* device clock at the end of the round, microseconds since round 0's graph kernel started */
     float us_S, us_R, us_E; /* tail rounds: duration of the choose/scan, flatten and edge phases (else 0) */
     int32_t n_pages;      /* pages of the edge list entering the round */
-    int32_t n_edges_dedup; /* != 0: the list was de-duplicated right before this round, to this many edges */
+    int32_t n_edges_dedup; /* != 0: duplicates have been dropped from the list this round ran on (by the sort step in front of
+                              this round or of an earlier one); the edges it ran on */
 } gseg_round_stat;
 
 typedef struct gseg_ctx gseg_ctx;
@@ -128,6 +129,15 @@ int gseg_set_tail(gseg_ctx *ctx, uint32_t max_edges, uint32_t max_components);
 /* Scheduling knob (no effect on results): resident blocks per SM the grid-wide kernels are sized for
  * (1..8, default 4).  With several contexts in flight per GPU, 2 leaves room for their kernels to overlap. */
 int gseg_set_blocks_per_sm(gseg_ctx *ctx, int blocks);
+
+/* Duplicate-edge elimination between rounds (the reference's DPP branches sort the packed
+ * edge keys every round and keep the lightest of every run of duplicates, Report.pdf p3 s3.2.2).  When on, FELZ / HIER
+ * runs sort the list by component pair with the in-house onesweep radix sort once the graph has at most 65536
+ * components while the list holds >= min_edges edges and >= min_ratio edges per component (0 = keep the current value;
+ * defaults 8192 and 8), keep the minimum (weight, list position) of every run and re-compact the list in order.  The
+ * result is identical either way.  Default: off (on B200 the remaining rounds cost less than the sort at 1080p / 4K;
+ * DESIGN.md has the A/B); environment GSEG_DEDUP=1 switches it on for every context of the process. */
+int gseg_set_dedup(gseg_ctx *ctx, int on, uint32_t min_edges, uint32_t min_ratio);
 
 /* Replaces: L3 pre-filter + L2 graph creation + L1 segmentation core of one reference executable
  * (Report p2 Fig.1; p3 s3.2.1; p2-3 s3.1 steps 1-9; p3-4 s3.2.2; p4 s3.2.4).
@@ -321,6 +331,8 @@ int gseg_pool_copy_ceiling(gseg_pool *pool, const gseg_pool_job *jobs, const gse
 
 /* Stand-alone primitives of the edge-dedup path (Report p3 s3.2.2
  * "sort"): in-house onesweep radix sort of 64-bit keys with 32-bit payload, on device memory. */
+/* Runs on the context's stream and returns when the arrays are sorted; keys / vals must be complete when it is
+ * called (work enqueued on other streams is not waited for). */
 int gseg_sort_pairs_u64(gseg_ctx *ctx, uint64_t *keys, uint32_t *vals, int64_t n, int begin_bit, int end_bit);
 
 #ifdef __cplusplus

@@ -75,7 +75,7 @@ def test_felz_partition_bit_exact(gseg, oracle, seg, w, h, conn, flags):
         # live edges per round equal the oracle's (which carries every parallel edge) up to and including the round in
         # front of which the engine eliminated duplicates; V, merged and phase of every round are unaffected by that
         dd = seg.dedup_rounds()
-        upto = dd[0][0] + 1 if dd else len(st)
+        upto = dd[0][0] + 1 if dd else len(st)   # the sort step reports the carried count for the round it ran in front of
         assert [int(r[1]) for r in ref["stats"]][1:upto] == [b for a, b, c, d in st][1:upto]
 
 
@@ -298,6 +298,7 @@ def test_sort_pairs(gseg, seg):
         vals = torch.arange(n, dtype=torch.int32, device="cuda")
         ref_k, ref_i = torch.sort(keys, stable=True)
         k2, v2 = keys.clone(), vals.clone()
+        torch.cuda.synchronize()  # the sort runs on the context's own stream: its inputs must be complete (torch wrote them on another)
         seg.sort_pairs(k2.data_ptr(), v2.data_ptr(), n, 0, bits)
         assert torch.equal(k2, ref_k)
         assert torch.equal(v2.long(), ref_i)
