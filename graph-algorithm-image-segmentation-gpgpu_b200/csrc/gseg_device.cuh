@@ -307,8 +307,12 @@ __device__ __forceinline__ void warp_run_min2(u64 *best, u32 ida, u32 idb, u32 k
         if (leadb && act && kbb <= atomicMin(sfilter + idb, kbb)) atomicMin(best + idb, make_key(kbb, qb));
         return;
     }
+#ifndef GSEG_EXP_NOATOMIC
     if (leada && act && (!FILTER || ka <= hia)) atomicMin(best + ida, make_key(ka, qa));
     if (leadb && act && (!FILTER || kbb <= hib)) atomicMin(best + idb, make_key(kbb, qb));
+#else
+    if (leada && act && ka == 0x12345678u && qa == 77u) best[ida] = make_key(kbb, qb); // keeps the reduction alive
+#endif
 }
 
 // Same run structure for the size / Int(C) accumulation of phase R: the run's first lane adds the

@@ -632,11 +632,15 @@ __device__ __forceinline__ void emit_row(const GsegBufs &B, int nxt, u32 pos, bo
                                          u32 fa = 0xFFFFFFFFu, u32 fb = 0xFFFFFFFFu, u32 *sfilter = nullptr) {
     u32 kb = wv;
     if (act) {
+#ifndef GSEG_EXP_NOSTORE
         B.eab[nxt][pos] = make_uint2(a, b);
         B.ew[nxt][pos] = wv;
+#endif
         if (SP) kb = __float_as_uint(__fmul_rn(__uint_as_float(wv), mean_dist_m(B.cmean[nxt], a, b)));
     }
+#ifndef GSEG_EXP_NOMIN
     warp_run_min2<FILTER, FILTER ? 32 : RUNWIN>(B.best[nxt], a, b, kb, pos, act, fa, fb, sfilter);
+#endif
 }
 
 // a10 (round 0): grid edges -> paged list of inter-component edges, in edge-index order

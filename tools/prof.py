@@ -10,7 +10,8 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 gseg = importlib.import_module("graph-algorithm-image-segmentation-gpgpu_b200")
-gseg.build()
+if not os.environ.get("GSEG_NOBUILD"):
+    gseg.build()
 import torch
 
 w, h, conn, variant = (int(x) for x in (sys.argv[1:5] if len(sys.argv) >= 5 else (1920, 1080, 4, 0)))
