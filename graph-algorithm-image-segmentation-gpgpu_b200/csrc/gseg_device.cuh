@@ -268,6 +268,29 @@ __device__ __forceinline__ void warp_run_min(u64 *best, u32 id, u32 kb, u32 pos,
     }
 }
 
+// Rows in which no two neighbouring surviving edges share an end on the same side (every run has length one): the shuffle
+// minima would reduce nothing.  What such rows do have -- they are the stretches of the list that come from direction-E
+// grid edges: a row of the image crosses components A|B|C|..., giving edges (A,B), (B,C), ... -- is that the RIGHT end of
+// a surviving edge is the LEFT end of the next surviving one.  So a lane folds the previous surviving lane's key into
+// its own before it updates its left end's minimum, and a lane whose right end the next surviving lane takes care of
+// issues no second atomic: about one atomic per edge instead of two, 4 shuffles instead of 10.  Valid for any row (the
+// equalities are tested, not assumed).  `pos` increases with the lane.  All 32 lanes must call.
+__device__ __forceinline__ void warp_chain_min(u64 *best, u32 a, u32 b, u32 kb, u32 pos, bool act, u32 actm) {
+    const int lane = threadIdx.x & 31;
+    const u32 below = actm & ((1u << lane) - 1u), above = actm & ~((2u << lane) - 1u);
+    const int pl = below ? 31 - __clz(below) : lane, nl = above ? __ffs(above) - 1 : lane;
+    const u32 pk = __shfl_sync(0xFFFFFFFFu, kb, pl), pp = __shfl_sync(0xFFFFFFFFu, pos, pl), pb = __shfl_sync(0xFFFFFFFFu, b, pl);
+    const u32 na = __shfl_sync(0xFFFFFFFFu, a, nl);
+#ifndef GSEG_EXP_NOATOMIC
+    if (act) {
+        u32 ka = kb, qa = pos;
+        if (below && pb == a && pk <= kb) { ka = pk; qa = pp; } // the earlier edge wins ties: its position is lower
+        atomicMin(best + a, make_key(ka, qa));
+        if (!(above && na == b)) atomicMin(best + b, make_key(kb, pos)); // else the next surviving lane folds this edge in
+    }
+#endif
+}
+
 // Both ends of a row of edges at once: the two segmented minima are independent dependency chains, so
 // interleaving their shuffles halves the latency of the row (these kernels run few warps per SM in late
 // rounds and are bound by exactly this chain).
@@ -280,6 +303,10 @@ __device__ __forceinline__ void warp_run_min2(u64 *best, u32 ida, u32 idb, u32 k
     const bool prev_act = lane != 0 && ((actm >> (lane - 1)) & 1u);
     const bool heada = !prev_act || pa != ida, headb = !prev_act || pb != idb;
     const u32 headsa = __ballot_sync(0xFFFFFFFFu, heada || !act), headsb = __ballot_sync(0xFFFFFFFFu, headb || !act);
+    if (!FILTER && (headsa & headsb) == 0xFFFFFFFFu) { // warp-uniform: every run has length one on both sides
+        warp_chain_min(best, ida, idb, kb, pos, act, actm);
+        return;
+    }
     if (!act) kb = 0xFFFFFFFFu;
     const u32 hmask = ~((2u << lane) - 1u), lmask = (2u << lane) - 1u;
     const u32 abva = headsa & hmask, abvb = headsb & hmask;

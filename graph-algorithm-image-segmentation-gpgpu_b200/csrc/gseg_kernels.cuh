@@ -643,6 +643,23 @@ __device__ __forceinline__ void emit_row(const GsegBufs &B, int nxt, u32 pos, bo
 #endif
 }
 
+// Round 0, direction E (pixel p -> p + 1): consecutive lanes are consecutive pixels, so every run of equal ends has length
+// one by construction and the row goes straight to the chain form of the minima (warp_chain_min).
+template <bool SP>
+__device__ __forceinline__ void emit_row_east(const GsegBufs &B, int nxt, u32 pos, bool act, u32 a, u32 b, u32 wv) {
+    u32 kb = wv;
+    if (act) {
+#ifndef GSEG_EXP_NOSTORE
+        B.eab[nxt][pos] = make_uint2(a, b);
+        B.ew[nxt][pos] = wv;
+#endif
+        if (SP) kb = __float_as_uint(__fmul_rn(__uint_as_float(wv), mean_dist_m(B.cmean[nxt], a, b)));
+    }
+#ifndef GSEG_EXP_NOMIN
+    warp_chain_min(B.best[nxt], a, b, kb, pos, act, __ballot_sync(0xFFFFFFFFu, act));
+#endif
+}
+
 // a10 (round 0): grid edges -> paged list of inter-component edges, in edge-index order
 // (direction-major: all E edges in pixel order, then S, SE, NE).
 //
@@ -702,7 +719,8 @@ __global__ void __launch_bounds__(NT, 4) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
         for (int j = 0; j < ROWS; ++j) {
             if (m[j] == 0u) continue; // warp-uniform
             const bool act = (m[j] >> lane) & 1u;
-            emit_row<SP, false>(B, 1, rowoff + __popc(m[j] & lt), act, a[j], b[j], wv[j]);
+            if (d == 0) emit_row_east<SP>(B, 1, rowoff + __popc(m[j] & lt), act, a[j], b[j], wv[j]);
+            else emit_row<SP, false>(B, 1, rowoff + __popc(m[j] & lt), act, a[j], b[j], wv[j]);
             rowoff += __popc(m[j]);
         }
     }
