@@ -575,43 +575,80 @@ __device__ __forceinline__ void block_scan_pages(const u32 *pcnt, u32 P, u32 *ps
 // ------------------------------------------------------------------------------------------------
 template <int NTH, bool R0, bool SP, bool SPREAD = false>
 __device__ __forceinline__ void phase_R(const GsegCtl *ctl, const GsegBufs &B, const RoundState &st) {
+    // RPT rows of 32 consecutive components per warp and step: the pointer chases of a thread's RPT components are
+    // independent dependency chains, issued together (ncu: the kernel waits on these gathers, 25-28 cycles of
+    // long-scoreboard stall per issued instruction with one chain per thread).  Measured on a 2^27-pixel image: rounds
+    // >= 1 620 -> 396 us (round 1), 172 -> 111 us (round 2); round 0 (components = pixels, chains short and local,
+    // occupancy matters more than chains per thread) 1250 -> 1400 us, so it keeps one chain per thread.
+    constexpr int RPT = (SPREAD || R0) ? 1 : 4;
     const int cur = st.round & 1, nxt = cur ^ 1;
-    const u32 V = st.V, Vr = (V + 31u) & ~31u;
+    const u32 V = st.V;
     u32 *map = B.arena + st.map_off;
     const u32 V0 = (u32)ctl->p.w * (u32)ctl->p.h;
+    const u32 lane = threadIdx.x & 31u, wid = threadIdx.x >> 5, nwarp = NTH / 32;
     // SPREAD (tail): consecutive warps' worth of components go to different blocks (see phase_S)
-    const u32 c_first = SPREAD ? ((threadIdx.x >> 5) * gridDim.x + blockIdx.x) * 32u + (threadIdx.x & 31u) : blockIdx.x * NTH + threadIdx.x;
-    for (u32 c = c_first; c < Vr; c += gridDim.x * NTH) {
-        const bool act = c < V;
-        u32 m = 0u, sz = 1u, iv = 0u;
-        if (act) {
-            u32 r = SPREAD ? ld_relaxed_u32(B.succ + c) : B.succ[c];
-            if (r != c) {
-                u32 steps = 0;
-                for (;;) {
-                    const u32 rr = SPREAD ? ld_relaxed_u32(B.succ + r) : B.succ[r]; // stale = an older ancestor: still valid
-                    if (rr == r) break;
-                    r = rr;
-                    if (++steps > V) { ((GsegCtl *)ctl)->error = DERR_CHASE; break; } // a cycle can only come from a bug: fail, do not hang
-                }
-                B.succ[c] = r;
-            }
-            m = ld_prev<!SPREAD>(B.rank + r);
-            map[c] = m;
-            if (!R0) { const uint2 at = ld_prev<!SPREAD>(B.attr[cur] + c); sz = at.x; iv = at.y; }
-            if (r != c) iv = max(iv, __ldcg(B.wsel + c));
+    const u32 tile0 = SPREAD ? wid * gridDim.x + blockIdx.x : blockIdx.x * nwarp + wid;
+    const u32 ntile = (V + 32u * RPT - 1u) / (32u * RPT);
+    for (u32 tile = tile0; tile < ntile; tile += gridDim.x * nwarp) {
+        u32 c[RPT], r[RPT];
+        bool act[RPT], moved[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            c[k] = (tile * RPT + (u32)k) * 32u + lane;
+            act[k] = c[k] < V;
+            r[k] = act[k] ? (SPREAD ? ld_relaxed_u32(B.succ + c[k]) : B.succ[c[k]]) : c[k];
+            moved[k] = r[k] != c[k];
         }
-        warp_run_accumulate(B.attr[nxt], m, sz, iv, act);
-        if (SP && act) {
-            long long v0, v1, v2;
-            if (R0) { v0 = fx8(B.planes[c]); v1 = fx8(B.planes[V0 + c]); v2 = fx8(B.planes[2 * V0 + c]); }
-            else {
-                v0 = __ldcg(B.csum[cur] + 3 * (size_t)c); v1 = __ldcg(B.csum[cur] + 3 * (size_t)c + 1);
-                v2 = __ldcg(B.csum[cur] + 3 * (size_t)c + 2);
+        // chase to the roots; stale values are older ancestors: still valid
+        bool busy[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) busy[k] = moved[k];
+        for (u32 steps = 0;; ++steps) {
+            u32 rr[RPT];
+            bool any = false;
+#pragma unroll
+            for (int k = 0; k < RPT; ++k)
+                if (busy[k]) rr[k] = SPREAD ? ld_relaxed_u32(B.succ + r[k]) : B.succ[r[k]];
+#pragma unroll
+            for (int k = 0; k < RPT; ++k)
+                if (busy[k]) {
+                    if (rr[k] == r[k]) busy[k] = false;
+                    else { r[k] = rr[k]; any = true; }
+                }
+            if (!any) break;
+            if (steps > V) { ((GsegCtl *)ctl)->error = DERR_CHASE; break; } // a cycle can only come from a bug: fail, do not hang
+        }
+        u32 m[RPT], sz[RPT], iv[RPT];
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            m[k] = 0u; sz[k] = 1u; iv[k] = 0u;
+            if (act[k]) {
+                if (moved[k]) B.succ[c[k]] = r[k];
+                m[k] = ld_prev<!SPREAD>(B.rank + r[k]);
             }
-            atomicAdd((u64 *)(B.csum[nxt] + 3 * (size_t)m), (u64)v0);
-            atomicAdd((u64 *)(B.csum[nxt] + 3 * (size_t)m + 1), (u64)v1);
-            atomicAdd((u64 *)(B.csum[nxt] + 3 * (size_t)m + 2), (u64)v2);
+        }
+#pragma unroll
+        for (int k = 0; k < RPT; ++k)
+            if (act[k]) {
+                map[c[k]] = m[k];
+                if (!R0) { const uint2 at = ld_prev<!SPREAD>(B.attr[cur] + c[k]); sz[k] = at.x; iv[k] = at.y; }
+                if (moved[k]) iv[k] = max(iv[k], __ldcg(B.wsel + c[k]));
+            }
+#pragma unroll
+        for (int k = 0; k < RPT; ++k) {
+            warp_run_accumulate(B.attr[nxt], m[k], sz[k], iv[k], act[k]);
+            if (SP && act[k]) {
+                long long v0, v1, v2;
+                const u32 cc = c[k];
+                if (R0) { v0 = fx8(B.planes[cc]); v1 = fx8(B.planes[V0 + cc]); v2 = fx8(B.planes[2 * V0 + cc]); }
+                else {
+                    v0 = __ldcg(B.csum[cur] + 3 * (size_t)cc); v1 = __ldcg(B.csum[cur] + 3 * (size_t)cc + 1);
+                    v2 = __ldcg(B.csum[cur] + 3 * (size_t)cc + 2);
+                }
+                atomicAdd((u64 *)(B.csum[nxt] + 3 * (size_t)m[k]), (u64)v0);
+                atomicAdd((u64 *)(B.csum[nxt] + 3 * (size_t)m[k] + 1), (u64)v1);
+                atomicAdd((u64 *)(B.csum[nxt] + 3 * (size_t)m[k] + 2), (u64)v2);
+            }
         }
     }
 }
