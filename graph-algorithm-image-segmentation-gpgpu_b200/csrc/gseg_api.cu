@@ -643,6 +643,10 @@ static cudaError_t enqueue_tail(gseg_ctx *c, cudaStream_t s) {
     return cudaLaunchKernelEx(&cfg, k_tail<false>, ctl, B);
 }
 
+static size_t edge_slots(const gseg_ctx *ctx) {
+    return (size_t)ctx->Dmax * ((ctx->Vmax + GSEG_PAGE - 1) / GSEG_PAGE + 1) * GSEG_PAGE;
+}
+
 static int max_rounds_of(const gseg_params *p) {
     int r = p->max_rounds > 0 ? p->max_rounds : 48;
     return r > GSEG_MAXR ? GSEG_MAXR : r;
@@ -659,6 +663,10 @@ static int finish(gseg_ctx *ctx) {
     if (ctx->h_ctl->error == DERR_SCAN) return fail(ctx, GSEG_E_INTERNAL, "look-back watchdog", cudaSuccess);
     if (ctx->h_ctl->error == DERR_ARENA) return fail(ctx, GSEG_E_ARENA, "map arena", cudaSuccess);
     if (ctx->h_ctl->error == DERR_CHASE) return fail(ctx, GSEG_E_INTERNAL, "successor cycle", cudaSuccess);
+    if (ctx->h_ctl->error >= DERR_CHECK) {
+        snprintf(ctx->err, sizeof(ctx->err), "checked build: bounds check at site %u failed", ctx->h_ctl->error - DERR_CHECK);
+        return GSEG_E_INTERNAL;
+    }
     // remember how many grid-wide rounds this kind of image needed before the tail could take over
     const GsegCtl *h = ctx->h_ctl;
     int nbig = 0;
@@ -831,7 +839,7 @@ static int segment_async_impl(gseg_ctx *ctx, const uint8_t *rgb, int w, int h, i
     hp->h_in = h_in; hp->y_off = halo_top;
     hp->k = p->k; hp->min_size = p->min_size; hp->max_rounds = R;
     hp->max_levels = p->max_levels > 0 ? p->max_levels : INT_MAX;
-    hp->arena_cap = (u32)ctx->arena_cap;
+    hp->arena_cap = (u32)ctx->arena_cap; hp->edge_slots = (u32)edge_slots(ctx);
     hp->epoch_base = ctx->epoch_next;
     hp->mask_len = len;
     hp->filter_shift = ctx->filter_shift;
@@ -1252,7 +1260,7 @@ static int graph_run(gseg_ctx *ctx, size_t V, size_t E, const gseg_params *p) {
     hp->w = (int)V; hp->h = 1; hp->h_in = 1; hp->D = 2; hp->variant = p->variant;
     hp->k = p->k; hp->min_size = p->min_size; hp->max_rounds = R + 1 > GSEG_MAXR ? GSEG_MAXR : R + 1; // rounds are numbered from 1 here
     hp->max_levels = p->max_levels > 0 ? p->max_levels : INT_MAX;
-    hp->arena_cap = (u32)ctx->arena_cap;
+    hp->arena_cap = (u32)ctx->arena_cap; hp->edge_slots = (u32)edge_slots(ctx);
     hp->epoch_base = ctx->epoch_next;
     hp->filter_shift = ctx->filter_shift;
     const bool host_loop = (p->flags & GSEG_FLAG_HOST_LOOP) != 0;
@@ -1301,6 +1309,10 @@ static int graph_run(gseg_ctx *ctx, size_t V, size_t E, const gseg_params *p) {
     if (ctx->h_ctl->error == DERR_SCAN) return fail(ctx, GSEG_E_INTERNAL, "look-back watchdog", cudaSuccess);
     if (ctx->h_ctl->error == DERR_ARENA) return fail(ctx, GSEG_E_ARENA, "map arena", cudaSuccess);
     if (ctx->h_ctl->error == DERR_CHASE) return fail(ctx, GSEG_E_INTERNAL, "successor cycle", cudaSuccess);
+    if (ctx->h_ctl->error >= DERR_CHECK) {
+        snprintf(ctx->err, sizeof(ctx->err), "checked build: bounds check at site %u failed", ctx->h_ctl->error - DERR_CHECK);
+        return GSEG_E_INTERNAL;
+    }
     // labels of the input components: the maps of rounds 1 .. last composed
     const int last = (int)ctx->h_ctl->st.round - 1;
     ++ctx->launches;
@@ -1309,9 +1321,6 @@ static int graph_run(gseg_ctx *ctx, size_t V, size_t E, const gseg_params *p) {
     return (int)ctx->h_ctl->st.V;
 }
 
-static size_t edge_slots(const gseg_ctx *ctx) {
-    return (size_t)ctx->Dmax * ((ctx->Vmax + GSEG_PAGE - 1) / GSEG_PAGE + 1) * GSEG_PAGE;
-}
 
 extern "C" int gseg_segment_graph(gseg_ctx *ctx, int64_t n_components, const uint32_t *size, const float *Int, int64_t n_edges,
                                   const uint32_t *ea, const uint32_t *eb, const float *w, const gseg_params *p,

@@ -90,6 +90,7 @@ __global__ void __launch_bounds__(NT) k_dd_keys(const GsegCtl *ctl, GsegBufs B, 
             const u32 w = __ldcg(B.ew[cur] + src + i);
             const u32 key = (min(ab.x, ab.y) << bits) | max(ab.x, ab.y);
             const u32 o = dst + i;
+            GSEG_CHK(ctl, o < dd->cap && src + i < ctl->p.edge_slots && ab.x < st.V && ab.y < st.V, 11);
             keys[o] = (u64)key; vals[o] = o;
             dd->xab[o] = ab; dd->xw[o] = w;
             dd->winner[o] = GSEG_KEY_NONE; dd->keep[o] = 0u;

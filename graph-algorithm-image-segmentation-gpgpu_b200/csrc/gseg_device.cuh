@@ -15,7 +15,20 @@ typedef unsigned long long u64;
 #define GSEG_PAGE 256u /* slots per page of the edge list = one warp tile (8 rows of 32) */
 
 enum { PH_PRED = 0, PH_MINSIZE = 1, PH_DONE = 2 };
-enum { DERR_NONE = 0, DERR_SCAN = 1, DERR_ARENA = 2, DERR_CHASE = 3 };
+enum { DERR_NONE = 0, DERR_SCAN = 1, DERR_ARENA = 2, DERR_CHASE = 3, DERR_CHECK = 100 /* + site: a bounds check of a checked build */ };
+
+// Checked build (-DGSEG_CHECKED, tools/checked_run.sh): index / capacity assertions at the places where an id, a list slot
+// or an arena offset computed on the device is used as an address.  compute-sanitizer is closed on the GPU pool this was
+// developed on, so this is the memcheck that could be run: a failed check records its site in the control block and the
+// run ends with GSEG_E_INTERNAL.  Compiled out of the product build.
+#ifdef GSEG_CHECKED
+#define GSEG_CHK(ctl, cond, site)                                                         \
+    do {                                                                                  \
+        if (!(cond)) atomicMax(&(const_cast<GsegCtl *>(ctl))->error, (u32)DERR_CHECK + (u32)(site)); \
+    } while (0)
+#else
+#define GSEG_CHK(ctl, cond, site) ((void)0)
+#endif
 
 // Parameters of one run; filled by the host in pinned memory and copied into GsegCtl::p.
 struct GsegRunParams {
@@ -26,6 +39,7 @@ struct GsegRunParams {
     float k;
     int min_size, max_rounds, max_levels;
     u32 arena_cap;  // capacity of the supervertex-map arena in u32 entries
+    u32 edge_slots; // capacity of each parity of the edge list, in slots (checked builds)
     u32 epoch_base; // first look-back tag of this run (monotonic across runs)
     int mask_len;
     u32 filter_shift;   // read-before-atomic filter when (E >> filter_shift) > surviving components

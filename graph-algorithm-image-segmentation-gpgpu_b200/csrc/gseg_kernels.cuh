@@ -259,6 +259,7 @@ __device__ __forceinline__ void r0_finish_tile(GsegCtl *ctl, const GsegBufs &B, 
     }
     __syncthreads();
     const u32 pre = s_scan[33];
+    GSEG_CHK(ctl, (unsigned long long)pre + total <= (unsigned long long)ctl->p.w * ctl->p.h, 1);
     if (tile == ntiles - 1 && threadIdx.x == 0) ctl->Vnext = pre + total;
     const u32 w = (u32)ctl->p.w;
     u32 id = pre + ex;
@@ -623,8 +624,10 @@ __device__ __forceinline__ void phase_R(const GsegCtl *ctl, const GsegBufs &B, c
         for (int k = 0; k < RPT; ++k) {
             m[k] = 0u; sz[k] = 1u; iv[k] = 0u;
             if (act[k]) {
+                GSEG_CHK(ctl, r[k] < V, 2);
                 if (moved[k]) B.succ[c[k]] = r[k];
                 m[k] = ld_prev<!SPREAD>(B.rank + r[k]);
+                GSEG_CHK(ctl, m[k] < V && (unsigned long long)st.map_off + c[k] < ctl->p.arena_cap, 3);
             }
         }
 #pragma unroll
@@ -750,6 +753,7 @@ __global__ void __launch_bounds__(NT, 4) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
 #pragma unroll
         for (int j = 0; j < ROWS; ++j) total += __popc(m[j]);
         if (lane == 0) { B.pcnt[1][tile] = total; B.poff[1][tile] = tile * GSEG_PAGE; }
+        GSEG_CHK(ctl, (unsigned long long)tile * GSEG_PAGE + total <= ctl->p.edge_slots, 4);
         esum += total;
         u32 rowoff = tile * GSEG_PAGE;
 #pragma unroll
@@ -844,12 +848,16 @@ __device__ __forceinline__ void phase_S(GsegCtl *ctl, const GsegBufs &B, const R
 #pragma unroll
         for (int j = 0; j < CPT; ++j) key[j] = base + 32u * j < V ? ld_prev<!SPREAD>(best + base + 32u * j) : GSEG_KEY_NONE;
 #pragma unroll
-        for (int j = 0; j < CPT; ++j) ab[j] = key[j] != GSEG_KEY_NONE ? ld_prev<!SPREAD>(eab + (u32)key[j]) : make_uint2(0u, 0u);
+        for (int j = 0; j < CPT; ++j) {
+            GSEG_CHK(ctl, key[j] == GSEG_KEY_NONE || (u32)key[j] < ctl->p.edge_slots, 5);
+            ab[j] = key[j] != GSEG_KEY_NONE ? ld_prev<!SPREAD>(eab + (u32)key[j]) : make_uint2(0u, 0u);
+        }
 #pragma unroll
         for (int j = 0; j < CPT; ++j) {
             key2[j] = GSEG_KEY_NONE; ta[j] = tb[j] = make_uint2(1u, 0u);
             if (key[j] != GSEG_KEY_NONE) {
                 const u32 c = base + 32u * j, other = ab[j].x == c ? ab[j].y : ab[j].x;
+                GSEG_CHK(ctl, (ab[j].x == c || ab[j].y == c) && other < V && other != c, 6);
                 key2[j] = ld_prev<!SPREAD>(best + other);
                 if (pred || msz) { ta[j] = ld_prev<!SPREAD>(attr + ab[j].x); tb[j] = ld_prev<!SPREAD>(attr + ab[j].y); }
             }
@@ -977,7 +985,11 @@ __device__ __forceinline__ void phase_E_rows(GsegCtl *ctl, const GsegBufs &B, co
                 const u32 src = __shfl_sync(0xFFFFFFFFu, myoff, (int)k) + (i - __shfl_sync(0xFFFFFFFFu, excl, (int)k));
                 uint2 ab = make_uint2(0u, 0u);
                 wv[j] = 0u;
-                if (i < cnt) { ab = __ldcg(eab + src); wv[j] = __ldcg(ew + src); }
+                if (i < cnt) {
+                    GSEG_CHK(ctl, src < ctl->p.edge_slots, 7);
+                    ab = __ldcg(eab + src); wv[j] = __ldcg(ew + src);
+                    GSEG_CHK(ctl, ab.x < st.V && ab.y < st.V, 8);
+                }
                 a[j] = ab.x; b[j] = ab.y;
             }
             u32 sub = 0;
@@ -1003,6 +1015,7 @@ __device__ __forceinline__ void phase_E_rows(GsegCtl *ctl, const GsegBufs &B, co
                 parity ^= 1u;
             }
             u32 rowoff = out_base + written + before;
+            GSEG_CHK(ctl, (unsigned long long)out_base + written + total <= ctl->p.edge_slots, 9);
             if (filter && staged) {
 #pragma unroll
                 for (int j = 0; j < RW; ++j) {
@@ -1346,7 +1359,10 @@ __global__ void __launch_bounds__(NT) k_compose(const GsegCtl *__restrict__ ctl,
     for (u32 p = blockIdx.x * NT + threadIdx.x; p < V0; p += gridDim.x * NT) {
         u32 l = arena[p];
         for (int r = 1; r <= last_round; ++r)
-            if (!ctl->map_skip[r]) l = arena[ctl->map_off[r] + l];
+            if (!ctl->map_skip[r]) {
+                GSEG_CHK(ctl, l < ctl->stV[r] && (unsigned long long)ctl->map_off[r] + l < ctl->p.arena_cap, 10);
+                l = arena[ctl->map_off[r] + l];
+            }
         out[p] = (OutT)l;
     }
 }
