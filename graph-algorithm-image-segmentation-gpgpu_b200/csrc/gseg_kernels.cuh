@@ -31,6 +31,12 @@
 namespace cg = cooperative_groups;
 
 #define NT 256   // threads per block of the grid-wide kernels
+#ifndef GSEG_LB_SUCC
+#define GSEG_LB_SUCC 4  // resident blocks per SM the successor kernel is compiled for
+#endif
+#ifndef GSEG_LB_EDGES
+#define GSEG_LB_EDGES 4 // ... and the edge kernels (64 registers; more blocks means spills: measured, tools/lb_sweep.sh)
+#endif
 #define NTT 1024 // threads per block of the single-cluster tail kernel
 #define CPT 4    // rows of 32 components per warp tile of phase S
 #ifndef RUNWIN
@@ -714,7 +720,7 @@ __device__ __forceinline__ void emit_row_east(const GsegBufs &B, int nxt, u32 po
 // the pages have become sparse (< 1/4 full) does one round re-pack the list densely with the ordered
 // scan; by then the list is small.
 template <int D, bool SP>
-__global__ void __launch_bounds__(NT, 4) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
+__global__ void __launch_bounds__(NT, GSEG_LB_EDGES) k_r0_edges(GsegCtl *ctl, GsegBufs B) {
     constexpr int ROWS = GSEG_PAGE / 32;
     const int lane = threadIdx.x & 31;
     const u32 lt = (1u << lane) - 1u;
@@ -1118,7 +1124,7 @@ __global__ void __launch_bounds__(1024) k_page_scan(GsegCtl *ctl, GsegBufs B) {
     }
 }
 template <bool SP>
-__global__ void __launch_bounds__(NT) k_succ_scan(GsegCtl *ctl, GsegBufs B) {
+__global__ void __launch_bounds__(NT, GSEG_LB_SUCC) k_succ_scan(GsegCtl *ctl, GsegBufs B) {
     __shared__ u32 sh[66];
     const RoundState st = ctl->st;
     if (st.phase == PH_DONE || in_tail(ctl, st)) return;
@@ -1129,7 +1135,7 @@ __global__ void __launch_bounds__(NT) k_succ_scan(GsegCtl *ctl, GsegBufs B) {
     phase_S<SP, false>(ctl, B, st, sh);
 }
 template <bool SP>
-__global__ void __launch_bounds__(NT, 4) k_edges(GsegCtl *ctl, GsegBufs B) {
+__global__ void __launch_bounds__(NT, GSEG_LB_EDGES) k_edges(GsegCtl *ctl, GsegBufs B) {
     const RoundState st = ctl->st;
     if (st.phase == PH_DONE || in_tail(ctl, st)) return;
     phase_E<SP>(ctl, B, st, ctl->Vnext);
