@@ -10,4 +10,4 @@ O="python tools/one.py 1920 1080 4 0 1 2"
 $O > gpurun_out/plain_one.log 2>&1 &&
 ncu --set full --clock-control none --import-source on -k 'regex:k_blur_tile|k_r0_graph|k_relabel|k_r0_edges|k_succ_scan|k_edges' -s 43 -c 10 -f -o gpurun_out/prof_r2 $O > gpurun_out/ncu_one.log 2>&1
 echo "full capture rc=$?"
-tail -3 gpurun_out/ncu_bench.log gpurun_out/ncu_one.log
+tail -n 3 gpurun_out/ncu_bench.log; tail -n 3 gpurun_out/ncu_one.log
