@@ -146,6 +146,8 @@ def load():
     L.gseg_set_dedup.argtypes = [vp, i32, C.c_uint32, C.c_uint32]
     L.gseg_host_alloc.argtypes = [C.c_size_t]
     L.gseg_host_alloc.restype = vp
+    L.gseg_host_alloc_wc.argtypes = [C.c_size_t]
+    L.gseg_host_alloc_wc.restype = vp
     L.gseg_host_free.argtypes = [vp]
     L.gseg_host_free.restype = None
     L.gseg_get_stream.argtypes = [vp]
@@ -179,6 +181,32 @@ def load():
 
 class GsegError(RuntimeError):
     pass
+
+
+class HostBuffer:
+    """Pinned host memory from gseg_host_alloc (write_combined: gseg_host_alloc_wc, for inputs the CPU only writes) as a
+    numpy array; freed when the object goes away."""
+
+    def __init__(self, shape, dtype=np.uint8, write_combined=False):
+        self.L = load()
+        self.nbytes = int(np.prod(shape)) * np.dtype(dtype).itemsize
+        fn = self.L.gseg_host_alloc_wc if write_combined else self.L.gseg_host_alloc
+        self.ptr = fn(self.nbytes)
+        if not self.ptr:
+            raise GsegError("pinned host allocation of %d bytes failed" % self.nbytes)
+        self.array = np.ctypeslib.as_array((C.c_uint8 * self.nbytes).from_address(self.ptr)).view(dtype).reshape(shape)
+
+    def close(self):
+        if self.ptr:
+            self.array = None
+            self.L.gseg_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
 
 
 def jpeg_info(data):

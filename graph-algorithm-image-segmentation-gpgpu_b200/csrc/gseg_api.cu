@@ -764,6 +764,11 @@ extern "C" void *gseg_host_alloc(size_t bytes) {
     if (!bytes || cudaHostAlloc(&p, bytes, cudaHostAllocPortable) != cudaSuccess) { cudaGetLastError(); return nullptr; }
     return p;
 }
+extern "C" void *gseg_host_alloc_wc(size_t bytes) {
+    void *p = nullptr;
+    if (!bytes || cudaHostAlloc(&p, bytes, cudaHostAllocPortable | cudaHostAllocWriteCombined) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+    return p;
+}
 extern "C" void gseg_host_free(void *p) {
     if (p) cudaFreeHost(p);
 }

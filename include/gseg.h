@@ -115,6 +115,9 @@ int gseg_reserve(gseg_ctx *ctx, uint32_t caps);
 /* Pinned host memory for inputs/outputs of the asynchronous calls (cudaHostAlloc behind a plain pointer, so a
  * C/C++ caller needs no CUDA headers). */
 void *gseg_host_alloc(size_t bytes);
+/* Write-combined pinned memory: for INPUT buffers the CPU only writes (reading it from the CPU is very slow); the
+ * device's reads do not snoop the CPU caches. */
+void *gseg_host_alloc_wc(size_t bytes);
 void gseg_host_free(void *p);
 
 /* Run the context's work on a caller-owned CUDA stream (cudaStream_t as void*); NULL = own stream. */
