@@ -4,8 +4,8 @@
 // format) and write a random-colour image (Report.pdf p2 Fig.1, p4 s3.2.3); upstream `segment` reads
 // and writes PPM.  OpenCV's C++ headers are not in this image, zlib is, so PNG is done here directly:
 // decoder for every non-interlaced PNG colour type / bit depth (grey, RGB, palette, with or without
-// alpha; 16-bit samples keep their high byte, alpha is dropped), encoder for 8-bit RGB.  JPEG is not
-// supported (no libjpeg here); convert to PNG/PPM first.
+// alpha; 16-bit samples keep their high byte, alpha is dropped), encoder for 8-bit RGB.  JPEG files are
+// not decoded here: the CLI hands their bytes to gseg_segment_jpeg / a pool job, which decodes them on the GPU (nvJPEG).
 #pragma once
 #include <cstdint>
 #include <cstdio>

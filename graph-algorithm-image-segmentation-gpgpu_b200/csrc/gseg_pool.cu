@@ -85,6 +85,14 @@ extern "C" void gseg_pool_destroy(gseg_pool *p) {
     delete p;
 }
 
+// sizeof of every struct that crosses the ABI, for bindings to check their mirrors against
+extern "C" int gseg_abi_sizes(int32_t *out, int cap) {
+    const int32_t v[5] = {(int32_t)sizeof(gseg_params), (int32_t)sizeof(gseg_round_stat), (int32_t)sizeof(gseg_kernel_time),
+                          (int32_t)sizeof(gseg_pool_job), (int32_t)sizeof(gseg_pool_result)};
+    for (int i = 0; i < 5 && i < cap && out; ++i) out[i] = v[i];
+    return 5;
+}
+
 extern "C" int gseg_pool_contexts(const gseg_pool *p) { return p ? p->S : GSEG_E_ARG; }
 extern "C" gseg_ctx *gseg_pool_context(gseg_pool *p, int i) { return p && i >= 0 && i < p->S ? p->ctx[(size_t)i] : nullptr; }
 extern "C" int gseg_pool_pending(const gseg_pool *p) { return p ? (int)p->q.size() : GSEG_E_ARG; }

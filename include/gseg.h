@@ -94,6 +94,9 @@ typedef struct gseg_round_stat {
 typedef struct gseg_ctx gseg_ctx;
 
 int gseg_version(void);
+/* sizeof of gseg_params, gseg_round_stat, gseg_kernel_time, gseg_pool_job, gseg_pool_result (in this order), so that a
+ * binding (ctypes, cgo, JNI ...) can check its mirrors of the structs; returns how many there are. */
+int gseg_abi_sizes(int32_t *out, int cap);
 const char *gseg_strerror(int status);
 const char *gseg_last_error(const gseg_ctx *ctx);
 

@@ -31,6 +31,29 @@ def test_version_and_strerror(gseg):
 def test_struct_layout_matches_header(gseg):
     assert C.sizeof(gseg.Params) == 32
     assert C.sizeof(gseg.RoundStat) == 56
+    L = gseg.load()
+    out = (C.c_int32 * 8)()
+    L.gseg_abi_sizes.argtypes = [C.POINTER(C.c_int32), C.c_int]
+    assert L.gseg_abi_sizes(out, 8) == 5
+    mirrors = [gseg.Params, gseg.RoundStat, gseg.KernelTime, gseg.PoolJob, gseg.PoolResult]
+    assert [out[i] for i in range(5)] == [C.sizeof(m) for m in mirrors]
+
+
+def test_pool_and_new_entry_points_fail_cleanly_without_gpu(gseg):
+    """Argument errors need no device; creation without a device is GSEG_E_CUDA, never a fallback."""
+    import torch
+    L = gseg.load()
+    h = C.c_void_p()
+    assert L.gseg_pool_create(C.byref(h), 0, 64, 64, 8, 0, 0) == -1          # no contexts
+    assert L.gseg_pool_create(None, 0, 64, 64, 8, 4, 0) == -1
+    assert L.gseg_pool_next(None, None) == -1 and L.gseg_pool_pending(None) == -1
+    assert L.gseg_labels_ex(None, 0, None, 4, 0) == -1 and L.gseg_label_bytes(None, 0) < 0
+    assert L.gseg_strip_record(None, 1, None, 0, None) == -1
+    assert L.gseg_join_segment(None, None, 1, 0, 0, None, None, 4, 0, None, None) == -1
+    assert L.gseg_set_dedup(None, 1, 0, 0) == -1 and L.gseg_reserve(None, 1) == -1
+    assert L.gseg_strerror(-9).decode().startswith("label type too narrow")
+    if not torch.cuda.is_available():
+        assert L.gseg_pool_create(C.byref(h), 0, 64, 64, 8, 2, 0) == -2
 
 
 def test_no_gpu_fails_loudly(gseg):

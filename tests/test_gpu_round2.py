@@ -335,3 +335,35 @@ def test_duplicate_elimination_forced_everywhere(gseg, oracle, monkeypatch):
         assert ran >= 30
     finally:
         s.close()
+
+
+def test_cli_batch_directory(gseg, oracle, tmp_path):
+    """`gseg --batch IN_DIR OUT_DIR`: a directory of images of different sizes and formats through the C++ batch pipeline;
+    component counts equal the oracle's and every output is the same colour image the single-image mode writes."""
+    ind, outd = tmp_path / "in", tmp_path / "out"
+    ind.mkdir(); outd.mkdir()
+    sizes = [(160, 120), (97, 140), (200, 90), (64, 64), (131, 77)]
+    imgs = []
+    for i, (w, h) in enumerate(sizes):
+        img = oracle.synth(w, h, 700 + i)
+        imgs.append(img)
+        ppm = ind / ("img%02d.ppm" % i)
+        with open(ppm, "wb") as f:
+            f.write(b"P6\n%d %d\n255\n" % (w, h))
+            f.write(img.tobytes())
+        if i % 2:                                                  # every other one as PNG
+            assert subprocess.run([gseg.CLI_PATH, "--convert", str(ppm), str(ind / ("img%02d.png" % i))]).returncode == 0
+            os.remove(ppm)
+    r = subprocess.run([gseg.CLI_PATH, "--batch", str(ind), str(outd), "--contexts", "3", "--conn", "8", "0.8", "300", "20"],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert "batch of 5 images, 3 contexts" in r.stdout and "Mpixel/s" in r.stdout
+    for i, (w, h) in enumerate(sizes):
+        ref = oracle.pipeline(imgs[i], 0.8, 300.0, 20, 8, oracle.FELZ)
+        name = "img%02d.%s" % (i, "png" if i % 2 else "ppm")
+        assert "%s: got %d components" % (name, ref["n"]) in r.stdout, r.stdout
+        # the same picture as the single-image mode (same labels, same colour hash)
+        one = tmp_path / "one.png"
+        r1 = subprocess.run([gseg.CLI_PATH, "--conn", "8", "0.8", "300", "20", str(ind / name), str(one)], capture_output=True, text=True)
+        assert r1.returncode == 0, r1.stderr
+        assert open(one, "rb").read() == open(outd / ("img%02d.png" % i), "rb").read()
