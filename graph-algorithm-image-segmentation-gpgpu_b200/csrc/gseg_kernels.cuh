@@ -45,7 +45,9 @@ namespace cg = cooperative_groups;
 
 // round-0 image tiles
 #define TW 64
+#ifndef TH
 #define TH 32
+#endif
 #define BW (TW + 4)
 #define GH 28            // rows of a round-0 graph tile (28: five 256-thread blocks per SM fit in shared memory)
 #define GRPT (GH / 4)    // rows per thread in the successor step: 256 threads = 64 columns x 4 row groups
