@@ -143,7 +143,7 @@ def load():
     L.gseg_launch_count.restype = C.c_longlong
     L.gseg_sort_pairs_u64.argtypes = [vp, vp, vp, C.c_int64, i32, i32]
     L.gseg_reserve.argtypes = [vp, C.c_uint32]
-    L.gseg_set_dedup.argtypes = [vp, i32, C.c_uint32, C.c_uint32]
+    L.gseg_set_dedup.argtypes = [vp, i32, C.c_uint32, C.c_uint32, C.c_uint32]
     L.gseg_host_alloc.argtypes = [C.c_size_t]
     L.gseg_host_alloc.restype = vp
     L.gseg_host_alloc_wc.argtypes = [C.c_size_t]
@@ -273,9 +273,9 @@ class Segmenter:
     def set_tail(self, max_edges, max_components):
         self._ck(self.L.gseg_set_tail(self.h, max_edges, max_components), "gseg_set_tail")
 
-    def set_dedup(self, on, min_edges=0, min_ratio=0):
+    def set_dedup(self, on, min_edges=0, min_ratio=0, max_components=0):
         """Duplicate-edge elimination between rounds (sort by component pair, keep the lightest of every run)."""
-        self._ck(self.L.gseg_set_dedup(self.h, int(on), min_edges, min_ratio), "gseg_set_dedup")
+        self._ck(self.L.gseg_set_dedup(self.h, int(on), min_edges, min_ratio, max_components), "gseg_set_dedup")
 
     def set_blocks_per_sm(self, blocks):
         self._ck(self.L.gseg_set_blocks_per_sm(self.h, blocks), "gseg_set_blocks_per_sm")

@@ -70,8 +70,9 @@ struct gseg_ctx {
     DedupDev *d_dd;
     u64 *d_winner;
     size_t dd_cap;
-    u32 dd_min_edges, dd_min_ratio;
+    u32 dd_min_edges, dd_min_ratio, dd_V;
     bool dd_on;
+    bool dd_skip; // the last image of this shape never triggered the elimination: do not enqueue its (self-skipping) launches again
     // export of the final component graph (tiled schedule): cached dense / de-duplicated edge list; shares the
     // arrays below with the duplicate elimination
     u64 *d_xkeys;
@@ -216,9 +217,11 @@ extern "C" int gseg_create_ex(gseg_ctx **out, int device, int max_w, int max_h, 
     // shrunk far below the grid's edge count), sort scratch included -- nothing of this allocates later
     ctx->dd_cap = V < ((size_t)1 << 24) ? V : ((size_t)1 << 24);
     if (ctx->dd_cap < 4096) ctx->dd_cap = 4096;
-    // Off by default: measured on B200 (DESIGN.md "Duplicate elimination"), at 1080p and 4K the rounds that remain once
-    // V <= 65536 cost less than the sort; gseg_set_dedup / GSEG_DEDUP=1 switch it on.
-    ctx->dd_on = false; ctx->dd_min_edges = 8192u; ctx->dd_min_ratio = 8u;
+    // Thresholds from measurements on B200: the sort pays once the graph is down to <= 4096
+    // components (two 12-bit ids: three 8-bit passes) while the list still holds >= 2^19 edges (4K 8-connected
+    // hierarchies, large images); below that the remaining rounds cost less than the sort and it does not run.
+    ctx->dd_on = true; ctx->dd_min_edges = 1u << 19; ctx->dd_min_ratio = 8u; ctx->dd_V = 4096u;
+    if (const char *ev = getenv("GSEG_DEDUP_V")) ctx->dd_V = (u32)strtoul(ev, nullptr, 10);
     if (const char *ev = getenv("GSEG_DEDUP")) ctx->dd_on = atoi(ev) != 0;
     if (const char *ev = getenv("GSEG_DEDUP_MIN")) ctx->dd_min_edges = (u32)strtoul(ev, nullptr, 10);
     if (const char *ev = getenv("GSEG_DEDUP_RATIO")) ctx->dd_min_ratio = (u32)strtoul(ev, nullptr, 10);
@@ -419,14 +422,15 @@ extern "C" int gseg_set_tail(gseg_ctx *ctx, uint32_t max_edges, uint32_t max_com
     return GSEG_OK;
 }
 
-extern "C" int gseg_set_dedup(gseg_ctx *ctx, int on, uint32_t min_edges, uint32_t min_ratio) {
+extern "C" int gseg_set_dedup(gseg_ctx *ctx, int on, uint32_t min_edges, uint32_t min_ratio, uint32_t max_components) {
     if (!ctx) return GSEG_E_ARG;
     if (ctx->pending) return GSEG_E_STATE;
     CK(cudaSetDevice(ctx->device));
     ctx->dd_on = on != 0;
     if (min_edges) ctx->dd_min_edges = min_edges;
     if (min_ratio) ctx->dd_min_ratio = min_ratio;
-    ctx->nbig_hint = -1;
+    if (max_components) ctx->dd_V = max_components;
+    ctx->nbig_hint = -1; ctx->dd_skip = false;
     CK(upload_dd(ctx));
     return GSEG_OK;
 }
@@ -588,12 +592,18 @@ static void enqueue_round(gseg_ctx *c, cudaStream_t s, int r, size_t Vb, size_t 
 
 // Duplicate elimination between rounds (gseg_dedup.cuh): 11 launches that size themselves from the device-resident
 // state and exit at once unless the plan kernel decides to run.  Enqueued in front of every tail launch.
-static u32 dedup_V(const gseg_ctx *c) { // components from which on the list is de-duplicated: where the tail takes over
-    const u32 v = c->tail_V > 1024u ? c->tail_V : 1024u;
+static u32 dedup_V(const gseg_ctx *c) { // components from which on the list is de-duplicated (<= 65536: two ids in a 32-bit key)
+    const u32 v = c->dd_V > 2u ? c->dd_V : 2u;
     return v < 65536u ? v : 65536u;
 }
 static bool dedup_enabled(const gseg_ctx *c) {
     return c->dd_on && c->params.variant != GSEG_SUPERPIX && !(c->params.flags & GSEG_FLAG_NO_DEDUP);
+}
+// Device-driven schedule: the sequence is enqueued blind.  Once an image of this shape has shown that it never meets the
+// thresholds, its eleven self-skipping launches are left out for the following images of the same shape.
+static bool dedup_enqueue(const gseg_ctx *c) {
+    return dedup_enabled(c) &&
+           !(c->dd_skip && c->hint_w == c->w && c->hint_h == c->h && c->hint_variant == c->params.variant && c->hint_conn == c->params.connectivity);
 }
 static void enqueue_dedup(gseg_ctx *c, cudaStream_t s, int round) {
     const GsegBufs B = bufs_of(c);
@@ -667,13 +677,20 @@ static int finish(gseg_ctx *ctx) {
         snprintf(ctx->err, sizeof(ctx->err), "checked build: bounds check at site %u failed", ctx->h_ctl->error - DERR_CHECK);
         return GSEG_E_INTERNAL;
     }
-    // remember how many grid-wide rounds this kind of image needed before the tail could take over
+    // remember how many grid-wide rounds this kind of image needed before the tail could take over, and whether the
+    // duplicate elimination ever ran (device-driven runs only: a host-driven run has no tail and decides per round)
     const GsegCtl *h = ctx->h_ctl;
-    int nbig = 0;
-    for (u32 r = 1; r < h->st.round; ++r)
-        if (!h->stTail[r]) nbig = (int)r;
-    ctx->nbig_hint = nbig;
-    ctx->hint_w = ctx->w; ctx->hint_h = ctx->h; ctx->hint_variant = ctx->params.variant; ctx->hint_conn = ctx->params.connectivity;
+    if (!(ctx->params.flags & GSEG_FLAG_HOST_LOOP)) {
+        int nbig = 0;
+        bool ran = false;
+        for (u32 r = 1; r < h->st.round; ++r) {
+            if (!h->stTail[r]) nbig = (int)r;
+            ran = ran || h->stDedupOut[r] != 0u;
+        }
+        ctx->nbig_hint = nbig;
+        ctx->dd_skip = dedup_enabled(ctx) && !ran;
+        ctx->hint_w = ctx->w; ctx->hint_h = ctx->h; ctx->hint_variant = ctx->params.variant; ctx->hint_conn = ctx->params.connectivity;
+    }
     ctx->valid = true;
     return GSEG_OK;
 }
@@ -780,8 +797,8 @@ static int estimate_nbig(const gseg_ctx *c) {
     int n = 0;
     // with the duplicate elimination in front of the tail, the tail takes over as soon as V <= tail_V (the list then
     // shrinks to ~3 V edges); without it, when the list itself has shrunk to tail_E
-    const bool dd = dedup_enabled(c);
-    while ((V > c->tail_V || (dd ? V > dedup_V(c) : E > c->tail_E)) && n < GSEG_MAXR) { E *= 0.6; V *= 0.27; ++n; }
+    const bool dd = dedup_enqueue(c);
+    while ((V > c->tail_V || E > c->tail_E) && !(dd && V <= dedup_V(c) && E >= c->dd_min_edges) && n < GSEG_MAXR) { E *= 0.6; V *= 0.27; ++n; }
     return n;
 }
 
@@ -874,7 +891,7 @@ static int segment_async_impl(gseg_ctx *ctx, const uint8_t *rgb, int w, int h, i
         if (nbig > R - 1) nbig = R - 1;
         const size_t V = (size_t)w * h;
         for (int r = 1; r <= nbig; ++r) enqueue_round(ctx, ctx->stream, r, V, (size_t)ctx->D * (V / GSEG_PAGE + 1));
-        if (dedup_enabled(ctx)) enqueue_dedup(ctx, ctx->stream, -1);
+        if (dedup_enqueue(ctx)) enqueue_dedup(ctx, ctx->stream, -1);
         CK(cudaGetLastError());
         CK(enqueue_tail(ctx, ctx->stream));
         ctx->pending = true;
@@ -913,7 +930,7 @@ static int wait_rounds(gseg_ctx *ctx) {
         const int r = (int)ctx->h_ctl->st.round;
         enqueue_round(ctx, ctx->stream, r, ctx->h_ctl->st.V, ctx->h_ctl->st.P);
         enqueue_round(ctx, ctx->stream, r + 1, ctx->h_ctl->st.V, ctx->h_ctl->st.P);
-        if (dedup_enabled(ctx)) enqueue_dedup(ctx, ctx->stream, -1);
+        if (dedup_enqueue(ctx)) enqueue_dedup(ctx, ctx->stream, -1);
         cudaError_t e = cudaGetLastError();
         if (e == cudaSuccess) e = enqueue_tail(ctx, ctx->stream);
         if (e != cudaSuccess) return fail(ctx, GSEG_E_CUDA, "continuation launch", e);

@@ -3,10 +3,11 @@
 // The reference's DPP branches sort the packed (u', v', w) keys of the contracted graph every round and keep the
 // lightest edge of every run of duplicates (Report.pdf p3 s3.2.2 "bit concatenation ... single 64 bit integer";
 // p2 s2.2 "only keeping the lightest edge out of all duplicate edges when creating the supervertex").  Here the
-// step runs ONCE per image, at the point where it pays: when the graph has shrunk to V <= tail_V components while
-// its list still carries E >> V parallel edges (1080p Felzenszwalb: V = 37 k, E = 820 k; 4K 8-connected hierarchy:
-// V = 32 k, E = 4.5 M).  After it the list holds one edge per pair of adjacent components (E ~ 3 V), so every
-// remaining round fits the single-cluster tail kernel and touches a handful of pages.
+// step runs ONCE per image, at the point where it pays (measured): when the graph has
+// shrunk to V <= 4096 components while its list still carries E >= 2^19 parallel edges (4K 8-connected hierarchy:
+// V = 2.4 k, E = 958 k -> 7 k).  After it the list holds one edge per pair of adjacent components (E ~ 3 V), so every
+// remaining round fits the single-cluster tail kernel and touches a handful of pages.  Earlier (V <= 65536) the
+// remaining rounds cost less than the sort.
 //
 //   plan     one block: decide from the device-resident round state; exclusive scan of the page counts
 //   keys     pages -> dense arrays: key = (min(a,b) << bits | max(a,b)), payload = dense list position; digit

@@ -137,13 +137,14 @@ int gseg_set_tail(gseg_ctx *ctx, uint32_t max_edges, uint32_t max_components);
 int gseg_set_blocks_per_sm(gseg_ctx *ctx, int blocks);
 
 /* Duplicate-edge elimination between rounds (the reference's DPP branches sort the packed
- * edge keys every round and keep the lightest of every run of duplicates, Report.pdf p3 s3.2.2).  When on, FELZ / HIER
- * runs sort the list by component pair with the in-house onesweep radix sort once the graph has at most 65536
- * components while the list holds >= min_edges edges and >= min_ratio edges per component (0 = keep the current value;
- * defaults 8192 and 8), keep the minimum (weight, list position) of every run and re-compact the list in order.  The
- * result is identical either way.  Default: off (on B200 the remaining rounds cost less than the sort at 1080p / 4K;
- * DESIGN.md has the A/B); environment GSEG_DEDUP=1 switches it on for every context of the process. */
-int gseg_set_dedup(gseg_ctx *ctx, int on, uint32_t min_edges, uint32_t min_ratio);
+ * edge keys every round and keep the lightest of every run of duplicates, Report.pdf p3 s3.2.2).  FELZ / HIER runs sort
+ * the list by component pair with the in-house onesweep radix sort once the graph has at most max_components components
+ * (default 4096, at most 65536) while the list still holds >= min_edges edges (default 2^19) and >= min_ratio edges per
+ * component (default 8); they keep the minimum (weight, list position) of every run and re-compact the list in order
+ * (0 = keep the current value of a threshold).  The result is identical either way; the thresholds are where the sort
+ * costs less than the rounds it shortens on B200 (DESIGN.md has the A/B).  GSEG_DEDUP=0 in the environment switches it
+ * off for every context of the process, GSEG_DEDUP_V / GSEG_DEDUP_MIN / GSEG_DEDUP_RATIO set the thresholds. */
+int gseg_set_dedup(gseg_ctx *ctx, int on, uint32_t min_edges, uint32_t min_ratio, uint32_t max_components);
 
 /* Replaces: L3 pre-filter + L2 graph creation + L1 segmentation core of one reference executable
  * (Report p2 Fig.1; p3 s3.2.1; p2-3 s3.1 steps 1-9; p3-4 s3.2.2; p4 s3.2.4).

@@ -50,7 +50,7 @@ def test_pool_and_new_entry_points_fail_cleanly_without_gpu(gseg):
     assert L.gseg_labels_ex(None, 0, None, 4, 0) == -1 and L.gseg_label_bytes(None, 0) < 0
     assert L.gseg_strip_record(None, 1, None, 0, None) == -1
     assert L.gseg_join_segment(None, None, 1, 0, 0, None, None, 4, 0, None, None) == -1
-    assert L.gseg_set_dedup(None, 1, 0, 0) == -1 and L.gseg_reserve(None, 1) == -1
+    assert L.gseg_set_dedup(None, 1, 0, 0, 0) == -1 and L.gseg_reserve(None, 1) == -1
     assert L.gseg_strerror(-9).decode().startswith("label type too narrow")
     if not torch.cuda.is_available():
         assert L.gseg_pool_create(C.byref(h), 0, 64, 64, 8, 2, 0) == -2

@@ -275,8 +275,8 @@ def test_duplicate_elimination_between_rounds(gseg, oracle, monkeypatch, variant
     sorted by component pair (in-house onesweep), the lightest edge of every run is kept and the list is re-compacted.
     Same partition (every hierarchy level) with and without it, in both schedules; the step actually ran; it shrinks
     E."""
-    monkeypatch.setenv("GSEG_DEDUP", "1")
     s = gseg.Segmenter(w, h)
+    s.set_dedup(True, min_edges=8192, min_ratio=8, max_components=65536)
     try:
         img = oracle.synth(w, h, seed)
         kw = dict(sigma=0.8, k=300.0, min_size=20, connectivity=conn, variant=variant)
@@ -313,9 +313,9 @@ def test_duplicate_elimination_between_rounds(gseg, oracle, monkeypatch, variant
 def test_duplicate_elimination_forced_everywhere(gseg, oracle, monkeypatch):
     """With the thresholds at their minimum the step runs on tiny and degenerate graphs too (ties everywhere, a handful
     of components): partitions still equal the oracle's."""
-    monkeypatch.setenv("GSEG_DEDUP", "1")
     monkeypatch.setenv("GSEG_DEDUP_MIN", "1")
     monkeypatch.setenv("GSEG_DEDUP_RATIO", "1")
+    monkeypatch.setenv("GSEG_DEDUP_V", "65536")
     rng = np.random.default_rng(17)
     s = gseg.Segmenter(300, 300)
     try:

@@ -42,7 +42,7 @@ for case in range(n_cases):
     s = gseg.Segmenter(w, h) if matched else seg
     s.set_tail(*tail)
     s.set_blocks_per_sm(int(rng.choice([1, 2, 4])))
-    s.set_dedup(int(rng.integers(0, 2)), int(rng.choice([1, 8192])), int(rng.choice([1, 8])))
+    s.set_dedup(int(rng.integers(0, 2)), int(rng.choice([1, 8192])), int(rng.choice([1, 8])), int(rng.choice([65536, 4096, 300])))
     s.segment(np.ascontiguousarray(img), sigma=sigma, k=k, min_size=ms, connectivity=conn, variant=variant, flags=flags)
     got = s.labels()
     compactions += s.compaction_count() if matched else 0
