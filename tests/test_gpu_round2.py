@@ -367,3 +367,28 @@ def test_cli_batch_directory(gseg, oracle, tmp_path):
         r1 = subprocess.run([gseg.CLI_PATH, "--conn", "8", "0.8", "300", "20", str(ind / name), str(one)], capture_output=True, text=True)
         assert r1.returncode == 0, r1.stderr
         assert open(one, "rb").read() == open(outd / ("img%02d.png" % i), "rb").read()
+
+
+def test_config3_batch_through_pool_matches_oracle(gseg, oracle):
+    """BASELINE configs[3] at full image size: a batch of 1080p images (seeds of the bench's global batch) through the C++
+    pool with the superpixel variant, level-4 label images in the narrowest type; a sample of the batch is checked against
+    the oracle's level 4 (every image: level count and level-4 component count are plausible and consistent)."""
+    import torch
+    batch = importlib.import_module(gseg.__name__ + ".batch")
+    w, h, n = 1920, 1080, 24
+    pool = batch.Pool(gseg, w, h, contexts=8, max_connectivity=4, caps=gseg.CAP_SUPERPIX)
+    try:
+        imgs = torch.empty((n, h, w, 3), dtype=torch.uint8).pin_memory()
+        for i in range(n):
+            imgs[i] = torch.from_numpy(oracle.synth(w, h, 1000 + i))
+        outs = torch.zeros((n, h * w), dtype=torch.int32).pin_memory()
+        kw = dict(sigma=0.8, k=0.0, min_size=0, connectivity=4, variant=gseg.SUPERPIX)
+        res = pool.run(pool.jobs([imgs[i] for i in range(n)], [outs[i] for i in range(n)], out_mode=gseg.OUT_LABELS, level=3, **kw))
+        assert all(r.status == 0 and r.n_levels >= 8 and 256 < r.n_components <= 65536 and r.elem_bytes == 2 for r in res)
+        for i in (0, 11, n - 1):
+            ref = oracle.pipeline(imgs[i].numpy(), 0.8, 0.0, 0, 4, oracle.SUPERPIX, max_levels=64)
+            assert res[i].n_levels == ref["nlevels"] and res[i].n_components == ref["ncomp"][3]
+            got = outs[i].numpy().view(np.uint16)[:w * h].reshape(h, w).astype(np.int32)
+            assert same_partition(oracle, got, ref["levels"][3]), i
+    finally:
+        pool.close()
