@@ -114,6 +114,9 @@ def load():
     L.gseg_set_stream.argtypes = [vp, vp]
     L.gseg_set_tail.argtypes = [vp, C.c_uint32, C.c_uint32]
     L.gseg_set_blocks_per_sm.argtypes = [vp, i32]
+    L.gseg_set_tail_cluster.argtypes = [vp, i32]
+    L.gseg_tail_cluster.argtypes = [vp]
+    L.gseg_tail_cluster_from_env.argtypes = [vp]
     L.gseg_segment.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(Params)]
     L.gseg_segment_async.argtypes = [vp, vp, i32, i32, i32, i32, C.POINTER(Params)]
     L.gseg_wait.argtypes = [vp]
@@ -276,6 +279,12 @@ class Segmenter:
     def set_dedup(self, on, min_edges=0, min_ratio=0, max_components=0):
         """Duplicate-edge elimination between rounds (sort by component pair, keep the lightest of every run)."""
         self._ck(self.L.gseg_set_dedup(self.h, int(on), min_edges, min_ratio, max_components), "gseg_set_dedup")
+
+    def set_tail_cluster(self, ctas):
+        self._ck(self.L.gseg_set_tail_cluster(self.h, ctas), "gseg_set_tail_cluster")
+
+    def tail_cluster(self):
+        return self._ck(self.L.gseg_tail_cluster(self.h), "gseg_tail_cluster")
 
     def set_blocks_per_sm(self, blocks):
         self._ck(self.L.gseg_set_blocks_per_sm(self.h, blocks), "gseg_set_blocks_per_sm")

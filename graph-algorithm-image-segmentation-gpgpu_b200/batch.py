@@ -32,6 +32,8 @@ class ContextPool:
         if len(self.segs) >= 4:  # many contexts in flight: size each grid for 2 blocks per SM so kernels overlap
             for s in self.segs:
                 s.set_blocks_per_sm(int(os.environ.get("GSEG_POOL_BLOCKS_PER_SM", "2")))
+                if hasattr(s, "set_tail_cluster") and "GSEG_TAIL_CLUSTER" not in os.environ:
+                    s.set_tail_cluster(8)    # as gseg_pool_create does: tails of several images leave SMs to the others
 
     def close(self):
         for s in self.segs:

@@ -61,6 +61,7 @@ struct gseg_ctx {
     int num_sms, occ_mult;
     u32 filter_shift;
     int tail_cluster;     // CTAs in the tail kernel's cluster (16 non-portable, else 8)
+    bool tail_cluster_env; // GSEG_TAIL_CLUSTER was given: a pool leaves the size alone
     u32 tail_E, tail_V, tail_P; // hand-over thresholds of the tail kernel
     u32 run_tail_E, run_tail_V; // thresholds the last run used
     int nbig_hint;        // grid-wide rounds to enqueue before the tail (-1: estimate; adapts to the last run)
@@ -140,6 +141,24 @@ static inline int grid_for(size_t n, int per_block, int cap = GRID_CAP) {
 
 template <typename T>
 static cudaError_t dalloc(T **p, size_t n) { return cudaMalloc((void **)p, n * sizeof(T)); }
+
+// Largest cluster size <= want that the device can co-schedule for the tail kernel.
+static int fit_tail_cluster(int want) {
+    if (want < 1) want = 1;
+    if (want > 16) want = 16;
+    for (; want > 1; --want) {
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute at[1];
+        cfg.gridDim = dim3(want); cfg.blockDim = dim3(NTT); cfg.dynamicSmemBytes = TAIL_SMEM;
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = want; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        int ncl = 0;
+        if (cudaOccupancyMaxActiveClusters(&ncl, k_tail<true>, &cfg) == cudaSuccess && ncl >= 1) break;
+        cudaGetLastError();
+    }
+    return want;
+}
 
 // The de-duplication's descriptor: pointers into the context's arrays (re-sent when a sort grew the scratch).
 static cudaError_t upload_dd(gseg_ctx *ctx) {
@@ -245,20 +264,8 @@ extern "C" int gseg_create_ex(gseg_ctx **out, int device, int max_w, int max_h, 
         cudaFuncSetAttribute(k_tail<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM);
         cudaFuncSetAttribute(k_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TAIL_SMEM);
         if (const char *ev = getenv("GSEG_TAIL_CLUSTER")) want = atoi(ev);
-        if (want < 1) want = 1;
-        if (want > 16) want = 16;
-        for (; want > 1; want >>= 1) {
-            cudaLaunchConfig_t cfg = {};
-            cudaLaunchAttribute at[1];
-            cfg.gridDim = dim3(want); cfg.blockDim = dim3(NTT); cfg.dynamicSmemBytes = TAIL_SMEM;
-            at[0].id = cudaLaunchAttributeClusterDimension;
-            at[0].val.clusterDim.x = want; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-            cfg.attrs = at; cfg.numAttrs = 1;
-            int ncl = 0;
-            if (cudaOccupancyMaxActiveClusters(&ncl, k_tail<true>, &cfg) == cudaSuccess && ncl >= 1) break;
-            cudaGetLastError();
-        }
-        ctx->tail_cluster = want;
+        ctx->tail_cluster = fit_tail_cluster(want);
+        ctx->tail_cluster_env = getenv("GSEG_TAIL_CLUSTER") != nullptr;
         ctx->tail_E = 256u * 1024u; ctx->tail_V = 64u * 1024u; ctx->tail_P = 4096u;
         if (const char *ev = getenv("GSEG_TAIL_P")) ctx->tail_P = (u32)strtoul(ev, nullptr, 10);
         if (const char *ev = getenv("GSEG_TAIL_E")) ctx->tail_E = (u32)strtoul(ev, nullptr, 10);
@@ -412,6 +419,8 @@ extern "C" int gseg_set_stream(gseg_ctx *ctx, void *s) {
     return GSEG_OK;
 }
 
+extern "C" int gseg_tail_cluster(const gseg_ctx *ctx) { return ctx ? ctx->tail_cluster : GSEG_E_ARG; }
+extern "C" int gseg_tail_cluster_from_env(const gseg_ctx *ctx) { return ctx && ctx->tail_cluster_env ? 1 : 0; }
 extern "C" void *gseg_get_stream(const gseg_ctx *ctx) { return ctx ? (void *)ctx->stream : nullptr; }
 
 extern "C" int gseg_set_tail(gseg_ctx *ctx, uint32_t max_edges, uint32_t max_components) {
@@ -432,6 +441,14 @@ extern "C" int gseg_set_dedup(gseg_ctx *ctx, int on, uint32_t min_edges, uint32_
     if (max_components) ctx->dd_V = max_components;
     ctx->nbig_hint = -1; ctx->dd_skip = false;
     CK(upload_dd(ctx));
+    return GSEG_OK;
+}
+
+extern "C" int gseg_set_tail_cluster(gseg_ctx *ctx, int ctas) {
+    if (!ctx || ctas < 1 || ctas > 16) return GSEG_E_ARG;
+    if (ctx->pending) return GSEG_E_STATE;
+    CK(cudaSetDevice(ctx->device));
+    ctx->tail_cluster = fit_tail_cluster(ctas);
     return GSEG_OK;
 }
 

@@ -12,6 +12,7 @@
 // advances inside gseg_pool_submit / gseg_pool_next on the caller's thread (contexts are not thread-safe).
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <deque>
@@ -34,7 +35,15 @@ struct Rec {
 
 struct gseg_pool {
     int device, S;
+    size_t stage_bytes;    // capacity of one input staging buffer (max_w * max_h * 3)
     std::vector<gseg_ctx *> ctx;
+    // Input prefetch: every context has two device staging buffers and a copy stream.  The host->device copy of a job is
+    // issued BEFORE the pool waits for the context's previous job, into the buffer that job is not reading, so it runs
+    // under that job's kernels instead of in front of its own (SURVEY.md section 8e "pinned double-buffered H2D").
+    std::vector<cudaStream_t> copy_stream;
+    std::vector<uint8_t *> stage;      // [2 * S]
+    std::vector<cudaEvent_t> stage_ev; // [2 * S]
+    std::vector<int> stage_next;       // per context: which of its two buffers the next job takes
     std::vector<int> busy; // per context: 1 while its last job has not been retired
     std::deque<Rec> q;     // submission order
     std::vector<cudaEvent_t> free_ev;
@@ -56,6 +65,7 @@ extern "C" int gseg_pool_create(gseg_pool **out, int device, int max_w, int max_
     gseg_pool *p = new (std::nothrow) gseg_pool();
     if (!p) return GSEG_E_ARG;
     p->device = device; p->S = n_contexts; p->next_ticket = 0; p->err[0] = 0;
+    p->stage_bytes = (size_t)max_w * (size_t)max_h * 3;
     int rc = GSEG_OK;
     for (int i = 0; i < n_contexts && !rc; ++i) {
         gseg_ctx *c = nullptr;
@@ -63,10 +73,27 @@ extern "C" int gseg_pool_create(gseg_pool **out, int device, int max_w, int max_
         if (!rc) {
             p->ctx.push_back(c);
             p->busy.push_back(0);
+            p->stage_next.push_back(0);
+            cudaStream_t cs = nullptr;
+            if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) rc = GSEG_E_CUDA;
+            p->copy_stream.push_back(cs);
+            for (int b = 0; b < 2 && !rc; ++b) {
+                uint8_t *d = nullptr;
+                cudaEvent_t e = nullptr;
+                if (cudaMalloc((void **)&d, p->stage_bytes + 64) != cudaSuccess || cudaEventCreateWithFlags(&e, cudaEventDisableTiming) != cudaSuccess) rc = GSEG_E_CUDA;
+                p->stage.push_back(d);
+                p->stage_ev.push_back(e);
+            }
             if (caps) rc = gseg_reserve(c, caps);
             // several contexts share the SMs: size every grid for 2 resident blocks per SM so that kernels of
             // different images run side by side (measured in round 1: +12 % over 4 with 8 contexts)
-            if (!rc && n_contexts >= 4) rc = gseg_set_blocks_per_sm(c, 2);
+            int bps = 2;
+            if (const char *ev = getenv("GSEG_POOL_BLOCKS_PER_SM")) bps = atoi(ev) >= 1 && atoi(ev) <= 8 ? atoi(ev) : 2;
+            if (!rc && n_contexts >= 4) rc = gseg_set_blocks_per_sm(c, bps);
+            // ... and the tail cluster takes 8 SMs instead of 16: a tail CTA (1024 threads x 64 registers) owns its SM, and
+            // with eight images in flight three to four tails are running at any time -- at 16 CTAs each they hold a third of
+            // the GPU for latency-bound work (measured: 9 298 -> 9 686 Mpixel/s; 4 CTAs 9 619, 2 CTAs 8 881)
+            if (!rc && n_contexts >= 4 && !gseg_tail_cluster_from_env(c)) rc = gseg_set_tail_cluster(c, 8);
         }
     }
     if (rc) { gseg_pool_destroy(p); return rc; }
@@ -81,6 +108,9 @@ extern "C" void gseg_pool_destroy(gseg_pool *p) {
     for (Rec &r : p->q)
         if (r.ev) cudaEventDestroy(r.ev);
     for (cudaEvent_t e : p->free_ev) cudaEventDestroy(e);
+    for (cudaStream_t cs : p->copy_stream) if (cs) { cudaStreamSynchronize(cs); cudaStreamDestroy(cs); }
+    for (uint8_t *d : p->stage) cudaFree(d);
+    for (cudaEvent_t e : p->stage_ev) if (e) cudaEventDestroy(e);
     for (gseg_ctx *c : p->ctx) gseg_destroy(c);
     delete p;
 }
@@ -138,10 +168,25 @@ extern "C" int gseg_pool_submit(gseg_pool *p, const gseg_pool_job *job, int64_t 
         return GSEG_E_ARG;
     cudaSetDevice(p->device);
     const int slot = (int)(p->next_ticket % p->S);
+    gseg_ctx *c = p->ctx[(size_t)slot];
+    // host input: start its copy now, under the kernels of the context's previous job (which reads the other buffer)
+    const uint8_t *dev_input = nullptr;
+    if (!job->jpeg_bytes && job->mem_kind == GSEG_MEM_HOST && job->w > 0 && job->h > 0 &&
+        (size_t)job->w * (size_t)job->h * 3 <= p->stage_bytes) {
+        const int b = 2 * slot + p->stage_next[(size_t)slot];
+        const size_t row = (size_t)3 * job->w, stride = job->stride_bytes ? (size_t)job->stride_bytes : row;
+        cudaError_t e = stride == row
+                            ? cudaMemcpyAsync(p->stage[(size_t)b], job->input, row * job->h, cudaMemcpyHostToDevice, p->copy_stream[(size_t)slot])
+                            : cudaMemcpy2DAsync(p->stage[(size_t)b], row, job->input, stride, row, (size_t)job->h, cudaMemcpyHostToDevice,
+                                                p->copy_stream[(size_t)slot]);
+        if (e == cudaSuccess) e = cudaEventRecord(p->stage_ev[(size_t)b], p->copy_stream[(size_t)slot]);
+        if (e != cudaSuccess) { snprintf(p->err, sizeof(p->err), "submit: input copy: %s", cudaGetErrorString(e)); cudaGetLastError(); return GSEG_E_CUDA; }
+        dev_input = p->stage[(size_t)b];
+        p->stage_next[(size_t)slot] ^= 1;
+    }
     if (p->busy[(size_t)slot])
         for (Rec &r : p->q)
             if (r.running && r.slot == slot) { retire(p, r); break; }
-    gseg_ctx *c = p->ctx[(size_t)slot];
     Rec r;
     memset(&r, 0, sizeof(r));
     r.job = *job; r.slot = slot; r.running = true; r.ev = nullptr;
@@ -151,6 +196,10 @@ extern "C" int gseg_pool_submit(gseg_pool *p, const gseg_pool_job *job, int64_t 
         int w = 0, h = 0;
         rc = gseg_segment_jpeg_async(c, job->input, job->jpeg_bytes, &job->params, &w, &h);
         r.res.w = w; r.res.h = h;
+    } else if (dev_input) {
+        const int b = (int)((dev_input == p->stage[(size_t)(2 * slot)]) ? 2 * slot : 2 * slot + 1);
+        cudaStreamWaitEvent((cudaStream_t)gseg_get_stream(c), p->stage_ev[(size_t)b], 0);
+        rc = gseg_segment_async(c, dev_input, job->w, job->h, 3 * job->w, GSEG_MEM_DEVICE, &job->params);
     } else {
         rc = gseg_segment_async(c, (const uint8_t *)job->input, job->w, job->h, job->stride_bytes ? job->stride_bytes : 3 * job->w,
                                 job->mem_kind, &job->params);

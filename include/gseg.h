@@ -132,6 +132,13 @@ void *gseg_get_stream(const gseg_ctx *ctx); /* the cudaStream_t the context's wo
  * kernels.  (0, 0) disables the tail.  Defaults: 262144 edges, 65536 components. */
 int gseg_set_tail(gseg_ctx *ctx, uint32_t max_edges, uint32_t max_components);
 
+/* Scheduling knob (no effect on results): CTAs of the tail kernel's thread-block cluster (1..16, default 16 = lowest latency of
+ * one image alone; a pool of >= 4 contexts uses 8, which leaves more SMs to the other images' grid-wide kernels).
+ * gseg_tail_cluster returns the size in use; gseg_tail_cluster_from_env is 1 when GSEG_TAIL_CLUSTER set it. */
+int gseg_set_tail_cluster(gseg_ctx *ctx, int ctas);
+int gseg_tail_cluster(const gseg_ctx *ctx);
+int gseg_tail_cluster_from_env(const gseg_ctx *ctx);
+
 /* Scheduling knob (no effect on results): resident blocks per SM the grid-wide kernels are sized for
  * (1..8, default 4).  With several contexts in flight per GPU, 2 leaves room for their kernels to overlap. */
 int gseg_set_blocks_per_sm(gseg_ctx *ctx, int blocks);
