@@ -25,7 +25,8 @@ FELZ, HIER, SUPERPIX = 0, 1, 2
 MEM_HOST, MEM_DEVICE = 0, 1
 FLAG_HOST_LOOP = 1
 FLAG_NO_DEDUP = 2
-CAP_SUPERPIX, CAP_WIDE_SIGMA, CAP_LEVELS = 1, 2, 4
+CAP_SUPERPIX, CAP_WIDE_SIGMA, CAP_LEVELS, CAP_JPEG = 1, 2, 4, 8
+JPEG_AUTO, JPEG_OWN, JPEG_NVJPEG = 0, 1, 2  # decoders behind gseg_segment_jpeg (include/gseg.h)
 OUT_NONE, OUT_LABELS, OUT_HIERARCHY = 0, 1, 2
 POOL_MAXLEVELS = 64
 
@@ -124,6 +125,9 @@ def load():
     L.gseg_segment_jpeg.argtypes = [vp, vp, C.c_size_t, C.POINTER(Params), C.POINTER(i32), C.POINTER(i32)]
     L.gseg_segment_jpeg_async.argtypes = [vp, vp, C.c_size_t, C.POINTER(Params), C.POINTER(i32), C.POINTER(i32)]
     L.gseg_input_rgb.argtypes = [vp, vp, i32]
+    L.gseg_jpeg_decode_async.argtypes = [vp, vp, C.c_size_t, vp, C.c_size_t, vp, C.POINTER(i32), C.POINTER(i32)]
+    L.gseg_set_jpeg_backend.argtypes = [vp, i32]
+    L.gseg_jpeg_backend_used.argtypes = [vp]
     L.gseg_num_levels.argtypes = [vp]
     L.gseg_num_components.argtypes = [vp, i32]
     L.gseg_labels.argtypes = [vp, i32, vp, i32]
@@ -213,7 +217,7 @@ class HostBuffer:
 
 
 def jpeg_info(data):
-    """(w, h) of a JPEG (gseg_jpeg_info; needs a CUDA device and libnvjpeg like the decode itself)."""
+    """(w, h) of a JPEG (gseg_jpeg_info: a header parse on the host)."""
     L = load()
     w, h = C.c_int32(0), C.c_int32(0)
     rc = L.gseg_jpeg_info(data, len(data), C.byref(w), C.byref(h))
@@ -314,9 +318,16 @@ class Segmenter:
         self._ck(self.L.gseg_wait(self.h), "gseg_wait")
         return self
 
+    def set_jpeg_backend(self, backend):
+        """JPEG_AUTO / JPEG_OWN (hand-written kernels, parallel over restart intervals) / JPEG_NVJPEG."""
+        self._ck(self.L.gseg_set_jpeg_backend(self.h, backend), "gseg_set_jpeg_backend")
+
+    def jpeg_backend_used(self):
+        return int(self.L.gseg_jpeg_backend_used(self.h))
+
     def segment_jpeg(self, data, params=None, wait=True, **kw):
-        """data: the bytes of a JPEG file.  nvJPEG decodes them on the GPU into the context's staged RGB
-        buffer and the usual path runs on it (gseg_segment_jpeg); returns (w, h)."""
+        """data: the bytes of a JPEG file.  They are decoded on the GPU into the context's staged RGB buffer (in-house
+        kernels or nvJPEG, see set_jpeg_backend) and the usual path runs on it (gseg_segment_jpeg); returns (w, h)."""
         p = params if params is not None else self.params(**kw)
         buf = (C.c_char * len(data)).from_buffer_copy(data)
         w, h = C.c_int32(0), C.c_int32(0)

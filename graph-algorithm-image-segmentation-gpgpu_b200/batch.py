@@ -67,6 +67,15 @@ class ContextPool:
         return n
 
 
+class Jpeg:
+    """A JPEG file's bytes in caller-owned host memory (a 1-D uint8 numpy array or torch tensor, e.g. pinned), handed
+    to a pool job without a copy; plain `bytes` items are copied into a ctypes buffer instead."""
+
+    def __init__(self, buf, nbytes=None):
+        self.buf = buf
+        self.nbytes = int(nbytes if nbytes is not None else (buf.numel() if hasattr(buf, "numel") else buf.size))
+
+
 class Pool:
     """ctypes mirror of gseg_pool_* (include/gseg.h "batch pipeline").  No compute, no fallback."""
 
@@ -109,7 +118,12 @@ class Pool:
                      params.get("variant", g.FELZ), params.get("max_levels", 0), params.get("max_rounds", 0), params.get("flags", 0))
         for i, img in enumerate(images):
             j = arr[i]
-            if isinstance(img, (bytes, bytearray, memoryview)):
+            if isinstance(img, Jpeg):
+                ptr, kind = g._ptr(img.buf)
+                if kind != g.MEM_HOST:
+                    raise ValueError("JPEG bytes must be in host memory")
+                j.input, j.jpeg_bytes, j.mem_kind = ptr, img.nbytes, g.MEM_HOST
+            elif isinstance(img, (bytes, bytearray, memoryview)):
                 buf = (self.C.c_char * len(img)).from_buffer_copy(bytes(img))
                 keep.append(buf)
                 j.input, j.jpeg_bytes, j.mem_kind = self.C.cast(buf, self.C.c_void_p), len(img), g.MEM_HOST

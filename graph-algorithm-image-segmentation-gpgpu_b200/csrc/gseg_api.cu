@@ -18,6 +18,8 @@
 #include "gseg_kernels.cuh"
 #include "gseg_sort.cuh"
 #include "gseg_dedup.cuh"
+#include "gseg_jpeg.hpp"
+#include "gseg_jpeg.cuh"
 
 #define GSEG_MAXMARK 1024
 #define GRID_CAP (148 * 8)
@@ -92,6 +94,18 @@ struct gseg_ctx {
     long long compactions;        // arena compactions since creation (FELZ)
     bool rgb_staged;              // the last run read its input from d_rgb (host input or JPEG)
     nvjpegHandle_t jpg_handle; nvjpegJpegState_t jpg_state; // nvJPEG objects, created on first gseg_segment_jpeg
+    // in-house JPEG decoder (gseg_jpeg.cuh): staged file bytes, descriptor + interval starts, coefficients, sample planes
+    uint8_t *d_jfile, *d_jsamples, *h_jdesc;
+    JpegDev *d_jdev;
+    int16_t *d_jcoef;
+    size_t jfile_cap, jsamples_cap, jdev_cap, jcoef_cap, hjdesc_cap;
+    uint32_t *d_jerr;             // [2] JPG_ERR_* bits of the last two decodes (ping-pong)
+    cudaEvent_t ev_jdesc;         // the last descriptor copy out of h_jdesc
+    cudaEvent_t ev_jdone;         // end of the last decode (its buffers are free again)
+    int jerr_next;                // which of the two error words the next decode takes
+    int jflag_slot;               // error word the next segmentation hands to its control block (-1: none)
+    int jpeg_backend, jpeg_used;  // GSEG_JPEG_*: what the caller asked for / what the last JPEG run used
+    JpegPlan *jplan;
     u32 epoch_next;
     char err[256];
     // per-kernel profiling (host-driven schedule only) and launch accounting
@@ -188,7 +202,7 @@ extern "C" int gseg_create_ex(gseg_ctx **out, int device, int max_w, int max_h, 
     gseg_ctx *ctx = (gseg_ctx *)calloc(1, sizeof(gseg_ctx));
     if (!ctx) return GSEG_E_ARG;
     ctx->device = device; ctx->max_w = max_w; ctx->max_h = max_h; ctx->Vmax = V; ctx->Dmax = (int)Dmax;
-    ctx->epoch_next = 1;
+    ctx->epoch_next = 1; ctx->jflag_slot = -1;
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     ctx->stream = ctx->own_stream;
@@ -337,18 +351,121 @@ static int jpeg_size(NvJpegApi *a, nvjpegHandle_t hnd, const void *jpeg, size_t 
 
 extern "C" int gseg_jpeg_info(const void *jpeg, size_t nbytes, int *w, int *h) {
     if (!jpeg || !nbytes || !w || !h) return GSEG_E_ARG;
-    NvJpegApi *a = nvjpeg_api();
-    if (!a) return GSEG_E_UNSUPPORTED;
-    nvjpegHandle_t hnd = nullptr;
-    if (a->create(&hnd) != NVJPEG_STATUS_SUCCESS) return GSEG_E_CUDA; // needs a CUDA device, like everything else here
-    const int rc = jpeg_size(a, hnd, jpeg, nbytes, w, h);
-    a->destroy(hnd);
+    return jpeg_peek_size((const uint8_t *)jpeg, nbytes, w, h) == JPG_OK ? GSEG_OK : GSEG_E_ARG; // header parse on the host
+}
+
+#define GSEG_JPEG_AUTO_MCUS 512 // longest restart interval (MCUs) the automatic choice gives to the in-house decoder
+// ---- in-house decoder (gseg_jpeg.cuh) -------------------------------------------------------------------
+// (Re)allocates one of the decoder's device buffers; growing waits for the last decode first (rare: the buffers are
+// sized for the context's capacity by the first JPEG or by gseg_reserve(GSEG_CAP_JPEG)).
+template <typename T>
+static int jpeg_grow(gseg_ctx *ctx, T **p, size_t *cap, size_t need, size_t want) {
+    if (*p && *cap >= need) return GSEG_OK;
+    if (want < need) want = need;
+    if (*p) {
+        if (ctx->ev_jdone) CK(cudaEventSynchronize(ctx->ev_jdone));
+        cudaFree(*p); *p = nullptr; *cap = 0;
+    }
+    CK(cudaMalloc((void **)p, want * sizeof(T)));
+    *cap = want;
+    return GSEG_OK;
+}
+static int jpeg_reserve_own(gseg_ctx *ctx, size_t file_bytes, size_t nint, size_t nblocks) {
+    // default sizes: any 4:4:4 image of the context's capacity with one MCU per restart interval
+    const size_t V = ctx->Vmax, side = (size_t)(ctx->max_w + ctx->max_h);
+    const size_t blocks_max = 3 * (V / 64 + side / 2 + 64);
+    int rc = jpeg_grow(ctx, &ctx->d_jfile, &ctx->jfile_cap, file_bytes + 64, V + 4096);
+    if (!rc) rc = jpeg_grow(ctx, &ctx->d_jcoef, &ctx->jcoef_cap, nblocks * 64, blocks_max * 64);
+    if (!rc) rc = jpeg_grow(ctx, &ctx->d_jsamples, &ctx->jsamples_cap, nblocks * 64, blocks_max * 64);
+    const size_t desc = sizeof(JpegDev) + 4 * nint, desc_max = sizeof(JpegDev) + 4 * (V / 64 + side / 8 + 64);
+    if (!rc) rc = jpeg_grow(ctx, (uint8_t **)&ctx->d_jdev, &ctx->jdev_cap, desc, desc_max);
+    if (!rc && ctx->hjdesc_cap < desc) {
+        if (ctx->h_jdesc) {
+            if (ctx->ev_jdesc) CK(cudaEventSynchronize(ctx->ev_jdesc));
+            cudaFreeHost(ctx->h_jdesc); ctx->h_jdesc = nullptr; ctx->hjdesc_cap = 0;
+        }
+        const size_t want = desc > desc_max ? desc : desc_max;
+        CK(cudaMallocHost((void **)&ctx->h_jdesc, want));
+        ctx->hjdesc_cap = want;
+    }
+    if (!rc && !ctx->d_jerr) { CK(cudaMalloc((void **)&ctx->d_jerr, 2 * sizeof(uint32_t))); CK(cudaMemset(ctx->d_jerr, 0, 2 * sizeof(uint32_t))); }
+    if (!rc && !ctx->ev_jdesc) CK(cudaEventCreateWithFlags(&ctx->ev_jdesc, cudaEventDisableTiming));
+    if (!rc && !ctx->ev_jdone) CK(cudaEventCreateWithFlags(&ctx->ev_jdone, cudaEventDisableTiming));
+    if (!rc && !ctx->jplan) ctx->jplan = new JpegPlan();
     return rc;
 }
 
-extern "C" int gseg_segment_jpeg_async(gseg_ctx *ctx, const void *jpeg, size_t nbytes, const gseg_params *p, int *w, int *h) {
-    if (!ctx || !jpeg || !nbytes || !p) return GSEG_E_ARG;
-    if (ctx->pending) return fail(ctx, GSEG_E_STATE, "previous run not waited for", cudaSuccess);
+// Enqueue the decode of a parsed file on stream s: interleaved RGB, tightly packed, into rgb_out (device memory).
+// The decoder's buffers belong to the context, so a decode is ordered behind the previous one (whatever its stream).
+// The next segmentation of the context hands the decode's error word to its control block.
+static int jpeg_decode_enqueue(gseg_ctx *ctx, const uint8_t *file, const JpegPlan &plan, uint8_t *rgb_out, cudaStream_t s) {
+    const JpegDev &d = plan.dev;
+    const uint32_t base = d.data_off & ~15u; // the entropy-coded segment is all the device needs
+    const size_t nbytes = (size_t)d.data_end - base;
+    int rc = jpeg_reserve_own(ctx, nbytes, (size_t)d.nint, (size_t)d.nblocks);
+    if (rc) return rc;
+    // the descriptor (offsets relative to the staged bytes) goes through the context's pinned buffer; the restart
+    // intervals' start offsets are found on the device (k_jpeg_scan) -- the host never walks the compressed data
+    CK(cudaEventSynchronize(ctx->ev_jdesc)); // the previous image's copy out of this buffer
+    JpegDev *hd = (JpegDev *)ctx->h_jdesc;
+    *hd = d;
+    hd->data_off -= base; hd->data_end -= base;
+    CK(cudaStreamWaitEvent(s, ctx->ev_jdone, 0));
+    CK(cudaMemcpyAsync(ctx->d_jdev, ctx->h_jdesc, sizeof(JpegDev), cudaMemcpyHostToDevice, s));
+    CK(cudaEventRecord(ctx->ev_jdesc, s));
+    CK(cudaMemcpyAsync(ctx->d_jfile, file + base, nbytes, cudaMemcpyHostToDevice, s));
+    CK(cudaMemsetAsync(ctx->d_jcoef, 0, (size_t)d.nblocks * 64 * sizeof(int16_t), s));
+    const int slot = ctx->jerr_next;
+    ctx->jerr_next ^= 1;
+    uint32_t *d_starts = (uint32_t *)((uint8_t *)ctx->d_jdev + sizeof(JpegDev));
+    ctx->launches += 4;
+    k_jpeg_scan<<<1, JPG_NT_SCAN, 0, s>>>(ctx->d_jdev, ctx->d_jfile, d_starts, ctx->d_jerr + slot);
+    k_jpeg_huff<<<(d.nint + JPG_NT_HUFF - 1) / JPG_NT_HUFF, JPG_NT_HUFF, 0, s>>>(ctx->d_jdev, d_starts, ctx->d_jfile, ctx->d_jcoef, ctx->d_jerr + slot);
+    k_jpeg_idct<<<(d.nblocks + JPG_NT - 1) / JPG_NT, JPG_NT, 0, s>>>(ctx->d_jdev, ctx->d_jcoef, ctx->d_jsamples);
+    const size_t groups = (size_t)((d.w + 7) / 8) * d.h;
+    k_jpeg_rgb<<<(unsigned)((groups + JPG_NT - 1) / JPG_NT), JPG_NT, 0, s>>>(ctx->d_jdev, ctx->d_jsamples, rgb_out);
+    CK(cudaGetLastError());
+    CK(cudaEventRecord(ctx->ev_jdone, s));
+    ctx->jflag_slot = slot;
+    return GSEG_OK;
+}
+
+// Decode into d_rgb and enqueue the segmentation behind it, all on the context's stream.
+static int jpeg_own_async(gseg_ctx *ctx, const uint8_t *file, const JpegPlan &plan, const gseg_params *p) {
+    const JpegDev &d = plan.dev;
+    if ((size_t)d.w * d.h > ctx->Vmax) return fail(ctx, GSEG_E_SIZE, "image exceeds context capacity", cudaSuccess);
+    CK(cudaSetDevice(ctx->device));
+    ctx->valid = false;
+    int rc = jpeg_decode_enqueue(ctx, file, plan, ctx->d_rgb, ctx->stream);
+    if (!rc) rc = gseg_segment_async(ctx, ctx->d_rgb, d.w, d.h, 3 * d.w, GSEG_MEM_DEVICE, p);
+    if (!rc) ctx->jpeg_used = GSEG_JPEG_OWN;
+    return rc;
+}
+
+// The decode alone, into caller-owned device memory on a caller-chosen stream (the batch pipeline decodes the next
+// image of a context on its copy stream while the context's current image is still being segmented).  In-house decoder
+// only: GSEG_E_UNSUPPORTED for files that need nvJPEG under the context's backend setting.
+extern "C" int gseg_jpeg_decode_async(gseg_ctx *ctx, const void *jpeg, size_t nbytes, uint8_t *rgb_out_device, size_t out_capacity,
+                                      void *cuda_stream, int *w, int *h) {
+    if (!ctx || !jpeg || !nbytes || !rgb_out_device) return GSEG_E_ARG;
+    if (!ctx->jplan) ctx->jplan = new JpegPlan();
+    JpegPlan &plan = *ctx->jplan;
+    const int prc = jpeg_parse((const uint8_t *)jpeg, nbytes, plan, false);
+    if (prc == JPG_NOT_JPEG) { snprintf(ctx->err, sizeof(ctx->err), "not a JPEG: %s", plan.why); return GSEG_E_ARG; }
+    if (prc != JPG_OK) { snprintf(ctx->err, sizeof(ctx->err), "in-house JPEG decoder: %s", plan.why); return GSEG_E_UNSUPPORTED; }
+    if (w) *w = plan.dev.w;
+    if (h) *h = plan.dev.h;
+    if (ctx->jpeg_backend == GSEG_JPEG_NVJPEG || (ctx->jpeg_backend == GSEG_JPEG_AUTO && plan.dev.ri > GSEG_JPEG_AUTO_MCUS && nvjpeg_api()))
+        return fail(ctx, GSEG_E_UNSUPPORTED, "this file goes to nvJPEG under the context's backend setting", cudaSuccess);
+    if ((size_t)3 * plan.dev.w * plan.dev.h > out_capacity) return fail(ctx, GSEG_E_RANGE, "output buffer too small for the decoded image", cudaSuccess);
+    CK(cudaSetDevice(ctx->device));
+    const int rc = jpeg_decode_enqueue(ctx, (const uint8_t *)jpeg, plan, rgb_out_device, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream);
+    if (!rc) ctx->jpeg_used = GSEG_JPEG_OWN;
+    return rc;
+}
+
+// Decode with nvJPEG (CUDA toolkit library, dlopen): files the in-house decoder does not take.
+static int jpeg_nvjpeg_async(gseg_ctx *ctx, const void *jpeg, size_t nbytes, const gseg_params *p, int *w, int *h) {
     NvJpegApi *a = nvjpeg_api();
     if (!a) return fail(ctx, GSEG_E_UNSUPPORTED, "libnvjpeg.so.12 could not be loaded", cudaSuccess);
     CK(cudaSetDevice(ctx->device));
@@ -370,8 +487,40 @@ extern "C" int gseg_segment_jpeg_async(gseg_ctx *ctx, const void *jpeg, size_t n
     ctx->valid = false;
     if (a->decode(ctx->jpg_handle, ctx->jpg_state, (const unsigned char *)jpeg, nbytes, NVJPEG_OUTPUT_RGBI, &out, ctx->stream) != NVJPEG_STATUS_SUCCESS)
         return fail(ctx, GSEG_E_ARG, "nvjpegDecode failed (unsupported or corrupt JPEG)", cudaSuccess);
-    return gseg_segment_async(ctx, ctx->d_rgb, iw, ih, 3 * iw, GSEG_MEM_DEVICE, p); // same stream: ordered after the decode
+    const int rc = gseg_segment_async(ctx, ctx->d_rgb, iw, ih, 3 * iw, GSEG_MEM_DEVICE, p); // same stream: ordered after the decode
+    if (!rc) ctx->jpeg_used = GSEG_JPEG_NVJPEG;
+    return rc;
 }
+
+// Which decoder: the in-house kernels take baseline Huffman files (gseg_jpeg_core.h) and get their parallelism from
+// restart markers.  Automatic choice: in-house when an interval is at most GSEG_JPEG_AUTO_MCUS MCUs long (a thread
+// decodes its interval serially: ~1 us per MCU), nvJPEG otherwise, in-house again when nvJPEG is not loadable.
+extern "C" int gseg_segment_jpeg_async(gseg_ctx *ctx, const void *jpeg, size_t nbytes, const gseg_params *p, int *w, int *h) {
+    if (!ctx || !jpeg || !nbytes || !p) return GSEG_E_ARG;
+    if (ctx->pending) return fail(ctx, GSEG_E_STATE, "previous run not waited for", cudaSuccess);
+    if (!ctx->jplan) ctx->jplan = new JpegPlan();
+    JpegPlan &plan = *ctx->jplan;
+    const int prc = jpeg_parse((const uint8_t *)jpeg, nbytes, plan, false);
+    if (prc == JPG_NOT_JPEG) { snprintf(ctx->err, sizeof(ctx->err), "not a JPEG: %s", plan.why); return GSEG_E_ARG; }
+    if (prc == JPG_OK) {
+        if (w) *w = plan.dev.w;
+        if (h) *h = plan.dev.h;
+    }
+    bool own = prc == JPG_OK && ctx->jpeg_backend != GSEG_JPEG_NVJPEG;
+    if (own && ctx->jpeg_backend == GSEG_JPEG_AUTO && plan.dev.ri > GSEG_JPEG_AUTO_MCUS && nvjpeg_api()) own = false;
+    if (ctx->jpeg_backend == GSEG_JPEG_OWN && prc != JPG_OK) {
+        snprintf(ctx->err, sizeof(ctx->err), "in-house JPEG decoder: %s", plan.why);
+        return GSEG_E_UNSUPPORTED;
+    }
+    if (own) return jpeg_own_async(ctx, (const uint8_t *)jpeg, plan, p);
+    return jpeg_nvjpeg_async(ctx, jpeg, nbytes, p, w, h);
+}
+extern "C" int gseg_set_jpeg_backend(gseg_ctx *ctx, int backend) {
+    if (!ctx || backend < GSEG_JPEG_AUTO || backend > GSEG_JPEG_NVJPEG) return GSEG_E_ARG;
+    ctx->jpeg_backend = backend;
+    return GSEG_OK;
+}
+extern "C" int gseg_jpeg_backend_used(const gseg_ctx *ctx) { return ctx ? ctx->jpeg_used : GSEG_E_ARG; }
 extern "C" int gseg_segment_jpeg(gseg_ctx *ctx, const void *jpeg, size_t nbytes, const gseg_params *p, int *w, int *h) {
     const int rc = gseg_segment_jpeg_async(ctx, jpeg, nbytes, p, w, h);
     return rc ? rc : gseg_wait(ctx);
@@ -401,6 +550,12 @@ extern "C" void gseg_destroy(gseg_ctx *ctx) {
     }
     cudaFree(ctx->d_pscan); cudaFree(ctx->d_arena); cudaFree(ctx->d_statusC); cudaFree(ctx->d_statusE); cudaFree(ctx->d_ctl);
     jpeg_release(ctx);
+    cudaFree(ctx->d_jfile); cudaFree(ctx->d_jsamples); cudaFree(ctx->d_jdev); cudaFree(ctx->d_jcoef);
+    if (ctx->h_jdesc) cudaFreeHost(ctx->h_jdesc);
+    cudaFree(ctx->d_jerr);
+    if (ctx->ev_jdesc) cudaEventDestroy(ctx->ev_jdesc);
+    if (ctx->ev_jdone) cudaEventDestroy(ctx->ev_jdone);
+    delete ctx->jplan;
     sort_scratch_free(&ctx->sort);
     cudaFree(ctx->d_xkeys); cudaFree(ctx->d_xvals); cudaFree(ctx->d_xkeep); cudaFree(ctx->d_xab); cudaFree(ctx->d_xw);
     cudaFree(ctx->d_winner); cudaFree(ctx->d_dd);
@@ -690,6 +845,7 @@ static int finish(gseg_ctx *ctx) {
     if (ctx->h_ctl->error == DERR_SCAN) return fail(ctx, GSEG_E_INTERNAL, "look-back watchdog", cudaSuccess);
     if (ctx->h_ctl->error == DERR_ARENA) return fail(ctx, GSEG_E_ARENA, "map arena", cudaSuccess);
     if (ctx->h_ctl->error == DERR_CHASE) return fail(ctx, GSEG_E_INTERNAL, "successor cycle", cudaSuccess);
+    if (ctx->h_ctl->error == DERR_JPEG) return fail(ctx, GSEG_E_ARG, "corrupt JPEG: the entropy-coded data does not decode", cudaSuccess);
     if (ctx->h_ctl->error >= DERR_CHECK) {
         snprintf(ctx->err, sizeof(ctx->err), "checked build: bounds check at site %u failed", ctx->h_ctl->error - DERR_CHECK);
         return GSEG_E_INTERNAL;
@@ -783,13 +939,14 @@ static int ensure_csum(gseg_ctx *ctx) {
 }
 
 extern "C" int gseg_reserve(gseg_ctx *ctx, uint32_t caps) {
-    if (!ctx || (caps & ~(GSEG_CAP_SUPERPIX | GSEG_CAP_WIDE_SIGMA | GSEG_CAP_LEVELS))) return GSEG_E_ARG;
+    if (!ctx || (caps & ~(GSEG_CAP_SUPERPIX | GSEG_CAP_WIDE_SIGMA | GSEG_CAP_LEVELS | GSEG_CAP_JPEG))) return GSEG_E_ARG;
     if (ctx->pending) return GSEG_E_STATE;
     CK(cudaSetDevice(ctx->device));
     int rc = GSEG_OK;
     if (caps & GSEG_CAP_SUPERPIX) { rc = ensure_csum(ctx); if (!rc) rc = ensure(ctx, &ctx->d_G, ctx->Vmax + 64); }
     if (!rc && (caps & GSEG_CAP_WIDE_SIGMA)) rc = ensure(ctx, &ctx->d_tmp, 3 * (ctx->Vmax + 64));
     if (!rc && (caps & GSEG_CAP_LEVELS)) rc = ensure(ctx, &ctx->d_labels[1], ctx->Vmax + 64);
+    if (!rc && (caps & GSEG_CAP_JPEG)) rc = jpeg_reserve_own(ctx, 0, 0, 0);
     return rc;
 }
 
@@ -819,11 +976,22 @@ static int estimate_nbig(const gseg_ctx *c) {
     return n;
 }
 
+// The image this run reads was decoded by the in-house JPEG decoder: its error word goes to the control block, behind
+// every kernel of the run and in front of gseg_wait's read-back.
+static cudaError_t jpeg_flag_enqueue(gseg_ctx *ctx, int slot) {
+    if (slot < 0) return cudaSuccess;
+    k_jpeg_flag<<<1, 1, 0, ctx->stream>>>(ctx->d_jerr + slot, ctx->d_ctl);
+    ++ctx->launches;
+    return cudaGetLastError();
+}
+
 // rgb points at the first row of the buffer: halo_top rows of halo, the h rows to segment, halo_bottom rows of halo.
 static int segment_async_impl(gseg_ctx *ctx, const uint8_t *rgb, int w, int h, int stride, int mem_kind, int halo_top,
                               int halo_bottom, const gseg_params *p) {
     if (!ctx || !rgb || !p) return GSEG_E_ARG;
     if (ctx->pending) return fail(ctx, GSEG_E_STATE, "previous run not waited for", cudaSuccess);
+    const int jslot = ctx->jflag_slot; // this run's input came out of the in-house JPEG decoder (else -1)
+    ctx->jflag_slot = -1;
     if (w < 1 || h < 1 || stride < 3 * w || halo_top < 0 || halo_bottom < 0) return fail(ctx, GSEG_E_ARG, "image geometry", cudaSuccess);
     if ((size_t)w * h > ctx->Vmax) return fail(ctx, GSEG_E_SIZE, "image exceeds context capacity", cudaSuccess);
     const int h_in = h + halo_top + halo_bottom;
@@ -911,6 +1079,7 @@ static int segment_async_impl(gseg_ctx *ctx, const uint8_t *rgb, int w, int h, i
         if (dedup_enqueue(ctx)) enqueue_dedup(ctx, ctx->stream, -1);
         CK(cudaGetLastError());
         CK(enqueue_tail(ctx, ctx->stream));
+        CK(jpeg_flag_enqueue(ctx, jslot));
         ctx->pending = true;
         return GSEG_OK;
     }
@@ -933,6 +1102,7 @@ static int segment_async_impl(gseg_ctx *ctx, const uint8_t *rgb, int w, int h, i
         rc = readback(ctx);
         if (rc) return rc;
     }
+    CK(jpeg_flag_enqueue(ctx, jslot));
     ctx->pending = true;
     return GSEG_OK;
 }

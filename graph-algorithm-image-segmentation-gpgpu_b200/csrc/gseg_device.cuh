@@ -15,7 +15,7 @@ typedef unsigned long long u64;
 #define GSEG_PAGE 256u /* slots per page of the edge list = one warp tile (8 rows of 32) */
 
 enum { PH_PRED = 0, PH_MINSIZE = 1, PH_DONE = 2 };
-enum { DERR_NONE = 0, DERR_SCAN = 1, DERR_ARENA = 2, DERR_CHASE = 3, DERR_CHECK = 100 /* + site: a bounds check of a checked build */ };
+enum { DERR_NONE = 0, DERR_SCAN = 1, DERR_ARENA = 2, DERR_CHASE = 3, DERR_JPEG = 4 /* the in-house JPEG decoder met undecodable data */, DERR_CHECK = 100 /* + site: a bounds check of a checked build */ };
 
 // Checked build (-DGSEG_CHECKED, tools/checked_run.sh): index / capacity assertions at the places where an id, a list slot
 // or an arena offset computed on the device is used as an address.  compute-sanitizer is closed on the GPU pool this was

@@ -1,0 +1,195 @@
+// gseg_jpeg.cuh -- kernels of the in-house baseline-JPEG decoder ("GPU-side decode feeding
+// batched mode -- removes the host staging bound"; the reference reads its JPEG data set with cv::imread on the host,
+// README.md:26).  The compressed file crosses PCIe (7-10x fewer bytes than the RGB image) and is decoded here into
+// the context's staged RGB buffer, on the context's stream, in front of the blur:
+//   k_jpeg_huff  one thread per restart interval: Huffman decoding (T.81 F.2.2) of its MCUs into the coefficient
+//                array (cleared before; only non-zero coefficients are written)
+//   k_jpeg_idct  one thread per 8x8 block: dequantisation + libjpeg's accurate integer inverse DCT -> sample planes
+//   k_jpeg_rgb   four pixels per thread: chroma upsampling ("fancy" triangle filter) + YCbCr -> interleaved RGB
+//   k_jpeg_flag  hands a decoding error to the run's control block
+// The arithmetic lives in gseg_jpeg_core.h (shared with the CPU test harness) and reproduces libjpeg's default decoder
+// bit for bit (tests/test_jpeg.py against cv2.imdecode).  Parallelism comes from the file's restart markers; a file
+// without them is one interval and goes to nvJPEG instead unless the caller forces this decoder.
+#pragma once
+#include "gseg_device.cuh"
+#include "gseg_jpeg_core.h"
+
+#define JPG_NT_HUFF 64
+#define JPG_NT 128
+
+__constant__ uint8_t c_jpg_zigzag[JPG_ZIGZAG_LEN] = {
+    0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13,
+    6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31,
+    39, 46, 53, 60, 61, 54, 47, 55, 62, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63};
+
+// Restart markers of the entropy-coded segment: starts[i] = offset of the first byte of interval i (right behind the
+// i-th RSTn marker; T.81 B.2.1 / E.1.4).  In entropy-coded data a 0xFF is always followed by 0x00 unless it starts a
+// marker, so the byte pairs FF D0..D7 are exactly the restart markers.  ONE block: its 32 warps take 32 contiguous
+// parts of the data; pass 1 counts the markers of every part, a scan of the 32 counts gives each warp its first
+// interval number, pass 2 writes the offsets in file order (lane prefix by shuffles).  Sixteen bytes per lane and step;
+// a word is looked at byte by byte only if it holds a 0xFF (one word in ~64).
+#define JPG_NT_SCAN 1024
+__device__ __forceinline__ uint32_t jpg_ff_bytes(uint32_t w) { // 0x80 in every byte of w that is 0xFF
+    const uint32_t x = ~w;
+    return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+}
+// bit j set <=> bytes j, j + 1 of the chunk (byte 16 = `next`, the first byte behind it) are a restart marker that
+// lies inside [off, end)
+__device__ __forceinline__ uint32_t jpg_rst_mask(const uint4 v, uint32_t next, uint32_t pos0, uint32_t off, uint32_t end) {
+    const uint32_t w[5] = {v.x, v.y, v.z, v.w, next};
+    uint32_t mask = 0u;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        uint32_t f = jpg_ff_bytes(w[i]);
+        if (f) {
+            const uint64_t two = ((uint64_t)w[i + 1] << 32) | w[i]; // the word and the bytes behind it
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                if (f & (0x80u << (8 * k))) {
+                    const uint32_t m = (uint32_t)(two >> (8 * k + 8)) & 0xFFu;
+                    const uint32_t p = pos0 + 4 * i + k;
+                    if ((m & 0xF8u) == 0xD0u && p >= off && p + 1 < end) mask |= 1u << (4 * i + k);
+                }
+        }
+    }
+    return mask;
+}
+__global__ void __launch_bounds__(JPG_NT_SCAN) k_jpeg_scan(const JpegDev *__restrict__ gd, const uint8_t *__restrict__ file,
+                                                           uint32_t *__restrict__ starts, uint32_t *__restrict__ errp) {
+    __shared__ uint32_t s_cnt[32], s_off[33];
+    const uint32_t off = gd->data_off, end = gd->data_end;
+    const int nint = gd->nint;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) { starts[0] = off; *errp = 0u; }
+    if (nint <= 1) return;
+    const uint32_t c0 = off >> 4, c1 = (end + 15u) >> 4;                 // chunks [c0, c1)
+    const uint32_t per = (((c1 - c0 + 31u) / 32u) + 31u) / 32u * 32u;    // chunks per warp: whole steps of 32
+    const uint32_t wb = c0 + (uint32_t)warp * per, we = min(wb + per, c1);
+    const uint4 *f4 = reinterpret_cast<const uint4 *>(file);
+    uint32_t cnt = 0u;
+    for (uint32_t c = wb + lane; c < we; c += 32u) {
+        const uint4 v = __ldg(f4 + c);
+        if (jpg_ff_bytes(v.x) | jpg_ff_bytes(v.y) | jpg_ff_bytes(v.z) | jpg_ff_bytes(v.w))
+            cnt += __popc(jpg_rst_mask(v, __ldg(reinterpret_cast<const uint32_t *>(f4 + c + 1)), 16u * c, off, end));
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
+    if (lane == 0) s_cnt[warp] = cnt;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t v = s_cnt[lane], inc = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+        s_off[lane] = inc - v;
+        if (lane == 31) {
+            s_off[32] = inc;
+            if ((int)inc + 1 < nint) *errp = JPG_ERR_RST;
+        }
+    }
+    __syncthreads();
+    const uint32_t total = s_off[32];
+    // intervals the file has no marker for start at the end of the data (they decode to nothing and are flagged above)
+    for (uint32_t i = total + 1 + threadIdx.x; i < (uint32_t)nint; i += JPG_NT_SCAN) starts[i] = end;
+    uint32_t running = s_off[warp];
+    for (uint32_t cb = wb; cb < we; cb += 32u) {
+        const uint32_t c = cb + lane;
+        uint32_t mask = 0u;
+        if (c < we) {
+            const uint4 v = __ldg(f4 + c);
+            if (jpg_ff_bytes(v.x) | jpg_ff_bytes(v.y) | jpg_ff_bytes(v.z) | jpg_ff_bytes(v.w))
+                mask = jpg_rst_mask(v, __ldg(reinterpret_cast<const uint32_t *>(f4 + c + 1)), 16u * c, off, end);
+        }
+        if (__ballot_sync(0xFFFFFFFFu, mask != 0u) == 0u) continue;
+        const uint32_t n = __popc(mask);
+        uint32_t inc = n;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+        uint32_t idx = running + inc - n + 1u; // interval number of the lane's first marker
+        while (mask) {
+            const int j = __ffs(mask) - 1;
+            mask &= mask - 1u;
+            if (idx < (uint32_t)nint) starts[idx] = 16u * c + (uint32_t)j + 2u;
+            ++idx;
+        }
+        running += __shfl_sync(0xFFFFFFFFu, inc, 31);
+    }
+}
+
+__global__ void __launch_bounds__(JPG_NT_HUFF) k_jpeg_huff(const JpegDev *__restrict__ gd, const uint32_t *__restrict__ starts,
+                                                           const uint8_t *__restrict__ file, int16_t *__restrict__ coef,
+                                                           uint32_t *__restrict__ errp) {
+    __shared__ JpegDev sd; // geometry + the six Huffman tables (15 KB): a symbol is one shared-memory look-up, three for a long code
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(gd);
+        uint4 *dst = reinterpret_cast<uint4 *>(&sd);
+        for (int i = threadIdx.x; i < (int)(sizeof(JpegDev) / 16); i += JPG_NT_HUFF) dst[i] = src[i];
+    }
+    __shared__ uint8_t szz[JPG_ZIGZAG_LEN];
+    for (int i = threadIdx.x; i < JPG_ZIGZAG_LEN; i += JPG_NT_HUFF) szz[i] = c_jpg_zigzag[i];
+    __syncthreads();
+    const int i = blockIdx.x * JPG_NT_HUFF + threadIdx.x;
+    if (i >= sd.nint) return;
+    const int first = i * sd.ri;
+    const int last = first + sd.ri < sd.nmcu ? first + sd.ri : sd.nmcu;
+    uint32_t err = 0u;
+    jpg_decode_interval(sd, sd.dc, sd.ac, szz, file, starts[i], first, last, coef, err);
+    if (err) atomicOr(errp, err);
+}
+
+__global__ void __launch_bounds__(JPG_NT) k_jpeg_idct(const JpegDev *__restrict__ gd, const int16_t *__restrict__ coef,
+                                                      uint8_t *__restrict__ samples) {
+    __shared__ uint16_t sq[JPG_MAXCOMP][64];
+    for (int i = threadIdx.x; i < JPG_MAXCOMP * 64; i += JPG_NT) sq[i >> 6][i & 63] = gd->quant[i >> 6][i & 63];
+    __syncthreads();
+    const int b = blockIdx.x * JPG_NT + threadIdx.x;
+    if (b >= gd->nblocks) return;
+    const int c = (gd->ncomp > 2 && b >= gd->blk_off[2]) ? 2 : ((gd->ncomp > 1 && b >= gd->blk_off[1]) ? 1 : 0);
+    const int lb = b - gd->blk_off[c], bwc = gd->bw[c];
+    const int by = lb / bwc, bx = lb - by * bwc;
+    union { int4 v[8]; int16_t s[64]; } in;
+    const int4 *src = reinterpret_cast<const int4 *>(coef + (size_t)b * 64);
+#pragma unroll
+    for (int i = 0; i < 8; ++i) in.v[i] = src[i];
+    union { uint2 v[8]; uint8_t s[64]; } out;
+    jpg_idct_block(in.s, sq[c], out.s, 8);
+    uint8_t *dst = samples + gd->pix_off[c] + ((size_t)by * 8 * bwc + bx) * 8;
+#pragma unroll
+    for (int r = 0; r < 8; ++r) *reinterpret_cast<uint2 *>(dst + (size_t)r * bwc * 8) = out.v[r];
+}
+
+__global__ void __launch_bounds__(JPG_NT) k_jpeg_rgb(const JpegDev *__restrict__ gd, const uint8_t *__restrict__ samples,
+                                                     uint8_t *__restrict__ rgb) {
+    __shared__ __align__(16) uint32_t sgeo[offsetof(JpegDev, quant) / 4]; // the geometry in front of the tables is all that is read
+    for (int i = threadIdx.x; i < (int)(offsetof(JpegDev, quant) / 4); i += JPG_NT) sgeo[i] = reinterpret_cast<const uint32_t *>(gd)[i];
+    __syncthreads();
+    const JpegDev &sdh = *reinterpret_cast<const JpegDev *>(sgeo);
+    const int w = sdh.w, h = sdh.h;
+    const int gpr = (w + 7) >> 3; // groups of eight pixels per row
+    const size_t g = (size_t)blockIdx.x * JPG_NT + threadIdx.x;
+    if (g >= (size_t)gpr * h) return;
+    const int y = (int)(g / gpr), x0 = 8 * (int)(g - (size_t)y * gpr);
+    const int n = w - x0 < 8 ? w - x0 : 8;
+    uint8_t *dst = rgb + ((size_t)y * w + x0) * 3;
+    if (n == 8 && jpg_fast8(sdh)) {
+        union { uint32_t v[6]; uint8_t s[24]; } px;
+        jpg_pixels8(sdh, samples, x0, y, px.s);
+        if ((w & 3) == 0) { // rows start 4-byte aligned
+            uint32_t *d4 = reinterpret_cast<uint32_t *>(dst);
+#pragma unroll
+            for (int k = 0; k < 6; ++k) d4[k] = px.v[k];
+        } else {
+#pragma unroll
+            for (int k = 0; k < 24; ++k) dst[k] = px.s[k];
+        }
+    } else { // rows' tails and the sampling layouts without an eight-pixel form
+        for (int j = 0; j < n; ++j) {
+            uint8_t t[3];
+            jpg_pixel(sdh, samples, x0 + j, y, t);
+            dst[3 * j] = t[0]; dst[3 * j + 1] = t[1]; dst[3 * j + 2] = t[2];
+        }
+    }
+}
+
+__global__ void k_jpeg_flag(const uint32_t *__restrict__ errp, GsegCtl *ctl) {
+    if (*errp && ctl->error == DERR_NONE) ctl->error = DERR_JPEG;
+}

@@ -25,23 +25,23 @@ struct JpegPlan {
 // Canonical Huffman table (T.81 Annex C) from the 16 length counts and the symbol list of a DHT segment.
 static inline bool jpeg_build_huff(const uint8_t *counts, const uint8_t *symbols, int nsym, JpegHuff &t) {
     memset(&t, 0, sizeof(t));
+    for (int i = 0; i < 8; ++i) t.thr[i] = 0xFFFFFFFFu;
     int code = 0, k = 0;
     for (int l = 1; l <= 16; ++l) {
         t.valoff[l] = k - code;
-        if (counts[l - 1]) {
-            for (int i = 0; i < counts[l - 1]; ++i, ++k, ++code) {
-                if (k >= nsym || code >= (1 << l)) return false;
-                t.vals[k] = symbols[k];
-                if (l <= JPG_LOOK) {
-                    const int base = code << (JPG_LOOK - l);
-                    for (int j = 0; j < (1 << (JPG_LOOK - l)); ++j) t.look[base + j] = (uint16_t)((l << 8) | symbols[k]);
-                }
+        for (int i = 0; i < counts[l - 1]; ++i, ++k, ++code) {
+            if (k >= nsym || code >= (1 << l)) return false;
+            t.vals[k] = symbols[k];
+            if (l <= JPG_LOOK) {
+                const int base = code << (JPG_LOOK - l);
+                for (int j = 0; j < (1 << (JPG_LOOK - l)); ++j) t.look[base + j] = (uint16_t)((l << 8) | symbols[k]);
             }
-            t.maxcode[l] = code - 1;
-        } else t.maxcode[l] = -1;
+        }
+        // `code` is now the first value of this length that is NOT a code: a 16-bit window below it (left-aligned)
+        // starts with a code of at most l bits
+        if (l > JPG_LOOK) t.thr[l - JPG_LOOK - 1] = (uint32_t)code << (16 - l);
         code <<= 1;
     }
-    t.maxcode[0] = -1; t.maxcode[17] = 0x7FFFFFFF;
     return true;
 }
 
@@ -67,7 +67,9 @@ static inline int jpeg_peek_size(const uint8_t *f, size_t n, int *w, int *h) {
     return JPG_NOT_JPEG;
 }
 
-static inline int jpeg_parse(const uint8_t *f, size_t n, JpegPlan &plan) {
+// scan_restarts: also walk the entropy-coded data for the restart markers (the CPU test harness; the product leaves that
+// to k_jpeg_scan and only bounds the data: data_end = the file's EOI, or its end).
+static inline int jpeg_parse(const uint8_t *f, size_t n, JpegPlan &plan, bool scan_restarts = true) {
     JpegDev &d = plan.dev;
     memset(&d, 0, sizeof(d));
     plan.starts.clear();
@@ -192,6 +194,11 @@ static inline int jpeg_parse(const uint8_t *f, size_t n, JpegPlan &plan) {
         }
         // every other segment (APPn, COM, DNL ...) is skipped
         p += 2 + len;
+    }
+    if (!scan_restarts) {
+        d.data_end = (uint32_t)((n >= 2 && f[n - 2] == 0xFF && f[n - 1] == 0xD9) ? n - 2 : n);
+        if (d.data_end < d.data_off) d.data_end = d.data_off;
+        return JPG_OK;
     }
     // Restart markers: interval i starts right behind the i-th RSTn.  memchr keeps this at memory speed (one 0xFF in
     // ~200 bytes of entropy-coded data, each followed by 0x00 unless it is a marker).

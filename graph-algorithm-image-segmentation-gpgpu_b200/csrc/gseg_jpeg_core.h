@@ -19,21 +19,22 @@
 #define GSEG_HD inline
 #endif
 
-#define JPG_LOOK 9            // bits of the first-level Huffman lookup
+#define JPG_LOOK 10           // bits of the first-level Huffman lookup
 #define JPG_MAXCOMP 3
 #define JPG_ERR_CODE 1u       // a bit pattern that is no Huffman code
 #define JPG_ERR_COEF 2u       // a run that leaves the block
+#define JPG_ERR_RST 4u        // fewer restart markers in the file than its restart interval promises
 
-struct JpegHuff {
+struct alignas(16) JpegHuff {
     uint16_t look[1 << JPG_LOOK]; // (code length << 8 | symbol) for codes of <= JPG_LOOK bits, else 0
-    int32_t maxcode[18];          // largest code of each length (-1: none), [17] = sentinel
-    int32_t valoff[17];           // index of a length's first symbol minus its first code
+    uint32_t thr[8];              // longer codes: a 16-bit window c has a code of <= JPG_LOOK+1+i bits iff c < thr[i]
+    int32_t valoff[20];           // index of a length's first symbol minus its first code
     uint8_t vals[256];
 };
 
 // Everything the kernels need to know about one image; built by jpeg_parse (gseg_jpeg.hpp) on the host and copied to
 // the device in front of the compressed bytes.
-struct JpegDev {
+struct alignas(16) JpegDev {
     int32_t w, h, ncomp;
     int32_t maxh, maxv;           // largest sampling factors
     int32_t mcus_x, mcus_y, nmcu; // MCU grid of the scan
@@ -44,115 +45,177 @@ struct JpegDev {
     int32_t blk_off[JPG_MAXCOMP];               // first block of the component in the coefficient array
     int32_t pix_off[JPG_MAXCOMP];               // first sample of the component in the sample array
     int32_t nblocks, nsamples;
-    uint32_t data_off, data_end;  // entropy-coded bytes [data_off, data_end) of the staged file
-    uint32_t error;               // JPG_ERR_* bits, set by the decoding threads
+    uint32_t data_off, data_end;  // entropy-coded bytes [data_off, data_end) of the staged file (data_end: an upper bound)
+    uint32_t pad0[2];
     uint16_t quant[JPG_MAXCOMP][64]; // per component, natural (row-major) order
     JpegHuff dc[JPG_MAXCOMP], ac[JPG_MAXCOMP]; // per component
 };
 
-// zigzag position -> row-major position (padded: a corrupt run may index past 63 before it is rejected)
-#define JPG_ZIGZAG_INIT                                                                                                        \
-    {0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13,             \
-     6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31,             \
-     39, 46, 53, 60, 61, 54, 47, 55, 62, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63}
-static const uint8_t jpg_zigzag_h[80] = JPG_ZIGZAG_INIT;
-#if defined(__CUDACC__)
-static __device__ __constant__ uint8_t jpg_zigzag_d[80] = JPG_ZIGZAG_INIT;
-#endif
-GSEG_HD int jpg_zigzag(int k) {
-#if defined(__CUDA_ARCH__)
-    return jpg_zigzag_d[k];
-#else
-    return jpg_zigzag_h[k];
-#endif
-}
+// zigzag position -> row-major position (padded: a corrupt run may index past 63 before it is rejected).  The kernels
+// copy it to shared memory: every thread of a warp asks for a different entry, which a __constant__ array serialises.
+#define JPG_ZIGZAG_LEN 80
+static const uint8_t jpg_zigzag_h[JPG_ZIGZAG_LEN] = {
+    0,  1,  8,  16, 9,  2,  3,  10, 17, 24, 32, 25, 18, 11, 4,  5,  12, 19, 26, 33, 40, 48, 41, 34, 27, 20, 13,
+    6,  7,  14, 21, 28, 35, 42, 49, 56, 57, 50, 43, 36, 29, 22, 15, 23, 30, 37, 44, 51, 58, 59, 52, 45, 38, 31,
+    39, 46, 53, 60, 61, 54, 47, 55, 62, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63, 63};
 
 // ---- bit reader over the entropy-coded segment (T.81 F.2.2.5): 0xFF00 is a stuffed 0xFF, any other marker ends the
 // data of the interval and the reader feeds zero bits from there on.
-struct JpegBits {
-    const uint8_t *data;
-    uint32_t pos, end;
-    uint32_t buf; // left-aligned
-    int n;
-};
-GSEG_HD void jpg_bits_init(JpegBits &b, const uint8_t *data, uint32_t pos, uint32_t end) {
-    b.data = data; b.pos = pos; b.end = end; b.buf = 0u; b.n = 0;
+// A thread walks its interval serially, so the reader is built around latency: the file is read in aligned 16-byte
+// chunks, one chunk ahead of its use (one global load per ~20 symbols, never waited for); bytes pass through a 64-bit
+// window and enter the 64-bit bit buffer four at a time unless one of the four is 0xFF; one refill per symbol covers
+// the code and its extra bits.  The staged file must be readable up to 32 bytes past data_end.
+struct JpegChunk { uint32_t w[4]; };
+GSEG_HD JpegChunk jpg_load16(const uint8_t *file, uint32_t chunk) {
+    JpegChunk c;
+#if defined(__CUDA_ARCH__)
+    const uint4 v = __ldg(reinterpret_cast<const uint4 *>(file) + chunk); // the staged file is 16-byte aligned
+    c.w[0] = v.x; c.w[1] = v.y; c.w[2] = v.z; c.w[3] = v.w;
+#else
+    for (int i = 0; i < 4; ++i) {
+        const uint8_t *p = file + 16 * (size_t)chunk + 4 * i;
+        c.w[i] = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+    }
+#endif
+    return c;
 }
-GSEG_HD void jpg_fill(JpegBits &b) { // at least 25 valid bits afterwards
-    while (b.n <= 24) {
-        uint32_t v = 0u;
-        if (b.pos < b.end) {
-            v = b.data[b.pos];
-            if (v == 0xFFu) {
-                const uint32_t m = b.pos + 1 < b.end ? b.data[b.pos + 1] : 0xD9u;
-                if (m == 0u) b.pos += 2;        // stuffed byte
-                else { v = 0u; b.end = b.pos; } // marker: stop here
-            } else ++b.pos;
-        }
-        b.buf |= v << (24 - b.n);
-        b.n += 8;
+GSEG_HD uint32_t jpg_bswap(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __byte_perm(v, 0u, 0x0123);
+#else
+    return (v >> 24) | ((v >> 8) & 0xFF00u) | ((v << 8) & 0xFF0000u) | (v << 24);
+#endif
+}
+struct JpegBits {
+    const uint8_t *file;
+    JpegChunk cur, nxt;  // the chunk being consumed and the one behind it
+    uint32_t chunk;      // index of cur
+    uint32_t widx;       // next word of cur
+    uint32_t rem;        // bytes of the stream that have not entered the bit buffer yet
+    uint64_t win;        // byte window: the next bytes of the stream, first byte on top
+    int wn;              // ... how many
+    uint64_t buf;        // bit buffer, left-aligned
+    int n;               // ... valid bits
+    bool eof;            // a marker or the end of the data was reached: zero bits from here on
+};
+GSEG_HD uint32_t jpg_next_word(JpegBits &b) { // the stream's next four bytes, first byte on top
+    const uint32_t w = b.widx == 0 ? b.cur.w[0] : (b.widx == 1 ? b.cur.w[1] : (b.widx == 2 ? b.cur.w[2] : b.cur.w[3]));
+    if (++b.widx == 4) {
+        b.cur = b.nxt;
+        ++b.chunk;
+        b.nxt = jpg_load16(b.file, b.chunk + 1);
+        b.widx = 0;
+    }
+    return jpg_bswap(w);
+}
+GSEG_HD void jpg_bits_init(JpegBits &b, const uint8_t *file, uint32_t pos, uint32_t end) {
+    b.file = file;
+    b.chunk = pos >> 4;
+    b.cur = jpg_load16(file, b.chunk);
+    b.nxt = jpg_load16(file, b.chunk + 1);
+    b.widx = (pos & 15u) >> 2;
+    b.rem = end > pos ? end - pos : 0u;
+    b.buf = 0; b.n = 0; b.win = 0; b.wn = 0; b.eof = false;
+    const uint32_t sub = pos & 3u;
+    if (sub) { // the stream starts inside a word
+        const uint32_t w = jpg_next_word(b);
+        b.win = (uint64_t)(w << (8 * sub)) << 32;
+        b.wn = 4 - (int)sub;
     }
 }
-GSEG_HD uint32_t jpg_peek(const JpegBits &b, int k) { return b.buf >> (32 - k); } // 1 <= k <= 16
+GSEG_HD void jpg_fill(JpegBits &b) { // at least 33 valid bits afterwards: a code (<= 16) and its extra bits (<= 16)
+    while (b.n <= 32) {
+        if (b.wn <= 4) { b.win |= (uint64_t)jpg_next_word(b) << (32 - 8 * b.wn); b.wn += 4; }
+        const uint32_t W = (uint32_t)(b.win >> 32);
+        const uint32_t x = ~W; // a byte of W is 0xFF <=> that byte of x is zero
+        const uint32_t ff = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
+        if (!b.eof && b.rem >= 4u && ff == 0u) { // four plain bytes
+            b.buf |= (uint64_t)W << (32 - b.n);
+            b.n += 32; b.win <<= 32; b.wn -= 4; b.rem -= 4u;
+        } else { // one byte at a time
+            uint32_t v = 0u;
+            if (!b.eof && b.rem > 0u) {
+                v = W >> 24;
+                if (v == 0xFFu) {
+                    const uint32_t m = b.rem > 1u ? ((W >> 16) & 0xFFu) : 0xD9u;
+                    if (m == 0u) { b.win <<= 16; b.wn -= 2; b.rem -= 2u; } // stuffed byte
+                    else { v = 0u; b.eof = true; }                          // marker: stop here
+                } else { b.win <<= 8; b.wn -= 1; b.rem -= 1u; }
+            } else b.eof = true;
+            b.buf |= (uint64_t)v << (56 - b.n);
+            b.n += 8;
+        }
+    }
+}
+GSEG_HD uint32_t jpg_peek(const JpegBits &b, int k) { return (uint32_t)(b.buf >> (64 - k)); } // 1 <= k <= 32
 GSEG_HD void jpg_skip(JpegBits &b, int k) { b.buf <<= k; b.n -= k; }
 
+// One Huffman symbol; the caller has filled the bit buffer.
 GSEG_HD int jpg_symbol(JpegBits &b, const JpegHuff &t, uint32_t &err) {
-    jpg_fill(b);
-    const uint32_t e = t.look[jpg_peek(b, JPG_LOOK)];
+    const uint32_t c = jpg_peek(b, 16);
+    const uint32_t e = t.look[c >> (16 - JPG_LOOK)];
     if (e) { jpg_skip(b, (int)(e >> 8)); return (int)(e & 255u); }
-    for (int l = JPG_LOOK + 1; l <= 16; ++l) {
-        const int32_t code = (int32_t)jpg_peek(b, l);
-        if (code <= t.maxcode[l]) { jpg_skip(b, l); return t.vals[(code + t.valoff[l]) & 255]; }
-    }
-    err |= JPG_ERR_CODE;
-    jpg_skip(b, 16);
-    return 0;
+    int l = JPG_LOOK + 1; // the thresholds grow with the length: count the lengths the window is too large for
+#pragma unroll
+    for (int i = 0; i < 16 - JPG_LOOK; ++i) l += c >= t.thr[i] ? 1 : 0;
+    if (l > 16) { err |= JPG_ERR_CODE; jpg_skip(b, 16); return 0; }
+    jpg_skip(b, l);
+    return t.vals[((int)(c >> (16 - l)) + t.valoff[l]) & 255];
 }
-// s more bits as a signed value (T.81 F.2.2.1 EXTEND)
+// s more bits as a signed value (T.81 F.2.2.1 EXTEND), s = 0 included (no bits, value 0); the caller has filled the
+// bit buffer.  Branch-free: every lane of a warp executes it on every symbol.
 GSEG_HD int jpg_receive_extend(JpegBits &b, int s) {
-    jpg_fill(b);
-    const int v = (int)jpg_peek(b, s);
-    jpg_skip(b, s);
-    return v < (1 << (s - 1)) ? v - (1 << s) + 1 : v;
+    const int v = (int)((b.buf >> 1) >> (63 - s));
+    b.buf <<= s; b.n -= s;
+    return v < (int)((1u << s) >> 1) ? v - (1 << s) + 1 : v;
 }
 
-// One 8x8 block: DC difference + AC run/size pairs (T.81 F.2.2); non-zero coefficients go to coef[] (row-major,
-// still quantised; the array was cleared before).  Returns the new DC predictor.
-GSEG_HD int jpg_decode_block(JpegBits &b, const JpegHuff &dc, const JpegHuff &ac, int pred, int16_t *coef, uint32_t &err) {
-    const int s = jpg_symbol(b, dc, err) & 15;
-    if (s) pred += jpg_receive_extend(b, s);
-    if (pred) coef[0] = (int16_t)pred;
-    for (int k = 1; k < 64; ++k) {
-        const int rs = jpg_symbol(b, ac, err);
-        const int r = rs >> 4, sz = rs & 15;
-        if (sz) {
-            k += r;
-            const int v = jpg_receive_extend(b, sz);
-            if (k > 63) { err |= JPG_ERR_COEF; break; }
-            coef[jpg_zigzag(k)] = (int16_t)v;
-        } else {
-            if (r != 15) break; // EOB
-            k += 15;
-        }
-    }
-    return pred;
-}
-
-// One restart interval: MCUs [first, last) of the scan, predictors start at zero.
-GSEG_HD void jpg_decode_interval(const JpegDev &d, const JpegHuff *dc, const JpegHuff *ac, const uint8_t *file, uint32_t start,
-                                 int first, int last, int16_t *coef, uint32_t &err) {
+// One restart interval: MCUs [first, last) of the scan, predictors start at zero (T.81 F.2.2: per block a DC
+// difference, then AC run/size pairs until 63 coefficients or EOB).  Non-zero coefficients go to coef[] (row-major
+// inside a block, still quantised; the array was cleared before).
+// Written as ONE loop over symbols with the position (MCU, component, block, coefficient) as state, not as nested
+// loops over blocks: the 32 intervals a warp decodes then advance symbol by symbol in the same instruction stream,
+// whatever block each of them is in -- with nested loops every block costs the warp its slowest lane's symbols.
+GSEG_HD void jpg_decode_interval(const JpegDev &d, const JpegHuff *dc, const JpegHuff *ac, const uint8_t *zz, const uint8_t *file,
+                                 uint32_t start, int first, int last, int16_t *coef, uint32_t &err) {
     JpegBits b;
     jpg_bits_init(b, file, start, d.data_end);
-    int pred[JPG_MAXCOMP] = {0, 0, 0};
-    int mx = first % d.mcus_x, my = first / d.mcus_x;
-    for (int m = first; m < last; ++m) {
-        for (int c = 0; c < d.ncomp; ++c)
-            for (int v = 0; v < d.vs[c]; ++v)
-                for (int hh = 0; hh < d.hs[c]; ++hh) {
-                    const int blk = d.blk_off[c] + (my * d.vs[c] + v) * d.bw[c] + mx * d.hs[c] + hh;
-                    pred[c] = jpg_decode_block(b, dc[c], ac[c], pred[c], coef + (size_t)blk * 64, err);
+    int p0 = 0, p1 = 0, p2 = 0;                         // DC predictors
+    int m = first, mx = first % d.mcus_x, my = first / d.mcus_x;
+    int c = 0, bi = 0, k = 0;                           // component, block of the component inside the MCU, coefficient
+    int16_t *cb = coef + ((size_t)d.blk_off[0] + (size_t)(my * d.vs[0]) * d.bw[0] + mx * d.hs[0]) * 64;
+    const JpegHuff *tdc = dc, *tac = ac;
+    while (m < last) {
+        jpg_fill(b);
+        const bool isdc = k == 0;
+        const int rs = jpg_symbol(b, isdc ? *tdc : *tac, err);
+        const int sz = rs & 15;
+        const int v = jpg_receive_extend(b, sz);
+        if (isdc) {
+            const int val = (c == 0 ? p0 : (c == 1 ? p1 : p2)) + v;
+            if (c == 0) p0 = val; else if (c == 1) p1 = val; else p2 = val;
+            if (val) cb[0] = (int16_t)val;
+            k = 1;
+        } else if (sz) {
+            k += rs >> 4;
+            if (k > 63) { err |= JPG_ERR_COEF; k = 64; }
+            else { cb[zz[k]] = (int16_t)v; ++k; }
+        } else {
+            k = (rs >> 4) == 15 ? k + 16 : 64;          // ZRL : EOB
+        }
+        if (k >= 64) {                                  // next block
+            k = 0;
+            if (++bi == d.hs[c] * d.vs[c]) {
+                bi = 0;
+                if (++c == d.ncomp) {
+                    c = 0; ++m;
+                    if (++mx == d.mcus_x) { mx = 0; ++my; }
                 }
-        if (++mx == d.mcus_x) { mx = 0; ++my; }
+                tdc = dc + c; tac = ac + c;
+            }
+            const int hsc = d.hs[c], bv = hsc == 1 ? bi : (hsc == 2 ? bi >> 1 : bi / hsc), bh = bi - bv * hsc;
+            cb = coef + ((size_t)d.blk_off[c] + (size_t)(my * d.vs[c] + bv) * d.bw[c] + mx * hsc + bh) * 64;
+        }
     }
 }
 
@@ -250,3 +313,73 @@ GSEG_HD void jpg_pixel(const JpegDev &d, const uint8_t *samples, int x, int y, u
     const int Cr = jpg_upsample(samples + d.pix_off[2], d.bw[2] * 8, d.dw[2], d.dh[2], d.maxh / d.hs[2], d.maxv / d.vs[2], x, y);
     jpg_ycc_rgb(Y, Cb, Cr, rgb);
 }
+
+// ---- the same, eight pixels at a time (x0 a multiple of 8, x0 + 8 <= w): what k_jpeg_rgb does wherever it can.  With
+// the neighbour's column index clamped to the plane, the inner formulas of the fancy filters ARE the edge formulas
+// ((3t + t + 8) >> 4 == (4t + 8) >> 4, (3t + t + 1) >> 2 == t, ...), so there is no edge case left.
+GSEG_HD uint32_t jpg_ld32(const uint8_t *p) { // 4-byte aligned
+#if defined(__CUDA_ARCH__)
+    return *reinterpret_cast<const uint32_t *>(p);
+#else
+    return (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+#endif
+}
+// Modes jpg_row8 handles for one component: 0 none, 1 full size, 2 h2v1 fancy, 3 h2v2 fancy
+GSEG_HD int jpg_mode8(const JpegDev &d, int c) {
+    const int hx = d.maxh / d.hs[c], vy = d.maxv / d.vs[c];
+    if (hx == 1 && vy == 1) return 1;
+    if (hx == 2 && vy == 1 && d.dw[c] > 2) return 2;
+    if (hx == 2 && vy == 2 && d.dw[c] > 2) return 3;
+    return 0;
+}
+GSEG_HD bool jpg_fast8(const JpegDev &d) {
+    for (int c = 0; c < d.ncomp; ++c)
+        if (!jpg_mode8(d, c)) return false;
+    return true;
+}
+GSEG_HD void jpg_row8(const JpegDev &d, const uint8_t *samples, int c, int mode, int x0, int y, int *o) {
+    const uint8_t *p = samples + d.pix_off[c];
+    const int pw = d.bw[c] * 8, dw = d.dw[c], dh = d.dh[c];
+    if (mode == 1) {
+        const uint32_t a = jpg_ld32(p + (size_t)y * pw + x0), b = jpg_ld32(p + (size_t)y * pw + x0 + 4);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) { o[k] = (int)((a >> (8 * k)) & 255u); o[4 + k] = (int)((b >> (8 * k)) & 255u); }
+        return;
+    }
+    const int c0 = x0 >> 1, cl = c0 > 0 ? c0 - 1 : 0, cr = c0 + 4 < dw ? c0 + 4 : dw - 1;
+    int t[6];
+    if (mode == 2) {
+        const uint8_t *r = p + (size_t)y * pw;
+        const uint32_t a = jpg_ld32(r + c0);
+        t[0] = r[cl]; t[5] = r[cr];
+#pragma unroll
+        for (int k = 0; k < 4; ++k) t[1 + k] = (int)((a >> (8 * k)) & 255u);
+#pragma unroll
+        for (int m = 0; m < 4; ++m) { o[2 * m] = (3 * t[1 + m] + t[m] + 1) >> 2; o[2 * m + 1] = (3 * t[1 + m] + t[2 + m] + 2) >> 2; }
+        return;
+    }
+    const int j = y >> 1;
+    int jn = (y & 1) ? j + 1 : j - 1;
+    jn = jn < 0 ? 0 : (jn > dh - 1 ? dh - 1 : jn);
+    const uint8_t *r0 = p + (size_t)j * pw, *r1 = p + (size_t)jn * pw;
+    const uint32_t a = jpg_ld32(r0 + c0), b = jpg_ld32(r1 + c0);
+    t[0] = 3 * r0[cl] + r1[cl]; t[5] = 3 * r0[cr] + r1[cr];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) t[1 + k] = 3 * (int)((a >> (8 * k)) & 255u) + (int)((b >> (8 * k)) & 255u);
+#pragma unroll
+    for (int m = 0; m < 4; ++m) { o[2 * m] = (3 * t[1 + m] + t[m] + 8) >> 4; o[2 * m + 1] = (3 * t[1 + m] + t[2 + m] + 7) >> 4; }
+}
+GSEG_HD void jpg_pixels8(const JpegDev &d, const uint8_t *samples, int x0, int y, uint8_t *rgb) { // 24 bytes
+    int Y[8], Cb[8], Cr[8];
+    jpg_row8(d, samples, 0, jpg_mode8(d, 0), x0, y, Y);
+    if (d.ncomp == 1) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) rgb[3 * k] = rgb[3 * k + 1] = rgb[3 * k + 2] = (uint8_t)Y[k];
+        return;
+    }
+    jpg_row8(d, samples, 1, jpg_mode8(d, 1), x0, y, Cb);
+    jpg_row8(d, samples, 2, jpg_mode8(d, 2), x0, y, Cr);
+#pragma unroll
+    for (int k = 0; k < 8; ++k) jpg_ycc_rgb(Y[k], Cb[k], Cr[k], rgb + 3 * k);
+}
+

@@ -44,6 +44,10 @@ struct gseg_pool {
     std::vector<uint8_t *> stage;      // [2 * S]
     std::vector<cudaEvent_t> stage_ev; // [2 * S]
     std::vector<int> stage_next;       // per context: which of its two buffers the next job takes
+    // JPEG jobs: the decode of a context's NEXT job (in-house kernels, on the copy stream, into the free staging buffer) is
+    // enqueued as soon as the current one has been submitted -- a whole pipeline turn ahead (gseg_pool_run knows the job)
+    struct Pref { const void *input; size_t bytes; int w, h, b; bool valid; };
+    std::vector<Pref> pref; // per context
     std::vector<int> busy; // per context: 1 while its last job has not been retired
     std::deque<Rec> q;     // submission order
     std::vector<cudaEvent_t> free_ev;
@@ -74,6 +78,7 @@ extern "C" int gseg_pool_create(gseg_pool **out, int device, int max_w, int max_
             p->ctx.push_back(c);
             p->busy.push_back(0);
             p->stage_next.push_back(0);
+            p->pref.push_back(gseg_pool::Pref{nullptr, 0, 0, 0, 0, false});
             cudaStream_t cs = nullptr;
             if (cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking) != cudaSuccess) rc = GSEG_E_CUDA;
             p->copy_stream.push_back(cs);
@@ -160,6 +165,24 @@ static void retire(gseg_pool *p, Rec &r) {
     }
 }
 
+// Decode a JPEG job of context `slot` ahead of its submission: file bytes over PCIe + the in-house decoder's kernels on the
+// context's copy stream, into the staging buffer the context's running job is not reading.  GSEG_E_UNSUPPORTED / GSEG_E_RANGE:
+// the file goes the nvJPEG way at submission (nothing was enqueued).
+static int jpeg_prefetch(gseg_pool *p, int slot, const gseg_pool_job *job) {
+    gseg_pool::Pref &pf = p->pref[(size_t)slot];
+    if (pf.valid) p->stage_next[(size_t)slot] = pf.b & 1; // a decode nobody came for: its buffer is free again
+    pf.valid = false;
+    gseg_ctx *c = p->ctx[(size_t)slot];
+    const int b = 2 * slot + p->stage_next[(size_t)slot];
+    int w = 0, h = 0;
+    const int rc = gseg_jpeg_decode_async(c, job->input, job->jpeg_bytes, p->stage[(size_t)b], p->stage_bytes, p->copy_stream[(size_t)slot], &w, &h);
+    if (rc) return rc;
+    if (cudaEventRecord(p->stage_ev[(size_t)b], p->copy_stream[(size_t)slot]) != cudaSuccess) { cudaGetLastError(); return GSEG_E_CUDA; }
+    p->stage_next[(size_t)slot] ^= 1;
+    pf.input = job->input; pf.bytes = job->jpeg_bytes; pf.w = w; pf.h = h; pf.b = b; pf.valid = true;
+    return GSEG_OK;
+}
+
 extern "C" int gseg_pool_submit(gseg_pool *p, const gseg_pool_job *job, int64_t *ticket) {
     if (!p || !job || !job->input) return GSEG_E_ARG;
     if (job->out_mode < GSEG_OUT_NONE || job->out_mode > GSEG_OUT_HIERARCHY) return GSEG_E_ARG;
@@ -184,6 +207,20 @@ extern "C" int gseg_pool_submit(gseg_pool *p, const gseg_pool_job *job, int64_t 
         dev_input = p->stage[(size_t)b];
         p->stage_next[(size_t)slot] ^= 1;
     }
+    // JPEG input the in-house decoder takes: decoded into the free staging buffer on the copy stream -- already a pipeline
+    // turn ago if gseg_pool_run looked ahead, else now (under the last kernels of the context's previous job)
+    int jw = 0, jh = 0;
+    if (job->jpeg_bytes && job->mem_kind == GSEG_MEM_HOST) {
+        gseg_pool::Pref &pf = p->pref[(size_t)slot];
+        if (!(pf.valid && pf.input == job->input && pf.bytes == job->jpeg_bytes)) {
+            const int drc = jpeg_prefetch(p, slot, job);
+            if (drc != GSEG_OK && drc != GSEG_E_UNSUPPORTED && drc != GSEG_E_RANGE) { // not a JPEG at all / CUDA error
+                snprintf(p->err, sizeof(p->err), "submit: %s", gseg_last_error(c));
+                return drc;
+            }
+        }
+        if (pf.valid) { dev_input = p->stage[(size_t)pf.b]; jw = pf.w; jh = pf.h; pf.valid = false; }
+    }
     if (p->busy[(size_t)slot])
         for (Rec &r : p->q)
             if (r.running && r.slot == slot) { retire(p, r); break; }
@@ -192,14 +229,16 @@ extern "C" int gseg_pool_submit(gseg_pool *p, const gseg_pool_job *job, int64_t 
     r.job = *job; r.slot = slot; r.running = true; r.ev = nullptr;
     r.res.ticket = p->next_ticket; r.res.user = job->user; r.res.out = job->out; r.res.w = job->w; r.res.h = job->h;
     int rc;
-    if (job->jpeg_bytes) {
+    if (job->jpeg_bytes && !dev_input) {
         int w = 0, h = 0;
         rc = gseg_segment_jpeg_async(c, job->input, job->jpeg_bytes, &job->params, &w, &h);
         r.res.w = w; r.res.h = h;
     } else if (dev_input) {
         const int b = (int)((dev_input == p->stage[(size_t)(2 * slot)]) ? 2 * slot : 2 * slot + 1);
+        const int w = job->jpeg_bytes ? jw : job->w, h = job->jpeg_bytes ? jh : job->h;
         cudaStreamWaitEvent((cudaStream_t)gseg_get_stream(c), p->stage_ev[(size_t)b], 0);
-        rc = gseg_segment_async(c, dev_input, job->w, job->h, 3 * job->w, GSEG_MEM_DEVICE, &job->params);
+        rc = gseg_segment_async(c, dev_input, w, h, 3 * w, GSEG_MEM_DEVICE, &job->params);
+        r.res.w = w; r.res.h = h;
     } else {
         rc = gseg_segment_async(c, (const uint8_t *)job->input, job->w, job->h, job->stride_bytes ? job->stride_bytes : 3 * job->w,
                                 job->mem_kind, &job->params);
@@ -236,6 +275,8 @@ extern "C" int gseg_pool_run(gseg_pool *p, const gseg_pool_job *jobs, int n, gse
     for (int i = 0; i < n; ++i) {
         const int rc = gseg_pool_submit(p, &jobs[i], nullptr);
         if (rc) { first_err = rc; n = i; break; }
+        if (i + p->S < n && jobs[i + p->S].jpeg_bytes && jobs[i + p->S].mem_kind == GSEG_MEM_HOST) // the same context's next job
+            jpeg_prefetch(p, (int)((p->next_ticket - 1) % p->S), &jobs[i + p->S]);
         // hand finished results out as we go so that the queue stays short
         while ((int)p->q.size() > p->S) { gseg_pool_next(p, &results[got]); ++got; }
     }

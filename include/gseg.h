@@ -113,6 +113,7 @@ void gseg_destroy(gseg_ctx *ctx);
 #define GSEG_CAP_SUPERPIX 1u   /* colour sums + means + Sobel plane of the superpixel variant */
 #define GSEG_CAP_WIDE_SIGMA 2u /* intermediate plane of the general blur (more than 8 one-sided taps) */
 #define GSEG_CAP_LEVELS 4u     /* second staging buffer of gseg_labels_all / gseg_colorize to host memory */
+#define GSEG_CAP_JPEG 8u       /* buffers of the in-house JPEG decoder (staged file, coefficients, sample planes) */
 int gseg_reserve(gseg_ctx *ctx, uint32_t caps);
 
 /* Pinned host memory for inputs/outputs of the asynchronous calls (cudaHostAlloc behind a plain pointer, so a
@@ -255,19 +256,45 @@ int gseg_join_segment(gseg_ctx *ctx, const void *dev_records, int n_strips, int6
 
 /* ---- JPEG input decoded on the GPU --------------------------------------
  * The reference's batch benchmark reads a JPEG data set through cv::imread on the host (README.md:26).
- * Here the compressed bytes go to the GPU: nvJPEG (CUDA toolkit library, loaded with dlopen on first
- * use -- libgseg.so itself does not depend on it) decodes into the context's staged RGB buffer on the
- * context's stream and the usual path runs on it; the decoded image never visits the host.
- *   gseg_jpeg_info          width / height of a JPEG (host only: parses the header).
+ * Here the compressed bytes go to the GPU (7-10x fewer bytes over PCIe than the RGB image) and are decoded
+ * there into the context's staged RGB buffer, on the context's stream, in front of the blur; the decoded
+ * image never visits the host.  Two decoders:
+ *   GSEG_JPEG_OWN     hand-written kernels (csrc/gseg_jpeg.cuh): baseline / extended-sequential Huffman,
+ *                     8-bit, grey or YCbCr, luma 1x1 / 2x1 / 1x2 / 2x2 / 4x1, one interleaved scan.  One
+ *                     thread per RESTART INTERVAL decodes the Huffman data, so files written with restart
+ *                     markers (cv::IMWRITE_JPEG_RST_INTERVAL, jpegtran -restart) decode in parallel; the
+ *                     pixels are bit-identical to libjpeg's default decoder (islow IDCT, fancy upsampling),
+ *                     i.e. to what cv::imread gives the reference.  A file without restart markers is ONE
+ *                     interval (correct, but decoded by a single thread).
+ *   GSEG_JPEG_NVJPEG  nvJPEG (CUDA toolkit library, loaded with dlopen on first use -- libgseg.so does not
+ *                     link it): everything else it can decode (progressive ...); Huffman stage on the host.
+ *   GSEG_JPEG_AUTO    (default) OWN for files it supports whose restart intervals are at most 512 MCUs
+ *                     long, or when nvJPEG is not loadable; NVJPEG otherwise.
+ *   gseg_jpeg_info          width / height of a JPEG (host only: parses the header, needs no device).
  *   gseg_segment_jpeg_async decode + enqueue the segmentation (complete it with gseg_wait, or use
  *   gseg_segment_jpeg       the blocking form); *w, *h receive the image size.
+ *   gseg_set_jpeg_backend / gseg_jpeg_backend_used   choose the decoder / which one the last JPEG run used.
  *   gseg_input_rgb          the interleaved RGB image the last run read, when it was staged by the
  *                           context (host input or JPEG); GSEG_E_STATE for caller-owned device input.
- * GSEG_E_UNSUPPORTED when libnvjpeg cannot be loaded, GSEG_E_ARG for data nvJPEG rejects. */
+ * GSEG_E_ARG for data that is no JPEG or does not decode (corrupt entropy-coded data is reported by
+ * gseg_wait), GSEG_E_UNSUPPORTED when the file needs nvJPEG and libnvjpeg cannot be loaded, or when
+ * GSEG_JPEG_OWN was forced for a file the in-house decoder does not take. */
+#define GSEG_JPEG_AUTO 0
+#define GSEG_JPEG_OWN 1
+#define GSEG_JPEG_NVJPEG 2
 int gseg_jpeg_info(const void *jpeg, size_t nbytes, int *w, int *h);
 int gseg_segment_jpeg_async(gseg_ctx *ctx, const void *jpeg, size_t nbytes, const gseg_params *params, int *w, int *h);
 int gseg_segment_jpeg(gseg_ctx *ctx, const void *jpeg, size_t nbytes, const gseg_params *params, int *w, int *h);
 int gseg_input_rgb(gseg_ctx *ctx, uint8_t *out_rgb, int mem_kind);
+/* The decode alone (in-house decoder only): interleaved RGB, tightly packed, into caller-owned DEVICE memory on a
+ * caller-chosen stream (NULL = the context's).  The batch pipeline uses it to decode a context's next image on its copy
+ * stream while the current one is still being segmented.  The context's next gseg_segment_async (give it rgb_out_device
+ * as GSEG_MEM_DEVICE input, ordered behind the decode) reports corrupt entropy-coded data through gseg_wait.
+ * GSEG_E_UNSUPPORTED when the file needs nvJPEG under the context's backend setting, GSEG_E_RANGE when it does not fit. */
+int gseg_jpeg_decode_async(gseg_ctx *ctx, const void *jpeg, size_t nbytes, uint8_t *rgb_out_device, size_t out_capacity,
+                           void *cuda_stream, int *w, int *h);
+int gseg_set_jpeg_backend(gseg_ctx *ctx, int backend);
+int gseg_jpeg_backend_used(const gseg_ctx *ctx);
 
 /* Per-round statistics of the last run; returns number of rounds (<= cap written). */
 int gseg_stats(const gseg_ctx *ctx, gseg_round_stat *out, int cap);

@@ -4,6 +4,7 @@ import ctypes as C
 import os
 import re
 
+import numpy as np
 import pytest
 
 
@@ -66,22 +67,30 @@ def test_no_gpu_fails_loudly(gseg):
 
 
 def test_jpeg_entry_points_without_gpu(gseg):
-    """nvJPEG is loaded with dlopen (libgseg.so must not link it); without a device the JPEG helpers fail
-    like everything else (no host decoder behind them); argument errors do not need a device."""
+    """nvJPEG is loaded with dlopen (libgseg.so must not link it); gseg_jpeg_info is a header parse on the host and
+    needs no device; the decode itself has no host path behind it (no context without a device); argument errors
+    do not need a device."""
     import subprocess
     import torch
     L = gseg.load()
     w, h = C.c_int32(0), C.c_int32(0)
     assert L.gseg_jpeg_info(None, 0, C.byref(w), C.byref(h)) == -1
     assert L.gseg_segment_jpeg(None, b"x", 1, None, None, None) == -1
+    assert L.gseg_jpeg_decode_async(None, b"x", 1, None, 0, None, None, None) == -1
+    assert L.gseg_set_jpeg_backend(None, 0) == -1 and L.gseg_jpeg_backend_used(None) == -1
     assert L.gseg_input_rgb(None, None, 0) == -1
     assert L.gseg_strerror(-8).decode().startswith("optional dependency")
     deps = subprocess.run(["ldd", gseg.LIB_PATH], capture_output=True, text=True).stdout
     assert "nvjpeg" not in deps
+    with pytest.raises(gseg.GsegError):  # SOI + a segment that runs past the end: not a JPEG
+        gseg.jpeg_info(b"\xff\xd8\xff\xe0" + bytes(32))
+    cv2 = pytest.importorskip("cv2")
+    ok, enc = cv2.imencode(".jpg", np.zeros((37, 53, 3), np.uint8))
+    assert gseg.jpeg_info(enc.tobytes()) == (53, 37)
     if not torch.cuda.is_available():
         with pytest.raises(gseg.GsegError) as e:
-            gseg.jpeg_info(b"\xff\xd8\xff\xe0" + bytes(32))
-        assert "no CPU fallback" in str(e.value) or "optional dependency" in str(e.value)
+            gseg.Segmenter(64, 64)
+        assert "no CPU fallback" in str(e.value)
 
 
 def test_bad_create_args(gseg):
