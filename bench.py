@@ -419,7 +419,7 @@ def main():
 
 
 # ---------------------------------------------------------------------------------------------------------------
-JPEG_QUALITY, JPEG_RST = 90, 8
+JPEG_QUALITY, JPEG_RST = 90, 1
 
 
 def bench_jpeg_fed(args, gseg, batch, torch, dist, world, pool, himgs, hlab, kw, timed, pix):

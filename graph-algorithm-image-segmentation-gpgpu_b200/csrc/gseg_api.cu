@@ -375,7 +375,14 @@ static int jpeg_reserve_own(gseg_ctx *ctx, size_t file_bytes, size_t nint, size_
     const size_t V = ctx->Vmax, side = (size_t)(ctx->max_w + ctx->max_h);
     const size_t blocks_max = 3 * (V / 64 + side / 2 + 64);
     int rc = jpeg_grow(ctx, &ctx->d_jfile, &ctx->jfile_cap, file_bytes + 64, V + 4096);
-    if (!rc) rc = jpeg_grow(ctx, &ctx->d_jcoef, &ctx->jcoef_cap, nblocks * 64, blocks_max * 64);
+    if (!rc && (!ctx->d_jcoef || ctx->jcoef_cap < nblocks * 64)) {
+        rc = jpeg_grow(ctx, &ctx->d_jcoef, &ctx->jcoef_cap, nblocks * 64, blocks_max * 64);
+        // all zero between images: the Huffman threads write non-zero coefficients only, k_jpeg_idct clears what it read
+        if (!rc) {
+            CK(cudaMemsetAsync(ctx->d_jcoef, 0, ctx->jcoef_cap * sizeof(int16_t), ctx->stream));
+            CK(cudaStreamSynchronize(ctx->stream)); // once per (re)allocation: the first decode may run on another stream
+        }
+    }
     if (!rc) rc = jpeg_grow(ctx, &ctx->d_jsamples, &ctx->jsamples_cap, nblocks * 64, blocks_max * 64);
     const size_t desc = sizeof(JpegDev) + 4 * nint, desc_max = sizeof(JpegDev) + 4 * (V / 64 + side / 8 + 64);
     if (!rc) rc = jpeg_grow(ctx, (uint8_t **)&ctx->d_jdev, &ctx->jdev_cap, desc, desc_max);
@@ -414,7 +421,6 @@ static int jpeg_decode_enqueue(gseg_ctx *ctx, const uint8_t *file, const JpegPla
     CK(cudaMemcpyAsync(ctx->d_jdev, ctx->h_jdesc, sizeof(JpegDev), cudaMemcpyHostToDevice, s));
     CK(cudaEventRecord(ctx->ev_jdesc, s));
     CK(cudaMemcpyAsync(ctx->d_jfile, file + base, nbytes, cudaMemcpyHostToDevice, s));
-    CK(cudaMemsetAsync(ctx->d_jcoef, 0, (size_t)d.nblocks * 64 * sizeof(int16_t), s));
     const int slot = ctx->jerr_next;
     ctx->jerr_next ^= 1;
     uint32_t *d_starts = (uint32_t *)((uint8_t *)ctx->d_jdev + sizeof(JpegDev));

@@ -2,10 +2,12 @@
 // batched mode -- removes the host staging bound"; the reference reads its JPEG data set with cv::imread on the host,
 // README.md:26).  The compressed file crosses PCIe (7-10x fewer bytes than the RGB image) and is decoded here into
 // the context's staged RGB buffer, on the context's stream, in front of the blur:
+//   k_jpeg_scan  one block: offsets of the restart intervals (the RSTn markers of the entropy-coded segment)
 //   k_jpeg_huff  one thread per restart interval: Huffman decoding (T.81 F.2.2) of its MCUs into the coefficient
-//                array (cleared before; only non-zero coefficients are written)
-//   k_jpeg_idct  one thread per 8x8 block: dequantisation + libjpeg's accurate integer inverse DCT -> sample planes
-//   k_jpeg_rgb   four pixels per thread: chroma upsampling ("fancy" triangle filter) + YCbCr -> interleaved RGB
+//                array (all zero between images; only non-zero coefficients are written)
+//   k_jpeg_idct  one thread per 8x8 block: dequantisation + libjpeg's accurate integer inverse DCT -> sample planes;
+//                clears the block's coefficients behind it
+//   k_jpeg_rgb   eight pixels per thread: chroma upsampling ("fancy" triangle filter) + YCbCr -> interleaved RGB
 //   k_jpeg_flag  hands a decoding error to the run's control block
 // The arithmetic lives in gseg_jpeg_core.h (shared with the CPU test harness) and reproduces libjpeg's default decoder
 // bit for bit (tests/test_jpeg.py against cv2.imdecode).  Parallelism comes from the file's restart markers; a file
@@ -14,7 +16,8 @@
 #include "gseg_device.cuh"
 #include "gseg_jpeg_core.h"
 
-#define JPG_NT_HUFF 64
+#define JPG_NT_HUFF 512 // big blocks on purpose: a block lives for the decode's whole latency, and an SM with a resident block
+                        // cannot take a CTA of the tail cluster (1024 threads x 64 registers = the whole register file)
 #define JPG_NT 128
 
 __constant__ uint8_t c_jpg_zigzag[JPG_ZIGZAG_LEN] = {
@@ -29,6 +32,7 @@ __constant__ uint8_t c_jpg_zigzag[JPG_ZIGZAG_LEN] = {
 // interval number, pass 2 writes the offsets in file order (lane prefix by shuffles).  Sixteen bytes per lane and step;
 // a word is looked at byte by byte only if it holds a 0xFF (one word in ~64).
 #define JPG_NT_SCAN 1024
+#define JPG_SCAN_MLP 4
 __device__ __forceinline__ uint32_t jpg_ff_bytes(uint32_t w) { // 0x80 in every byte of w that is 0xFF
     const uint32_t x = ~w;
     return ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
@@ -67,10 +71,19 @@ __global__ void __launch_bounds__(JPG_NT_SCAN) k_jpeg_scan(const JpegDev *__rest
     const uint32_t wb = c0 + (uint32_t)warp * per, we = min(wb + per, c1);
     const uint4 *f4 = reinterpret_cast<const uint4 *>(file);
     uint32_t cnt = 0u;
-    for (uint32_t c = wb + lane; c < we; c += 32u) {
-        const uint4 v = __ldg(f4 + c);
-        if (jpg_ff_bytes(v.x) | jpg_ff_bytes(v.y) | jpg_ff_bytes(v.z) | jpg_ff_bytes(v.w))
-            cnt += __popc(jpg_rst_mask(v, __ldg(reinterpret_cast<const uint32_t *>(f4 + c + 1)), 16u * c, off, end));
+    for (uint32_t cb = wb; cb < we; cb += 32u * JPG_SCAN_MLP) { // JPG_SCAN_MLP loads in flight per lane: the loop is latency-bound
+        uint4 v[JPG_SCAN_MLP];
+#pragma unroll
+        for (int u = 0; u < JPG_SCAN_MLP; ++u) {
+            const uint32_t c = cb + 32u * u + lane;
+            v[u] = c < we ? __ldg(f4 + c) : make_uint4(0u, 0u, 0u, 0u);
+        }
+#pragma unroll
+        for (int u = 0; u < JPG_SCAN_MLP; ++u) {
+            const uint32_t c = cb + 32u * u + lane;
+            if (jpg_ff_bytes(v[u].x) | jpg_ff_bytes(v[u].y) | jpg_ff_bytes(v[u].z) | jpg_ff_bytes(v[u].w))
+                cnt += __popc(jpg_rst_mask(v[u], __ldg(reinterpret_cast<const uint32_t *>(f4 + c + 1)), 16u * c, off, end));
+        }
     }
 #pragma unroll
     for (int o = 16; o; o >>= 1) cnt += __shfl_xor_sync(0xFFFFFFFFu, cnt, o);
@@ -91,27 +104,33 @@ __global__ void __launch_bounds__(JPG_NT_SCAN) k_jpeg_scan(const JpegDev *__rest
     // intervals the file has no marker for start at the end of the data (they decode to nothing and are flagged above)
     for (uint32_t i = total + 1 + threadIdx.x; i < (uint32_t)nint; i += JPG_NT_SCAN) starts[i] = end;
     uint32_t running = s_off[warp];
-    for (uint32_t cb = wb; cb < we; cb += 32u) {
-        const uint32_t c = cb + lane;
-        uint32_t mask = 0u;
-        if (c < we) {
-            const uint4 v = __ldg(f4 + c);
-            if (jpg_ff_bytes(v.x) | jpg_ff_bytes(v.y) | jpg_ff_bytes(v.z) | jpg_ff_bytes(v.w))
-                mask = jpg_rst_mask(v, __ldg(reinterpret_cast<const uint32_t *>(f4 + c + 1)), 16u * c, off, end);
-        }
-        if (__ballot_sync(0xFFFFFFFFu, mask != 0u) == 0u) continue;
-        const uint32_t n = __popc(mask);
-        uint32_t inc = n;
+    for (uint32_t cb0 = wb; cb0 < we; cb0 += 32u * JPG_SCAN_MLP) {
+        uint4 v[JPG_SCAN_MLP];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
-        uint32_t idx = running + inc - n + 1u; // interval number of the lane's first marker
-        while (mask) {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1u;
-            if (idx < (uint32_t)nint) starts[idx] = 16u * c + (uint32_t)j + 2u;
-            ++idx;
+        for (int u = 0; u < JPG_SCAN_MLP; ++u) {
+            const uint32_t c = cb0 + 32u * u + lane;
+            v[u] = c < we ? __ldg(f4 + c) : make_uint4(0u, 0u, 0u, 0u);
         }
-        running += __shfl_sync(0xFFFFFFFFu, inc, 31);
+#pragma unroll
+        for (int u = 0; u < JPG_SCAN_MLP; ++u) { // file order: step by step, lane by lane, bit by bit
+            const uint32_t c = cb0 + 32u * u + lane;
+            uint32_t mask = 0u;
+            if (jpg_ff_bytes(v[u].x) | jpg_ff_bytes(v[u].y) | jpg_ff_bytes(v[u].z) | jpg_ff_bytes(v[u].w))
+                mask = jpg_rst_mask(v[u], __ldg(reinterpret_cast<const uint32_t *>(f4 + c + 1)), 16u * c, off, end);
+            if (__ballot_sync(0xFFFFFFFFu, mask != 0u) == 0u) continue;
+            const uint32_t n = __popc(mask);
+            uint32_t inc = n;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+            uint32_t idx = running + inc - n + 1u; // interval number of the lane's first marker
+            while (mask) {
+                const int j = __ffs(mask) - 1;
+                mask &= mask - 1u;
+                if (idx < (uint32_t)nint) starts[idx] = 16u * c + (uint32_t)j + 2u;
+                ++idx;
+            }
+            running += __shfl_sync(0xFFFFFFFFu, inc, 31);
+        }
     }
 }
 
@@ -136,7 +155,9 @@ __global__ void __launch_bounds__(JPG_NT_HUFF) k_jpeg_huff(const JpegDev *__rest
     if (err) atomicOr(errp, err);
 }
 
-__global__ void __launch_bounds__(JPG_NT) k_jpeg_idct(const JpegDev *__restrict__ gd, const int16_t *__restrict__ coef,
+// Reads a block's coefficients and clears them behind it: the coefficient array is all zero again when the kernel ends,
+// which is what the next image's Huffman threads (they only write non-zero coefficients) need -- no memset per image.
+__global__ void __launch_bounds__(JPG_NT) k_jpeg_idct(const JpegDev *__restrict__ gd, int16_t *__restrict__ coef,
                                                       uint8_t *__restrict__ samples) {
     __shared__ uint16_t sq[JPG_MAXCOMP][64];
     for (int i = threadIdx.x; i < JPG_MAXCOMP * 64; i += JPG_NT) sq[i >> 6][i & 63] = gd->quant[i >> 6][i & 63];
@@ -147,9 +168,11 @@ __global__ void __launch_bounds__(JPG_NT) k_jpeg_idct(const JpegDev *__restrict_
     const int lb = b - gd->blk_off[c], bwc = gd->bw[c];
     const int by = lb / bwc, bx = lb - by * bwc;
     union { int4 v[8]; int16_t s[64]; } in;
-    const int4 *src = reinterpret_cast<const int4 *>(coef + (size_t)b * 64);
+    int4 *src = reinterpret_cast<int4 *>(coef + (size_t)b * 64);
 #pragma unroll
     for (int i = 0; i < 8; ++i) in.v[i] = src[i];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) src[i] = make_int4(0, 0, 0, 0);
     union { uint2 v[8]; uint8_t s[64]; } out;
     jpg_idct_block(in.s, sq[c], out.s, 8);
     uint8_t *dst = samples + gd->pix_off[c] + ((size_t)by * 8 * bwc + bx) * 8;
