@@ -99,6 +99,9 @@ struct gseg_ctx {
     JpegDev *d_jdev;
     int16_t *d_jcoef;
     size_t jfile_cap, jsamples_cap, jdev_cap, jcoef_cap, hjdesc_cap;
+    uint8_t *d_jsub;              // sub-sequence states of the marker-less decode (k_jpeg_sync): entry, exit, counts, flags
+    size_t jsub_cap;
+    uint32_t jsub_bytes;          // bytes per sub-sequence (GSEG_JPEG_SUB, default 128)
     uint32_t *d_jerr;             // [2] JPG_ERR_* bits of the last two decodes (ping-pong)
     cudaEvent_t ev_jdesc;         // the last descriptor copy out of h_jdesc
     cudaEvent_t ev_jdone;         // end of the last decode (its buffers are free again)
@@ -203,6 +206,8 @@ extern "C" int gseg_create_ex(gseg_ctx **out, int device, int max_w, int max_h, 
     if (!ctx) return GSEG_E_ARG;
     ctx->device = device; ctx->max_w = max_w; ctx->max_h = max_h; ctx->Vmax = V; ctx->Dmax = (int)Dmax;
     ctx->epoch_next = 1; ctx->jflag_slot = -1;
+    ctx->jsub_bytes = 128u;
+    if (const char *ev = getenv("GSEG_JPEG_SUB")) { const int v = atoi(ev); if (v >= 8 && v <= 65536) ctx->jsub_bytes = (uint32_t)v; }
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
     ctx->stream = ctx->own_stream;
@@ -384,6 +389,8 @@ static int jpeg_reserve_own(gseg_ctx *ctx, size_t file_bytes, size_t nint, size_
         }
     }
     if (!rc) rc = jpeg_grow(ctx, &ctx->d_jsamples, &ctx->jsamples_cap, nblocks * 64, blocks_max * 64);
+    const size_t nsub_max = (V + 4096) / ctx->jsub_bytes + 2, nsub = file_bytes / ctx->jsub_bytes + 2;
+    if (!rc) rc = jpeg_grow(ctx, &ctx->d_jsub, &ctx->jsub_cap, nsub * 24 + 64, nsub_max * 24 + 64);
     const size_t desc = sizeof(JpegDev) + 4 * nint, desc_max = sizeof(JpegDev) + 4 * (V / 64 + side / 8 + 64);
     if (!rc) rc = jpeg_grow(ctx, (uint8_t **)&ctx->d_jdev, &ctx->jdev_cap, desc, desc_max);
     if (!rc && ctx->hjdesc_cap < desc) {
@@ -424,9 +431,28 @@ static int jpeg_decode_enqueue(gseg_ctx *ctx, const uint8_t *file, const JpegPla
     const int slot = ctx->jerr_next;
     ctx->jerr_next ^= 1;
     uint32_t *d_starts = (uint32_t *)((uint8_t *)ctx->d_jdev + sizeof(JpegDev));
-    ctx->launches += 4;
-    k_jpeg_scan<<<1, JPG_NT_SCAN, 0, s>>>(ctx->d_jdev, ctx->d_jfile, d_starts, ctx->d_jerr + slot);
-    k_jpeg_huff<<<(d.nint + JPG_NT_HUFF - 1) / JPG_NT_HUFF, JPG_NT_HUFF, 0, s>>>(ctx->d_jdev, d_starts, ctx->d_jfile, ctx->d_jcoef, ctx->d_jerr + slot);
+    const uint32_t S = ctx->jsub_bytes;
+    const size_t nsub = (nbytes - (d.data_off - base) + S - 1) / S;
+    if (d.nint == 1 && nsub >= 2) {
+        // no restart markers: self-synchronising sub-sequences, one cluster (k_jpeg_sync), then the DC prefix sums
+        uint64_t *entryS = (uint64_t *)ctx->d_jsub, *exitS = entryS + nsub;
+        uint32_t *nblk = (uint32_t *)(exitS + nsub), *blk0 = nblk + nsub, *flags = blk0 + nsub;
+        cudaLaunchConfig_t cfg = {};
+        cudaLaunchAttribute at[1];
+        const int cs = (int)((nsub + JPG_NT_SYNC - 1) / JPG_NT_SYNC);
+        cfg.gridDim = dim3(cs < 1 ? 1 : (cs > 8 ? 8 : cs)); cfg.blockDim = dim3(JPG_NT_SYNC); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cfg.gridDim.x; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        ctx->launches += 4;
+        CK(cudaLaunchKernelEx(&cfg, k_jpeg_sync, (const JpegDev *)ctx->d_jdev, (const uint8_t *)ctx->d_jfile, entryS, exitS, nblk, blk0, flags,
+                              ctx->d_jcoef, ctx->d_jerr + slot, S));
+        k_jpeg_dcscan<<<d.ncomp, JPG_NT_SYNC, 0, s>>>(ctx->d_jdev, ctx->d_jcoef);
+    } else {
+        ctx->launches += 4;
+        k_jpeg_scan<<<1, JPG_NT_SCAN, 0, s>>>(ctx->d_jdev, ctx->d_jfile, d_starts, ctx->d_jerr + slot);
+        k_jpeg_huff<<<(d.nint + JPG_NT_HUFF - 1) / JPG_NT_HUFF, JPG_NT_HUFF, 0, s>>>(ctx->d_jdev, d_starts, ctx->d_jfile, ctx->d_jcoef, ctx->d_jerr + slot);
+    }
     k_jpeg_idct<<<(d.nblocks + JPG_NT - 1) / JPG_NT, JPG_NT, 0, s>>>(ctx->d_jdev, ctx->d_jcoef, ctx->d_jsamples);
     const size_t groups = (size_t)((d.w + 7) / 8) * d.h;
     k_jpeg_rgb<<<(unsigned)((groups + JPG_NT - 1) / JPG_NT), JPG_NT, 0, s>>>(ctx->d_jdev, ctx->d_jsamples, rgb_out);
@@ -461,7 +487,7 @@ extern "C" int gseg_jpeg_decode_async(gseg_ctx *ctx, const void *jpeg, size_t nb
     if (prc != JPG_OK) { snprintf(ctx->err, sizeof(ctx->err), "in-house JPEG decoder: %s", plan.why); return GSEG_E_UNSUPPORTED; }
     if (w) *w = plan.dev.w;
     if (h) *h = plan.dev.h;
-    if (ctx->jpeg_backend == GSEG_JPEG_NVJPEG || (ctx->jpeg_backend == GSEG_JPEG_AUTO && plan.dev.ri > GSEG_JPEG_AUTO_MCUS && nvjpeg_api()))
+    if (ctx->jpeg_backend == GSEG_JPEG_NVJPEG || (ctx->jpeg_backend == GSEG_JPEG_AUTO && plan.dev.nint > 1 && plan.dev.ri > GSEG_JPEG_AUTO_MCUS && nvjpeg_api()))
         return fail(ctx, GSEG_E_UNSUPPORTED, "this file goes to nvJPEG under the context's backend setting", cudaSuccess);
     if ((size_t)3 * plan.dev.w * plan.dev.h > out_capacity) return fail(ctx, GSEG_E_RANGE, "output buffer too small for the decoded image", cudaSuccess);
     CK(cudaSetDevice(ctx->device));
@@ -513,7 +539,7 @@ extern "C" int gseg_segment_jpeg_async(gseg_ctx *ctx, const void *jpeg, size_t n
         if (h) *h = plan.dev.h;
     }
     bool own = prc == JPG_OK && ctx->jpeg_backend != GSEG_JPEG_NVJPEG;
-    if (own && ctx->jpeg_backend == GSEG_JPEG_AUTO && plan.dev.ri > GSEG_JPEG_AUTO_MCUS && nvjpeg_api()) own = false;
+    if (own && ctx->jpeg_backend == GSEG_JPEG_AUTO && plan.dev.nint > 1 && plan.dev.ri > GSEG_JPEG_AUTO_MCUS && nvjpeg_api()) own = false;
     if (ctx->jpeg_backend == GSEG_JPEG_OWN && prc != JPG_OK) {
         snprintf(ctx->err, sizeof(ctx->err), "in-house JPEG decoder: %s", plan.why);
         return GSEG_E_UNSUPPORTED;
@@ -558,7 +584,7 @@ extern "C" void gseg_destroy(gseg_ctx *ctx) {
     jpeg_release(ctx);
     cudaFree(ctx->d_jfile); cudaFree(ctx->d_jsamples); cudaFree(ctx->d_jdev); cudaFree(ctx->d_jcoef);
     if (ctx->h_jdesc) cudaFreeHost(ctx->h_jdesc);
-    cudaFree(ctx->d_jerr);
+    cudaFree(ctx->d_jerr); cudaFree(ctx->d_jsub);
     if (ctx->ev_jdesc) cudaEventDestroy(ctx->ev_jdesc);
     if (ctx->ev_jdone) cudaEventDestroy(ctx->ev_jdone);
     delete ctx->jplan;

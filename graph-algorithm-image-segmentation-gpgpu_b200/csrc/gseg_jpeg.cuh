@@ -13,8 +13,12 @@
 // bit for bit (tests/test_jpeg.py against cv2.imdecode).  Parallelism comes from the file's restart markers; a file
 // without them is one interval and goes to nvJPEG instead unless the caller forces this decoder.
 #pragma once
+#include <cooperative_groups.h>
+
 #include "gseg_device.cuh"
 #include "gseg_jpeg_core.h"
+
+namespace cg = cooperative_groups;
 
 #define JPG_NT_HUFF 512 // big blocks on purpose: a block lives for the decode's whole latency, and an SM with a resident block
                         // cannot take a CTA of the tail cluster (1024 threads x 64 registers = the whole register file)
@@ -153,6 +157,131 @@ __global__ void __launch_bounds__(JPG_NT_HUFF) k_jpeg_huff(const JpegDev *__rest
     uint32_t err = 0u;
     jpg_decode_interval(sd, sd.dc, sd.ac, szz, file, starts[i], first, last, coef, err);
     if (err) atomicOr(errp, err);
+}
+
+// ---- files without restart markers: the self-synchronising sub-sequence decode (gseg_jpeg_core.h) in ONE launch of a
+// single thread-block cluster (hardware co-scheduled, barrier.cluster between the passes -- like k_tail):
+//   pass 1   every thread decodes its sub-sequence(s) from the guessed entry state and publishes the exit state;
+//   rounds   a thread whose predecessor's exit differs from the entry it used decodes again; a round in which nobody
+//            decoded ends the iteration (flag words rotate over three slots so that a reset never races a reader);
+//   scan     blocks completed per sub-sequence -> number of the block each sub-sequence starts in (block 0 of the cluster);
+//   write    every thread decodes once more, now storing the coefficients (DC as differences).
+// State words are 64-bit and read with ld.cg: a reader sees the old or the new state of its neighbour, never a mix.
+#define JPG_NT_SYNC 1024
+__global__ void __launch_bounds__(JPG_NT_SYNC, 1) k_jpeg_sync(const JpegDev *__restrict__ gd, const uint8_t *__restrict__ file,
+                                                              uint64_t *entryS, uint64_t *exitS, uint32_t *nblk, uint32_t *blk0,
+                                                              uint32_t *flags, int16_t *__restrict__ coef, uint32_t *errp, uint32_t S) {
+    __shared__ JpegDev sd;
+    __shared__ uint8_t szz[JPG_ZIGZAG_LEN];
+    __shared__ uint32_t s_part[32];
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(gd);
+        uint4 *dst = reinterpret_cast<uint4 *>(&sd);
+        for (int i = threadIdx.x; i < (int)(sizeof(JpegDev) / 16); i += JPG_NT_SYNC) dst[i] = src[i];
+    }
+    for (int i = threadIdx.x; i < JPG_ZIGZAG_LEN; i += JPG_NT_SYNC) szz[i] = c_jpg_zigzag[i];
+    __syncthreads();
+    cg::cluster_group cl = cg::this_cluster();
+    const uint32_t T = gridDim.x * JPG_NT_SYNC, tid = blockIdx.x * JPG_NT_SYNC + threadIdx.x;
+    const uint32_t off = sd.data_off, end = sd.data_end;
+    const uint32_t nsub = end > off ? (end - off + S - 1u) / S : 1u;
+    if (tid == 0) { flags[0] = 0u; flags[1] = 0u; flags[2] = 0u; *errp = 0u; }
+    uint32_t err = 0u, nb = 0u;
+    for (uint32_t i = tid; i < nsub; i += T) { // pass 1
+        const uint32_t e1 = min(off + (i + 1u) * S, end) * 8u;
+        const uint64_t en = i == 0u ? JPG_STATE(off * 8u, 0, 0) : jpg_sub_guess(file, off + i * S, off);
+        entryS[i] = en;
+        exitS[i] = jpg_sub_decode<false>(sd, sd.dc, sd.ac, szz, file, en, e1, nullptr, 0u, &nb, err);
+        nblk[i] = nb;
+    }
+    __threadfence();
+    cl.sync();
+    for (uint32_t r = 0;; ++r) { // rounds
+        if (tid == 0) flags[(r + 1u) % 3u] = 0u;
+        int ch = 0;
+        for (uint32_t i = tid; i < nsub; i += T) {
+            if (i == 0u) continue;
+            const uint64_t en = __ldcg(exitS + i - 1u);
+            if (en != entryS[i]) {
+                const uint32_t e1 = min(off + (i + 1u) * S, end) * 8u;
+                entryS[i] = en;
+                exitS[i] = jpg_sub_decode<false>(sd, sd.dc, sd.ac, szz, file, en, e1, nullptr, 0u, &nb, err);
+                nblk[i] = nb;
+                ch = 1;
+            }
+        }
+        if (__syncthreads_or(ch) && threadIdx.x == 0) atomicOr(&flags[r % 3u], 1u);
+        __threadfence();
+        cl.sync();
+        if (__ldcg(&flags[r % 3u]) == 0u) break; // the same word for every thread of the cluster
+        if (r > nsub + 2u) { if (tid == 0) atomicOr(errp, JPG_ERR_BLOCKS); break; } // cannot happen: round r fixes sub-sequence r
+    }
+    if (blockIdx.x == 0) { // exclusive scan of the block counts
+        const uint32_t per = (nsub + JPG_NT_SYNC - 1u) / JPG_NT_SYNC;
+        const uint32_t b = threadIdx.x * per, e = min(b + per, nsub);
+        uint32_t sum = 0u;
+        for (uint32_t i = b; i < e; ++i) sum += __ldcg(nblk + i);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_part[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t v = s_part[lane], w2 = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, w2, o); if (lane >= o) w2 += t; }
+            s_part[lane] = w2 - v;
+            if (lane == 31 && w2 < (uint32_t)sd.nblocks) atomicOr(errp, JPG_ERR_BLOCKS); // (padding behind the last block may decode to more)
+        }
+        __syncthreads();
+        uint32_t run = s_part[warp] + inc - sum;
+        for (uint32_t i = b; i < e; ++i) { blk0[i] = run; run += __ldcg(nblk + i); }
+    }
+    __threadfence();
+    cl.sync();
+    err = 0u; // the passes above ran from guessed states: their impossible codes mean nothing
+    for (uint32_t i = tid; i < nsub; i += T) { // write
+        const uint32_t e1 = min(off + (i + 1u) * S, end) * 8u;
+        jpg_sub_decode<true>(sd, sd.dc, sd.ac, szz, file, entryS[i], e1, coef, __ldcg(blk0 + i), &nb, err);
+    }
+    if (err) atomicOr(errp, err);
+}
+
+// DC differences -> DC values (T.81 F.1.1.5.1: the predictor of a component runs over its blocks in scan order): one block
+// per component; a thread sums a contiguous run of the component's blocks, a block-wide scan, a second walk writes the values.
+__global__ void __launch_bounds__(JPG_NT_SYNC) k_jpeg_dcscan(const JpegDev *__restrict__ gd, int16_t *__restrict__ coef) {
+    __shared__ __align__(16) uint32_t sgeo[offsetof(JpegDev, quant) / 4];
+    __shared__ int s_part[32];
+    for (int i = threadIdx.x; i < (int)(offsetof(JpegDev, quant) / 4); i += JPG_NT_SYNC) sgeo[i] = reinterpret_cast<const uint32_t *>(gd)[i];
+    __syncthreads();
+    const JpegDev &d = *reinterpret_cast<const JpegDev *>(sgeo);
+    const int c = blockIdx.x;
+    if (c >= d.ncomp) return;
+    const uint32_t n = (uint32_t)d.nmcu * (uint32_t)(d.hs[c] * d.vs[c]);
+    const uint32_t per = (n + JPG_NT_SYNC - 1u) / JPG_NT_SYNC;
+    const uint32_t b = threadIdx.x * per, e = min(b + per, n);
+    int sum = 0;
+    for (uint32_t t = b; t < e; ++t) sum += coef[jpg_comp_block(d, c, t) * 64];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int inc = sum;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) s_part[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+        int v = s_part[lane], w2 = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, w2, o); if (lane >= o) w2 += t; }
+        s_part[lane] = w2 - v;
+    }
+    __syncthreads();
+    int pred = s_part[warp] + inc - sum;
+    for (uint32_t t = b; t < e; ++t) {
+        int16_t *p = coef + jpg_comp_block(d, c, t) * 64;
+        pred += p[0];
+        p[0] = (int16_t)pred;
+    }
 }
 
 // Reads a block's coefficients and clears them behind it: the coefficient array is all zero again when the kernel ends,

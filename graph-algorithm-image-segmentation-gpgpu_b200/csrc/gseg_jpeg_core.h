@@ -24,6 +24,7 @@
 #define JPG_ERR_CODE 1u       // a bit pattern that is no Huffman code
 #define JPG_ERR_COEF 2u       // a run that leaves the block
 #define JPG_ERR_RST 4u        // fewer restart markers in the file than its restart interval promises
+#define JPG_ERR_BLOCKS 8u     // the entropy-coded data does not hold the image's number of blocks
 
 struct alignas(16) JpegHuff {
     uint16_t look[1 << JPG_LOOK]; // (code length << 8 | symbol) for codes of <= JPG_LOOK bits, else 0
@@ -92,11 +93,14 @@ struct JpegBits {
     uint32_t chunk;      // index of cur
     uint32_t widx;       // next word of cur
     uint32_t rem;        // bytes of the stream that have not entered the bit buffer yet
+    uint32_t end0;       // end of the stream (file offset): end0 - rem = offset of the next byte to enter the bit buffer
+    uint32_t ffhist;     // bit i: the (i+1)-th last byte that entered the bit buffer was a stuffed 0xFF (two file bytes)
     uint64_t win;        // byte window: the next bytes of the stream, first byte on top
     int wn;              // ... how many
     uint64_t buf;        // bit buffer, left-aligned
     int n;               // ... valid bits
     bool eof;            // a marker or the end of the data was reached: zero bits from here on
+    int nfake;           // ... how many of the buffer's bits are such zeros (they sit behind the real ones)
 };
 GSEG_HD uint32_t jpg_next_word(JpegBits &b) { // the stream's next four bytes, first byte on top
     const uint32_t w = b.widx == 0 ? b.cur.w[0] : (b.widx == 1 ? b.cur.w[1] : (b.widx == 2 ? b.cur.w[2] : b.cur.w[3]));
@@ -115,7 +119,8 @@ GSEG_HD void jpg_bits_init(JpegBits &b, const uint8_t *file, uint32_t pos, uint3
     b.nxt = jpg_load16(file, b.chunk + 1);
     b.widx = (pos & 15u) >> 2;
     b.rem = end > pos ? end - pos : 0u;
-    b.buf = 0; b.n = 0; b.win = 0; b.wn = 0; b.eof = false;
+    b.end0 = end > pos ? end : pos; b.ffhist = 0u;
+    b.buf = 0; b.n = 0; b.win = 0; b.wn = 0; b.eof = false; b.nfake = 0;
     const uint32_t sub = pos & 3u;
     if (sub) { // the stream starts inside a word
         const uint32_t w = jpg_next_word(b);
@@ -131,17 +136,19 @@ GSEG_HD void jpg_fill(JpegBits &b) { // at least 33 valid bits afterwards: a cod
         const uint32_t ff = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
         if (!b.eof && b.rem >= 4u && ff == 0u) { // four plain bytes
             b.buf |= (uint64_t)W << (32 - b.n);
-            b.n += 32; b.win <<= 32; b.wn -= 4; b.rem -= 4u;
+            b.n += 32; b.win <<= 32; b.wn -= 4; b.rem -= 4u; b.ffhist <<= 4;
         } else { // one byte at a time
             uint32_t v = 0u;
+            b.ffhist <<= 1;
             if (!b.eof && b.rem > 0u) {
                 v = W >> 24;
                 if (v == 0xFFu) {
                     const uint32_t m = b.rem > 1u ? ((W >> 16) & 0xFFu) : 0xD9u;
-                    if (m == 0u) { b.win <<= 16; b.wn -= 2; b.rem -= 2u; } // stuffed byte
-                    else { v = 0u; b.eof = true; }                          // marker: stop here
+                    if (m == 0u) { b.win <<= 16; b.wn -= 2; b.rem -= 2u; b.ffhist |= 1u; } // stuffed byte
+                    else { v = 0u; b.eof = true; }                                         // marker: stop here
                 } else { b.win <<= 8; b.wn -= 1; b.rem -= 1u; }
             } else b.eof = true;
+            if (b.eof) b.nfake += 8;
             b.buf |= (uint64_t)v << (56 - b.n);
             b.n += 8;
         }
@@ -149,6 +156,29 @@ GSEG_HD void jpg_fill(JpegBits &b) { // at least 33 valid bits afterwards: a cod
 }
 GSEG_HD uint32_t jpg_peek(const JpegBits &b, int k) { return (uint32_t)(b.buf >> (64 - k)); } // 1 <= k <= 32
 GSEG_HD void jpg_skip(JpegBits &b, int k) { b.buf <<= k; b.n -= k; }
+
+// File position of the first unread bit, in bits (byte offset * 8 + bits of that byte already consumed): the unread
+// real bits are the tail of the last bytes that entered the buffer, and every stuffed 0xFF among them stands for two
+// file bytes.  A position never names the 0x00 of a stuffed pair.  End of the data once only padding zeros are left.
+GSEG_HD uint32_t jpg_bits_pos(const JpegBits &b) {
+    const int nr = b.n - b.nfake;
+    if (nr <= 0) return b.end0 * 8u;
+    const uint32_t q = (uint32_t)(nr + 7) >> 3;
+    const uint32_t m = (b.ffhist >> (b.nfake >> 3)) & ((1u << q) - 1u);
+#if defined(__CUDA_ARCH__)
+    const uint32_t st = (uint32_t)__popc(m);
+#else
+    uint32_t st = 0u;
+    for (uint32_t t = m; t; t &= t - 1u) ++st;
+#endif
+    return (b.end0 - b.rem - q - st) * 8u + (8u * q - (uint32_t)nr);
+}
+// Reader positioned at a bit position as jpg_bits_pos reports them; the buffer is filled.
+GSEG_HD void jpg_bits_init_bit(JpegBits &b, const uint8_t *file, uint32_t bitpos, uint32_t end) {
+    jpg_bits_init(b, file, bitpos >> 3, end);
+    jpg_fill(b);
+    jpg_skip(b, (int)(bitpos & 7u));
+}
 
 // One Huffman symbol; the caller has filled the bit buffer.
 GSEG_HD int jpg_symbol(JpegBits &b, const JpegHuff &t, uint32_t &err) {
@@ -217,6 +247,101 @@ GSEG_HD void jpg_decode_interval(const JpegDev &d, const JpegHuff *dc, const Jpe
             cb = coef + ((size_t)d.blk_off[c] + (size_t)(my * d.vs[c] + bv) * d.bw[c] + mx * hsc + bh) * 64;
         }
     }
+}
+
+// ---- files WITHOUT restart markers: self-synchronising sub-sequences ---------------------------------------------
+// The entropy-coded segment is cut into sub-sequences of a fixed number of bytes; thread i decodes sub-sequence i.  Only
+// the first one knows where its first code starts and what it means -- the decoder's state at a bit position is (position
+// of the coefficient inside its block, block inside its MCU: k, j) -- so every other thread starts from a guess and the
+// threads then iterate: take the exit state of the sub-sequence before (the state at the first code that starts behind
+// the own sub-sequence's first byte), decode again if it differs from the entry state used last time.  Huffman codes
+// re-synchronise after a few symbols, EOBs re-align k, and wrong guesses of j die out with the tables' differences, so
+// most exits are right after the first pass and the iteration ends after a few rounds; in the worst case it is a serial
+// decode, it is never wrong: sub-sequence 0 is right from the start and round r makes sub-sequence r right.  A last pass
+// writes the coefficients (DC as differences: k_jpeg_dcscan turns them into values).  After Weissenberger & Schmidt,
+// "Massively Parallel Huffman Decoding on GPUs" (ICPP 2018) -- restated for T.81's block structure.
+// State word: bits 0..31 bit position, 32..39 k, 40..47 j.
+#define JPG_STATE(p, k, j) ((uint64_t)(p) | ((uint64_t)(k) << 32) | ((uint64_t)(j) << 40))
+// Decodes from `entry` until the first symbol that starts at or behind bit position end_bits (or the data / the image's
+// blocks end); returns the state there.  WRITE: coefficients of the blocks, the first of which is block blk (counted over
+// the scan: MCU by MCU, the MCU's blocks in order), go to coef[]; *nblk = blocks completed.
+template <bool WRITE>
+GSEG_HD uint64_t jpg_sub_decode(const JpegDev &d, const JpegHuff *dc, const JpegHuff *ac, const uint8_t *zz, const uint8_t *file,
+                                uint64_t entry, uint32_t end_bits, int16_t *coef, uint32_t blk, uint32_t *nblk, uint32_t &err) {
+    JpegBits b;
+    jpg_bits_init_bit(b, file, (uint32_t)entry, d.data_end);
+    int k = (int)((entry >> 32) & 63u), j = (int)((entry >> 40) & 255u);
+    int bpm = 0;
+    for (int c = 0; c < d.ncomp; ++c) bpm += d.hs[c] * d.vs[c];
+    if (j >= bpm) j = 0;
+    int c = 0, bi = j;
+    while (bi >= d.hs[c] * d.vs[c]) { bi -= d.hs[c] * d.vs[c]; ++c; }
+    int m = 0, mx = 0, my = 0;
+    int16_t *cb = coef;
+    if (WRITE) {
+        m = (int)(blk / (uint32_t)bpm); mx = m % d.mcus_x; my = m / d.mcus_x;
+        j = (int)(blk - (uint32_t)m * (uint32_t)bpm); // == the entry state's j when the iteration has converged
+        c = 0; bi = j;
+        while (bi >= d.hs[c] * d.vs[c]) { bi -= d.hs[c] * d.vs[c]; ++c; }
+        const int hsc = d.hs[c], bv = hsc == 1 ? bi : (hsc == 2 ? bi >> 1 : bi / hsc), bh = bi - bv * hsc;
+        cb = coef + ((size_t)d.blk_off[c] + (size_t)(my * d.vs[c] + bv) * d.bw[c] + mx * hsc + bh) * 64;
+    }
+    const JpegHuff *tdc = dc + c, *tac = ac + c;
+    uint32_t done = 0u, e2 = 0u;
+    uint32_t pos = (uint32_t)entry;
+    while (pos < end_bits && (!WRITE || m < d.nmcu)) {
+        jpg_fill(b);
+        const bool isdc = k == 0;
+        const int rs = jpg_symbol(b, isdc ? *tdc : *tac, e2);
+        const int sz = rs & 15;
+        const int v = jpg_receive_extend(b, sz);
+        if (isdc) {
+            if (WRITE && v) cb[0] = (int16_t)v; // the difference; k_jpeg_dcscan sums them up
+            k = 1;
+        } else if (sz) {
+            k += rs >> 4;
+            if (k > 63) { e2 |= JPG_ERR_COEF; k = 64; }
+            else { if (WRITE) cb[zz[k]] = (int16_t)v; ++k; }
+        } else {
+            k = (rs >> 4) == 15 ? k + 16 : 64;
+        }
+        if (k >= 64) {
+            k = 0; ++done;
+            if (++j == bpm) j = 0;
+            if (++bi == d.hs[c] * d.vs[c]) {
+                bi = 0;
+                if (++c == d.ncomp) {
+                    c = 0; ++m;
+                    if (++mx == d.mcus_x) { mx = 0; ++my; }
+                }
+                tdc = dc + c; tac = ac + c;
+            }
+            if (WRITE) {
+                const int hsc = d.hs[c], bv = hsc == 1 ? bi : (hsc == 2 ? bi >> 1 : bi / hsc), bh = bi - bv * hsc;
+                cb = coef + ((size_t)d.blk_off[c] + (size_t)(my * d.vs[c] + bv) * d.bw[c] + mx * hsc + bh) * 64;
+            }
+        }
+        pos = jpg_bits_pos(b);
+    }
+    if (WRITE) err |= e2; // a pass from a guessed state runs into impossible codes all the time: only the last pass counts
+    *nblk = done;
+    return JPG_STATE(pos, k, j);
+}
+// First guess of the entry state of the sub-sequence that starts at file byte `start`: a code starts there, and it is a
+// block's DC code of the MCU's first block.  (The 0x00 of a stuffed pair is not a position.)
+GSEG_HD uint64_t jpg_sub_guess(const uint8_t *file, uint32_t start, uint32_t first) {
+    if (start > first && file[start - 1] == 0xFFu && file[start] == 0x00u) ++start;
+    return JPG_STATE(start * 8u, 0, 0);
+}
+
+// Block number t of component c in scan order (MCU by MCU, the component's blocks inside an MCU in order) -> its index
+// in the coefficient array.  The DC predictor of a component runs over its blocks in exactly this order (T.81 F.1.1.5.1).
+GSEG_HD size_t jpg_comp_block(const JpegDev &d, int c, uint32_t t) {
+    const uint32_t per = (uint32_t)(d.hs[c] * d.vs[c]);
+    const uint32_t m = t / per, bi = t - m * per;
+    const uint32_t mx = m % (uint32_t)d.mcus_x, my = m / (uint32_t)d.mcus_x;
+    const uint32_t bv = bi / (uint32_t)d.hs[c], bh = bi - bv * (uint32_t)d.hs[c];
+    return (size_t)d.blk_off[c] + (size_t)(my * (uint32_t)d.vs[c] + bv) * (uint32_t)d.bw[c] + mx * (uint32_t)d.hs[c] + bh;
 }
 
 // ---- inverse DCT: libjpeg's accurate integer method (jidctint.c, "islow": Loeffler-Ligtenberg-Moschytz, 13-bit

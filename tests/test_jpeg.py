@@ -31,6 +31,7 @@ def host():
     L.jpeg_host_why.restype = C.c_char_p
     L.jpeg_host_why.argtypes = [C.c_char_p, C.c_size_t]
     L.jpeg_host_info.argtypes = [C.c_char_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int)]
+    L.jpeg_host_decode_sync.argtypes = [C.c_char_p, C.c_size_t, C.c_void_p, C.c_size_t, C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_int, C.POINTER(C.c_int)]
 
     def decode(data):
         w, h, ni = C.c_int(), C.c_int(), C.c_int()
@@ -39,7 +40,16 @@ def host():
         if rc:
             return rc, L.jpeg_host_why(data, len(data)).decode()
         return out[:3 * w.value * h.value].reshape(h.value, w.value, 3).copy(), ni.value
+    def decode_sync(data, sub_bytes):
+        """the marker-less path: self-synchronising sub-sequences of sub_bytes bytes; returns (pixels | rc, rounds)"""
+        w, h, r = C.c_int(), C.c_int(), C.c_int()
+        out = np.zeros(3 << 22, np.uint8)
+        rc = L.jpeg_host_decode_sync(data, len(data), out.ctypes.data, out.size, C.byref(w), C.byref(h), sub_bytes, C.byref(r))
+        if rc:
+            return rc, r.value
+        return out[:3 * w.value * h.value].reshape(h.value, w.value, 3).copy(), r.value
     decode.lib = L
+    decode.sync = decode_sync
     return decode
 
 
@@ -95,6 +105,41 @@ def test_host_restart_intervals_and_grey(host, oracle):
     for q in (10, 100):
         enc = encode(noise, q, "444", 3)
         assert np.array_equal(host(enc.tobytes())[0], libjpeg(enc))
+
+
+@pytest.mark.parametrize("sampling", sorted(SAMPLING))
+def test_host_self_synchronising_decode_matches_libjpeg(host, oracle, sampling):
+    """Files WITHOUT restart markers: sub-sequences decoded from guessed states, iterated until every entry state equals
+    its predecessor's exit state, then written (DC as differences + prefix sums).  Identical pixels to libjpeg whatever
+    the sub-sequence size; the number of rounds stays small for ordinary qualities."""
+    worst = 0
+    for (w, h) in [(160, 120), (161, 123), (17, 9), (8, 8), (1, 1)]:
+        img = oracle.synth(w, h, 11 + w)
+        for q in (50, 90, 100):
+            enc = encode(img, q, sampling, 0, optimize=(q == 50))
+            ref = libjpeg(enc)
+            for sub in (16, 64, 128):
+                got, rounds = host.sync(enc.tobytes(), sub)
+                assert not isinstance(got, int), (w, h, q, sub, got)
+                assert np.array_equal(got, ref), (w, h, q, sub)
+                if q <= 90 and sub == 128:
+                    worst = max(worst, rounds)
+    assert worst <= 16
+    # a file WITH restart markers is not this path's business
+    assert host.sync(encode(oracle.synth(64, 48, 1), 90, sampling, 2).tobytes(), 64)[0] == 5
+
+
+def test_host_self_synchronising_decode_of_stuffing_heavy_data(host):
+    """Noise at quality 100: one 0xFF in ~100 bytes, i.e. sub-sequence borders that fall on and next to stuffed bytes."""
+    rng = np.random.default_rng(3)
+    noise = rng.integers(0, 256, (96, 128, 3), dtype=np.uint8)
+    for sampling in ("444", "420"):
+        enc = encode(noise, 100, sampling, 0)
+        assert enc.tobytes().count(b"\xff\x00") > 100
+        ref = libjpeg(enc)
+        for sub in (8, 9, 31, 128):
+            got, _ = host.sync(enc.tobytes(), sub)
+            assert not isinstance(got, int) and np.array_equal(got, ref), (sampling, sub)
 
 
 def test_host_parser_rejects_what_it_does_not_decode(host, oracle):
@@ -174,17 +219,69 @@ def test_gpu_decode_identical_to_libjpeg_and_partition_to_oracle(gseg, oracle):
 
 
 @pytest.mark.gpu
+def test_gpu_files_without_restart_markers(gseg, oracle, monkeypatch):
+    """k_jpeg_sync + k_jpeg_dcscan: what cv::imwrite / a camera writes (no DRI).  Pixels == libjpeg, partition == oracle;
+    sub-sequence sizes that give every thread one sub-sequence and several."""
+    for sub in ("128", "32"):
+        monkeypatch.setenv("GSEG_JPEG_SUB", sub)
+        seg = gseg.Segmenter(640, 480)
+        seg.set_jpeg_backend(gseg.JPEG_OWN)
+        cases = [(640, 480, "420", 90), (321, 243, "444", 75), (200, 150, "422", 100), (64, 300, "440", 50), (400, 96, "411", 95),
+                 (17, 9, "420", 90), (8, 8, "444", 100), (1, 1, "420", 90)]
+        for i, (w, h, sampling, q) in enumerate(cases):
+            img = oracle.synth(w, h, 150 + i)
+            enc = encode(img, q, sampling, 0, optimize=i & 1)
+            assert seg.segment_jpeg(enc.tobytes(), sigma=0.8, k=300.0, min_size=20, connectivity=4, variant=0) == (w, h)
+            assert seg.jpeg_backend_used() == gseg.JPEG_OWN
+            rgb = seg.input_rgb()
+            assert np.array_equal(rgb, libjpeg(enc)), (sub, w, h, sampling, q)
+            if i < 3:
+                ref = oracle.pipeline(rgb, 0.8, 300.0, 20, 4, oracle.FELZ)
+                assert seg.num_components() == ref["n"] and same_partition(oracle, seg.labels(), ref["labels"])
+        # alternating with a restart-marker file on the same context (the coefficient array is shared and must be clean)
+        a = encode(oracle.synth(320, 240, 5), 90, "420", 0)
+        b = encode(oracle.synth(320, 240, 6), 90, "444", 3)
+        for enc in (a, b, a, b):
+            seg.segment_jpeg(enc.tobytes(), sigma=0.8, k=300.0, min_size=20)
+            assert np.array_equal(seg.input_rgb(), libjpeg(enc))
+        # stuffing-heavy data, and corrupt data: an error or an image, never a crash
+        rng = np.random.default_rng(4)
+        enc = encode(rng.integers(0, 256, (240, 320, 3), dtype=np.uint8), 100, "420", 0)
+        seg.segment_jpeg(enc.tobytes(), sigma=0.8, k=300.0, min_size=20)
+        assert np.array_equal(seg.input_rgb(), libjpeg(enc))
+        bad = bytearray(a.tobytes())
+        sos = bad.rfind(b"\xff\xda") + 14
+        for i in range(sos + 200, len(bad) - 2, 7):
+            if bad[i] != 0xFF and bad[i - 1] != 0xFF and bad[i] != 0:
+                bad[i] ^= 0x5A if (bad[i] ^ 0x5A) not in (0xFF, 0x00) else 0x11
+        try:
+            seg.segment_jpeg(bytes(bad), sigma=0.8, k=300.0, min_size=20)
+        except gseg.GsegError as e:
+            assert "corrupt JPEG" in str(e)
+        seg.segment_jpeg(a.tobytes(), sigma=0.8, k=300.0, min_size=20)
+        assert np.array_equal(seg.input_rgb(), libjpeg(a))
+        seg.close()
+
+
+@pytest.mark.gpu
 def test_gpu_backends_and_errors(gseg, oracle):
     seg = gseg.Segmenter(400, 300)
     img = oracle.synth(320, 240, 21)
-    # automatic choice: restart markers -> in-house; none (one long interval) -> nvJPEG when it is loadable
+    # automatic choice: baseline files -> in-house, with restart markers (one thread per interval) or without (self-
+    # synchronising sub-sequences); progressive -> nvJPEG when it is loadable
     seg.segment_jpeg(encode(img, 90, "420", 4).tobytes(), sigma=0.8, k=300.0, min_size=20)
     assert seg.jpeg_backend_used() == gseg.JPEG_OWN
     big = oracle.synth(400, 300, 22)
     seg.segment_jpeg(encode(big, 90, "444", 0).tobytes(), sigma=0.8, k=300.0, min_size=20)   # 1900 MCUs, no restart markers
-    used = seg.jpeg_backend_used()
-    assert used in (gseg.JPEG_NVJPEG, gseg.JPEG_OWN)
-    # forced in-house: a progressive file is refused, a file without restart markers decodes (one thread)
+    assert seg.jpeg_backend_used() == gseg.JPEG_OWN
+    prog = encode(img, 90, "420", 0, extra=(cv2.IMWRITE_JPEG_PROGRESSIVE, 1))
+    try:
+        seg.segment_jpeg(prog.tobytes(), sigma=0.8, k=300.0, min_size=20)
+        assert seg.jpeg_backend_used() == gseg.JPEG_NVJPEG
+        assert np.abs(seg.input_rgb().astype(np.int32) - libjpeg(prog).astype(np.int32)).mean() < 8.0
+    except gseg.GsegError as e:
+        assert "optional dependency" in str(e)
+    # forced in-house: a progressive file is refused
     seg.set_jpeg_backend(gseg.JPEG_OWN)
     with pytest.raises(gseg.GsegError) as e:
         seg.segment_jpeg(encode(img, 90, "420", 0, extra=(cv2.IMWRITE_JPEG_PROGRESSIVE, 1)).tobytes(), sigma=0.8, k=300.0, min_size=20)

@@ -63,7 +63,7 @@ for S_ in (S,):
     print("pool %2d contexts, raw RGB (pinned):              %.3f ms/image  %8.1f Mpixel/s  (%.2f MB/image in)" %
           (S_, t / nimg * 1e3, nimg * w * h / 1e6 / t, w * h * 3 / 1e6), flush=True)
     for name, sf in (("4:2:0", cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420), ("4:4:4", cv2.IMWRITE_JPEG_SAMPLING_FACTOR_444)):
-        for rst in (1, 2, 4, 8, 16):
+        for rst in (0, 1, 2, 4, 8, 16):
             encs = [enc(im, rst, sf) for im in imgs]
             tot = sum((e.size + 63) // 64 * 64 for e in encs)
             hj = torch.empty(tot, dtype=torch.uint8).pin_memory()
