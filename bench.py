@@ -341,12 +341,13 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_copy = float(t.item())
     pix = world * B * W * H / 1e6
-    jpeg_entry = None
+    jpeg_entries = []
     if args.mode == "all":
-        try:
-            jpeg_entry = bench_jpeg_fed(args, gseg, batch, torch, dist, world, pool, himgs, hlab, kw, timed, pix)
-        except Exception as ex:  # an extra must not take the headline down with it
-            jpeg_entry = {"name": "configs[1] JPEG-fed", "error": "%s: %s" % (type(ex).__name__, str(ex)[:300])}
+        for rst, nm in ((None, "configs[1] JPEG-fed"), (0, "configs[1] JPEG-fed, files without restart markers")):
+            try:
+                jpeg_entries.append(bench_jpeg_fed(args, gseg, batch, torch, dist, world, pool, himgs, hlab, kw, timed, pix, rst, nm))
+            except Exception as ex:  # an extra must not take the headline down with it
+                jpeg_entries.append({"name": nm, "error": "%s: %s" % (type(ex).__name__, str(ex)[:300])})
     clocks = sampler.finish() if sampler else None
     value, e2e, ceil = pix / (ms_dev / 1e3), pix / (ms_e2e / 1e3), pix / (ms_copy / 1e3)
 
@@ -378,8 +379,7 @@ def main():
 
     # ---------------- the other BASELINE configs ----------------
     extra = []
-    if jpeg_entry is not None:
-        extra.append(jpeg_entry)
+    extra.extend(jpeg_entries)
     if args.mode == "all":
         del jobs_dev, jobs_e2e
         pool.close()
@@ -422,7 +422,7 @@ def main():
 JPEG_QUALITY, JPEG_RST = 90, 1
 
 
-def bench_jpeg_fed(args, gseg, batch, torch, dist, world, pool, himgs, hlab, kw, timed, pix):
+def bench_jpeg_fed(args, gseg, batch, torch, dist, world, pool, himgs, hlab, kw, timed, pix, rst=None, name="configs[1] JPEG-fed"):
     """the headline workload fed the way the reference's batch benchmark is fed (a JPEG data set,
     README.md:26) -- the files' bytes wait in pinned host memory, cross PCIe compressed and are decoded on the GPU by the
     in-house kernels (csrc/gseg_jpeg.cuh) on each context's copy stream, under the previous image's kernels; label images
@@ -431,8 +431,9 @@ def bench_jpeg_fed(args, gseg, batch, torch, dist, world, pool, himgs, hlab, kw,
     import numpy as np
     from multiprocessing.pool import ThreadPool
     B = himgs.shape[0]
+    rst = JPEG_RST if rst is None else rst
     params = [cv2.IMWRITE_JPEG_QUALITY, JPEG_QUALITY, cv2.IMWRITE_JPEG_SAMPLING_FACTOR, cv2.IMWRITE_JPEG_SAMPLING_FACTOR_420,
-              cv2.IMWRITE_JPEG_RST_INTERVAL, JPEG_RST]
+              cv2.IMWRITE_JPEG_RST_INTERVAL, rst]
     src = himgs.numpy()
 
     def enc(i):
@@ -467,8 +468,10 @@ def bench_jpeg_fed(args, gseg, batch, torch, dist, world, pool, himgs, hlab, kw,
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_copy = float(t.item())
     h2d = int(sum(e.size for e in encs))
-    return {"name": "configs[1] JPEG-fed", "workload": WORKLOAD + "; input = the same images as JPEG files (quality %d, 4:2:0, restart "
-            "interval %d MCUs = %d intervals per image) in pinned host memory" % (JPEG_QUALITY, JPEG_RST, (120 * 68 + JPEG_RST - 1) // JPEG_RST),
+    how = ("restart interval %d MCU(s) = %d intervals per image: one thread per interval" % (rst, (120 * 68 + rst - 1) // rst) if rst
+           else "no restart markers, as cv::imwrite writes them: self-synchronising sub-sequences, one cluster per image")
+    return {"name": name, "workload": WORKLOAD + "; input = the same images as JPEG files (quality %d, 4:2:0, %s) in pinned host memory"
+            % (JPEG_QUALITY, how),
             "decoder": {1: "in-house kernels (gseg_jpeg.cuh), bit-identical to libjpeg", 2: "nvJPEG"}.get(used, str(used)),
             "steps": args.steps, "warmup": args.warmup,
             "e2e": {"value": round(pix / (ms / 1e3), 1), "unit": "Mpixel/s", "ms_per_step": round(ms, 4), "h2d_bytes_per_step": h2d,

@@ -5,7 +5,8 @@
 // and writes PPM.  OpenCV's C++ headers are not in this image, zlib is, so PNG is done here directly:
 // decoder for every non-interlaced PNG colour type / bit depth (grey, RGB, palette, with or without
 // alpha; 16-bit samples keep their high byte, alpha is dropped), encoder for 8-bit RGB.  JPEG files are
-// not decoded here: the CLI hands their bytes to gseg_segment_jpeg / a pool job, which decodes them on the GPU (nvJPEG).
+// not decoded here: the CLI hands their bytes to gseg_segment_jpeg / a pool job, which decodes them on the GPU (the kernels of
+// gseg_jpeg.cuh; nvJPEG for progressive files).
 #pragma once
 #include <cstdint>
 #include <cstdio>
@@ -212,7 +213,7 @@ inline bool read_image(const char *path, std::vector<uint8_t> &rgb, int &w, int 
     std::vector<uint8_t> buf;
     if (!read_file(path, buf)) { err = "cannot open file"; return false; }
     if (is_png(buf)) return decode_png(buf, rgb, w, h, err);
-    if (buf.size() >= 2 && buf[0] == 0xFF && buf[1] == 0xD8) { err = "JPEG is not supported (no libjpeg in this build): convert to PNG or PPM"; return false; }
+    if (buf.size() >= 2 && buf[0] == 0xFF && buf[1] == 0xD8) { err = "JPEG is decoded on the GPU (gseg_segment_jpeg), not by this host reader"; return false; }
     return decode_pnm(buf, rgb, w, h, err);
 }
 
