@@ -7,7 +7,7 @@ edge weights -> Boruvka rounds with predicate -> min-size rounds -> label image)
 synthetic images, through the C++ batch pipeline of the C-ABI (gseg_pool_run).  N > 1: one process per GPU, every
 rank segments its own B images per step (images shard, no data-path collective; weak scaling).
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl gseg|reference] [--batch B] [--mode all|headline|tiled]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--impl gseg|reference] [--batch B] [--mode all|headline|tiled|jpeg]
 
 Prints ONE JSON line (rank 0).  `value` = Mpixel/s with the inputs resident in HBM; `e2e` = the same through the
 C-ABI with pinned HOST buffers (H2D image in, D2H label image out -- in the narrowest lossless label type --
@@ -257,8 +257,9 @@ def main():
     ap.add_argument("--impl", default="gseg", choices=["gseg", "reference"])
     ap.add_argument("--batch", type=int, default=256, help="images per step per GPU")
     ap.add_argument("--contexts", type=int, default=8, help="gseg contexts (one CUDA stream each) in flight per GPU")
-    ap.add_argument("--mode", default="all", choices=["all", "headline", "tiled"],
-                    help="all: headline + the other BASELINE configs as `extra`; tiled: configs[4] as the line's value")
+    ap.add_argument("--mode", default="all", choices=["all", "headline", "tiled", "jpeg"],
+                    help="all: headline + the other BASELINE configs as `extra`; tiled: configs[4] as the line's value; "
+                         "jpeg: headline + the JPEG-fed entries only")
     ap.add_argument("--tiled-size", type=int, default=32768, help="side of the square image of the tiled run")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -342,7 +343,7 @@ def main():
         ms_copy = float(t.item())
     pix = world * B * W * H / 1e6
     jpeg_entries = []
-    if args.mode == "all":
+    if args.mode in ("all", "jpeg"):
         for rst, nm in ((None, "configs[1] JPEG-fed"), (0, "configs[1] JPEG-fed, files without restart markers")):
             try:
                 jpeg_entries.append(bench_jpeg_fed(args, gseg, batch, torch, dist, world, pool, himgs, hlab, kw, timed, pix, rst, nm))
