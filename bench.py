@@ -249,6 +249,15 @@ def roofline_of(agg, peak, peak_src, traffic_table):
                           "dram_frac (ncu DRAM bytes / time / peak) is far below frac and the kernels are L2/latency-bound"}
 
 
+_T0 = time.perf_counter()
+
+
+def note(what, rank=0):
+    """wall-clock of the bench's sections on stderr (rank 0): where a run's minutes go"""
+    if rank == 0:
+        print("[bench %6.1f s] %s" % (time.perf_counter() - _T0, what), file=sys.stderr, flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -331,6 +340,7 @@ def main():
     def step_e2e():
         res_box["e2e"] = pool.run(jobs_e2e)
 
+    note("set-up done: %d images per GPU, %d contexts" % (B, S), rank)
     l0 = pool.launch_count()
     ms_dev = timed(step_dev, args.steps, args.warmup)
     launches = (pool.launch_count() - l0) * args.steps // (args.steps + args.warmup)
@@ -342,6 +352,7 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_copy = float(t.item())
     pix = world * B * W * H / 1e6
+    note("headline: device-resident, end to end, copy ceiling", rank)
     jpeg_entries = []
     if args.mode in ("all", "jpeg"):
         for rst, nm in ((None, "configs[1] JPEG-fed"), (0, "configs[1] JPEG-fed, files without restart markers")):
@@ -351,6 +362,7 @@ def main():
                 jpeg_entries.append({"name": nm, "error": "%s: %s" % (type(ex).__name__, str(ex)[:300])})
     clocks = sampler.finish() if sampler else None
     value, e2e, ceil = pix / (ms_dev / 1e3), pix / (ms_e2e / 1e3), pix / (ms_copy / 1e3)
+    note("JPEG-fed entries", rank)
 
     # ---------------- roofline of the dominant kernel (host-driven schedule, one context alone) ----------------
     roof = None
@@ -378,6 +390,7 @@ def main():
                          "CPU path, gcc -O3 -march=x86-64-v3, %.1f s)" % (nimg, cores, sec)}
         cpu0 = kruskal_baseline(O)
 
+    note("roofline profile + CPU baselines", rank)
     # ---------------- the other BASELINE configs ----------------
     extra = []
     extra.extend(jpeg_entries)
@@ -398,6 +411,7 @@ def main():
                 e = {"workload": fn.__name__, "error": "%s: %s" % (type(ex).__name__, str(ex)[:300])}
             if e is not None:
                 extra.append(e)
+            note(fn.__name__, rank)
             torch.cuda.empty_cache()
     else:
         pool.close()
