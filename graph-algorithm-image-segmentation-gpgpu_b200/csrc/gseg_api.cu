@@ -12,6 +12,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <new>
 #include <vector>
 
 #include "../../include/gseg.h"
@@ -405,7 +406,7 @@ static int jpeg_reserve_own(gseg_ctx *ctx, size_t file_bytes, size_t nint, size_
     if (!rc && !ctx->d_jerr) { CK(cudaMalloc((void **)&ctx->d_jerr, 2 * sizeof(uint32_t))); CK(cudaMemset(ctx->d_jerr, 0, 2 * sizeof(uint32_t))); }
     if (!rc && !ctx->ev_jdesc) CK(cudaEventCreateWithFlags(&ctx->ev_jdesc, cudaEventDisableTiming));
     if (!rc && !ctx->ev_jdone) CK(cudaEventCreateWithFlags(&ctx->ev_jdone, cudaEventDisableTiming));
-    if (!rc && !ctx->jplan) ctx->jplan = new JpegPlan();
+    if (!rc && !ctx->jplan && !(ctx->jplan = new (std::nothrow) JpegPlan())) return fail(ctx, GSEG_E_ARG, "out of host memory", cudaSuccess);
     return rc;
 }
 
@@ -480,7 +481,7 @@ static int jpeg_own_async(gseg_ctx *ctx, const uint8_t *file, const JpegPlan &pl
 extern "C" int gseg_jpeg_decode_async(gseg_ctx *ctx, const void *jpeg, size_t nbytes, uint8_t *rgb_out_device, size_t out_capacity,
                                       void *cuda_stream, int *w, int *h) {
     if (!ctx || !jpeg || !nbytes || !rgb_out_device) return GSEG_E_ARG;
-    if (!ctx->jplan) ctx->jplan = new JpegPlan();
+    if (!ctx->jplan && !(ctx->jplan = new (std::nothrow) JpegPlan())) return fail(ctx, GSEG_E_ARG, "out of host memory", cudaSuccess);
     JpegPlan &plan = *ctx->jplan;
     const int prc = jpeg_parse((const uint8_t *)jpeg, nbytes, plan, false);
     if (prc == JPG_NOT_JPEG) { snprintf(ctx->err, sizeof(ctx->err), "not a JPEG: %s", plan.why); return GSEG_E_ARG; }
@@ -530,7 +531,7 @@ static int jpeg_nvjpeg_async(gseg_ctx *ctx, const void *jpeg, size_t nbytes, con
 extern "C" int gseg_segment_jpeg_async(gseg_ctx *ctx, const void *jpeg, size_t nbytes, const gseg_params *p, int *w, int *h) {
     if (!ctx || !jpeg || !nbytes || !p) return GSEG_E_ARG;
     if (ctx->pending) return fail(ctx, GSEG_E_STATE, "previous run not waited for", cudaSuccess);
-    if (!ctx->jplan) ctx->jplan = new JpegPlan();
+    if (!ctx->jplan && !(ctx->jplan = new (std::nothrow) JpegPlan())) return fail(ctx, GSEG_E_ARG, "out of host memory", cudaSuccess);
     JpegPlan &plan = *ctx->jplan;
     const int prc = jpeg_parse((const uint8_t *)jpeg, nbytes, plan, false);
     if (prc == JPG_NOT_JPEG) { snprintf(ctx->err, sizeof(ctx->err), "not a JPEG: %s", plan.why); return GSEG_E_ARG; }
