@@ -250,6 +250,24 @@ __global__ void __launch_bounds__(JPG_NT_SYNC, 1) k_jpeg_sync(const JpegDev *__r
 
 // DC differences -> DC values (T.81 F.1.1.5.1: the predictor of a component runs over its blocks in scan order): one block
 // per component; a thread sums a contiguous run of the component's blocks, a block-wide scan, a second walk writes the values.
+// The walk keeps (MCU column, MCU row, block inside the MCU) as state -- one division per thread, not three per block (the
+// first version spent 84 us of one SM on them) -- and has eight loads in flight (blocks are 128 bytes apart).
+struct JpgWalk {
+    uint32_t mx, my, bi, per, hs, sh, mcus_x, row, bw, base; // sh = log2(hs); row = vs * bw; base = blk_off
+    __device__ __forceinline__ void init(const JpegDev &d, int c, uint32_t t) {
+        per = (uint32_t)(d.hs[c] * d.vs[c]); hs = (uint32_t)d.hs[c]; sh = hs == 4u ? 2u : (hs == 2u ? 1u : 0u);
+        mcus_x = (uint32_t)d.mcus_x; bw = (uint32_t)d.bw[c]; row = (uint32_t)d.vs[c] * bw; base = (uint32_t)d.blk_off[c];
+        const uint32_t m = t / per;
+        bi = t - m * per; mx = m % mcus_x; my = m / mcus_x;
+    }
+    __device__ __forceinline__ size_t index() const { // == jpg_comp_block
+        const uint32_t bv = bi >> sh, bh = bi - (bv << sh);
+        return (size_t)base + (size_t)my * row + (size_t)bv * bw + mx * hs + bh;
+    }
+    __device__ __forceinline__ void next() {
+        if (++bi == per) { bi = 0; if (++mx == mcus_x) { mx = 0; ++my; } }
+    }
+};
 __global__ void __launch_bounds__(JPG_NT_SYNC) k_jpeg_dcscan(const JpegDev *__restrict__ gd, int16_t *__restrict__ coef) {
     __shared__ __align__(16) uint32_t sgeo[offsetof(JpegDev, quant) / 4];
     __shared__ int s_part[32];
@@ -260,9 +278,17 @@ __global__ void __launch_bounds__(JPG_NT_SYNC) k_jpeg_dcscan(const JpegDev *__re
     if (c >= d.ncomp) return;
     const uint32_t n = (uint32_t)d.nmcu * (uint32_t)(d.hs[c] * d.vs[c]);
     const uint32_t per = (n + JPG_NT_SYNC - 1u) / JPG_NT_SYNC;
-    const uint32_t b = threadIdx.x * per, e = min(b + per, n);
+    const uint32_t b = min(threadIdx.x * per, n), e = min(b + per, n);
+    JpgWalk wk;
+    wk.init(d, c, b);
     int sum = 0;
-    for (uint32_t t = b; t < e; ++t) sum += coef[jpg_comp_block(d, c, t) * 64];
+    for (uint32_t t0 = b; t0 < e; t0 += 8u) {
+        int x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { x[u] = t0 + u < e ? (int)coef[wk.index() * 64] : 0; wk.next(); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sum += x[u];
+    }
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     int inc = sum;
 #pragma unroll
@@ -277,10 +303,15 @@ __global__ void __launch_bounds__(JPG_NT_SYNC) k_jpeg_dcscan(const JpegDev *__re
     }
     __syncthreads();
     int pred = s_part[warp] + inc - sum;
-    for (uint32_t t = b; t < e; ++t) {
-        int16_t *p = coef + jpg_comp_block(d, c, t) * 64;
-        pred += p[0];
-        p[0] = (int16_t)pred;
+    wk.init(d, c, b);
+    for (uint32_t t0 = b; t0 < e; t0 += 8u) {
+        int16_t *p[8];
+        int x[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) { p[u] = coef + wk.index() * 64; x[u] = t0 + u < e ? (int)*p[u] : 0; wk.next(); }
+#pragma unroll
+        for (int u = 0; u < 8; ++u)
+            if (t0 + u < e) { pred += x[u]; *p[u] = (int16_t)pred; }
     }
 }
 
