@@ -270,6 +270,10 @@ extern "C" int gseg_pool_next(gseg_pool *p, gseg_pool_result *out) {
 extern "C" int gseg_pool_run(gseg_pool *p, const gseg_pool_job *jobs, int n, gseg_pool_result *results) {
     if (!p || (n > 0 && (!jobs || !results)) || n < 0) return GSEG_E_ARG;
     if (!p->q.empty()) return GSEG_E_STATE; // results of earlier submits would mix in
+    for (int sl = 0; sl < p->S; ++sl) { // a look-ahead decode an earlier, failed run left behind must not be mistaken for this run's
+        gseg_pool::Pref &pf = p->pref[(size_t)sl];
+        if (pf.valid) { p->stage_next[(size_t)sl] = pf.b & 1; pf.valid = false; }
+    }
     int first_err = GSEG_OK;
     int got = 0;
     for (int i = 0; i < n; ++i) {
