@@ -347,21 +347,24 @@ GSEG_HD size_t jpg_comp_block(const JpegDev &d, int c, uint32_t t) {
 // ---- inverse DCT: libjpeg's accurate integer method (jidctint.c, "islow": Loeffler-Ligtenberg-Moschytz, 13-bit
 // constants, two passes with 2 extra bits kept between them), restated.  in: 64 quantised coefficients, q: the
 // quantisation table, out: 8 rows of 8 samples, `pitch` apart.
-#define JPG_DESCALE(x, n) (((x) + (1 << ((n) - 1))) >> (n))
+// The arithmetic is done in uint32_t: the same bits as libjpeg's for every decodable image (its intermediate values fit 32 bits
+// with room to spare) and a defined wrap-around instead of a signed overflow for the garbage a corrupt file decodes to.
+#define JPG_DESCALE(x, n) ((int)((x) + (1u << ((n) - 1))) >> (n))
 GSEG_HD void jpg_idct_1d(int i0, int i1, int i2, int i3, int i4, int i5, int i6, int i7, int shift, int *o) {
-    int z2 = i2, z3 = i6;
-    int z1 = (z2 + z3) * 4433;
-    int tmp2 = z1 + z3 * (-15137);
-    int tmp3 = z1 + z2 * 6270;
-    int tmp0 = (i0 + i4) * 8192;
-    int tmp1 = (i0 - i4) * 8192;
-    const int tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
-    tmp0 = i7; tmp1 = i5; tmp2 = i3; tmp3 = i1;
+    typedef uint32_t u;
+    u z2 = (u)i2, z3 = (u)i6;
+    u z1 = (z2 + z3) * 4433u;
+    u tmp2 = z1 - z3 * 15137u;
+    u tmp3 = z1 + z2 * 6270u;
+    u tmp0 = ((u)i0 + (u)i4) * 8192u;
+    u tmp1 = ((u)i0 - (u)i4) * 8192u;
+    const u tmp10 = tmp0 + tmp3, tmp13 = tmp0 - tmp3, tmp11 = tmp1 + tmp2, tmp12 = tmp1 - tmp2;
+    tmp0 = (u)i7; tmp1 = (u)i5; tmp2 = (u)i3; tmp3 = (u)i1;
     z1 = tmp0 + tmp3; z2 = tmp1 + tmp2; z3 = tmp0 + tmp2;
-    int z4 = tmp1 + tmp3;
-    const int z5 = (z3 + z4) * 9633;
-    tmp0 *= 2446; tmp1 *= 16819; tmp2 *= 25172; tmp3 *= 12299;
-    z1 *= -7373; z2 *= -20995; z3 *= -16069; z4 *= -3196;
+    u z4 = tmp1 + tmp3;
+    const u z5 = (z3 + z4) * 9633u;
+    tmp0 *= 2446u; tmp1 *= 16819u; tmp2 *= 25172u; tmp3 *= 12299u;
+    z1 = 0u - z1 * 7373u; z2 = 0u - z2 * 20995u; z3 = 0u - z3 * 16069u; z4 = 0u - z4 * 3196u;
     z3 += z5; z4 += z5;
     tmp0 += z1 + z3; tmp1 += z2 + z4; tmp2 += z2 + z3; tmp3 += z1 + z4;
     o[0] = JPG_DESCALE(tmp10 + tmp3, shift); o[7] = JPG_DESCALE(tmp10 - tmp3, shift);

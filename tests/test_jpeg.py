@@ -179,6 +179,38 @@ def test_host_random_streams_never_crash(host):
         assert isinstance(r[0], np.ndarray) or r[0] in (1, 4)
 
 
+def test_host_sanitizer_fuzz(oracle, tmp_path):
+    """The parser reads untrusted files inside the product, the decoder's arithmetic runs on whatever they contain: a
+    mutation fuzzer (tests/jpeg_fuzz_host.cpp) built with AddressSanitizer + UBSan, both decode paths on exactly sized
+    buffers.  Any wild access, out-of-range shift or signed overflow aborts it."""
+    exe = os.path.join(HERE, "_build", "jpeg_fuzz_host")
+    src = os.path.join(HERE, "jpeg_fuzz_host.cpp")
+    csrc = os.path.join(HERE, "..", "graph-algorithm-image-segmentation-gpgpu_b200", "csrc")
+    deps = [src] + [os.path.join(csrc, f) for f in ("gseg_jpeg_core.h", "gseg_jpeg.hpp")]
+    os.makedirs(os.path.dirname(exe), exist_ok=True)
+    if not os.path.exists(exe) or any(os.path.getmtime(d) > os.path.getmtime(exe) for d in deps):
+        r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address,undefined", "-fno-sanitize-recover=undefined",
+                            "-o", exe, src], capture_output=True, text=True)
+        if r.returncode != 0:
+            pytest.skip("no sanitizer runtime for g++ here: " + r.stderr[-200:])
+    files = []
+    for i, (w, h) in enumerate([(64, 48), (33, 17), (120, 80), (8, 8)]):
+        img = oracle.synth(w, h, i + 1)
+        for j, sampling in enumerate(sorted(SAMPLING)):
+            for rst in (0, 3):
+                f = tmp_path / ("s%d_%d_%d.jpg" % (i, j, rst))
+                f.write_bytes(encode(img, (50, 90, 100)[(i + j) % 3], sampling, rst, optimize=j & 1).tobytes())
+                files.append(str(f))
+    g = tmp_path / "grey.jpg"
+    g.write_bytes(encode(oracle.synth(40, 40, 9)[..., 0], 90, "444", 0).tobytes())
+    files.append(str(g))
+    r = subprocess.run([exe, "6000", "5"] + files, capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, ASAN_OPTIONS="detect_leaks=0"))
+    assert r.returncode == 0, (r.stdout[-500:], r.stderr[-3000:])
+    n = [int(x) for x in r.stdout.split() if x.isdigit()]
+    assert n[0] == 6000 and n[1] > 500 and n[3] > 500, r.stdout   # both outcomes are exercised: rejected and decoded
+
+
 # ---------------------------------------------------------------- GPU ----------------------------------------------
 def same_partition(oracle, a, b):
     ca, na = oracle.canon(a)
