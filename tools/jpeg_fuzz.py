@@ -61,6 +61,37 @@ for i in range(ncases):
 seg.close()
 print("single calls: %d cases, %d mismatches, %.1f s" % (ncases, bad, time.time() - t0), flush=True)
 
+# corrupt files: mutated headers and data -- an error or an image, never a crash; the context must decode a good file afterwards
+# (an out-of-bounds access on the device would poison it)
+seg = gseg.Segmenter(256, 256)
+seg.set_jpeg_backend(gseg.JPEG_OWN)
+good, _ = encode(picture(200, 144, 0))
+nerr = ncuda = 0
+for i in range(ncases):
+    w, h = int(rng.integers(8, 200)), int(rng.integers(8, 200))
+    e, info = encode(picture(w, h, int(rng.integers(0, 2))))
+    f = bytearray(e.tobytes())
+    sos = f.find(b"\xff\xda")
+    for m in range(int(rng.integers(1, 7))):
+        lim = sos + 14 if (i & 1) else len(f)
+        p = int(rng.integers(2, max(3, lim)))
+        f[p] = int(rng.choice([int(rng.integers(0, 256)), 0xFF, 0x00, f[p] ^ (1 << int(rng.integers(0, 8)))]))
+    if i % 9 == 0:
+        f = f[:int(rng.integers(4, len(f)))]
+    try:
+        seg.segment_jpeg(bytes(f), **kw)
+    except gseg.GsegError as ex:
+        nerr += 1
+        if "CUDA" in str(ex) and "no CUDA device" not in str(ex):
+            ncuda += 1
+            print("CUDA ERROR on a corrupt file:", ex, info, flush=True)
+            break
+seg.segment_jpeg(good.tobytes(), **kw)
+ok = np.array_equal(seg.input_rgb(), libjpeg(good))
+bad += ncuda + (0 if ok else 1)
+seg.close()
+print("corrupt files: %d cases, %d rejected or flagged, %d CUDA errors, context fine afterwards: %s" % (ncases, nerr, ncuda, ok), flush=True)
+
 # pool jobs: mixed files, decode-ahead on the copy streams, device label output; the decoded pixels are checked through the
 # partition's component count against a second run of the same file through a plain context
 w, h = 480, 320
