@@ -103,6 +103,7 @@ struct gseg_ctx {
     uint8_t *d_jsub;              // sub-sequence states of the marker-less decode (k_jpeg_sync): entry, exit, counts, flags
     size_t jsub_cap;
     uint32_t jsub_bytes;          // bytes per sub-sequence (GSEG_JPEG_SUB, default 128)
+    bool jsync_grid;              // marker-less decode as a grid of small blocks with a software barrier (GSEG_JPEG_SYNC=grid) instead of one cluster
     uint32_t *d_jerr;             // [2] JPG_ERR_* bits of the last two decodes (ping-pong)
     cudaEvent_t ev_jdesc;         // the last descriptor copy out of h_jdesc
     cudaEvent_t ev_jdone;         // end of the last decode (its buffers are free again)
@@ -208,6 +209,7 @@ extern "C" int gseg_create_ex(gseg_ctx **out, int device, int max_w, int max_h, 
     ctx->device = device; ctx->max_w = max_w; ctx->max_h = max_h; ctx->Vmax = V; ctx->Dmax = (int)Dmax;
     ctx->epoch_next = 1; ctx->jflag_slot = -1;
     ctx->jsub_bytes = 128u;
+    if (const char *ev = getenv("GSEG_JPEG_SYNC")) ctx->jsync_grid = !strcmp(ev, "grid");
     if (const char *ev = getenv("GSEG_JPEG_SUB")) { const int v = atoi(ev); if (v >= 8 && v <= 65536) ctx->jsub_bytes = (uint32_t)v; }
     cudaError_t e = cudaSetDevice(device);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking);
@@ -391,7 +393,7 @@ static int jpeg_reserve_own(gseg_ctx *ctx, size_t file_bytes, size_t nint, size_
     }
     if (!rc) rc = jpeg_grow(ctx, &ctx->d_jsamples, &ctx->jsamples_cap, nblocks * 64, blocks_max * 64);
     const size_t nsub_max = (V + 4096) / ctx->jsub_bytes + 2, nsub = file_bytes / ctx->jsub_bytes + 2;
-    if (!rc) rc = jpeg_grow(ctx, &ctx->d_jsub, &ctx->jsub_cap, nsub * 24 + 64, nsub_max * 24 + 64);
+    if (!rc) rc = jpeg_grow(ctx, &ctx->d_jsub, &ctx->jsub_cap, nsub * 24 + 64, nsub_max * 24 + 64); // + the flag / barrier words
     const size_t desc = sizeof(JpegDev) + 4 * nint, desc_max = sizeof(JpegDev) + 4 * (V / 64 + side / 8 + 64);
     if (!rc) rc = jpeg_grow(ctx, (uint8_t **)&ctx->d_jdev, &ctx->jdev_cap, desc, desc_max);
     if (!rc && ctx->hjdesc_cap < desc) {
@@ -446,6 +448,12 @@ static int jpeg_decode_enqueue(gseg_ctx *ctx, const uint8_t *file, const JpegPla
         at[0].val.clusterDim.x = cfg.gridDim.x; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
         ctx->launches += 4;
+        if (ctx->jsync_grid) { // small blocks + software grid barrier (every block must become resident: at most 2 per SM)
+            int gs = (int)((nsub + JPG_NT_GRID - 1) / JPG_NT_GRID);
+            if (gs > 2 * ctx->num_sms) gs = 2 * ctx->num_sms;
+            CK(cudaMemsetAsync(flags, 0, 5 * sizeof(uint32_t), s));
+            k_jpeg_sync_grid<<<gs, JPG_NT_GRID, 0, s>>>(ctx->d_jdev, ctx->d_jfile, entryS, exitS, nblk, blk0, flags, ctx->d_jcoef, ctx->d_jerr + slot, S);
+        } else
         CK(cudaLaunchKernelEx(&cfg, k_jpeg_sync, (const JpegDev *)ctx->d_jdev, (const uint8_t *)ctx->d_jfile, entryS, exitS, nblk, blk0, flags,
                               ctx->d_jcoef, ctx->d_jerr + slot, S));
         k_jpeg_dcscan<<<d.ncomp, JPG_NT_SYNC, 0, s>>>(ctx->d_jdev, ctx->d_jcoef);

@@ -248,6 +248,112 @@ __global__ void __launch_bounds__(JPG_NT_SYNC, 1) k_jpeg_sync(const JpegDev *__r
     if (err) atomicOr(errp, err);
 }
 
+// The same algorithm as a plain grid of SMALL blocks with a software grid barrier (one atomic counter; every block's
+// thread 0 adds itself and spins until all have).  A cluster block of 1024 threads x 58 registers needs an SM to itself,
+// and five of them at the same moment: with eight images in flight the block scheduler rarely has that, and the decode
+// waits; 128-thread blocks fit anywhere.  All blocks of the grid become resident without anybody's help -- the kernels
+// they share the GPU with are short and never wait for them -- so the barrier cannot deadlock; a bounded spin turns a
+// scheduling surprise into an error code instead of a hung GPU (like the look-back watchdog of the segmentation).
+#define JPG_NT_GRID 128
+__device__ __forceinline__ bool jpg_grid_barrier(uint32_t *bar, uint32_t *abortp, uint32_t &gen, uint32_t nblocks, uint32_t *s_flag) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ++gen;
+        __threadfence();
+        atomicAdd(bar, 1u);
+        const uint32_t target = gen * nblocks;
+        uint32_t spins = 0u, ab = 0u;
+        while (*reinterpret_cast<volatile uint32_t *>(bar) < target) {
+            ab = *reinterpret_cast<volatile uint32_t *>(abortp);
+            if (ab) break;
+            if (++spins > (1u << 22)) { atomicExch(abortp, 1u); ab = 1u; break; } // ~1 s
+            __nanosleep(spins < 64u ? 50u : 250u);
+        }
+        __threadfence();
+        *s_flag = ab;
+    }
+    __syncthreads();
+    return *s_flag == 0u;
+}
+__global__ void __launch_bounds__(JPG_NT_GRID) k_jpeg_sync_grid(const JpegDev *__restrict__ gd, const uint8_t *__restrict__ file,
+                                                                uint64_t *entryS, uint64_t *exitS, uint32_t *nblk, uint32_t *blk0,
+                                                                uint32_t *flags, int16_t *__restrict__ coef, uint32_t *errp, uint32_t S) {
+    __shared__ JpegDev sd;
+    __shared__ uint8_t szz[JPG_ZIGZAG_LEN];
+    __shared__ uint32_t s_part[32], s_flag;
+    {
+        const uint4 *src = reinterpret_cast<const uint4 *>(gd);
+        uint4 *dst = reinterpret_cast<uint4 *>(&sd);
+        for (int i = threadIdx.x; i < (int)(sizeof(JpegDev) / 16); i += JPG_NT_GRID) dst[i] = src[i];
+    }
+    for (int i = threadIdx.x; i < JPG_ZIGZAG_LEN; i += JPG_NT_GRID) szz[i] = c_jpg_zigzag[i];
+    if (threadIdx.x < 32) s_part[threadIdx.x] = 0u;
+    __syncthreads();
+    uint32_t *bar = flags + 3, *abortp = flags + 4; // flags[0..4] were cleared by the host in front of the launch
+    uint32_t gen = 0u;
+    const uint32_t T = gridDim.x * JPG_NT_GRID, tid = blockIdx.x * JPG_NT_GRID + threadIdx.x;
+    const uint32_t off = sd.data_off, end = sd.data_end;
+    const uint32_t nsub = end > off ? (end - off + S - 1u) / S : 1u;
+    if (tid == 0) *errp = 0u;
+    uint32_t err = 0u, nb = 0u;
+    for (uint32_t i = tid; i < nsub; i += T) { // pass 1
+        const uint32_t e1 = min(off + (i + 1u) * S, end) * 8u;
+        const uint64_t en = i == 0u ? JPG_STATE(off * 8u, 0, 0) : jpg_sub_guess(file, off + i * S, off);
+        entryS[i] = en;
+        exitS[i] = jpg_sub_decode<false>(sd, sd.dc, sd.ac, szz, file, en, e1, nullptr, 0u, &nb, err);
+        nblk[i] = nb;
+    }
+    if (!jpg_grid_barrier(bar, abortp, gen, gridDim.x, &s_flag)) { if (tid == 0) atomicOr(errp, JPG_ERR_BLOCKS); return; }
+    for (uint32_t r = 0;; ++r) { // rounds
+        if (tid == 0) flags[(r + 1u) % 3u] = 0u;
+        int ch = 0;
+        for (uint32_t i = tid; i < nsub; i += T) {
+            if (i == 0u) continue;
+            const uint64_t en = __ldcg(exitS + i - 1u);
+            if (en != entryS[i]) {
+                const uint32_t e1 = min(off + (i + 1u) * S, end) * 8u;
+                entryS[i] = en;
+                exitS[i] = jpg_sub_decode<false>(sd, sd.dc, sd.ac, szz, file, en, e1, nullptr, 0u, &nb, err);
+                nblk[i] = nb;
+                ch = 1;
+            }
+        }
+        if (__syncthreads_or(ch) && threadIdx.x == 0) atomicOr(&flags[r % 3u], 1u);
+        if (!jpg_grid_barrier(bar, abortp, gen, gridDim.x, &s_flag)) { if (tid == 0) atomicOr(errp, JPG_ERR_BLOCKS); return; }
+        if (__ldcg(&flags[r % 3u]) == 0u) break; // the same word for every thread of the grid
+        if (r > nsub + 2u) { if (tid == 0) atomicOr(errp, JPG_ERR_BLOCKS); break; } // cannot happen: round r fixes sub-sequence r
+    }
+    if (blockIdx.x == 0) { // exclusive scan of the block counts (one block: 128 threads, a contiguous run each)
+        const uint32_t per = (nsub + JPG_NT_GRID - 1u) / JPG_NT_GRID;
+        const uint32_t b = min(threadIdx.x * per, nsub), e = min(b + per, nsub);
+        uint32_t sum = 0u;
+        for (uint32_t i = b; i < e; ++i) sum += __ldcg(nblk + i);
+        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+        uint32_t inc = sum;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
+        if (lane == 31) s_part[warp] = inc;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t v = s_part[lane], w2 = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t t = __shfl_up_sync(0xFFFFFFFFu, w2, o); if (lane >= o) w2 += t; }
+            s_part[lane] = w2 - v;
+            if (lane == 31 && w2 < (uint32_t)sd.nblocks) atomicOr(errp, JPG_ERR_BLOCKS);
+        }
+        __syncthreads();
+        uint32_t run = s_part[warp] + inc - sum;
+        for (uint32_t i = b; i < e; ++i) { blk0[i] = run; run += __ldcg(nblk + i); }
+    }
+    if (!jpg_grid_barrier(bar, abortp, gen, gridDim.x, &s_flag)) { if (tid == 0) atomicOr(errp, JPG_ERR_BLOCKS); return; }
+    err = 0u;
+    for (uint32_t i = tid; i < nsub; i += T) { // write
+        const uint32_t e1 = min(off + (i + 1u) * S, end) * 8u;
+        jpg_sub_decode<true>(sd, sd.dc, sd.ac, szz, file, entryS[i], e1, coef, __ldcg(blk0 + i), &nb, err);
+    }
+    if (err) atomicOr(errp, err);
+}
+
 // DC differences -> DC values (T.81 F.1.1.5.1: the predictor of a component runs over its blocks in scan order): one block
 // per component; a thread sums a contiguous run of the component's blocks, a block-wide scan, a second walk writes the values.
 // The walk keeps (MCU column, MCU row, block inside the MCU) as state -- one division per thread, not three per block (the
