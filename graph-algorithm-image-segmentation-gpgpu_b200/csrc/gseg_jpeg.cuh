@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(JPG_NT_HUFF) k_jpeg_huff(const JpegDev *__rest
         for (int i = threadIdx.x; i < (int)(sizeof(JpegDev) / 16); i += JPG_NT_HUFF) dst[i] = src[i];
     }
     __shared__ uint8_t szz[JPG_ZIGZAG_LEN];
+    __shared__ uint32_t s_ring[8 * JPG_NT_HUFF]; // the readers' chunk rings: word k of thread t at [k * JPG_NT_HUFF + t], its own bank
     for (int i = threadIdx.x; i < JPG_ZIGZAG_LEN; i += JPG_NT_HUFF) szz[i] = c_jpg_zigzag[i];
     __syncthreads();
     const int i = blockIdx.x * JPG_NT_HUFF + threadIdx.x;
@@ -155,7 +156,7 @@ __global__ void __launch_bounds__(JPG_NT_HUFF) k_jpeg_huff(const JpegDev *__rest
     const int first = i * sd.ri;
     const int last = first + sd.ri < sd.nmcu ? first + sd.ri : sd.nmcu;
     uint32_t err = 0u;
-    jpg_decode_interval(sd, sd.dc, sd.ac, szz, file, starts[i], first, last, coef, err);
+    jpg_decode_interval(sd, sd.dc, sd.ac, szz, file, s_ring + threadIdx.x, JPG_NT_HUFF, starts[i], first, last, coef, err);
     if (err) atomicOr(errp, err);
 }
 
@@ -173,6 +174,7 @@ __global__ void __launch_bounds__(JPG_NT_SYNC, 1) k_jpeg_sync(const JpegDev *__r
                                                               uint32_t *flags, int16_t *__restrict__ coef, uint32_t *errp, uint32_t S) {
     __shared__ JpegDev sd;
     __shared__ uint8_t szz[JPG_ZIGZAG_LEN];
+    __shared__ uint32_t s_ring[8 * JPG_NT_SYNC];
     __shared__ uint32_t s_part[32];
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(gd);
@@ -191,7 +193,7 @@ __global__ void __launch_bounds__(JPG_NT_SYNC, 1) k_jpeg_sync(const JpegDev *__r
         const uint32_t e1 = min(off + (i + 1u) * S, end) * 8u;
         const uint64_t en = i == 0u ? JPG_STATE(off * 8u, 0, 0) : jpg_sub_guess(file, off + i * S, off);
         entryS[i] = en;
-        exitS[i] = jpg_sub_decode<false>(sd, sd.dc, sd.ac, szz, file, en, e1, nullptr, 0u, &nb, err);
+        exitS[i] = jpg_sub_decode<false>(sd, sd.dc, sd.ac, szz, file, s_ring + threadIdx.x, JPG_NT_SYNC, en, e1, nullptr, 0u, &nb, err);
         nblk[i] = nb;
     }
     __threadfence();
@@ -205,7 +207,7 @@ __global__ void __launch_bounds__(JPG_NT_SYNC, 1) k_jpeg_sync(const JpegDev *__r
             if (en != entryS[i]) {
                 const uint32_t e1 = min(off + (i + 1u) * S, end) * 8u;
                 entryS[i] = en;
-                exitS[i] = jpg_sub_decode<false>(sd, sd.dc, sd.ac, szz, file, en, e1, nullptr, 0u, &nb, err);
+                exitS[i] = jpg_sub_decode<false>(sd, sd.dc, sd.ac, szz, file, s_ring + threadIdx.x, JPG_NT_SYNC, en, e1, nullptr, 0u, &nb, err);
                 nblk[i] = nb;
                 ch = 1;
             }
@@ -243,7 +245,7 @@ __global__ void __launch_bounds__(JPG_NT_SYNC, 1) k_jpeg_sync(const JpegDev *__r
     err = 0u; // the passes above ran from guessed states: their impossible codes mean nothing
     for (uint32_t i = tid; i < nsub; i += T) { // write
         const uint32_t e1 = min(off + (i + 1u) * S, end) * 8u;
-        jpg_sub_decode<true>(sd, sd.dc, sd.ac, szz, file, entryS[i], e1, coef, __ldcg(blk0 + i), &nb, err);
+        jpg_sub_decode<true>(sd, sd.dc, sd.ac, szz, file, s_ring + threadIdx.x, JPG_NT_SYNC, entryS[i], e1, coef, __ldcg(blk0 + i), &nb, err);
     }
     if (err) atomicOr(errp, err);
 }
@@ -280,6 +282,7 @@ __global__ void __launch_bounds__(JPG_NT_GRID) k_jpeg_sync_grid(const JpegDev *_
                                                                 uint32_t *flags, int16_t *__restrict__ coef, uint32_t *errp, uint32_t S) {
     __shared__ JpegDev sd;
     __shared__ uint8_t szz[JPG_ZIGZAG_LEN];
+    __shared__ uint32_t s_ring[8 * JPG_NT_GRID];
     __shared__ uint32_t s_part[32], s_flag;
     {
         const uint4 *src = reinterpret_cast<const uint4 *>(gd);
@@ -300,7 +303,7 @@ __global__ void __launch_bounds__(JPG_NT_GRID) k_jpeg_sync_grid(const JpegDev *_
         const uint32_t e1 = min(off + (i + 1u) * S, end) * 8u;
         const uint64_t en = i == 0u ? JPG_STATE(off * 8u, 0, 0) : jpg_sub_guess(file, off + i * S, off);
         entryS[i] = en;
-        exitS[i] = jpg_sub_decode<false>(sd, sd.dc, sd.ac, szz, file, en, e1, nullptr, 0u, &nb, err);
+        exitS[i] = jpg_sub_decode<false>(sd, sd.dc, sd.ac, szz, file, s_ring + threadIdx.x, JPG_NT_GRID, en, e1, nullptr, 0u, &nb, err);
         nblk[i] = nb;
     }
     if (!jpg_grid_barrier(bar, abortp, gen, gridDim.x, &s_flag)) { if (tid == 0) atomicOr(errp, JPG_ERR_BLOCKS); return; }
@@ -313,7 +316,7 @@ __global__ void __launch_bounds__(JPG_NT_GRID) k_jpeg_sync_grid(const JpegDev *_
             if (en != entryS[i]) {
                 const uint32_t e1 = min(off + (i + 1u) * S, end) * 8u;
                 entryS[i] = en;
-                exitS[i] = jpg_sub_decode<false>(sd, sd.dc, sd.ac, szz, file, en, e1, nullptr, 0u, &nb, err);
+                exitS[i] = jpg_sub_decode<false>(sd, sd.dc, sd.ac, szz, file, s_ring + threadIdx.x, JPG_NT_GRID, en, e1, nullptr, 0u, &nb, err);
                 nblk[i] = nb;
                 ch = 1;
             }
@@ -349,7 +352,7 @@ __global__ void __launch_bounds__(JPG_NT_GRID) k_jpeg_sync_grid(const JpegDev *_
     err = 0u;
     for (uint32_t i = tid; i < nsub; i += T) { // write
         const uint32_t e1 = min(off + (i + 1u) * S, end) * 8u;
-        jpg_sub_decode<true>(sd, sd.dc, sd.ac, szz, file, entryS[i], e1, coef, __ldcg(blk0 + i), &nb, err);
+        jpg_sub_decode<true>(sd, sd.dc, sd.ac, szz, file, s_ring + threadIdx.x, JPG_NT_GRID, entryS[i], e1, coef, __ldcg(blk0 + i), &nb, err);
     }
     if (err) atomicOr(errp, err);
 }

@@ -62,10 +62,11 @@ static const uint8_t jpg_zigzag_h[JPG_ZIGZAG_LEN] = {
 
 // ---- bit reader over the entropy-coded segment (T.81 F.2.2.5): 0xFF00 is a stuffed 0xFF, any other marker ends the
 // data of the interval and the reader feeds zero bits from there on.
-// A thread walks its interval serially, so the reader is built around latency: the file is read in aligned 16-byte
-// chunks, one chunk ahead of its use (one global load per ~20 symbols, never waited for); bytes pass through a 64-bit
-// window and enter the 64-bit bit buffer four at a time unless one of the four is 0xFF; one refill per symbol covers
-// the code and its extra bits.  The staged file must be readable up to 32 bytes past data_end.
+// A thread walks its interval serially, so the reader is built around latency and instruction count: the file is read
+// in aligned 16-byte chunks, a chunk ahead of its use (one global load per ~20 symbols, never waited for), into a
+// 32-byte ring per thread (shared memory on the device); four bytes at any offset are two ring words and a funnel
+// shift, and enter the 64-bit bit buffer together unless one of them is 0xFF; one refill per symbol covers the code
+// and its extra bits.  The staged file must be readable up to 64 bytes past data_end.
 struct JpegChunk { uint32_t w[4]; };
 GSEG_HD JpegChunk jpg_load16(const uint8_t *file, uint32_t chunk) {
     JpegChunk c;
@@ -89,64 +90,65 @@ GSEG_HD uint32_t jpg_bswap(uint32_t v) {
 }
 struct JpegBits {
     const uint8_t *file;
-    JpegChunk cur, nxt;  // the chunk being consumed and the one behind it
-    uint32_t chunk;      // index of cur
-    uint32_t widx;       // next word of cur
-    uint32_t rem;        // bytes of the stream that have not entered the bit buffer yet
-    uint32_t end0;       // end of the stream (file offset): end0 - rem = offset of the next byte to enter the bit buffer
+    uint32_t *ring;      // eight words, word k at ring[k * rs]: the two 16-byte chunks the stream is in (chunk c in half c & 1)
+    uint32_t rs;         // ... in shared memory with rs = threads per block (every thread's word k in its own bank), 1 on the host
+    JpegChunk pend;      // the chunk behind them, loaded ahead of its use
+    uint32_t pos;        // file offset of the next byte to enter the bit buffer
+    uint32_t end0;       // end of the stream (file offset)
     uint32_t ffhist;     // bit i: the (i+1)-th last byte that entered the bit buffer was a stuffed 0xFF (two file bytes)
-    uint64_t win;        // byte window: the next bytes of the stream, first byte on top
-    int wn;              // ... how many
     uint64_t buf;        // bit buffer, left-aligned
     int n;               // ... valid bits
     bool eof;            // a marker or the end of the data was reached: zero bits from here on
     int nfake;           // ... how many of the buffer's bits are such zeros (they sit behind the real ones)
 };
-GSEG_HD uint32_t jpg_next_word(JpegBits &b) { // the stream's next four bytes, first byte on top
-    const uint32_t w = b.widx == 0 ? b.cur.w[0] : (b.widx == 1 ? b.cur.w[1] : (b.widx == 2 ? b.cur.w[2] : b.cur.w[3]));
-    if (++b.widx == 4) {
-        b.cur = b.nxt;
-        ++b.chunk;
-        b.nxt = jpg_load16(b.file, b.chunk + 1);
-        b.widx = 0;
-    }
-    return jpg_bswap(w);
+GSEG_HD void jpg_ring_put(JpegBits &b, uint32_t half, const JpegChunk &c) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i) b.ring[(4u * half + (uint32_t)i) * b.rs] = c.w[i];
 }
-GSEG_HD void jpg_bits_init(JpegBits &b, const uint8_t *file, uint32_t pos, uint32_t end) {
-    b.file = file;
-    b.chunk = pos >> 4;
-    b.cur = jpg_load16(file, b.chunk);
-    b.nxt = jpg_load16(file, b.chunk + 1);
-    b.widx = (pos & 15u) >> 2;
-    b.rem = end > pos ? end - pos : 0u;
+GSEG_HD void jpg_bits_init(JpegBits &b, const uint8_t *file, uint32_t *ring, uint32_t rs, uint32_t pos, uint32_t end) {
+    b.file = file; b.ring = ring; b.rs = rs;
+    const uint32_t c = pos >> 4;
+    jpg_ring_put(b, c & 1u, jpg_load16(file, c));
+    jpg_ring_put(b, (c + 1u) & 1u, jpg_load16(file, c + 1u));
+    b.pend = jpg_load16(file, c + 2u);
+    b.pos = pos;
     b.end0 = end > pos ? end : pos; b.ffhist = 0u;
-    b.buf = 0; b.n = 0; b.win = 0; b.wn = 0; b.eof = false; b.nfake = 0;
-    const uint32_t sub = pos & 3u;
-    if (sub) { // the stream starts inside a word
-        const uint32_t w = jpg_next_word(b);
-        b.win = (uint64_t)(w << (8 * sub)) << 32;
-        b.wn = 4 - (int)sub;
+    b.buf = 0; b.n = 0; b.eof = false; b.nfake = 0;
+}
+GSEG_HD void jpg_advance(JpegBits &b, uint32_t nbytes) { // nbytes <= 4: at most one chunk border
+    const uint32_t oldc = b.pos >> 4;
+    b.pos += nbytes;
+    if ((b.pos >> 4) != oldc) { // the chunk left behind makes room for the one loaded ahead; load the next
+        jpg_ring_put(b, oldc & 1u, b.pend);
+        b.pend = jpg_load16(b.file, oldc + 3u);
     }
 }
 GSEG_HD void jpg_fill(JpegBits &b) { // at least 33 valid bits afterwards: a code (<= 16) and its extra bits (<= 16)
     while (b.n <= 32) {
-        if (b.wn <= 4) { b.win |= (uint64_t)jpg_next_word(b) << (32 - 8 * b.wn); b.wn += 4; }
-        const uint32_t W = (uint32_t)(b.win >> 32);
+        const uint32_t wi = (b.pos >> 2) & 7u, sh = (b.pos & 3u) * 8u;
+        const uint32_t w0 = b.ring[wi * b.rs], w1 = b.ring[((wi + 1u) & 7u) * b.rs];
+#if defined(__CUDA_ARCH__)
+        const uint32_t W = jpg_bswap(__funnelshift_r(w0, w1, sh)); // the stream's next four bytes, first byte on top
+#else
+        const uint32_t W = jpg_bswap(sh ? (w0 >> sh) | (w1 << (32u - sh)) : w0);
+#endif
         const uint32_t x = ~W; // a byte of W is 0xFF <=> that byte of x is zero
         const uint32_t ff = ~(((x & 0x7F7F7F7Fu) + 0x7F7F7F7Fu) | x | 0x7F7F7F7Fu);
-        if (!b.eof && b.rem >= 4u && ff == 0u) { // four plain bytes
+        const uint32_t rem = b.end0 - b.pos;
+        if (!b.eof && rem >= 4u && ff == 0u) { // four plain bytes
             b.buf |= (uint64_t)W << (32 - b.n);
-            b.n += 32; b.win <<= 32; b.wn -= 4; b.rem -= 4u; b.ffhist <<= 4;
+            b.n += 32; b.ffhist <<= 4;
+            jpg_advance(b, 4u);
         } else { // one byte at a time
             uint32_t v = 0u;
             b.ffhist <<= 1;
-            if (!b.eof && b.rem > 0u) {
+            if (!b.eof && rem > 0u) {
                 v = W >> 24;
                 if (v == 0xFFu) {
-                    const uint32_t m = b.rem > 1u ? ((W >> 16) & 0xFFu) : 0xD9u;
-                    if (m == 0u) { b.win <<= 16; b.wn -= 2; b.rem -= 2u; b.ffhist |= 1u; } // stuffed byte
-                    else { v = 0u; b.eof = true; }                                         // marker: stop here
-                } else { b.win <<= 8; b.wn -= 1; b.rem -= 1u; }
+                    const uint32_t m = rem > 1u ? ((W >> 16) & 0xFFu) : 0xD9u;
+                    if (m == 0u) { jpg_advance(b, 2u); b.ffhist |= 1u; } // stuffed byte
+                    else { v = 0u; b.eof = true; }                      // marker: stop here
+                } else jpg_advance(b, 1u);
             } else b.eof = true;
             if (b.eof) b.nfake += 8;
             b.buf |= (uint64_t)v << (56 - b.n);
@@ -171,11 +173,11 @@ GSEG_HD uint32_t jpg_bits_pos(const JpegBits &b) {
     uint32_t st = 0u;
     for (uint32_t t = m; t; t &= t - 1u) ++st;
 #endif
-    return (b.end0 - b.rem - q - st) * 8u + (8u * q - (uint32_t)nr);
+    return (b.pos - q - st) * 8u + (8u * q - (uint32_t)nr);
 }
 // Reader positioned at a bit position as jpg_bits_pos reports them; the buffer is filled.
-GSEG_HD void jpg_bits_init_bit(JpegBits &b, const uint8_t *file, uint32_t bitpos, uint32_t end) {
-    jpg_bits_init(b, file, bitpos >> 3, end);
+GSEG_HD void jpg_bits_init_bit(JpegBits &b, const uint8_t *file, uint32_t *ring, uint32_t rs, uint32_t bitpos, uint32_t end) {
+    jpg_bits_init(b, file, ring, rs, bitpos >> 3, end);
     jpg_fill(b);
     jpg_skip(b, (int)(bitpos & 7u));
 }
@@ -207,9 +209,9 @@ GSEG_HD int jpg_receive_extend(JpegBits &b, int s) {
 // loops over blocks: the 32 intervals a warp decodes then advance symbol by symbol in the same instruction stream,
 // whatever block each of them is in -- with nested loops every block costs the warp its slowest lane's symbols.
 GSEG_HD void jpg_decode_interval(const JpegDev &d, const JpegHuff *dc, const JpegHuff *ac, const uint8_t *zz, const uint8_t *file,
-                                 uint32_t start, int first, int last, int16_t *coef, uint32_t &err) {
+                                 uint32_t *ring, uint32_t rs, uint32_t start, int first, int last, int16_t *coef, uint32_t &err) {
     JpegBits b;
-    jpg_bits_init(b, file, start, d.data_end);
+    jpg_bits_init(b, file, ring, rs, start, d.data_end);
     int p0 = 0, p1 = 0, p2 = 0;                         // DC predictors
     int m = first, mx = first % d.mcus_x, my = first / d.mcus_x;
     int c = 0, bi = 0, k = 0;                           // component, block of the component inside the MCU, coefficient
@@ -267,9 +269,10 @@ GSEG_HD void jpg_decode_interval(const JpegDev &d, const JpegHuff *dc, const Jpe
 // the scan: MCU by MCU, the MCU's blocks in order), go to coef[]; *nblk = blocks completed.
 template <bool WRITE>
 GSEG_HD uint64_t jpg_sub_decode(const JpegDev &d, const JpegHuff *dc, const JpegHuff *ac, const uint8_t *zz, const uint8_t *file,
-                                uint64_t entry, uint32_t end_bits, int16_t *coef, uint32_t blk, uint32_t *nblk, uint32_t &err) {
+                                uint32_t *ring, uint32_t rs, uint64_t entry, uint32_t end_bits, int16_t *coef, uint32_t blk, uint32_t *nblk,
+                                uint32_t &err) {
     JpegBits b;
-    jpg_bits_init_bit(b, file, (uint32_t)entry, d.data_end);
+    jpg_bits_init_bit(b, file, ring, rs, (uint32_t)entry, d.data_end);
     int k = (int)((entry >> 32) & 63u), j = (int)((entry >> 40) & 255u);
     int bpm = 0;
     for (int c = 0; c < d.ncomp; ++c) bpm += d.hs[c] * d.vs[c];

@@ -34,6 +34,7 @@ static void decode(const std::vector<uint8_t> &file, const JpegPlan &plan, bool 
     std::vector<uint8_t> samples((size_t)d.nsamples);
     std::vector<uint8_t> rgb((size_t)3 * d.w * d.h);
     uint32_t err = 0;
+    uint32_t ring[8];
     if (sync && d.nint == 1) {
         const uint32_t off = d.data_off, end = d.data_end;
         const uint32_t nsub = end > off ? (end - off + sub - 1) / sub : 1;
@@ -42,7 +43,7 @@ static void decode(const std::vector<uint8_t> &file, const JpegPlan &plan, bool 
         auto endbits = [&](uint32_t i) { const uint64_t e = (uint64_t)off + (uint64_t)(i + 1) * sub; return (uint32_t)((e < end ? e : end) * 8u); };
         for (uint32_t i = 0; i < nsub; ++i) {
             entry[i] = i == 0 ? JPG_STATE(off * 8u, 0, 0) : jpg_sub_guess(staged.data(), off + i * sub, off);
-            ex[i] = jpg_sub_decode<false>(d, d.dc, d.ac, jpg_zigzag_h, staged.data(), entry[i], endbits(i), nullptr, 0u, &nblk[i], err);
+            ex[i] = jpg_sub_decode<false>(d, d.dc, d.ac, jpg_zigzag_h, staged.data(), ring, 1u, entry[i], endbits(i), nullptr, 0u, &nblk[i], err);
         }
         uint32_t rounds = 0;
         for (bool ch = true; ch && rounds <= nsub + 2; ++rounds) {
@@ -51,7 +52,7 @@ static void decode(const std::vector<uint8_t> &file, const JpegPlan &plan, bool 
             for (uint32_t i = 1; i < nsub; ++i)
                 if (prev[i - 1] != entry[i]) {
                     entry[i] = prev[i - 1];
-                    ex[i] = jpg_sub_decode<false>(d, d.dc, d.ac, jpg_zigzag_h, staged.data(), entry[i], endbits(i), nullptr, 0u, &nblk[i], err);
+                    ex[i] = jpg_sub_decode<false>(d, d.dc, d.ac, jpg_zigzag_h, staged.data(), ring, 1u, entry[i], endbits(i), nullptr, 0u, &nblk[i], err);
                     ch = true;
                 }
         }
@@ -60,7 +61,7 @@ static void decode(const std::vector<uint8_t> &file, const JpegPlan &plan, bool 
         for (uint32_t i = 0; i < nsub; ++i) { blk0[i] = run; run += nblk[i]; }
         for (uint32_t i = 0; i < nsub; ++i) {
             uint32_t dummy;
-            jpg_sub_decode<true>(d, d.dc, d.ac, jpg_zigzag_h, staged.data(), entry[i], endbits(i), coef.data(), blk0[i], &dummy, err);
+            jpg_sub_decode<true>(d, d.dc, d.ac, jpg_zigzag_h, staged.data(), ring, 1u, entry[i], endbits(i), coef.data(), blk0[i], &dummy, err);
         }
         for (int c = 0; c < d.ncomp; ++c) {
             const uint32_t nb = (uint32_t)d.nmcu * (uint32_t)(d.hs[c] * d.vs[c]);
@@ -75,7 +76,7 @@ static void decode(const std::vector<uint8_t> &file, const JpegPlan &plan, bool 
         if ((int)plan.starts.size() != d.nint) return;
         for (int i = 0; i < d.nint; ++i) {
             const int first = i * d.ri, last = first + d.ri < d.nmcu ? first + d.ri : d.nmcu;
-            jpg_decode_interval(d, d.dc, d.ac, jpg_zigzag_h, staged.data(), plan.starts[(size_t)i], first, last, coef.data(), err);
+            jpg_decode_interval(d, d.dc, d.ac, jpg_zigzag_h, staged.data(), ring, 1u, plan.starts[(size_t)i], first, last, coef.data(), err);
         }
     }
     for (int c = 0; c < d.ncomp; ++c)

@@ -22,9 +22,10 @@ int jpeg_host_decode(const uint8_t *file, size_t n, uint8_t *rgb, size_t cap, in
     int16_t *coef = (int16_t *)calloc((size_t)d.nblocks * 64, sizeof(int16_t));
     uint8_t *samples = (uint8_t *)malloc((size_t)d.nsamples);
     uint32_t err = 0;
+    uint32_t ring[8]; // the reader's chunk ring (shared memory on the device)
     for (int i = 0; i < d.nint; ++i) { // k_jpeg_huff: one thread per restart interval
         const int first = i * d.ri, last = first + d.ri < d.nmcu ? first + d.ri : d.nmcu;
-        jpg_decode_interval(d, d.dc, d.ac, jpg_zigzag_h, file, plan.starts[i], first, last, coef, err);
+        jpg_decode_interval(d, d.dc, d.ac, jpg_zigzag_h, file, ring, 1u, plan.starts[i], first, last, coef, err);
     }
     for (int c = 0; c < d.ncomp; ++c) // k_jpeg_idct: one thread per block
         for (int by = 0; by < d.bh[c]; ++by)
@@ -60,6 +61,7 @@ int jpeg_host_decode_sync(const uint8_t *file, size_t n, uint8_t *rgb, size_t ca
     int16_t *coef = (int16_t *)calloc((size_t)d.nblocks * 64, sizeof(int16_t));
     uint8_t *samples = (uint8_t *)malloc((size_t)d.nsamples);
     uint32_t err = 0;
+    uint32_t ring[8];
     const uint32_t off = d.data_off, end = d.data_end, S = (uint32_t)sub_bytes;
     const uint32_t nsub = end > off ? (end - off + S - 1) / S : 1;
     std::vector<uint64_t> entry(nsub), exit_(nsub), prev(nsub);
@@ -67,7 +69,7 @@ int jpeg_host_decode_sync(const uint8_t *file, size_t n, uint8_t *rgb, size_t ca
     auto endbits = [&](uint32_t i) { const uint64_t e = (uint64_t)off + (uint64_t)(i + 1) * S; return (uint32_t)((e < end ? e : end) * 8u); };
     for (uint32_t i = 0; i < nsub; ++i) { // pass 1: from the guesses
         entry[i] = i == 0 ? JPG_STATE(off * 8u, 0, 0) : jpg_sub_guess(file, off + i * S, off);
-        exit_[i] = jpg_sub_decode<false>(d, d.dc, d.ac, jpg_zigzag_h, file, entry[i], endbits(i), nullptr, 0u, &nblk[i], err);
+        exit_[i] = jpg_sub_decode<false>(d, d.dc, d.ac, jpg_zigzag_h, file, ring, 1u, entry[i], endbits(i), nullptr, 0u, &nblk[i], err);
     }
     int r = 0;
     for (bool changed = true; changed; ++r) { // rounds
@@ -76,7 +78,7 @@ int jpeg_host_decode_sync(const uint8_t *file, size_t n, uint8_t *rgb, size_t ca
         for (uint32_t i = 1; i < nsub; ++i)
             if (prev[i - 1] != entry[i]) {
                 entry[i] = prev[i - 1];
-                exit_[i] = jpg_sub_decode<false>(d, d.dc, d.ac, jpg_zigzag_h, file, entry[i], endbits(i), nullptr, 0u, &nblk[i], err);
+                exit_[i] = jpg_sub_decode<false>(d, d.dc, d.ac, jpg_zigzag_h, file, ring, 1u, entry[i], endbits(i), nullptr, 0u, &nblk[i], err);
                 changed = true;
             }
     }
@@ -87,7 +89,7 @@ int jpeg_host_decode_sync(const uint8_t *file, size_t n, uint8_t *rgb, size_t ca
     err &= JPG_ERR_BLOCKS; // the passes above ran from guessed states
     for (uint32_t i = 0; i < nsub; ++i) { // last pass: write
         uint32_t dummy;
-        jpg_sub_decode<true>(d, d.dc, d.ac, jpg_zigzag_h, file, entry[i], endbits(i), coef, blk0[i], &dummy, err);
+        jpg_sub_decode<true>(d, d.dc, d.ac, jpg_zigzag_h, file, ring, 1u, entry[i], endbits(i), coef, blk0[i], &dummy, err);
     }
     for (int c = 0; c < d.ncomp; ++c) { // k_jpeg_dcscan: differences -> values
         const uint32_t nb = (uint32_t)d.nmcu * (uint32_t)(d.hs[c] * d.vs[c]);
