@@ -362,7 +362,8 @@ extern "C" int gseg_jpeg_info(const void *jpeg, size_t nbytes, int *w, int *h) {
     return jpeg_peek_size((const uint8_t *)jpeg, nbytes, w, h) == JPG_OK ? GSEG_OK : GSEG_E_ARG; // header parse on the host
 }
 
-#define GSEG_JPEG_AUTO_MCUS 512 // longest restart interval (MCUs) the automatic choice gives to the in-house decoder
+#define GSEG_JPEG_SYNC_MIN_RI 8 // restart intervals longer than this many MCUs are not decoded one thread per interval but as
+                                // self-synchronising sub-sequences (1080p 4:2:0: 0.8 ms at 8 MCUs per thread, 1.2 ms for the other way)
 // ---- in-house decoder (gseg_jpeg.cuh) -------------------------------------------------------------------
 // (Re)allocates one of the decoder's device buffers; growing waits for the last decode first (rare: the buffers are
 // sized for the context's capacity by the first JPEG or by gseg_reserve(GSEG_CAP_JPEG)).
@@ -436,8 +437,9 @@ static int jpeg_decode_enqueue(gseg_ctx *ctx, const uint8_t *file, const JpegPla
     uint32_t *d_starts = (uint32_t *)((uint8_t *)ctx->d_jdev + sizeof(JpegDev));
     const uint32_t S = ctx->jsub_bytes;
     const size_t nsub = (nbytes - (d.data_off - base) + S - 1) / S;
-    if (d.nint == 1 && nsub >= 2) {
-        // no restart markers: self-synchronising sub-sequences, one cluster (k_jpeg_sync), then the DC prefix sums
+    if ((d.nint == 1 || d.ri > GSEG_JPEG_SYNC_MIN_RI) && nsub >= 2) {
+        // no restart markers, or long intervals (every marker is one more point of re-synchronisation): self-synchronising
+        // sub-sequences, one cluster (k_jpeg_sync), then the DC prefix sums
         uint64_t *entryS = (uint64_t *)ctx->d_jsub, *exitS = entryS + nsub;
         uint32_t *nblk = (uint32_t *)(exitS + nsub), *blk0 = nblk + nsub, *flags = blk0 + nsub;
         cudaLaunchConfig_t cfg = {};
@@ -496,8 +498,7 @@ extern "C" int gseg_jpeg_decode_async(gseg_ctx *ctx, const void *jpeg, size_t nb
     if (prc != JPG_OK) { snprintf(ctx->err, sizeof(ctx->err), "in-house JPEG decoder: %s", plan.why); return GSEG_E_UNSUPPORTED; }
     if (w) *w = plan.dev.w;
     if (h) *h = plan.dev.h;
-    if (ctx->jpeg_backend == GSEG_JPEG_NVJPEG || (ctx->jpeg_backend == GSEG_JPEG_AUTO && plan.dev.nint > 1 && plan.dev.ri > GSEG_JPEG_AUTO_MCUS && nvjpeg_api()))
-        return fail(ctx, GSEG_E_UNSUPPORTED, "this file goes to nvJPEG under the context's backend setting", cudaSuccess);
+    if (ctx->jpeg_backend == GSEG_JPEG_NVJPEG) return fail(ctx, GSEG_E_UNSUPPORTED, "this file goes to nvJPEG under the context's backend setting", cudaSuccess);
     if ((size_t)3 * plan.dev.w * plan.dev.h > out_capacity) return fail(ctx, GSEG_E_RANGE, "output buffer too small for the decoded image", cudaSuccess);
     CK(cudaSetDevice(ctx->device));
     const int rc = jpeg_decode_enqueue(ctx, (const uint8_t *)jpeg, plan, rgb_out_device, cuda_stream ? (cudaStream_t)cuda_stream : ctx->stream);
@@ -533,9 +534,9 @@ static int jpeg_nvjpeg_async(gseg_ctx *ctx, const void *jpeg, size_t nbytes, con
     return rc;
 }
 
-// Which decoder: the in-house kernels take baseline Huffman files (gseg_jpeg_core.h) and get their parallelism from
-// restart markers.  Automatic choice: in-house when an interval is at most GSEG_JPEG_AUTO_MCUS MCUs long (a thread
-// decodes its interval serially: ~1 us per MCU), nvJPEG otherwise, in-house again when nvJPEG is not loadable.
+// Which decoder: the in-house kernels take every baseline / extended-sequential Huffman file (gseg_jpeg_core.h) -- one
+// thread per restart interval when the intervals are short, self-synchronising sub-sequences otherwise; nvJPEG gets
+// what they do not decode (progressive, arithmetic, CMYK ...).
 extern "C" int gseg_segment_jpeg_async(gseg_ctx *ctx, const void *jpeg, size_t nbytes, const gseg_params *p, int *w, int *h) {
     if (!ctx || !jpeg || !nbytes || !p) return GSEG_E_ARG;
     if (ctx->pending) return fail(ctx, GSEG_E_STATE, "previous run not waited for", cudaSuccess);
@@ -547,8 +548,7 @@ extern "C" int gseg_segment_jpeg_async(gseg_ctx *ctx, const void *jpeg, size_t n
         if (w) *w = plan.dev.w;
         if (h) *h = plan.dev.h;
     }
-    bool own = prc == JPG_OK && ctx->jpeg_backend != GSEG_JPEG_NVJPEG;
-    if (own && ctx->jpeg_backend == GSEG_JPEG_AUTO && plan.dev.nint > 1 && plan.dev.ri > GSEG_JPEG_AUTO_MCUS && nvjpeg_api()) own = false;
+    const bool own = prc == JPG_OK && ctx->jpeg_backend != GSEG_JPEG_NVJPEG;
     if (ctx->jpeg_backend == GSEG_JPEG_OWN && prc != JPG_OK) {
         snprintf(ctx->err, sizeof(ctx->err), "in-house JPEG decoder: %s", plan.why);
         return GSEG_E_UNSUPPORTED;

@@ -379,40 +379,64 @@ struct JpgWalk {
 };
 __global__ void __launch_bounds__(JPG_NT_SYNC) k_jpeg_dcscan(const JpegDev *__restrict__ gd, int16_t *__restrict__ coef) {
     __shared__ __align__(16) uint32_t sgeo[offsetof(JpegDev, quant) / 4];
-    __shared__ int s_part[32];
+    __shared__ int s_val[32], s_flag[32];
     for (int i = threadIdx.x; i < (int)(offsetof(JpegDev, quant) / 4); i += JPG_NT_SYNC) sgeo[i] = reinterpret_cast<const uint32_t *>(gd)[i];
     __syncthreads();
     const JpegDev &d = *reinterpret_cast<const JpegDev *>(sgeo);
     const int c = blockIdx.x;
     if (c >= d.ncomp) return;
-    const uint32_t n = (uint32_t)d.nmcu * (uint32_t)(d.hs[c] * d.vs[c]);
+    const uint32_t bpc = (uint32_t)(d.hs[c] * d.vs[c]);
+    const uint32_t n = (uint32_t)d.nmcu * bpc;
+    const uint32_t seg = (uint32_t)d.ri * bpc; // the predictor restarts with every restart interval: a SEGMENTED prefix sum
     const uint32_t per = (n + JPG_NT_SYNC - 1u) / JPG_NT_SYNC;
     const uint32_t b = min(threadIdx.x * per, n), e = min(b + per, n);
     JpgWalk wk;
     wk.init(d, c, b);
-    int sum = 0;
+    // the thread's run as (flag: a segment starts inside, val: sum since the run's last segment start)
+    int val = 0, flag = 0;
+    uint32_t left = seg - b % seg; // blocks until the next segment start (== seg: b itself is one)
+    if (left == seg) left = 0u;
     for (uint32_t t0 = b; t0 < e; t0 += 8u) {
         int x[8];
 #pragma unroll
         for (int u = 0; u < 8; ++u) { x[u] = t0 + u < e ? (int)coef[wk.index() * 64] : 0; wk.next(); }
 #pragma unroll
-        for (int u = 0; u < 8; ++u) sum += x[u];
+        for (int u = 0; u < 8; ++u)
+            if (t0 + u < e) {
+                if (left == 0u) { val = 0; flag = 1; left = seg; }
+                val += x[u];
+                --left;
+            }
     }
+    // inclusive scan over the threads with (f1, v1) + (f2, v2) = (f1 | f2, f2 ? v2 : v1 + v2)
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    int inc = sum;
+    int iv = val, ifl = flag;
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, inc, o); if (lane >= o) inc += t; }
-    if (lane == 31) s_part[warp] = inc;
+    for (int o = 1; o < 32; o <<= 1) {
+        const int pv = __shfl_up_sync(0xFFFFFFFFu, iv, o), pf = __shfl_up_sync(0xFFFFFFFFu, ifl, o);
+        if (lane >= o) { iv = ifl ? iv : iv + pv; ifl |= pf; }
+    }
+    if (lane == 31) { s_val[warp] = iv; s_flag[warp] = ifl; }
     __syncthreads();
     if (warp == 0) {
-        int v = s_part[lane], w2 = v;
+        int wv = s_val[lane], wf = s_flag[lane];
 #pragma unroll
-        for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xFFFFFFFFu, w2, o); if (lane >= o) w2 += t; }
-        s_part[lane] = w2 - v;
+        for (int o = 1; o < 32; o <<= 1) {
+            const int pv = __shfl_up_sync(0xFFFFFFFFu, wv, o), pf = __shfl_up_sync(0xFFFFFFFFu, wf, o);
+            if (lane >= o) { wv = wf ? wv : wv + pv; wf |= pf; }
+        }
+        // exclusive over the warps: what the warps before this one carry into it
+        const int ev = __shfl_up_sync(0xFFFFFFFFu, wv, 1), ef = __shfl_up_sync(0xFFFFFFFFu, wf, 1);
+        s_val[lane] = lane ? ev : 0; s_flag[lane] = lane ? ef : 0;
     }
     __syncthreads();
-    int pred = s_part[warp] + inc - sum;
+    // carry into this thread = (warps before) + (lanes before in the warp), exclusive
+    int cv = __shfl_up_sync(0xFFFFFFFFu, iv, 1), cf = __shfl_up_sync(0xFFFFFFFFu, ifl, 1);
+    if (lane == 0) { cv = 0; cf = 0; }
+    int pred = cf ? cv : cv + s_val[warp];
     wk.init(d, c, b);
+    left = seg - b % seg;
+    if (left == seg) left = 0u;
     for (uint32_t t0 = b; t0 < e; t0 += 8u) {
         int16_t *p[8];
         int x[8];
@@ -420,7 +444,12 @@ __global__ void __launch_bounds__(JPG_NT_SYNC) k_jpeg_dcscan(const JpegDev *__re
         for (int u = 0; u < 8; ++u) { p[u] = coef + wk.index() * 64; x[u] = t0 + u < e ? (int)*p[u] : 0; wk.next(); }
 #pragma unroll
         for (int u = 0; u < 8; ++u)
-            if (t0 + u < e) { pred += x[u]; *p[u] = (int16_t)pred; }
+            if (t0 + u < e) {
+                if (left == 0u) { pred = 0; left = seg; }
+                pred += x[u];
+                *p[u] = (int16_t)pred;
+                --left;
+            }
     }
 }
 

@@ -99,6 +99,8 @@ struct JpegBits {
     uint64_t buf;        // bit buffer, left-aligned
     int n;               // ... valid bits
     bool eof;            // a marker or the end of the data was reached: zero bits from here on
+    bool rst;            // ... and it was a restart marker, at file offset `mark`
+    uint32_t mark;
     int nfake;           // ... how many of the buffer's bits are such zeros (they sit behind the real ones)
 };
 GSEG_HD void jpg_ring_put(JpegBits &b, uint32_t half, const JpegChunk &c) {
@@ -113,7 +115,7 @@ GSEG_HD void jpg_bits_init(JpegBits &b, const uint8_t *file, uint32_t *ring, uin
     b.pend = jpg_load16(file, c + 2u);
     b.pos = pos;
     b.end0 = end > pos ? end : pos; b.ffhist = 0u;
-    b.buf = 0; b.n = 0; b.eof = false; b.nfake = 0;
+    b.buf = 0; b.n = 0; b.eof = false; b.rst = false; b.mark = 0u; b.nfake = 0;
 }
 GSEG_HD void jpg_advance(JpegBits &b, uint32_t nbytes) { // nbytes <= 4: at most one chunk border
     const uint32_t oldc = b.pos >> 4;
@@ -147,7 +149,7 @@ GSEG_HD void jpg_fill(JpegBits &b) { // at least 33 valid bits afterwards: a cod
                 if (v == 0xFFu) {
                     const uint32_t m = rem > 1u ? ((W >> 16) & 0xFFu) : 0xD9u;
                     if (m == 0u) { jpg_advance(b, 2u); b.ffhist |= 1u; } // stuffed byte
-                    else { v = 0u; b.eof = true; }                      // marker: stop here
+                    else { v = 0u; b.eof = true; b.rst = (m & 0xF8u) == 0xD0u; b.mark = b.pos; } // marker: stop here
                 } else jpg_advance(b, 1u);
             } else b.eof = true;
             if (b.eof) b.nfake += 8;
@@ -164,7 +166,7 @@ GSEG_HD void jpg_skip(JpegBits &b, int k) { b.buf <<= k; b.n -= k; }
 // file bytes.  A position never names the 0x00 of a stuffed pair.  End of the data once only padding zeros are left.
 GSEG_HD uint32_t jpg_bits_pos(const JpegBits &b) {
     const int nr = b.n - b.nfake;
-    if (nr <= 0) return b.end0 * 8u;
+    if (nr <= 0) return b.eof ? b.end0 * 8u : b.pos * 8u;
     const uint32_t q = (uint32_t)(nr + 7) >> 3;
     const uint32_t m = (b.ffhist >> (b.nfake >> 3)) & ((1u << q) - 1u);
 #if defined(__CUDA_ARCH__)
@@ -322,6 +324,20 @@ GSEG_HD uint64_t jpg_sub_decode(const JpegDev &d, const JpegHuff *dc, const Jpeg
             if (WRITE) {
                 const int hsc = d.hs[c], bv = hsc == 1 ? bi : (hsc == 2 ? bi >> 1 : bi / hsc), bh = bi - bv * hsc;
                 cb = coef + ((size_t)d.blk_off[c] + (size_t)(my * d.vs[c] + bv) * d.bw[c] + mx * hsc + bh) * 64;
+            }
+        }
+        // End of a restart interval: the reader stands at an RSTn marker and all that is left in front of it are the 1-bits
+        // that pad the last byte (no Huffman code is all ones, T.81 Annex C, so a symbol still to come shows a zero).
+        // Decoding goes on behind the marker with a block's DC code of an MCU's first block -- whatever state a guessed
+        // entry had brought along: every marker re-synchronises.  (The DC predictors restart too: k_jpeg_dcscan.)
+        if (b.eof && b.rst) {
+            const int nr = b.n - b.nfake;
+            if (nr <= 0 || (nr <= 7 && (uint32_t)(b.buf >> (64 - nr)) == (1u << nr) - 1u)) {
+                if (k != 0 || j != 0) e2 |= JPG_ERR_RST;
+                jpg_bits_init(b, file, b.ring, b.rs, b.mark + 2u, d.data_end); // (`rs` is the run/size symbol in here)
+                k = 0; j = 0; c = 0; bi = 0;
+                tdc = dc; tac = ac;
+                if (WRITE) cb = coef + ((size_t)d.blk_off[0] + (size_t)(my * d.vs[0]) * d.bw[0] + mx * d.hs[0]) * 64;
             }
         }
         pos = jpg_bits_pos(b);

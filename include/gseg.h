@@ -262,14 +262,14 @@ int gseg_join_segment(gseg_ctx *ctx, const void *dev_records, int n_strips, int6
  *   GSEG_JPEG_OWN     hand-written kernels (csrc/gseg_jpeg.cuh): baseline / extended-sequential Huffman,
  *                     8-bit, grey or YCbCr, luma 1x1 / 2x1 / 1x2 / 2x2 / 4x1, one interleaved scan.  The
  *                     pixels are bit-identical to libjpeg's default decoder (islow IDCT, fancy upsampling),
- *                     i.e. to what cv::imread gives the reference.  Files with restart markers
- *                     (cv::IMWRITE_JPEG_RST_INTERVAL, jpegtran -restart): one thread per restart interval,
- *                     the shorter the intervals the lower the latency.  Files without: self-synchronising
- *                     sub-sequences in one thread-block cluster (1080p: ~1.3 ms).
+ *                     i.e. to what cv::imread gives the reference.  Files with short restart intervals
+ *                     (<= 8 MCUs; cv::IMWRITE_JPEG_RST_INTERVAL, jpegtran -restart): one thread per
+ *                     interval, the lowest latency (1080p: 0.15-0.8 ms).  Files without restart markers or
+ *                     with longer intervals: self-synchronising sub-sequences in one thread-block cluster
+ *                     (1080p: ~1.2 ms).
  *   GSEG_JPEG_NVJPEG  nvJPEG (CUDA toolkit library, loaded with dlopen on first use -- libgseg.so does not
  *                     link it): everything else it can decode (progressive ...); Huffman stage on the host.
- *   GSEG_JPEG_AUTO    (default) OWN for every file it supports, except files with restart intervals longer
- *                     than 512 MCUs when nvJPEG is loadable; NVJPEG otherwise.
+ *   GSEG_JPEG_AUTO    (default) OWN for every file it supports, NVJPEG otherwise.
  *   gseg_jpeg_info          width / height of a JPEG (host only: parses the header, needs no device).
  *   gseg_segment_jpeg_async decode + enqueue the segmentation (complete it with gseg_wait, or use
  *   gseg_segment_jpeg       the blocking form); *w, *h receive the image size.

@@ -35,7 +35,7 @@ static void decode(const std::vector<uint8_t> &file, const JpegPlan &plan, bool 
     std::vector<uint8_t> rgb((size_t)3 * d.w * d.h);
     uint32_t err = 0;
     uint32_t ring[8];
-    if (sync && d.nint == 1) {
+    if (sync) {
         const uint32_t off = d.data_off, end = d.data_end;
         const uint32_t nsub = end > off ? (end - off + sub - 1) / sub : 1;
         std::vector<uint64_t> entry(nsub), ex(nsub), prev;
@@ -68,6 +68,7 @@ static void decode(const std::vector<uint8_t> &file, const JpegPlan &plan, bool 
             int pred = 0;
             for (uint32_t t = 0; t < nb; ++t) {
                 int16_t *p = coef.data() + jpg_comp_block(d, c, t) * 64;
+                if (t % ((uint32_t)d.ri * (uint32_t)(d.hs[c] * d.vs[c])) == 0) pred = 0;
                 pred = (int16_t)(pred + p[0]);
                 p[0] = (int16_t)pred;
             }

@@ -46,14 +46,13 @@ int jpeg_host_decode(const uint8_t *file, size_t n, uint8_t *rgb, size_t cap, in
 
 // The same for a file without restart markers through the self-synchronising sub-sequence decode (k_jpeg_sync + k_jpeg_dcscan):
 // every "thread" of a round sees the exits of the round before (what the kernel's barrier gives it at worst).
-// *rounds = iterations until no entry state changed.  5: the file has restart markers.
+// *rounds = iterations until no entry state changed.  Files with restart markers too: every marker re-synchronises.
 int jpeg_host_decode_sync(const uint8_t *file, size_t n, uint8_t *rgb, size_t cap, int *w, int *h, int sub_bytes, int *rounds) {
     JpegPlan plan;
     const int rc = jpeg_parse(file, n, plan, false);
     if (rc) return rc;
     const JpegDev &d = plan.dev;
     *w = d.w; *h = d.h;
-    if (d.nint != 1) return 5;
     if ((size_t)3 * d.w * d.h > cap) return 3;
     uint8_t *staged = (uint8_t *)calloc(n + 64, 1);
     memcpy(staged, file, n);
@@ -96,6 +95,7 @@ int jpeg_host_decode_sync(const uint8_t *file, size_t n, uint8_t *rgb, size_t ca
         int pred = 0;
         for (uint32_t t = 0; t < nb; ++t) {
             int16_t *p = coef + jpg_comp_block(d, c, t) * 64;
+            if (t % ((uint32_t)d.ri * (uint32_t)(d.hs[c] * d.vs[c])) == 0) pred = 0; // the predictors restart with every interval
             pred += p[0];
             p[0] = (int16_t)pred;
         }

@@ -125,8 +125,16 @@ def test_host_self_synchronising_decode_matches_libjpeg(host, oracle, sampling):
                 if q <= 90 and sub == 128:
                     worst = max(worst, rounds)
     assert worst <= 16
-    # a file WITH restart markers is not this path's business
-    assert host.sync(encode(oracle.synth(64, 48, 1), 90, sampling, 2).tobytes(), 64)[0] == 5
+    # files WITH restart markers through the same path: every marker re-synchronises (the padding in front of it is
+    # recognised, decoding goes on behind it, the DC predictors restart in the prefix sums)
+    img = oracle.synth(200, 120, 5)
+    for rst in (1, 3, 20, 97):
+        for q in (50, 95):
+            enc = encode(img, q, sampling, rst)
+            ref = libjpeg(enc)
+            for sub in (16, 128, 4096):
+                got, _ = host.sync(enc.tobytes(), sub)
+                assert not isinstance(got, int) and np.array_equal(got, ref), (rst, q, sub)
 
 
 def test_host_self_synchronising_decode_of_stuffing_heavy_data(host):
@@ -223,7 +231,8 @@ def test_gpu_decode_identical_to_libjpeg_and_partition_to_oracle(gseg, oracle):
     seg = gseg.Segmenter(400, 300)
     seg.set_jpeg_backend(gseg.JPEG_OWN)
     cases = [(320, 240, "420", 90, 4), (321, 243, "444", 75, 1), (200, 150, "422", 85, 7), (64, 300, "440", 95, 2),
-             (400, 96, "411", 60, 3), (17, 9, "420", 90, 0), (8, 8, "444", 100, 0), (1, 1, "420", 90, 0)]
+             (400, 96, "411", 60, 3), (17, 9, "420", 90, 0), (8, 8, "444", 100, 0), (1, 1, "420", 90, 0),
+             (400, 300, "420", 90, 25), (333, 222, "444", 80, 42), (400, 300, "422", 95, 100)]   # long intervals: the sub-sequence path, with markers
     for i, (w, h, sampling, q, rst) in enumerate(cases):
         img = oracle.synth(w, h, 50 + i)
         enc = encode(img, q, sampling, rst, optimize=i & 1)
