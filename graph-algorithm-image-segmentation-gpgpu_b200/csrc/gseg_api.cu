@@ -455,9 +455,10 @@ static int jpeg_decode_enqueue(gseg_ctx *ctx, const uint8_t *file, const JpegPla
             if (gs > 2 * ctx->num_sms) gs = 2 * ctx->num_sms;
             CK(cudaMemsetAsync(flags, 0, 5 * sizeof(uint32_t), s));
             k_jpeg_sync_grid<<<gs, JPG_NT_GRID, 0, s>>>(ctx->d_jdev, ctx->d_jfile, entryS, exitS, nblk, blk0, flags, ctx->d_jcoef, ctx->d_jerr + slot, S);
-        } else
-        CK(cudaLaunchKernelEx(&cfg, k_jpeg_sync, (const JpegDev *)ctx->d_jdev, (const uint8_t *)ctx->d_jfile, entryS, exitS, nblk, blk0, flags,
-                              ctx->d_jcoef, ctx->d_jerr + slot, S));
+        } else {
+            CK(cudaLaunchKernelEx(&cfg, k_jpeg_sync, (const JpegDev *)ctx->d_jdev, (const uint8_t *)ctx->d_jfile, entryS, exitS, nblk, blk0,
+                                  flags, ctx->d_jcoef, ctx->d_jerr + slot, S));
+        }
         k_jpeg_dcscan<<<d.ncomp, JPG_NT_SYNC, 0, s>>>(ctx->d_jdev, ctx->d_jcoef);
     } else {
         ctx->launches += 4;

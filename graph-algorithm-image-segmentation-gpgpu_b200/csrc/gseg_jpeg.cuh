@@ -1,17 +1,20 @@
 // gseg_jpeg.cuh -- kernels of the in-house baseline-JPEG decoder ("GPU-side decode feeding
 // batched mode -- removes the host staging bound"; the reference reads its JPEG data set with cv::imread on the host,
 // README.md:26).  The compressed file crosses PCIe (7-10x fewer bytes than the RGB image) and is decoded here into
-// the context's staged RGB buffer, on the context's stream, in front of the blur:
-//   k_jpeg_scan  one block: offsets of the restart intervals (the RSTn markers of the entropy-coded segment)
-//   k_jpeg_huff  one thread per restart interval: Huffman decoding (T.81 F.2.2) of its MCUs into the coefficient
-//                array (all zero between images; only non-zero coefficients are written)
+// the context's staged RGB buffer (or a caller's), on the context's stream or the pool's copy stream, in front of the blur:
+//   entropy decoding, one of two ways (gseg_api.cu chooses by the file's restart interval):
+//     k_jpeg_scan    one block: offsets of the restart intervals (the RSTn markers of the entropy-coded segment)
+//     k_jpeg_huff    one thread per restart interval: Huffman decoding (T.81 F.2.2) of its MCUs into the coefficient
+//                    array (all zero between images; only non-zero coefficients are written)
+//   or, for files without restart markers and for long intervals,
+//     k_jpeg_sync    one cluster (k_jpeg_sync_grid: a grid of small blocks): self-synchronising sub-sequences
+//     k_jpeg_dcscan  DC differences -> values (segmented prefix sums per component)
 //   k_jpeg_idct  one thread per 8x8 block: dequantisation + libjpeg's accurate integer inverse DCT -> sample planes;
 //                clears the block's coefficients behind it
 //   k_jpeg_rgb   eight pixels per thread: chroma upsampling ("fancy" triangle filter) + YCbCr -> interleaved RGB
 //   k_jpeg_flag  hands a decoding error to the run's control block
 // The arithmetic lives in gseg_jpeg_core.h (shared with the CPU test harness) and reproduces libjpeg's default decoder
-// bit for bit (tests/test_jpeg.py against cv2.imdecode).  Parallelism comes from the file's restart markers; a file
-// without them is one interval and goes to nvJPEG instead unless the caller forces this decoder.
+// bit for bit (tests/test_jpeg.py against cv2.imdecode).
 #pragma once
 #include <cooperative_groups.h>
 
