@@ -150,6 +150,71 @@ def test_host_self_synchronising_decode_of_stuffing_heavy_data(host):
             assert not isinstance(got, int) and np.array_equal(got, ref), (sampling, sub)
 
 
+def _segments(data):
+    """[(marker, start, end)] of the header segments in front of the scan data."""
+    out, p = [], 2
+    while data[p + 1] != 0xDA:
+        n = (data[p + 2] << 8) | data[p + 3]
+        out.append((data[p + 1], p, p + 2 + n))
+        p += 2 + n
+    out.append((0xDA, p, p + 2 + ((data[p + 2] << 8) | data[p + 3])))
+    return out
+
+
+def test_host_parser_header_variants(host, oracle):
+    """Header forms cv2's encoder never writes, made by rewriting its files: 16-bit quantisation tables, SOF1, comment and
+    application segments, fill bytes in front of markers, one table per DHT / DQT segment, a grey image that declares
+    2x2 sampling.  Same pixels as libjpeg decodes from the rewritten file (and as from the original)."""
+    img = oracle.synth(120, 88, 4)
+    for sampling, rst in (("420", 0), ("444", 5)):
+        orig = encode(img, 85, sampling, rst).tobytes()
+        ref = libjpeg(np.frombuffer(orig, np.uint8))
+        segs = _segments(orig)
+        out = bytearray(orig[:2])
+        for m, a, b in segs:
+            body = orig[a + 4:b]
+            if m == 0xDB:                                   # DQT: split into one table per segment, 16-bit entries
+                i = 0
+                while i < len(body):
+                    tq = body[i] & 15
+                    vals = body[i + 1:i + 65]
+                    wide = bytes([0x10 | tq]) + b"".join(bytes([0, v]) for v in vals)
+                    out += b"\xff\xff\xff\xdb" + (len(wide) + 2).to_bytes(2, "big") + wide   # with fill bytes in front
+                    i += 65
+            elif m == 0xC4:                                 # DHT: one table per segment
+                i = 0
+                while i < len(body):
+                    ns = sum(body[i + 1:i + 17])
+                    tab = body[i:i + 17 + ns]
+                    out += b"\xff\xc4" + (len(tab) + 2).to_bytes(2, "big") + tab
+                    i += 17 + ns
+            elif m == 0xC0:                                 # baseline -> extended sequential (same coding)
+                out += b"\xff\xfe" + (2 + 11).to_bytes(2, "big") + b"hello gseg!"                # a comment
+                out += b"\xff\xe5" + (2 + 4).to_bytes(2, "big") + b"\x00\x01\x02\x03"           # an application segment
+                out += b"\xff\xc1" + orig[a + 2:b]
+            else:
+                out += orig[a:b]
+        out += orig[segs[-1][2]:]
+        data = bytes(out)
+        dec = cv2.imdecode(np.frombuffer(data, np.uint8), cv2.IMREAD_COLOR)
+        assert dec is not None and np.array_equal(dec[..., ::-1], ref)        # libjpeg takes the rewritten file
+        got, _ = host(data)
+        assert not isinstance(got, int) and np.array_equal(got, ref), sampling
+        got, _ = host.sync(data, 64)
+        assert not isinstance(got, int) and np.array_equal(got, ref), sampling
+    # single component with declared sampling factors 2x2: still one block per MCU (T.81 A.2.2)
+    g = encode(img[..., 1], 90, "444", 3).tobytes()
+    segs = _segments(g)
+    sof = [s for s in segs if s[0] == 0xC0][0]
+    patched = bytearray(g)
+    assert patched[sof[1] + 9] == 1 and patched[sof[1] + 11] == 0x11
+    patched[sof[1] + 11] = 0x22
+    ref = cv2.imdecode(np.frombuffer(bytes(patched), np.uint8), cv2.IMREAD_COLOR)
+    assert ref is not None
+    got, _ = host(bytes(patched))
+    assert not isinstance(got, int) and np.array_equal(got, ref)
+
+
 def test_host_parser_rejects_what_it_does_not_decode(host, oracle):
     img = oracle.synth(64, 48, 9)
     enc = encode(img, 90, "420", 0, extra=(cv2.IMWRITE_JPEG_PROGRESSIVE, 1)).tobytes()
