@@ -341,9 +341,10 @@ def test_cli_ppm_roundtrip(gseg, oracle, tmp_path):
 
 
 def test_jpeg_input_decoded_on_gpu(gseg, oracle, tmp_path):
-    """JPEG bytes -> nvJPEG on the context's stream -> the usual path.  The partition is
-    checked against the oracle run on the very pixels the GPU decoded (gseg_input_rgb); the decode itself
-    is checked for sanity against libjpeg (cv2)."""
+    """JPEG bytes -> decoded on the GPU on the context's stream (the in-house kernels for these
+    baseline files; tests/test_jpeg.py checks their pixels bit for bit) -> the usual path.  The partition is checked
+    against the oracle run on the very pixels the GPU decoded (gseg_input_rgb); the decode is compared loosely with
+    libjpeg (cv2) here so that the test also holds for the nvJPEG backend."""
     import subprocess
     import torch
     cv2 = pytest.importorskip("cv2")
@@ -365,8 +366,8 @@ def test_jpeg_input_decoded_on_gpu(gseg, oracle, tmp_path):
         assert wh == (w, h) and gseg.jpeg_info(data) == (w, h)
         rgb = seg.input_rgb()
         dec = cv2.imdecode(enc, cv2.IMREAD_COLOR)[..., ::-1]
-        # the same picture as libjpeg's decode (chroma upsampling and IDCT rounding differ between the decoders:
-        # a few grey levels on noisy 4:2:0 content; a wrong decode would be off by tens)
+        # the same picture as libjpeg's decode (nvJPEG's chroma upsampling and IDCT rounding differ from it by a few grey
+        # levels on noisy 4:2:0 content; the in-house decoder is identical; a wrong decode would be off by tens)
         assert np.abs(rgb.astype(np.int32) - dec.astype(np.int32)).mean() < 8.0
         ref = oracle.pipeline(rgb, 0.8, 300.0, 20, 8, oracle.FELZ)
         assert seg.num_components() == ref["n"]
